@@ -1,0 +1,310 @@
+// fpsb_api.cu — the C ABI of libfpsb200.so (include/fpsb.h): handle management, host<->device
+// staging for FPSB_HOST callers, argument checking, exception firewall.
+#include "fpsb_internal.h"
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <new>
+
+namespace fpsb {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// pinned staging area large enough for `count` doubles
+static double *pin(Handle *h, size_t count) {
+    if (count > h->pin_count) {
+        if (h->pin) cudaFreeHost(h->pin);
+        h->pin = nullptr;
+        h->pin_count = 0;
+        FPSB_CUDA(cudaMallocHost((void **)&h->pin, count * sizeof(double)));
+        h->pin_count = count;
+    }
+    return h->pin;
+}
+
+struct Staged {
+    // device views of the caller's vectors; for FPSB_HOST they live in the handle's stage buffers
+    Handle *h;
+    int loc;
+    size_t in_off = 0, out_off = 0;
+    std::vector<std::pair<double *, std::pair<size_t, size_t>>> outs;   // (host dst, (offset, count))
+    Staged(Handle *hh, int l, size_t in_total, size_t out_total) : h(hh), loc(l) {
+        if (loc == FPSB_HOST) {
+            if (h->stage_in.n < in_total + 8) h->stage_in.alloc(in_total + 8);
+            if (h->stage_out.n < out_total + 8) h->stage_out.alloc(out_total + 8);
+            pin(h, in_total + out_total + 8);
+        }
+    }
+    const double *in(const double *p, size_t count) {
+        if (loc == FPSB_DEVICE) return p;
+        double *hp = h->pin + in_off;
+        memcpy(hp, p, count * sizeof(double));
+        double *d = h->stage_in.p + in_off;
+        FPSB_CUDA(cudaMemcpyAsync(d, hp, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        in_off += count;
+        return d;
+    }
+    double *out(double *p, size_t count) {
+        if (loc == FPSB_DEVICE) return p;
+        double *d = h->stage_out.p + out_off;
+        outs.push_back({p, {out_off, count}});
+        out_off += count;
+        return d;
+    }
+    void finish() {
+        if (loc == FPSB_DEVICE) { FPSB_CUDA(cudaStreamSynchronize(h->stream)); return; }
+        double *hp = h->pin + in_off;   // place results after the inputs in the pinned area
+        if (out_off)
+            FPSB_CUDA(cudaMemcpyAsync(hp, h->stage_out.p, out_off * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        FPSB_CUDA(cudaStreamSynchronize(h->stream));
+        for (auto &o : outs) memcpy(o.first, hp + o.second.first, o.second.second * sizeof(double));
+    }
+};
+
+}  // namespace fpsb
+
+using namespace fpsb;
+
+#define FPSB_TRY try {
+#define FPSB_CATCH                                                        \
+    }                                                                     \
+    catch (const fpsb::CudaFail &f) { return f.code; }                    \
+    catch (const std::bad_alloc &) { fpsb::set_error("out of host memory"); return FPSB_ENOMEM; } \
+    catch (...) { fpsb::set_error("unexpected C++ exception"); return FPSB_ECUDA; }
+
+#define REQUIRE(cond, code, msg)                       \
+    do { if (!(cond)) { fpsb::set_error(msg); return code; } } while (0)
+
+extern "C" {
+
+int fpsb_version(void) { return FPSB_VERSION; }
+const char *fpsb_last_error(void) { return g_err; }
+int fpsb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int fpsb_create(int64_t nvar, int64_t ncon, int64_t nnzj, const int64_t *jrow, const int64_t *jcol,
+                int index_base, int device, fpsb_handle *out) {
+    REQUIRE(out, FPSB_EINVAL, "fpsb_create: out is NULL");
+    *out = nullptr;
+    REQUIRE(nvar >= 0 && ncon >= 0 && nnzj >= 0, FPSB_EINVAL, "fpsb_create: negative size");
+    REQUIRE(nnzj == 0 || (jrow && jcol), FPSB_EINVAL, "fpsb_create: NULL structure");
+    REQUIRE(nvar + ncon < 2000000000LL && nnzj < 2000000000LL, FPSB_EINVAL, "fpsb_create: sizes exceed int32 device indices");
+    REQUIRE(index_base == 0 || index_base == 1, FPSB_EINVAL, "fpsb_create: index_base must be 0 or 1");
+    for (int64_t k = 0; k < nnzj; ++k) {
+        int64_t r = jrow[k] - index_base, c = jcol[k] - index_base;
+        REQUIRE(r >= 0 && r < ncon && c >= 0 && c < nvar, FPSB_EINVAL, "fpsb_create: Jacobian index out of range");
+    }
+    int ndev = fpsb_device_count();
+    REQUIRE(ndev > 0, FPSB_ECUDA, "fpsb_create: no CUDA device available (libfpsb200 has no CPU fallback)");
+    REQUIRE(device >= 0 && device < ndev, FPSB_EINVAL, "fpsb_create: bad device ordinal");
+    Handle *h = nullptr;
+    FPSB_TRY
+    FPSB_CUDA(cudaSetDevice(device));
+    h = new Handle();
+    h->device = device;
+    h->nvar = nvar; h->ncon = ncon; h->nnzj = nnzj;
+    h->jrow.resize((size_t)nnzj); h->jcol.resize((size_t)nnzj);
+    for (int64_t k = 0; k < nnzj; ++k) { h->jrow[(size_t)k] = jrow[k] - index_base; h->jcol[(size_t)k] = jcol[k] - index_base; }
+    FPSB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    FPSB_CUDA(cudaEventCreate(&h->ev0));
+    FPSB_CUDA(cudaEventCreate(&h->ev1));
+    csr_build(h);
+    fpsb_iter_default_opts(nvar, ncon, &h->iopts);
+    *out = reinterpret_cast<fpsb_handle>(h);
+    return FPSB_OK;
+    }
+    catch (const fpsb::CudaFail &f) { if (h) fpsb_destroy(reinterpret_cast<fpsb_handle>(h)); return f.code; }
+    catch (const std::bad_alloc &) { fpsb::set_error("out of host memory"); return FPSB_ENOMEM; }
+    catch (...) { fpsb::set_error("unexpected C++ exception"); return FPSB_ECUDA; }
+}
+
+int fpsb_destroy(fpsb_handle hh) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h) return FPSB_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    iter_free(h);
+    ldlt_free(h);
+    if (h->pin) cudaFreeHost(h->pin);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return FPSB_OK;
+}
+
+int fpsb_dims(fpsb_handle hh, int64_t *nvar, int64_t *ncon, int64_t *nnzj) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQUIRE(h, FPSB_EINVAL, "NULL handle");
+    if (nvar) *nvar = h->nvar;
+    if (ncon) *ncon = h->ncon;
+    if (nnzj) *nnzj = h->nnzj;
+    return FPSB_OK;
+}
+void *fpsb_stream(fpsb_handle hh) { return hh ? (void *)reinterpret_cast<Handle *>(hh)->stream : nullptr; }
+int fpsb_synchronize(fpsb_handle hh) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQUIRE(h, FPSB_EINVAL, "NULL handle");
+    FPSB_TRY
+    FPSB_CUDA(cudaSetDevice(h->device));
+    FPSB_CUDA(cudaStreamSynchronize(h->stream));
+    return FPSB_OK;
+    FPSB_CATCH
+}
+int fpsb_timer_start(fpsb_handle hh) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQUIRE(h, FPSB_EINVAL, "NULL handle");
+    FPSB_TRY
+    FPSB_CUDA(cudaSetDevice(h->device));
+    FPSB_CUDA(cudaEventRecord(h->ev0, h->stream));
+    return FPSB_OK;
+    FPSB_CATCH
+}
+int fpsb_timer_stop(fpsb_handle hh, double *ms) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQUIRE(h && ms, FPSB_EINVAL, "NULL argument");
+    FPSB_TRY
+    FPSB_CUDA(cudaSetDevice(h->device));
+    FPSB_CUDA(cudaEventRecord(h->ev1, h->stream));
+    FPSB_CUDA(cudaEventSynchronize(h->ev1));
+    float f = 0;
+    FPSB_CUDA(cudaEventElapsedTime(&f, h->ev0, h->ev1));
+    *ms = f;
+    return FPSB_OK;
+    FPSB_CATCH
+}
+int64_t fpsb_launch_count(fpsb_handle hh) { return hh ? reinterpret_cast<Handle *>(hh)->launches : 0; }
+
+int fpsb_set_jac_values(fpsb_handle hh, const double *vals, int loc) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQUIRE(h, FPSB_EINVAL, "NULL handle");
+    REQUIRE(vals || h->nnzj == 0, FPSB_EINVAL, "fpsb_set_jac_values: NULL vals");
+    FPSB_TRY
+    FPSB_CUDA(cudaSetDevice(h->device));
+    size_t nz = (size_t)h->nnzj;
+    if (nz) {
+        if (loc == FPSB_HOST) {
+            double *hp = pin(h, nz);
+            memcpy(hp, vals, nz * sizeof(double));
+            FPSB_CUDA(cudaMemcpyAsync(h->coo_vals.p, hp, nz * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        } else {
+            FPSB_CUDA(cudaMemcpyAsync(h->coo_vals.p, vals, nz * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        }
+    }
+    csr_refresh_values(h);
+    FPSB_CUDA(cudaStreamSynchronize(h->stream));
+    h->have_vals = true;
+    return FPSB_OK;
+    FPSB_CATCH
+}
+
+static int do_spmv(fpsb_handle hh, bool transpose, const double *x, double *y, int loc, int ncols) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQUIRE(h && x && y, FPSB_EINVAL, "NULL argument");
+    REQUIRE(h->have_vals, FPSB_ESTATE, "Jacobian values not set (call fpsb_set_jac_values first)");
+    FPSB_TRY
+    FPSB_CUDA(cudaSetDevice(h->device));
+    size_t nin = (size_t)(transpose ? h->ncon : h->nvar) * ncols, nout = (size_t)(transpose ? h->nvar : h->ncon) * ncols;
+    Staged S(h, loc, nin, nout);
+    const double *dx = S.in(x, nin);
+    double *dy = S.out(y, nout);
+    if (nout) {
+        if ((transpose ? h->At.nblk : h->A.nblk) == 0) FPSB_CUDA(cudaMemsetAsync(dy, 0, nout * sizeof(double), h->stream));
+        spmv_plain(h, transpose, dx, dy, ncols);
+    }
+    S.finish();
+    return FPSB_OK;
+    FPSB_CATCH
+}
+int fpsb_jprod(fpsb_handle h, const double *v, double *Av, int loc) { return do_spmv(h, false, v, Av, loc, 1); }
+int fpsb_jtprod(fpsb_handle h, const double *u, double *Atu, int loc) { return do_spmv(h, true, u, Atu, loc, 1); }
+int fpsb_jprod2(fpsb_handle h, const double *v, double *Av, int loc) { return do_spmv(h, false, v, Av, loc, 2); }
+int fpsb_jtprod2(fpsb_handle h, const double *u, double *Atu, int loc) { return do_spmv(h, true, u, Atu, loc, 2); }
+
+int fpsb_iter_default_opts(int64_t nvar, int64_t ncon, fpsb_iter_opts *o) {
+    REQUIRE(o, FPSB_EINVAL, "NULL opts");
+    const double se = 1.4901161193847656e-08;
+    o->ls_atol = o->ls_rtol = se; o->ls_itmax = 5 * (ncon + nvar);
+    o->ln_atol = o->ln_rtol = o->ln_btol = se; o->ln_conlim = 1.0 / se; o->ln_itmax = 5 * (ncon + nvar);
+    o->ne_atol = o->ne_rtol = o->ne_etol = se; o->ne_conlim = 1.0 / se; o->ne_itmax = 0;
+    return FPSB_OK;
+}
+int fpsb_iter_setup(fpsb_handle hh, const fpsb_iter_opts *opts) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQUIRE(h, FPSB_EINVAL, "NULL handle");
+    FPSB_TRY
+    FPSB_CUDA(cudaSetDevice(h->device));
+    if (opts) h->iopts = *opts;
+    h->iopts_set = true;
+    iter_setup(h);
+    return FPSB_OK;
+    FPSB_CATCH
+}
+
+static int iter_solve(fpsb_handle hh, int kind, double delta, const double *rhs1, const double *rhs2,
+                      double *p1, double *q1, double *p2, double *q2, int loc, fpsb_krylov_stats *stats) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQUIRE(h && rhs1 && rhs2 && p1 && q1 && p2 && q2 && stats, FPSB_EINVAL, "NULL argument");
+    REQUIRE(h->have_vals, FPSB_ESTATE, "Jacobian values not set (call fpsb_set_jac_values first)");
+    REQUIRE(delta >= 0.0, FPSB_EINVAL, "delta must be >= 0");
+    FPSB_TRY
+    FPSB_CUDA(cudaSetDevice(h->device));
+    size_t n = (size_t)h->nvar, m = (size_t)h->ncon;
+    size_t n2 = (kind == 0) ? m : n;
+    Staged S(h, loc, n + n2, 2 * n + 2 * m);
+    const double *d1 = S.in(rhs1, n), *d2 = S.in(rhs2, n2);
+    double *dp1 = S.out(p1, n), *dq1 = S.out(q1, m), *dp2 = S.out(p2, n), *dq2 = S.out(q2, m);
+    if (kind == 0) iter_solve_two_mixed(h, delta, d1, d2, dp1, dq1, dp2, dq2, stats);
+    else iter_solve_two_least_squares(h, delta, d1, d2, dp1, dq1, dp2, dq2, stats);
+    S.finish();
+    return FPSB_OK;
+    FPSB_CATCH
+}
+int fpsb_iter_solve_two_mixed(fpsb_handle h, double delta, const double *rhs1, const double *rhs2,
+                              double *p1, double *q1, double *p2, double *q2, int loc,
+                              fpsb_krylov_stats stats[2]) {
+    return iter_solve(h, 0, delta, rhs1, rhs2, p1, q1, p2, q2, loc, stats);
+}
+int fpsb_iter_solve_two_least_squares(fpsb_handle h, double delta, const double *rhs1, const double *rhs2,
+                                      double *p1, double *q1, double *p2, double *q2, int loc,
+                                      fpsb_krylov_stats stats[2]) {
+    return iter_solve(h, 1, delta, rhs1, rhs2, p1, q1, p2, q2, loc, stats);
+}
+
+static int extras(fpsb_handle hh, bool ldlt_variant, double delta, const double *rhs1, const double *rhs2,
+                  double *u1, double *u2, int loc, fpsb_krylov_stats *stats) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQUIRE(h && rhs1 && rhs2 && u1 && u2 && stats, FPSB_EINVAL, "NULL argument");
+    REQUIRE(h->have_vals, FPSB_ESTATE, "Jacobian values not set (call fpsb_set_jac_values first)");
+    FPSB_TRY
+    FPSB_CUDA(cudaSetDevice(h->device));
+    size_t n = (size_t)h->nvar, m = (size_t)h->ncon;
+    Staged S(h, loc, n + m, 2 * m);
+    const double *d1 = S.in(rhs1, n), *d2 = S.in(rhs2, m);
+    double *du1 = S.out(u1, m), *du2 = S.out(u2, m);
+    iter_solve_two_extras(h, delta, d1, d2, du1, du2, stats, ldlt_variant);
+    S.finish();
+    return FPSB_OK;
+    FPSB_CATCH
+}
+int fpsb_iter_solve_two_extras(fpsb_handle h, double delta, const double *rhs1, const double *rhs2,
+                               double *u1, double *u2, int loc, fpsb_krylov_stats stats[2]) {
+    return extras(h, false, delta, rhs1, rhs2, u1, u2, loc, stats);
+}
+int fpsb_ldlt_solve_two_extras(fpsb_handle h, double delta, const double *rhs1, const double *rhs2,
+                               double *u1, double *u2, int loc, fpsb_krylov_stats stats[2]) {
+    return extras(h, true, delta, rhs1, rhs2, u1, u2, loc, stats);
+}
+
+}  // extern "C"

@@ -1,0 +1,100 @@
+// fpsb_device.cuh — sm_100a device helpers: TMA bulk copies + mbarrier, reductions, Givens.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fpsb {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a mis-programmed transaction count must not hang the GPU box
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity) {
+    for (int it = 0; it < (1 << 22); ++it)
+        if (mbar_try_wait(bar, parity)) return true;
+    return false;
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// fixed-tree block reduction of NV values per thread (blockDim.x == 256); result valid in thread 0
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double *scratch /* NV*8 */) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double x = warp_sum(v[k]);
+        if (lane == 0) scratch[k * 8 + w] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double x = 0.0;
+            for (int i = 0; i < (int)(blockDim.x >> 5); ++i) x += scratch[k * 8 + i];
+            v[k] = x;
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ double sgn(double a) { return (double)((a > 0.0) - (a < 0.0)); }
+
+// Krylov.jl sym_givens
+__device__ __forceinline__ void sym_givens(double a, double b, double &c, double &s, double &rho) {
+    if (b == 0.0) {
+        c = (a == 0.0) ? 1.0 : sgn(a);
+        s = 0.0;
+        rho = fabs(a);
+    } else if (a == 0.0) {
+        c = 0.0;
+        s = sgn(b);
+        rho = fabs(b);
+    } else if (fabs(b) > fabs(a)) {
+        double t = a / b;
+        s = sgn(b) / sqrt(1.0 + t * t);
+        c = s * t;
+        rho = b / s;
+    } else {
+        double t = b / a;
+        c = sgn(a) / sqrt(1.0 + t * t);
+        s = c * t;
+        rho = a / c;
+    }
+}
+
+}  // namespace fpsb

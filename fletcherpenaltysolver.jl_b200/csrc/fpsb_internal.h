@@ -1,0 +1,134 @@
+// fpsb_internal.h — shared declarations of libfpsb200 (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/fpsb.h"
+
+namespace fpsb {
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing: no exceptions cross the C ABI
+// ------------------------------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+struct CudaFail { int code; };
+
+#define FPSB_CUDA(call)                                                                  \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess) {                                                        \
+            fpsb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,                \
+                            cudaGetErrorString(e__));                                    \
+            throw fpsb::CudaFail{FPSB_ECUDA};                                            \
+        }                                                                                \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    void alloc(size_t count) {
+        release();
+        n = count;
+        FPSB_CUDA(cudaMalloc((void **)&p, (count ? count : 1) * sizeof(T)));
+    }
+    void zero(cudaStream_t s) { if (p) FPSB_CUDA(cudaMemsetAsync(p, 0, (n ? n : 1) * sizeof(T), s)); }
+    void upload(const T *h, size_t count, cudaStream_t s) {
+        if (count) FPSB_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    void from(const std::vector<T> &h, cudaStream_t s) { alloc(h.size() + 8); upload(h.data(), h.size(), s); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DevBuf() { release(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+};
+
+// ------------------------------------------------------------------------------------------------
+// CSR operator on the device with its row-block tiling (one CTA per row block)
+// ------------------------------------------------------------------------------------------------
+constexpr int kTile = 2048;       // nnz staged per CTA (TMA bulk copy into shared memory)
+constexpr int kBlock = 256;       // threads per CTA == max rows per row block
+
+struct CsrDev {
+    int nrows = 0, ncols = 0;
+    int64_t nnz = 0;
+    DevBuf<int> rp, ci, perm;     // perm: CSR slot -> COO index (value refresh)
+    DevBuf<double> vx;
+    DevBuf<int> blk;              // row-block boundaries (nblk + 1)
+    int nblk = 0;
+    int lanes = 8;                // sub-warp width used for the per-row reduction
+};
+
+// ------------------------------------------------------------------------------------------------
+// Krylov engine state (device-resident scalars; one per "slot" = one right-hand side)
+// ------------------------------------------------------------------------------------------------
+enum Algo { ALGO_NONE = 0, ALGO_LSQR = 1, ALGO_CRAIG = 2, ALGO_MINRES = 3, ALGO_CGLS = 4 };
+
+struct SlotState {
+    // configuration
+    int algo, itmax, sqd, pad0;
+    double lambda, atol, rtol, axtol, btol, etol, ctol, mscale;
+    // control
+    int active, iter, solved, inconsistent, status, first, pend, beta_zero;
+    int tired, ill_mach, ill_lim, zero_resid, fwd_err, pad1, pad2, pad3;
+    // shared scalars
+    double beta1, alpha, beta, Anorm2, Anorm, Acond, xNorm, xNorm2, dNorm2;
+    double rNorm, ArNorm, ArNorm0, phibar, rhobar, res2, xENorm2, err_lbnd, err_vec[5];
+    double c, s, rho, phi, psi, tau, c2, s2, z;
+    // coefficients consumed by the vector kernels
+    double su, sv, sigma, tr_prev;
+    // CRAIG
+    double theta, xi, deltag, rho_prev, c1, s1, s2g, trw, xr, beta1sq, eps_c;
+    // MINRES
+    double oldbeta, deltabar, eps_, rhs1, rhs2, gmax, gmin, cs, sn, delta, gamma, gammabar, root, tol;
+    // CGLS
+    double gamma_c, pp, delta_c, beta_c, bnorm;
+};
+
+struct IterWs;     // defined in fpsb_krylov.cu
+struct LdltPlan;   // defined in fpsb_ldlt.cu
+
+struct Handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int64_t nvar = 0, ncon = 0, nnzj = 0;
+    std::vector<int64_t> jrow, jcol;          // 0-based COO structure (host copy)
+    CsrDev A, At;                             // A (ncon x nvar) and A' (nvar x ncon)
+    DevBuf<double> coo_vals;                  // jac_coord values in COO order
+    bool have_vals = false;
+    int64_t launches = 0;
+    // host staging (pinned)
+    double *pin = nullptr;
+    size_t pin_count = 0;
+    DevBuf<double> stage_in, stage_out;
+    IterWs *iter = nullptr;
+    LdltPlan *ldlt = nullptr;
+    fpsb_iter_opts iopts{};
+    bool iopts_set = false;
+};
+
+// krylov.cu
+void csr_build(Handle *h);
+void csr_refresh_values(Handle *h);
+void spmv_plain(Handle *h, bool transpose, const double *x, double *y, int ncols_rhs);
+void iter_setup(Handle *h);
+void iter_free(Handle *h);
+void iter_solve_two_mixed(Handle *h, double delta, const double *rhs1, const double *rhs2, double *p1,
+                          double *q1, double *p2, double *q2, fpsb_krylov_stats *st);
+void iter_solve_two_least_squares(Handle *h, double delta, const double *rhs1, const double *rhs2,
+                                  double *p1, double *q1, double *p2, double *q2,
+                                  fpsb_krylov_stats *st);
+void iter_solve_two_extras(Handle *h, double delta, const double *rhs1, const double *rhs2, double *u1,
+                           double *u2, fpsb_krylov_stats *st, bool ldlt_variant);
+
+// symbolic.cpp / ldlt.cu
+void ldlt_analyze(Handle *h, const int64_t *P, const fpsb_ldlt_opts *opts);
+void ldlt_free(Handle *h);
+void ldlt_factorize(Handle *h, double delta, int *factorized);
+void ldlt_solve2(Handle *h, int kind, const double *rhs1, const double *rhs2, double *p1, double *q1,
+                 double *p2, double *q2, int *factorized);
+
+}  // namespace fpsb

@@ -1,0 +1,1377 @@
+// fpsb_krylov.cu — SpMV / fused two-column SpMM and the fused LSQR / CRAIG / MINRES / CGLS
+// iterations of the IterativeSolver path.
+//
+// Reference surface replaced (file:line under /root/reference):
+//   jac_op! products                         NLPModels, used at src/solve_linear_system.jl:119-121
+//   solve_least_square  (LSQR on A')         src/solve_two_systems_struct.jl:167-185
+//   solve_least_norm    (CRAIG, M=I/delta)   src/solve_two_systems_struct.jl:210-244
+//   solve_two_mixed / least_squares / extras src/solve_linear_system.jl:45-140 (Iterative), :142-159 (LDLt extras)
+//
+// Design (B200): the Jacobian lives in HBM as CSR(A) and CSR(A') (no atomics, deterministic).
+// One CTA per row block: the block's values+indices are staged into shared memory with two TMA
+// 1-D bulk copies (cp.async.bulk + mbarrier), a sub-warp reduces every row against BOTH
+// right-hand-side columns with a single 16-byte gather per nonzero (the two Golub-Kahan
+// vectors are interleaved), and the row epilogue applies the axpby / norm / delayed x,w updates
+// of the Krylov method so that every vector is read and written once per iteration.
+// Norms use fixed-order reductions (per-CTA partials, last CTA finishes) and the scalar
+// recurrences (Givens rotations, stopping tests) run on the device in the last CTA; the host only
+// polls a done flag every few iterations.
+#include "fpsb_internal.h"
+#include "fpsb_device.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace fpsb {
+
+static const double kSqrtEps = 1.4901161193847656e-08;
+
+enum Mode {
+    MD_NONE = 0,
+    MD_PLAIN,
+    MD_LSQR_INIT_M,   // v1 = A' u1 : first half step (row space of the LSQR solution)
+    MD_LSQR_U,        // u <- Op v - alpha u          (row space of the LSQR right-hand side)
+    MD_LSQR_V,        // w,x updates; v <- Op' u - beta v
+    MD_CRAIG_V,       // delayed x,w2 updates; v <- Op' u - beta v
+    MD_CRAIG_U,       // w,y updates; Mu <- Op v - alpha Mu
+    MD_MINRES_M,
+    MD_CGLS_INIT_M,
+    MD_CGLS_N,
+    MD_CGLS_M
+};
+
+enum EwOp {
+    EW_COPY = 0,          // out = c0 * in
+    EW_INIT_LSQR,         // self = b ; acc ||b||^2
+    EW_INIT_CRAIG,        // self = c0 * b ; w = y = 0 ; acc
+    EW_CRAIG_FLUSH,       // out = -(x + pending update)
+    EW_MINRES_INIT,
+    EW_MINRES_E1,
+    EW_MINRES_E2,
+    EW_CGLS_INIT,
+    EW_CGLS_EN,
+    EW_CGLS_EM
+};
+
+struct SlotIO {
+    int mode;
+    int pad;
+    const double *gin;   // gather source (non-pair kernels)
+    double *self;        // recurred vector of this row space (non-pair kernels)
+    double *a0, *a1, *a2;
+    double c0, c1;
+};
+
+struct StepParams {
+    const int *rp;
+    const int *ci;
+    const double *vx;
+    const int *blk;
+    int nrows;
+    int lanes;
+    const double2 *gin2;   // interleaved gather pair (PAIR kernels)
+    double2 *self2;        // interleaved recurred pair of this row space (PAIR kernels)
+    SlotIO io[2];
+    SlotState *st;
+    double *partials;      // [grid][4]
+    unsigned *counter;
+    int *done_flag;        // set to 1 when no slot remains active
+};
+
+// ------------------------------------------------------------------------------------------------
+// scalar recurrences (one thread, last CTA) — line-by-line the reference algorithms
+// ------------------------------------------------------------------------------------------------
+__device__ void slot_stop(SlotState &S) { S.active = 0; }
+
+__device__ void lsqr_status(SlotState &S) {
+    int st = FPSB_ST_UNKNOWN;
+    if (S.tired) st = FPSB_ST_TIRED;
+    if (S.ill_mach) st = FPSB_ST_ILLCOND_MACH;
+    if (S.ill_lim) st = FPSB_ST_ILLCOND_LIM;
+    if (S.solved) st = FPSB_ST_SOLVED;
+    if (S.zero_resid) st = FPSB_ST_ZERO_RESID;
+    if (S.fwd_err) st = FPSB_ST_FWD_ERR;
+    S.status = st;
+    S.inconsistent = !S.zero_resid;
+}
+
+__device__ void fin_init_lsqr(SlotState &S, double bb) {
+    double beta1 = sqrt(bb);
+    S.beta1 = beta1;
+    S.iter = 0;
+    if (beta1 == 0.0) {
+        S.active = 0; S.solved = 1; S.inconsistent = 0; S.status = FPSB_ST_ZERO_RHS;
+        return;
+    }
+    S.beta = beta1;
+    S.su = 1.0 / beta1;
+}
+
+__device__ void fin_lsqr_init_m(SlotState &S, double vv) {
+    S.Anorm2 = vv;
+    S.Anorm = sqrt(vv);
+    S.alpha = S.Anorm;
+    S.Acond = 0; S.xNorm = 0; S.xNorm2 = 0; S.dNorm2 = 0;
+    S.c2 = -1.0; S.s2 = 0.0; S.z = 0.0;
+    S.xENorm2 = 0; S.err_lbnd = 0;
+    for (int i = 0; i < 5; ++i) S.err_vec[i] = 0;
+    S.rNorm = S.beta1; S.res2 = 0;
+    S.ArNorm = S.ArNorm0 = S.alpha * S.beta;
+    if (S.alpha == 0.0) {
+        S.active = 0; S.solved = 1; S.inconsistent = 0; S.status = FPSB_ST_ZERO_ATB;
+        return;
+    }
+    S.sv = 1.0 / S.alpha;
+    S.phibar = S.beta1;
+    S.rhobar = S.alpha;
+    S.first = 1;
+    int solved_lim = S.ArNorm / (S.Anorm * S.rNorm) <= S.axtol;
+    int solved_mach = 1.0 + S.ArNorm / (S.Anorm * S.rNorm) <= 1.0;
+    S.solved = solved_mach | solved_lim;
+    S.tired = S.iter >= S.itmax;
+    S.zero_resid = (S.rNorm / S.beta1 <= S.axtol) | (1.0 + S.rNorm / S.beta1 <= 1.0);
+    S.ill_mach = S.ill_lim = S.fwd_err = 0;
+    if (S.solved || S.tired) { lsqr_status(S); S.active = 0; }
+}
+
+// after u <- Op v - alpha u
+__device__ void fin_lsqr_u(SlotState &S, double uu) {
+    S.iter += 1;
+    double beta = sqrt(uu);
+    S.beta = beta;
+    if (beta != 0.0) {
+        S.su = 1.0 / beta;
+        S.beta_zero = 0;
+        S.Anorm2 = S.Anorm2 + S.alpha * S.alpha + beta * beta;
+        if (S.lambda > 0) S.Anorm2 += S.lambda * S.lambda;
+    } else {
+        S.su = 0.0;
+        S.beta_zero = 1;
+    }
+    double c1, s1, rhobar1;
+    sym_givens(S.rhobar, S.lambda, c1, s1, rhobar1);
+    S.psi = s1 * S.phibar;
+    S.phibar = c1 * S.phibar;
+    sym_givens(rhobar1, beta, S.c, S.s, S.rho);
+    S.phi = S.c * S.phibar;
+    S.phibar = S.s * S.phibar;
+    S.xENorm2 += S.phi * S.phi;
+    S.err_vec[S.iter % 5] = S.phi;
+    if (S.iter >= 5) {
+        double e = 0;
+        for (int i = 0; i < 5; ++i) e += S.err_vec[i] * S.err_vec[i];
+        S.err_lbnd = sqrt(e);
+    }
+    S.tau = S.s * S.phi;
+    S.sigma = S.phi / S.rho;
+}
+
+// after v <- Op' u - beta v (and the x, w updates)
+__device__ void fin_lsqr_v(SlotState &S, double vv, double ww) {
+    if (!S.beta_zero) {
+        S.alpha = sqrt(vv);
+        S.sv = (S.alpha != 0.0) ? 1.0 / S.alpha : 0.0;
+    }
+    double theta = S.s * S.alpha;
+    S.rhobar = -S.c * S.alpha;
+    S.dNorm2 += ww / (S.rho * S.rho);
+    S.tr_prev = theta / S.rho;
+    S.first = 0;
+    double delta = S.s2 * S.rho;
+    double gammabar = -S.c2 * S.rho;
+    double rhs = S.phi - delta * S.z;
+    double zbar = rhs / gammabar;
+    S.xNorm = sqrt(S.xNorm2 + zbar * zbar);
+    double gamma;
+    sym_givens(gammabar, theta, S.c2, S.s2, gamma);
+    S.z = rhs / gamma;
+    S.xNorm2 += S.z * S.z;
+    S.Anorm = sqrt(S.Anorm2);
+    S.Acond = S.Anorm * sqrt(S.dNorm2);
+    double res1 = S.phibar * S.phibar;
+    S.res2 += S.psi * S.psi;
+    S.rNorm = sqrt(res1 + S.res2);
+    S.ArNorm = S.alpha * fabs(S.tau);
+    double test1 = S.rNorm / S.beta1;
+    double test2 = S.ArNorm / (S.Anorm * S.rNorm);
+    double test3 = 1.0 / S.Acond;
+    double t1 = test1 / (1.0 + S.Anorm * S.xNorm / S.beta1);
+    double rNormtol = S.btol + S.axtol * S.Anorm * S.xNorm / S.beta1;
+    S.ill_mach = (1.0 + test3 <= 1.0);
+    int solved_mach = (1.0 + test2 <= 1.0);
+    int zero_resid_mach = (1.0 + t1 <= 1.0);
+    S.tired = S.iter >= S.itmax;
+    S.ill_lim = (test3 <= S.ctol);
+    int solved_lim = (test2 <= S.axtol);
+    int solved_opt = S.ArNorm <= S.atol + S.rtol * S.ArNorm0;
+    int zero_resid_lim = (test1 <= rNormtol);
+    if (S.iter >= 5) S.fwd_err = S.err_lbnd <= S.etol * sqrt(S.xENorm2);
+    int ill_cond = S.ill_mach || S.ill_lim;
+    S.zero_resid = zero_resid_mach || zero_resid_lim;
+    S.solved = solved_mach || solved_lim || solved_opt || S.zero_resid || S.fwd_err;
+    if (S.solved || S.tired || ill_cond) { lsqr_status(S); S.active = 0; }
+}
+
+__device__ void craig_status(SlotState &S) {
+    int st = FPSB_ST_UNKNOWN;
+    if (S.tired) st = FPSB_ST_TIRED;
+    if (S.solved) st = FPSB_ST_SOLVED;
+    if (S.ill_mach) st = FPSB_ST_ILLCOND_MACH;
+    if (S.ill_lim) st = FPSB_ST_ILLCOND_LIM;
+    if (S.inconsistent) st = FPSB_ST_INCONSISTENT;
+    S.status = st;
+}
+
+__device__ void fin_init_craig(SlotState &S, double bb) {
+    double beta1 = sqrt(S.mscale * bb);   // sqrt(u'Mu), u = mscale * Mu
+    S.beta1 = beta1;
+    S.rNorm = beta1;
+    S.iter = 0;
+    if (beta1 == 0.0) {
+        S.active = 0; S.solved = 1; S.inconsistent = 0; S.status = FPSB_ST_ZERO_RHS;
+        return;
+    }
+    S.beta1sq = beta1 * beta1;
+    S.beta = beta1;
+    S.theta = beta1;
+    S.xi = -1.0;
+    S.deltag = S.lambda;
+    S.rho_prev = 1.0;
+    S.su = 1.0 / beta1;
+    S.sv = 0.0;
+    S.pend = 0;
+    S.c1 = 1.0; S.s1 = 0.0; S.s2g = 1.0;
+    S.Anorm2 = 0; S.Anorm = 0; S.dNorm2 = 0; S.Acond = 0; S.xNorm2 = 0;
+    S.eps_c = S.atol + S.rtol * S.rNorm;
+    double bkwerr = 1.0;
+    int solved_lim = bkwerr <= S.btol;
+    int solved_mach = 1.0 + bkwerr <= 1.0;
+    int solved_resid_tol = S.rNorm <= S.eps_c;
+    int solved_resid_lim = S.rNorm <= S.btol + S.atol * S.Anorm * sqrt(S.xNorm2) / beta1;
+    S.solved = solved_mach | solved_lim | solved_resid_tol | solved_resid_lim;
+    S.tired = S.iter >= S.itmax;
+    S.ill_mach = S.ill_lim = 0;
+    S.inconsistent = 0;
+    if (S.solved || S.tired) { craig_status(S); S.active = 0; }
+}
+
+// after v <- Op' u - beta v
+__device__ void fin_craig_v(SlotState &S, double vv) {
+    S.pend = 0;   // the previous iteration's x update was applied by this kernel
+    double alpha = sqrt(vv);
+    if (alpha == 0.0) {
+        S.inconsistent = 1;
+        craig_status(S);
+        S.active = 0;
+        return;
+    }
+    S.alpha = alpha;
+    S.sv = 1.0 / alpha;
+    S.Anorm2 += alpha * alpha;
+    if (S.lambda > 0) sym_givens(alpha, S.deltag, S.c1, S.s1, S.rho);
+    else S.rho = alpha;
+    S.xi = -S.theta / S.rho * S.xi;
+    S.trw = S.theta / S.rho_prev;
+    S.xr = S.xi / S.rho;
+    S.pend = 1;
+}
+
+// after Mu <- Op v - alpha Mu (and the w, y updates)
+__device__ void fin_craig_u(SlotState &S, double uu, double ww) {
+    double beta = sqrt(S.mscale * uu);
+    S.beta = beta;
+    S.su = (beta != 0.0) ? 1.0 / beta : 0.0;
+    if (S.lambda > 0) {
+        S.theta = S.c1 * beta;
+        double gamma = S.s1 * beta;
+        double c2;
+        sym_givens(S.lambda, gamma, c2, S.s2g, S.deltag);
+    } else {
+        S.theta = beta;
+    }
+    S.Anorm2 += beta * beta;
+    S.Anorm = sqrt(S.Anorm2);
+    S.dNorm2 += sqrt(ww);   // upstream craig.jl accumulates the 2-norm here (kept)
+    S.Acond = S.Anorm * sqrt(S.dNorm2);
+    S.xNorm2 += S.xi * S.xi;
+    S.rNorm = beta * fabs(S.xi);
+    if (S.lambda > 0) S.rNorm *= fabs(S.c1);
+    S.iter += 1;
+    double bkwerr = S.rNorm / sqrt(S.beta1sq + S.Anorm2 * S.xNorm2);
+    S.rho_prev = S.rho;
+    int solved_lim = bkwerr <= S.btol;
+    int solved_mach = 1.0 + bkwerr <= 1.0;
+    int solved_resid_tol = S.rNorm <= S.eps_c;
+    int solved_resid_lim = S.rNorm <= S.btol + S.atol * S.Anorm * sqrt(S.xNorm2) / S.beta1;
+    S.solved = solved_mach | solved_lim | solved_resid_tol | solved_resid_lim;
+    S.ill_mach = 1.0 + 1.0 / S.Acond <= 1.0;
+    S.ill_lim = 1.0 / S.Acond <= S.ctol;
+    S.inconsistent = 0;
+    S.tired = S.iter >= S.itmax;
+    S.xNorm = sqrt(S.xNorm2);
+    if (S.solved || S.ill_mach || S.ill_lim || S.tired) { craig_status(S); S.active = 0; }
+}
+
+// ---- MINRES ------------------------------------------------------------------------------------
+__device__ void fin_minres_init(SlotState &S, double bb) {
+    S.iter = 0;
+    if (bb == 0.0) {
+        S.active = 0; S.solved = 1; S.inconsistent = 0; S.status = FPSB_ST_ZERO_RHS;
+        S.beta1 = 0;
+        return;
+    }
+    double beta1 = sqrt(bb);
+    S.beta1 = beta1; S.beta = beta1; S.oldbeta = 0; S.deltabar = 0; S.eps_ = 0;
+    S.rNorm = beta1; S.phibar = beta1; S.rhs1 = beta1; S.rhs2 = 0;
+    S.gmax = 0; S.gmin = INFINITY; S.cs = -1.0; S.sn = 0;
+    S.Anorm2 = 0; S.Anorm = 0; S.Acond = 0; S.ArNorm = 0; S.xNorm = 0; S.xENorm2 = 0; S.err_lbnd = 0;
+    for (int i = 0; i < 5; ++i) S.err_vec[i] = 0;
+    S.tol = S.atol + S.rtol * beta1;
+    S.solved = (S.rNorm <= S.rtol);
+    S.tired = S.iter >= S.itmax;
+    S.zero_resid = (S.rNorm <= S.tol);
+    S.ill_mach = S.ill_lim = S.fwd_err = 0;
+    if (S.solved || S.tired) {
+        S.status = S.solved ? FPSB_ST_SOLVED : FPSB_ST_TIRED;
+        S.inconsistent = !S.zero_resid;
+        S.active = 0;
+    }
+}
+__device__ void fin_minres_m(SlotState &S, double vy) {
+    S.iter += 1;
+    S.alpha = vy / S.beta;
+    S.delta = S.cs * S.deltabar + S.sn * S.alpha;
+}
+__device__ void fin_minres_e1(SlotState &S, double yy) {
+    S.oldbeta = S.beta;
+    S.beta = sqrt(yy);
+    double alpha = S.alpha, beta = S.beta;
+    S.Anorm2 = S.Anorm2 + alpha * alpha + S.oldbeta * S.oldbeta + beta * beta;
+    S.gammabar = S.sn * S.deltabar - S.cs * alpha;
+    S.eps_ = S.sn * beta;
+    S.deltabar = -S.cs * beta;
+    S.root = sqrt(S.gammabar * S.gammabar + S.deltabar * S.deltabar);
+    S.ArNorm = S.phibar * S.root;
+    double gamma = sqrt(S.gammabar * S.gammabar + beta * beta);
+    gamma = fmax(gamma, 2.220446049250313e-16);
+    S.gamma = gamma;
+    S.cs = S.gammabar / gamma;
+    S.sn = beta / gamma;
+    S.phi = S.cs * S.phibar;
+    S.phibar = S.sn * S.phibar;
+}
+__device__ void fin_minres_e2(SlotState &S, double xx) {
+    const double epsM = 2.220446049250313e-16;
+    S.xENorm2 += S.phi * S.phi;
+    S.err_vec[S.iter % 5] = S.phi;
+    if (S.iter >= 5) {
+        double e = 0;
+        for (int i = 0; i < 5; ++i) e += S.err_vec[i] * S.err_vec[i];
+        S.err_lbnd = sqrt(e);
+    }
+    S.gmax = fmax(S.gmax, S.gamma);
+    S.gmin = fmin(S.gmin, S.gamma);
+    double zeta = S.rhs1 / S.gamma;
+    S.rhs1 = S.rhs2 - S.delta * zeta;
+    S.rhs2 = -S.eps_ * zeta;
+    S.Anorm = sqrt(S.Anorm2);
+    S.xNorm = sqrt(xx);
+    S.rNorm = S.phibar;
+    double test1 = S.rNorm / (S.Anorm * S.xNorm);
+    double test2 = S.root / S.Anorm;
+    S.Acond = S.gmax / S.gmin;
+    if (S.iter == 1 && S.beta / S.beta1 <= 10 * epsM) {
+        S.solved = 1; S.inconsistent = 1; S.status = FPSB_ST_ZERO_ATB; S.active = 0;
+        return;
+    }
+    S.ill_mach = (1.0 + 1.0 / S.Acond <= 1.0);
+    int solved_mach = (1.0 + test2 <= 1.0);
+    int zero_resid_mach = (1.0 + test1 <= 1.0);
+    int resid_decrease_mach = (S.rNorm + 1.0 <= 1.0);
+    S.tired = S.iter >= S.itmax;
+    S.ill_lim = (1.0 / S.Acond <= S.ctol);
+    int solved_lim = (test2 <= S.tol);
+    int zero_resid_lim = (test1 <= S.tol);
+    int resid_decrease_lim = (S.rNorm <= S.tol);
+    if (S.iter >= 5) S.fwd_err = S.err_lbnd <= S.etol * sqrt(S.xENorm2);
+    S.zero_resid = zero_resid_mach | zero_resid_lim;
+    int resid_decrease = resid_decrease_mach | resid_decrease_lim;
+    int ill_cond = S.ill_mach | S.ill_lim;
+    S.solved = solved_mach | solved_lim | S.zero_resid | S.fwd_err | resid_decrease;
+    if (S.solved || S.tired || ill_cond) {
+        int st = FPSB_ST_UNKNOWN;
+        if (S.tired) st = FPSB_ST_TIRED;
+        if (S.ill_mach) st = FPSB_ST_ILLCOND_MACH;
+        if (S.ill_lim) st = FPSB_ST_ILLCOND_LIM;
+        if (S.solved) st = FPSB_ST_SOLVED;
+        if (S.zero_resid) st = FPSB_ST_ZERO_RESID;
+        if (S.fwd_err) st = FPSB_ST_FWD_ERR;
+        if (resid_decrease) st = FPSB_ST_SOLVED;
+        S.status = st;
+        S.inconsistent = !S.zero_resid;
+        S.active = 0;
+    }
+}
+
+// ---- CGLS --------------------------------------------------------------------------------------
+__device__ void fin_cgls_init(SlotState &S, double bb) {
+    S.iter = 0;
+    S.bnorm = sqrt(bb);
+    S.rNorm = S.bnorm;
+    if (S.bnorm == 0.0) { S.active = 0; S.solved = 1; S.status = FPSB_ST_ZERO_RHS; }
+}
+__device__ void fin_cgls_init_m(SlotState &S, double ss) {
+    S.gamma_c = ss;
+    S.pp = ss;
+    S.ArNorm = sqrt(ss);
+    S.tol = S.atol + S.rtol * S.ArNorm;
+    S.solved = S.ArNorm <= S.tol;
+    S.tired = S.iter >= S.itmax;
+    if (S.solved || S.tired) { S.status = S.solved ? FPSB_ST_SOLVED : FPSB_ST_TIRED; S.active = 0; }
+}
+__device__ void fin_cgls_n(SlotState &S, double qq) {
+    double delta = qq;
+    if (S.lambda > 0) delta += S.lambda * S.pp;
+    S.alpha = S.gamma_c / delta;
+}
+__device__ void fin_cgls_en(SlotState &S, double rr) { S.rNorm = sqrt(rr); }
+__device__ void fin_cgls_m(SlotState &S, double ss) {
+    S.beta_c = ss / S.gamma_c;
+    S.gamma_c = ss;
+}
+__device__ void fin_cgls_em(SlotState &S, double pp) {
+    S.pp = pp;
+    S.ArNorm = sqrt(S.gamma_c);
+    S.iter += 1;
+    S.solved = S.ArNorm <= S.tol;
+    S.tired = S.iter >= S.itmax;
+    if (S.solved || S.tired) { S.status = S.solved ? FPSB_ST_SOLVED : FPSB_ST_TIRED; S.active = 0; }
+}
+
+__device__ void finish_step(SlotState &S, int mode, double a0, double a1) {
+    switch (mode) {
+        case MD_LSQR_INIT_M: fin_lsqr_init_m(S, a0); break;
+        case MD_LSQR_U: fin_lsqr_u(S, a0); break;
+        case MD_LSQR_V: fin_lsqr_v(S, a0, a1); break;
+        case MD_CRAIG_V: fin_craig_v(S, a0); break;
+        case MD_CRAIG_U: fin_craig_u(S, a0, a1); break;
+        case MD_MINRES_M: fin_minres_m(S, a0); break;
+        case MD_CGLS_INIT_M: fin_cgls_init_m(S, a0); break;
+        case MD_CGLS_N: fin_cgls_n(S, a0); break;
+        case MD_CGLS_M: fin_cgls_m(S, a0); break;
+        default: break;
+    }
+}
+__device__ void finish_ew(SlotState &S, int op, double a0) {
+    switch (op) {
+        case EW_INIT_LSQR: fin_init_lsqr(S, a0); break;
+        case EW_INIT_CRAIG: fin_init_craig(S, a0); break;
+        case EW_MINRES_INIT: fin_minres_init(S, a0); break;
+        case EW_MINRES_E1: fin_minres_e1(S, a0); break;
+        case EW_MINRES_E2: fin_minres_e2(S, a0); break;
+        case EW_CGLS_INIT: fin_cgls_init(S, a0); break;
+        case EW_CGLS_EN: fin_cgls_en(S, a0); break;
+        case EW_CGLS_EM: fin_cgls_em(S, a0); break;
+        default: break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-slot coefficients loaded once per CTA
+// ------------------------------------------------------------------------------------------------
+struct Coef {
+    int mode, first, pend, iter;
+    double gsc, ssc, alpha, beta, sigma, tr_prev, lambda;
+    double xi, c1, s1, s2g, trw, xr, mscale, oldbeta, c0, c1h;
+};
+
+__device__ __forceinline__ void load_coef(Coef &C, const SlotIO &io, const SlotState *st, bool use_state) {
+    C.mode = io.mode;
+    C.c0 = io.c0; C.c1h = io.c1;
+    C.gsc = 1.0; C.ssc = 1.0;
+    if (!use_state || io.mode == MD_NONE || io.mode == MD_PLAIN) return;
+    C.first = st->first; C.pend = st->pend; C.iter = st->iter;
+    C.alpha = st->alpha; C.beta = st->beta; C.sigma = st->sigma; C.tr_prev = st->tr_prev;
+    C.lambda = st->lambda; C.xi = st->xi; C.c1 = st->c1; C.s1 = st->s1; C.s2g = st->s2g;
+    C.trw = st->trw; C.xr = st->xr; C.mscale = st->mscale; C.oldbeta = st->oldbeta;
+    switch (io.mode) {
+        case MD_LSQR_INIT_M: C.gsc = st->su; break;
+        case MD_LSQR_U: C.gsc = st->sv; C.ssc = st->su; break;
+        case MD_LSQR_V: C.gsc = st->su; C.ssc = st->sv; break;
+        case MD_CRAIG_V: C.gsc = st->mscale * st->su; C.ssc = st->sv; break;
+        case MD_CRAIG_U: C.gsc = st->sv; C.ssc = st->su; break;
+        case MD_CGLS_M: case MD_CGLS_N: case MD_CGLS_INIT_M: case MD_MINRES_M: break;
+        default: break;
+    }
+}
+
+// row epilogue: returns the new value of the recurred ("self") vector entry
+__device__ __forceinline__ double row_epilogue(const Coef &C, const SlotIO &io, int row, double sraw,
+                                               double selfold, double &acc0, double &acc1) {
+    double out = 0.0;
+    switch (C.mode) {
+        case MD_PLAIN: {
+            out = C.c0 * sraw;
+            if (io.a0) out += C.c1h * io.a0[row];
+            acc0 += out * out;
+        } break;
+        case MD_LSQR_INIT_M: {
+            out = C.gsc * sraw;
+            acc0 += out * out;
+        } break;
+        case MD_LSQR_U: {
+            out = C.gsc * sraw - C.alpha * (selfold * C.ssc);
+            acc0 += out * out;
+        } break;
+        case MD_LSQR_V: {
+            double vj = selfold * C.ssc;
+            double wj = C.first ? vj : (vj - C.tr_prev * io.a0[row]);
+            acc1 += wj * wj;
+            io.a0[row] = wj;
+            io.a1[row] = (C.first ? 0.0 : io.a1[row]) + C.sigma * wj;
+            out = C.gsc * sraw - C.beta * vj;
+            acc0 += out * out;
+        } break;
+        case MD_CRAIG_V: {
+            double vp = selfold * C.ssc;
+            if (C.pend) {
+                if (C.lambda > 0) {
+                    double w2 = io.a1[row];
+                    double x = io.a0[row] + (C.xi * C.c1) * vp;
+                    x = x + (C.xi * C.s1) * w2;
+                    io.a0[row] = x;
+                    io.a1[row] = C.s2g * (C.s1 * vp - C.c1 * w2);
+                } else {
+                    io.a0[row] += C.xi * vp;
+                }
+            }
+            out = C.gsc * sraw - C.beta * vp;
+            acc0 += out * out;
+        } break;
+        case MD_CRAIG_U: {
+            double mu = selfold * C.ssc;
+            double uj = C.mscale * mu;
+            double wj = uj - C.trw * io.a0[row];
+            io.a0[row] = wj;
+            io.a1[row] += C.xr * wj;
+            acc1 += wj * wj;
+            out = C.gsc * sraw - C.alpha * mu;
+            acc0 += out * out;
+        } break;
+        case MD_MINRES_M: {
+            // a0 = r2 (= v), a1 = r1 ; self = y
+            double r2 = io.a0[row];
+            double y = sraw;
+            if (C.lambda != 0.0) y += C.lambda * r2;
+            y *= (1.0 / C.beta);
+            if (C.iter + 1 >= 2) y -= (C.beta / C.oldbeta) * io.a1[row];
+            out = y;
+            acc0 += r2 * y;
+        } break;
+        case MD_CGLS_INIT_M: {
+            out = sraw;           // p = s
+            acc0 += out * out;
+        } break;
+        case MD_CGLS_N: {
+            out = sraw;           // q
+            acc0 += out * out;
+        } break;
+        case MD_CGLS_M: {
+            // a0 = x, a1 = p ; self = s
+            double x = io.a0[row] + C.alpha * io.a1[row];
+            io.a0[row] = x;
+            double sv = sraw;
+            if (C.lambda > 0) sv -= C.lambda * x;
+            out = sv;
+            acc0 += sv * sv;
+        } break;
+        default: break;
+    }
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the fused SpMM step kernel
+// ------------------------------------------------------------------------------------------------
+template <bool PAIR>
+__global__ void __launch_bounds__(kBlock) gk_step_kernel(StepParams P, int use_state) {
+    __shared__ alignas(16) double s_val[kTile + 8];
+    __shared__ alignas(16) int s_col[kTile + 8];
+    __shared__ int s_rp[kBlock + 1];
+    __shared__ double s_sum[2][kBlock];
+    __shared__ double s_red[4 * 8];
+    __shared__ alignas(8) uint64_t s_bar;
+    __shared__ int s_last;
+
+    const int tid = threadIdx.x;
+    bool act0 = P.io[0].mode != MD_NONE && (!use_state || P.st[0].active);
+    bool act1 = P.io[1].mode != MD_NONE && (!use_state || P.st[1].active);
+    if (!act0 && !act1) return;
+
+    Coef C0, C1;
+    C0.mode = MD_NONE; C1.mode = MD_NONE;
+    if (act0) load_coef(C0, P.io[0], &P.st[0], use_state);
+    if (act1) load_coef(C1, P.io[1], &P.st[1], use_state);
+
+    const int b = blockIdx.x;
+    const int row_lo = P.blk[b], row_hi = P.blk[b + 1];
+    const int nr = row_hi - row_lo;
+    for (int i = tid; i <= nr; i += kBlock) s_rp[i] = P.rp[row_lo + i];
+    if (tid == 0) { mbar_init(&s_bar, 1); mbar_fence_init(); }
+    __syncthreads();
+    const int e0 = s_rp[0], e1 = s_rp[nr];
+    const int cnt = e1 - e0;
+    const int L = P.lanes;
+
+    if (cnt <= kTile) {
+        const int ea = e0 & ~3;
+        const int len = ((e1 - ea) + 3) & ~3;
+        if (len > 0) {
+            if (tid == 0) {
+                mbar_expect_tx(&s_bar, (uint32_t)len * 12u);
+                tma_bulk_g2s(s_val, P.vx + ea, (uint32_t)len * 8u, &s_bar);
+                tma_bulk_g2s(s_col, P.ci + ea, (uint32_t)len * 4u, &s_bar);
+            }
+            if (!mbar_wait(&s_bar, 0)) { if (tid == 0) atomicExch(P.done_flag, -1); return; }
+        }
+        const int g = tid / L, l = tid - g * L, ng = kBlock / L;
+        for (int r0 = 0; r0 < nr; r0 += ng) {
+            const int r = r0 + g;
+            double a0 = 0.0, a1 = 0.0;
+            if (r < nr) {
+                const int rs = s_rp[r] - ea, re = s_rp[r + 1] - ea;
+                if (PAIR) {
+                    for (int k = rs + l; k < re; k += L) {
+                        const double v = s_val[k];
+                        const double2 x = __ldg(P.gin2 + s_col[k]);
+                        a0 += v * x.x;
+                        a1 += v * x.y;
+                    }
+                } else {
+                    for (int k = rs + l; k < re; k += L) {
+                        const double v = s_val[k];
+                        const int c = s_col[k];
+                        if (act0) a0 += v * __ldg(P.io[0].gin + c);
+                        if (act1) a1 += v * __ldg(P.io[1].gin + c);
+                    }
+                }
+            }
+            for (int o = L >> 1; o > 0; o >>= 1) {
+                a0 += __shfl_down_sync(0xffffffffu, a0, o, L);
+                a1 += __shfl_down_sync(0xffffffffu, a1, o, L);
+            }
+            if (l == 0 && r < nr) { s_sum[0][r] = a0; s_sum[1][r] = a1; }
+        }
+    } else {
+        // a single long row: the whole CTA strides over it (plain coalesced loads)
+        double a[2] = {0.0, 0.0};
+        for (int k = e0 + tid; k < e1; k += kBlock) {
+            const double v = P.vx[k];
+            const int c = P.ci[k];
+            if (PAIR) {
+                const double2 x = __ldg(P.gin2 + c);
+                a[0] += v * x.x; a[1] += v * x.y;
+            } else {
+                if (act0) a[0] += v * __ldg(P.io[0].gin + c);
+                if (act1) a[1] += v * __ldg(P.io[1].gin + c);
+            }
+        }
+        block_sum<2>(a, s_red);
+        if (tid == 0) { s_sum[0][0] = a[0]; s_sum[1][0] = a[1]; }
+    }
+    __syncthreads();
+
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    if (tid < nr) {
+        const int row = row_lo + tid;
+        const double s0 = s_sum[0][tid], s1 = s_sum[1][tid];
+        if (PAIR) {
+            double2 old = P.self2[row];
+            double2 nw = old;
+            if (act0) nw.x = row_epilogue(C0, P.io[0], row, s0, old.x, acc[0], acc[1]);
+            if (act1) nw.y = row_epilogue(C1, P.io[1], row, s1, old.y, acc[2], acc[3]);
+            P.self2[row] = nw;
+        } else {
+            if (act0) {
+                double old = (C0.mode == MD_PLAIN || C0.mode >= MD_MINRES_M) ? 0.0 : P.io[0].self[row];
+                P.io[0].self[row] = row_epilogue(C0, P.io[0], row, s0, old, acc[0], acc[1]);
+            }
+            if (act1) {
+                double old = (C1.mode == MD_PLAIN || C1.mode >= MD_MINRES_M) ? 0.0 : P.io[1].self[row];
+                P.io[1].self[row] = row_epilogue(C1, P.io[1], row, s1, old, acc[2], acc[3]);
+            }
+        }
+    }
+    if (!use_state) return;
+
+    // deterministic norms: per-CTA partials, the last CTA reduces them in a fixed order
+    block_sum<4>(acc, s_red);
+    if (tid == 0) {
+        double *pp = P.partials + (size_t)b * 4;
+        pp[0] = acc[0]; pp[1] = acc[1]; pp[2] = acc[2]; pp[3] = acc[3];
+        __threadfence();
+        unsigned t = atomicAdd(P.counter, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double tot[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = tid; i < (int)gridDim.x; i += kBlock) {
+        const double *pp = P.partials + (size_t)i * 4;
+        tot[0] += __ldcg(pp + 0); tot[1] += __ldcg(pp + 1);
+        tot[2] += __ldcg(pp + 2); tot[3] += __ldcg(pp + 3);
+    }
+    block_sum<4>(tot, s_red);
+    if (tid == 0) {
+        if (act0) finish_step(P.st[0], P.io[0].mode, tot[0], tot[1]);
+        if (act1) finish_step(P.st[1], P.io[1].mode, tot[2], tot[3]);
+        if (!P.st[0].active && !P.st[1].active) *P.done_flag = 1;
+        *P.counter = 0;
+        __threadfence();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// element-wise fused kernels (initialisation, MINRES / CGLS vector updates, output flush)
+// ------------------------------------------------------------------------------------------------
+struct EwParams {
+    int op, slot, n, pair_slot;      // pair_slot: -1 plain, else column of the interleaved pair
+    const double *in0;
+    double *v0, *v1, *v2, *v3, *v4;
+    double2 *pair;
+    double c0;
+    SlotState *st;
+    double *partials;
+    unsigned *counter;
+    int *done_flag;
+    int use_state;
+};
+
+__global__ void __launch_bounds__(kBlock) ew_kernel(EwParams P) {
+    __shared__ double s_red[8];
+    __shared__ int s_last;
+    SlotState *S = P.st ? &P.st[P.slot] : nullptr;
+    const bool is_init = (P.op == EW_INIT_LSQR || P.op == EW_INIT_CRAIG || P.op == EW_MINRES_INIT ||
+                          P.op == EW_CGLS_INIT);
+    const bool is_out = (P.op == EW_COPY || P.op == EW_CRAIG_FLUSH);
+    if (P.use_state && !is_init && !is_out && !S->active) return;
+    double acc[1] = {0.0};
+    const int stride = gridDim.x * blockDim.x;
+    // coefficients
+    double alpha = 0, beta = 0, oldbeta = 0, delta = 0, eps_ = 0, gamma = 1, phi = 0, xi = 0, c1 = 0,
+           s1 = 0, sv = 0, lambda = 0, beta_c = 0;
+    int iter = 0, pend = 0;
+    if (S && !is_init) {
+        alpha = S->alpha; beta = S->beta; oldbeta = S->oldbeta; delta = S->delta; eps_ = S->eps_;
+        gamma = S->gamma; phi = S->phi; xi = S->xi; c1 = S->c1; s1 = S->s1; sv = S->sv;
+        lambda = S->lambda; beta_c = S->beta_c; iter = S->iter; pend = S->pend;
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
+        switch (P.op) {
+            case EW_COPY: P.v0[i] = P.c0 * P.in0[i]; break;
+            case EW_INIT_LSQR: {
+                double b = P.in0[i];
+                double *dst = reinterpret_cast<double *>(P.pair + i) + P.pair_slot;
+                *dst = b;
+                acc[0] += b * b;
+            } break;
+            case EW_INIT_CRAIG: {
+                double b = P.c0 * P.in0[i];
+                double *dst = reinterpret_cast<double *>(P.pair + i) + P.pair_slot;
+                *dst = b;
+                P.v0[i] = 0.0;   // w
+                P.v1[i] = 0.0;   // y
+                acc[0] += b * b;
+            } break;
+            case EW_CRAIG_FLUSH: {
+                // v0 = x, v1 = w2, pair = vhat ; out v2 = -(x + pending)
+                double x = P.v0[i];
+                if (pend) {
+                    double vp = (reinterpret_cast<const double *>(P.pair + i))[P.pair_slot] * sv;
+                    if (lambda > 0) { x = x + (xi * c1) * vp; x = x + (xi * s1) * P.v1[i]; }
+                    else x += xi * vp;
+                }
+                P.v2[i] = -x;
+            } break;
+            case EW_MINRES_INIT: {
+                double b = P.in0[i];
+                P.v0[i] = b;     // r1
+                P.v1[i] = b;     // r2
+                P.v2[i] = 0.0;   // w1
+                P.v3[i] = 0.0;   // w2
+                P.v4[i] = 0.0;   // x
+                acc[0] += b * b;
+            } break;
+            case EW_MINRES_E1: {
+                // in0 = y(pre) ; v0 = r1, v1 = r2, v2 = w1-role, v3 = w2-role ; iter already incremented
+                double r2 = P.v1[i];
+                double y = P.in0[i] - (alpha / beta) * r2;
+                double w;
+                if (iter == 1) {
+                    w = P.v3[i] + (1.0 / beta) * r2;
+                    P.v3[i] = w;
+                } else {
+                    double w1 = P.v2[i];
+                    if (iter >= 3) w1 *= -eps_;
+                    w1 -= delta * P.v3[i];
+                    w = w1 + (1.0 / beta) * r2;
+                    P.v2[i] = w;
+                }
+                P.v0[i] = r2;
+                P.v1[i] = y;
+                acc[0] += y * y;
+            } break;
+            case EW_MINRES_E2: {
+                // v2 = the w just written (role resolved by the host), v4 = x
+                double w = P.v2[i] * (1.0 / gamma);
+                P.v2[i] = w;
+                double x = P.v4[i] + phi * w;
+                P.v4[i] = x;
+                acc[0] += x * x;
+            } break;
+            case EW_CGLS_INIT: {
+                double b = P.in0[i];
+                P.v0[i] = b;     // r
+                acc[0] += b * b;
+            } break;
+            case EW_CGLS_EN: {   // r -= alpha q
+                double r = P.v0[i] - alpha * P.v1[i];
+                P.v0[i] = r;
+                acc[0] += r * r;
+            } break;
+            case EW_CGLS_EM: {   // p = s + beta p
+                double p = P.v0[i] + beta_c * P.v1[i];
+                P.v1[i] = p;
+                acc[0] += p * p;
+            } break;
+            default: break;
+        }
+    }
+    if (!P.use_state || is_out) return;
+    block_sum<1>(acc, s_red);
+    if (threadIdx.x == 0) {
+        P.partials[blockIdx.x] = acc[0];
+        __threadfence();
+        unsigned t = atomicAdd(P.counter, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double tot[1] = {0.0};
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += kBlock) tot[0] += __ldcg(P.partials + i);
+    block_sum<1>(tot, s_red);
+    if (threadIdx.x == 0) {
+        finish_ew(*S, P.op, tot[0]);
+        if (!P.st[0].active && !P.st[1].active) *P.done_flag = 1;
+        *P.counter = 0;
+        __threadfence();
+    }
+}
+
+__global__ void gather_vals_kernel(int nnz, const int *perm, const double *coo, double *vx) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nnz) vx[i] = coo[perm[i]];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct IterWs {
+    DevBuf<double2> Gn, Gm;              // interleaved Golub-Kahan pairs (n-space, m-space)
+    DevBuf<double> an[2][2];             // n-space aux per slot (CRAIG x, w2 ; CGLS r, q ; MINRES t)
+    DevBuf<double> am[2][5];             // m-space aux per slot
+    DevBuf<double> ym;                   // MINRES y / CGLS s
+    DevBuf<SlotState> st;
+    DevBuf<double> partials;
+    DevBuf<unsigned> counter;
+    DevBuf<int> done;
+    int *h_done = nullptr;               // pinned
+    SlotState *h_st = nullptr;           // pinned [2]
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int ew_grid = 0;
+};
+
+static void build_csr_host(int nrows, int ncols, int64_t nnz, const int64_t *ri, const int64_t *cj,
+                           std::vector<int> &rp, std::vector<int> &ci, std::vector<int> &perm) {
+    rp.assign((size_t)nrows + 1, 0);
+    for (int64_t k = 0; k < nnz; ++k) rp[(size_t)ri[k] + 1]++;
+    for (int i = 0; i < nrows; ++i) rp[i + 1] += rp[i];
+    ci.resize((size_t)nnz);
+    perm.resize((size_t)nnz);
+    // stable counting sort by column first, then by row => rows hold ascending columns
+    std::vector<int> cp((size_t)ncols + 1, 0);
+    for (int64_t k = 0; k < nnz; ++k) cp[(size_t)cj[k] + 1]++;
+    for (int j = 0; j < ncols; ++j) cp[j + 1] += cp[j];
+    std::vector<int> bycol((size_t)nnz);
+    for (int64_t k = 0; k < nnz; ++k) bycol[(size_t)cp[(size_t)cj[k]]++] = (int)k;
+    std::vector<int> pos(rp.begin(), rp.end() - 1);
+    for (int64_t t = 0; t < nnz; ++t) {
+        int k = bycol[(size_t)t];
+        int q = pos[(size_t)ri[k]]++;
+        ci[(size_t)q] = (int)cj[k];
+        perm[(size_t)q] = k;
+    }
+}
+
+static void build_blocks(const std::vector<int> &rp, int nrows, std::vector<int> &blk) {
+    blk.clear();
+    blk.push_back(0);
+    int r = 0;
+    while (r < nrows) {
+        int start = r;
+        int base = rp[r];
+        // always take at least one row (a long row gets a block of its own)
+        r++;
+        if (rp[r] - base <= kTile) {
+            while (r < nrows && (r - start) < kBlock && rp[r + 1] - base <= kTile) r++;
+        }
+        blk.push_back(r);
+    }
+}
+
+static int pick_lanes(int64_t nnz, int nrows) {
+    double avg = nrows > 0 ? (double)nnz / nrows : 1.0;
+    int L = 2;
+    while (L < 32 && L * 2 <= avg) L *= 2;     // largest power of two <= avg nnz per row
+    return std::max(2, std::min(32, L));
+}
+
+static void upload_csr(Handle *h, CsrDev &M, int nrows, int ncols, const std::vector<int> &rp,
+                       const std::vector<int> &ci, const std::vector<int> &perm) {
+    M.nrows = nrows; M.ncols = ncols; M.nnz = (int64_t)ci.size();
+    M.rp.from(rp, h->stream);
+    M.ci.from(ci, h->stream);
+    M.perm.from(perm, h->stream);
+    M.vx.alloc(ci.size() + 8);
+    M.vx.zero(h->stream);
+    std::vector<int> blk;
+    build_blocks(rp, nrows, blk);
+    M.nblk = (int)blk.size() - 1;
+    M.blk.from(blk, h->stream);
+    M.lanes = pick_lanes(M.nnz, nrows);
+}
+
+void csr_build(Handle *h) {
+    const int m = (int)h->ncon, n = (int)h->nvar;
+    std::vector<int> rp, ci, perm;
+    build_csr_host(m, n, h->nnzj, h->jrow.data(), h->jcol.data(), rp, ci, perm);
+    upload_csr(h, h->A, m, n, rp, ci, perm);
+    build_csr_host(n, m, h->nnzj, h->jcol.data(), h->jrow.data(), rp, ci, perm);
+    upload_csr(h, h->At, n, m, rp, ci, perm);
+    h->coo_vals.alloc((size_t)h->nnzj + 8);
+    FPSB_CUDA(cudaStreamSynchronize(h->stream));
+}
+
+void csr_refresh_values(Handle *h) {
+    int nnz = (int)h->nnzj;
+    if (nnz == 0) return;
+    int grid = (nnz + 255) / 256;
+    gather_vals_kernel<<<grid, 256, 0, h->stream>>>(nnz, h->A.perm.p, h->coo_vals.p, h->A.vx.p);
+    gather_vals_kernel<<<grid, 256, 0, h->stream>>>(nnz, h->At.perm.p, h->coo_vals.p, h->At.vx.p);
+    h->launches += 2;
+    FPSB_CUDA(cudaGetLastError());
+}
+
+static void fill_csr(StepParams &P, const CsrDev &M) {
+    P.rp = M.rp.p; P.ci = M.ci.p; P.vx = M.vx.p; P.blk = M.blk.p; P.nrows = M.nrows; P.lanes = M.lanes;
+}
+
+// y = Op x for 1 or 2 plain columns (columns contiguous in memory)
+void spmv_plain(Handle *h, bool transpose, const double *x, double *y, int ncols_rhs) {
+    const CsrDev &M = transpose ? h->At : h->A;
+    if (M.nrows == 0) return;
+    StepParams P{};
+    fill_csr(P, M);
+    for (int s = 0; s < 2; ++s) {
+        P.io[s].mode = (s < ncols_rhs) ? MD_PLAIN : MD_NONE;
+        P.io[s].gin = x + (size_t)s * M.ncols;
+        P.io[s].self = y + (size_t)s * M.nrows;
+        P.io[s].a0 = nullptr;
+        P.io[s].c0 = 1.0; P.io[s].c1 = 0.0;
+    }
+    gk_step_kernel<false><<<M.nblk, kBlock, 0, h->stream>>>(P, 0);
+    h->launches += 1;
+    FPSB_CUDA(cudaGetLastError());
+}
+
+void iter_setup(Handle *h) {
+    if (h->iter) return;
+    IterWs *W = new IterWs();
+    h->iter = W;
+    const size_t n = (size_t)h->nvar, m = (size_t)h->ncon;
+    W->Gn.alloc(n + 4); W->Gm.alloc(m + 4);
+    for (int s = 0; s < 2; ++s) {
+        for (int k = 0; k < 2; ++k) W->an[s][k].alloc(n + 4);
+        for (int k = 0; k < 5; ++k) W->am[s][k].alloc(m + 4);
+    }
+    W->ym.alloc(m + 4);
+    W->st.alloc(2);
+    int maxblk = std::max(h->A.nblk, h->At.nblk);
+    W->ew_grid = 148 * 4;
+    W->partials.alloc((size_t)std::max(maxblk, W->ew_grid) * 4 + 16);
+    W->counter.alloc(4);
+    W->done.alloc(4);
+    W->counter.zero(h->stream);
+    W->done.zero(h->stream);
+    FPSB_CUDA(cudaMallocHost((void **)&W->h_done, 2 * sizeof(int)));
+    FPSB_CUDA(cudaMallocHost((void **)&W->h_st, 2 * sizeof(SlotState)));
+    FPSB_CUDA(cudaEventCreateWithFlags(&W->ev[0], cudaEventDisableTiming));
+    FPSB_CUDA(cudaEventCreateWithFlags(&W->ev[1], cudaEventDisableTiming));
+    FPSB_CUDA(cudaStreamSynchronize(h->stream));
+}
+
+void iter_free(Handle *h) {
+    if (!h->iter) return;
+    IterWs *W = h->iter;
+    if (W->h_done) cudaFreeHost(W->h_done);
+    if (W->h_st) cudaFreeHost(W->h_st);
+    if (W->ev[0]) cudaEventDestroy(W->ev[0]);
+    if (W->ev[1]) cudaEventDestroy(W->ev[1]);
+    delete W;
+    h->iter = nullptr;
+}
+
+// ---- slot configuration (host fills a SlotState, uploaded before the solve) ---------------------
+static SlotState make_lsqr(double lambda, double atol, double rtol, int64_t itmax, int64_t m_op, int64_t n_op) {
+    SlotState S;
+    memset(&S, 0, sizeof(S));
+    S.algo = ALGO_LSQR;
+    S.lambda = lambda; S.atol = atol; S.rtol = rtol;
+    S.axtol = kSqrtEps; S.btol = kSqrtEps; S.etol = kSqrtEps; S.ctol = kSqrtEps;   // conlim = 1/sqrt(eps)
+    int64_t im = itmax == 0 ? m_op + n_op : itmax;
+    S.itmax = (int)std::min<int64_t>(im, 2000000000);
+    S.active = 1;
+    S.mscale = 1.0;
+    return S;
+}
+static SlotState make_craig(double delta, double atol, double rtol, double btol, double conlim,
+                            int64_t itmax, int64_t m_op, int64_t n_op) {
+    SlotState S;
+    memset(&S, 0, sizeof(S));
+    S.algo = ALGO_CRAIG;
+    S.sqd = delta != 0.0;
+    S.lambda = S.sqd ? 1.0 : 0.0;
+    S.mscale = S.sqd ? 1.0 / delta : 1.0;
+    S.atol = atol; S.rtol = rtol; S.btol = btol;
+    S.ctol = conlim > 0 ? 1.0 / conlim : 0.0;
+    int64_t im = itmax == 0 ? m_op + n_op : itmax;
+    S.itmax = (int)std::min<int64_t>(im, 2000000000);
+    S.active = 1;
+    return S;
+}
+static SlotState make_minres(double lambda, double atol, double rtol, double etol, double conlim,
+                             int64_t itmax, int64_t n_op) {
+    SlotState S;
+    memset(&S, 0, sizeof(S));
+    S.algo = ALGO_MINRES;
+    S.lambda = lambda; S.atol = atol; S.rtol = rtol; S.etol = etol;
+    S.ctol = conlim > 0 ? 1.0 / conlim : 0.0;
+    int64_t im = itmax == 0 ? 2 * n_op : itmax;
+    S.itmax = (int)std::min<int64_t>(im, 2000000000);
+    S.active = 1;
+    S.mscale = 1.0;
+    return S;
+}
+static SlotState make_cgls(double lambda, double atol, double rtol, int64_t itmax, int64_t m_op, int64_t n_op) {
+    SlotState S;
+    memset(&S, 0, sizeof(S));
+    S.algo = ALGO_CGLS;
+    S.lambda = lambda; S.atol = atol; S.rtol = rtol;
+    int64_t im = itmax == 0 ? m_op + n_op : itmax;
+    S.itmax = (int)std::min<int64_t>(im, 2000000000);
+    S.active = 1;
+    S.mscale = 1.0;
+    return S;
+}
+static SlotState make_none() {
+    SlotState S;
+    memset(&S, 0, sizeof(S));
+    S.algo = ALGO_NONE;
+    S.active = 0;
+    S.solved = 1;
+    return S;
+}
+
+static void stats_from(const SlotState &S, fpsb_krylov_stats &o) {
+    o.niter = S.iter; o.solved = S.solved; o.inconsistent = S.inconsistent; o.status = S.status;
+    o.pad_ = 0;
+    o.rnorm = S.rNorm; o.arnorm = S.ArNorm; o.anorm = S.Anorm; o.acond = S.Acond; o.xnorm = S.xNorm;
+}
+
+struct Engine {
+    Handle *h;
+    IterWs *W;
+    StepParams base_m, base_n;   // M: rows of A (m-space rows), N: rows of A' (n-space rows)
+    Engine(Handle *hh) : h(hh), W(hh->iter) {
+        memset(&base_m, 0, sizeof(base_m));
+        memset(&base_n, 0, sizeof(base_n));
+        fill_csr(base_m, h->A);
+        fill_csr(base_n, h->At);
+        for (StepParams *P : {&base_m, &base_n}) {
+            P->st = W->st.p; P->partials = W->partials.p; P->counter = W->counter.p; P->done_flag = W->done.p;
+        }
+        base_m.gin2 = W->Gn.p; base_m.self2 = W->Gm.p;
+        base_n.gin2 = W->Gm.p; base_n.self2 = W->Gn.p;
+    }
+    void begin(const SlotState &s0, const SlotState &s1) {
+        SlotState hs[2] = {s0, s1};
+        memcpy(W->h_st, hs, sizeof(hs));
+        FPSB_CUDA(cudaMemcpyAsync(W->st.p, W->h_st, sizeof(hs), cudaMemcpyHostToDevice, h->stream));
+        FPSB_CUDA(cudaMemsetAsync(W->done.p, 0, sizeof(int), h->stream));
+        FPSB_CUDA(cudaMemsetAsync(W->counter.p, 0, sizeof(unsigned), h->stream));
+    }
+    void step(bool mspace, bool pair, const SlotIO &io0, const SlotIO &io1) {
+        StepParams P = mspace ? base_m : base_n;
+        P.io[0] = io0; P.io[1] = io1;
+        const CsrDev &M = mspace ? h->A : h->At;
+        if (M.nblk == 0) return;
+        if (pair) gk_step_kernel<true><<<M.nblk, kBlock, 0, h->stream>>>(P, 1);
+        else gk_step_kernel<false><<<M.nblk, kBlock, 0, h->stream>>>(P, 1);
+        h->launches += 1;
+    }
+    void ew(int op, int slot, int n, const double *in0, double *v0, double *v1, double *v2, double *v3,
+            double *v4, double2 *pair, int pair_slot, double c0, int use_state = 1) {
+        if (n == 0 && !(use_state)) return;
+        EwParams P{};
+        P.op = op; P.slot = slot; P.n = n; P.pair_slot = pair_slot; P.in0 = in0;
+        P.v0 = v0; P.v1 = v1; P.v2 = v2; P.v3 = v3; P.v4 = v4; P.pair = pair; P.c0 = c0;
+        P.st = W->st.p; P.partials = W->partials.p; P.counter = W->counter.p; P.done_flag = W->done.p;
+        P.use_state = use_state;
+        int grid = std::max(1, std::min(W->ew_grid, (n + kBlock - 1) / kBlock));
+        ew_kernel<<<grid, kBlock, 0, h->stream>>>(P);
+        h->launches += 1;
+    }
+    // run `body(k)` (k = 1, 2, ...) until the device reports every slot stopped
+    template <class F>
+    void loop(F body, int chunk) {
+        int k = 0, pending = 0, slot = 0;
+        int64_t hard_cap = (int64_t)4000000000LL;
+        bool done = false;
+        while (!done && k < hard_cap) {
+            for (int c = 0; c < chunk; ++c) body(++k);
+            FPSB_CUDA(cudaMemcpyAsync(&W->h_done[slot], W->done.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            FPSB_CUDA(cudaEventRecord(W->ev[slot], h->stream));
+            pending++;
+            if (pending == 2) {
+                int prev = slot ^ 1;
+                FPSB_CUDA(cudaEventSynchronize(W->ev[prev]));
+                if (W->h_done[prev] != 0) done = true;
+                pending--;
+            }
+            slot ^= 1;
+        }
+        FPSB_CUDA(cudaStreamSynchronize(h->stream));
+        FPSB_CUDA(cudaGetLastError());
+        if (W->h_done[0] < 0 || W->h_done[1] < 0) {
+            set_error("TMA/mbarrier wait timed out inside gk_step_kernel");
+            throw CudaFail{FPSB_ECUDA};
+        }
+    }
+    void fetch(fpsb_krylov_stats *st) {
+        FPSB_CUDA(cudaMemcpyAsync(W->h_st, W->st.p, 2 * sizeof(SlotState), cudaMemcpyDeviceToHost, h->stream));
+        FPSB_CUDA(cudaStreamSynchronize(h->stream));
+        stats_from(W->h_st[0], st[0]);
+        stats_from(W->h_st[1], st[1]);
+    }
+};
+
+static SlotIO io_none() { SlotIO io{}; io.mode = MD_NONE; return io; }
+static SlotIO io_mode(int mode, double *a0 = nullptr, double *a1 = nullptr, double *a2 = nullptr) {
+    SlotIO io{};
+    io.mode = mode; io.a0 = a0; io.a1 = a1; io.a2 = a2; io.c0 = 1.0; io.c1 = 0.0;
+    return io;
+}
+
+// p = rhs - A' q  (n-space), plain kernel
+static void residual_p(Engine &E, const double *rhs, const double *q, double *p) {
+    Handle *h = E.h;
+    if (h->At.nblk == 0) return;
+    StepParams P = E.base_n;
+    P.io[0] = io_mode(MD_PLAIN, const_cast<double *>(rhs));
+    P.io[0].gin = q; P.io[0].self = p; P.io[0].c0 = -1.0; P.io[0].c1 = 1.0;
+    P.io[1] = io_none();
+    gk_step_kernel<false><<<h->At.nblk, kBlock, 0, h->stream>>>(P, 0);
+    h->launches += 1;
+}
+
+static const int kChunk = 4;
+
+// LSQR on A' occupies: Gn[:,slot] = u, Gm[:,slot] = v, am[slot][0] = w, am[slot][1] = x
+static void lsqr_init(Engine &E, int slot, const double *rhs) {
+    E.ew(EW_INIT_LSQR, slot, (int)E.h->nvar, rhs, nullptr, nullptr, nullptr, nullptr, nullptr, E.W->Gn.p, slot, 1.0);
+}
+
+void iter_solve_two_mixed(Handle *h, double delta, const double *rhs1, const double *rhs2, double *p1,
+                          double *q1, double *p2, double *q2, fpsb_krylov_stats *st) {
+    iter_setup(h);
+    Engine E(h);
+    IterWs *W = h->iter;
+    const fpsb_iter_opts &o = h->iopts;
+    const int64_t n = h->nvar, m = h->ncon;
+    E.begin(make_lsqr(sqrt(delta), o.ls_atol, o.ls_rtol, o.ls_itmax, n, m),
+            make_craig(delta, o.ln_atol, o.ln_rtol, o.ln_btol, o.ln_conlim, o.ln_itmax, m, n));
+    W->Gn.zero(h->stream); W->Gm.zero(h->stream);
+    W->an[1][0].zero(h->stream); W->an[1][1].zero(h->stream);   // CRAIG x, w2
+    W->am[0][1].zero(h->stream);                                // LSQR x
+    lsqr_init(E, 0, rhs1);
+    E.ew(EW_INIT_CRAIG, 1, (int)m, rhs2, W->am[1][0].p, W->am[1][1].p, nullptr, nullptr, nullptr, W->Gm.p, 1, -1.0);
+    SlotIO l_init = io_mode(MD_LSQR_INIT_M);
+    SlotIO l_u = io_mode(MD_LSQR_U);
+    SlotIO l_v = io_mode(MD_LSQR_V, W->am[0][0].p, W->am[0][1].p);
+    SlotIO c_v = io_mode(MD_CRAIG_V, W->an[1][0].p, W->an[1][1].p);
+    SlotIO c_u = io_mode(MD_CRAIG_U, W->am[1][0].p, W->am[1][1].p);
+    E.step(true, true, l_init, io_none());
+    E.loop([&](int) {
+        E.step(false, true, l_u, c_v);
+        E.step(true, true, l_v, c_u);
+    }, kChunk);
+    // outputs
+    E.ew(EW_COPY, 0, (int)m, W->am[0][1].p, q1, nullptr, nullptr, nullptr, nullptr, nullptr, -1, 1.0, 0);
+    residual_p(E, rhs1, q1, p1);
+    {
+        EwParams P{};
+        (void)P;
+    }
+    E.ew(EW_CRAIG_FLUSH, 1, (int)n, nullptr, W->an[1][0].p, W->an[1][1].p, p2, nullptr, nullptr, W->Gn.p, 1, 1.0, 1);
+    E.ew(EW_COPY, 1, (int)m, W->am[1][1].p, q2, nullptr, nullptr, nullptr, nullptr, nullptr, -1, 1.0, 0);
+    E.fetch(st);
+}
+
+void iter_solve_two_least_squares(Handle *h, double delta, const double *rhs1, const double *rhs2,
+                                  double *p1, double *q1, double *p2, double *q2,
+                                  fpsb_krylov_stats *st) {
+    iter_setup(h);
+    Engine E(h);
+    IterWs *W = h->iter;
+    const fpsb_iter_opts &o = h->iopts;
+    const int64_t n = h->nvar, m = h->ncon;
+    SlotState s = make_lsqr(sqrt(delta), o.ls_atol, o.ls_rtol, o.ls_itmax, n, m);
+    E.begin(s, s);
+    W->Gn.zero(h->stream); W->Gm.zero(h->stream);
+    W->am[0][1].zero(h->stream); W->am[1][1].zero(h->stream);
+    lsqr_init(E, 0, rhs1);
+    lsqr_init(E, 1, rhs2);
+    SlotIO init0 = io_mode(MD_LSQR_INIT_M), init1 = io_mode(MD_LSQR_INIT_M);
+    SlotIO u0 = io_mode(MD_LSQR_U), u1 = io_mode(MD_LSQR_U);
+    SlotIO v0 = io_mode(MD_LSQR_V, W->am[0][0].p, W->am[0][1].p);
+    SlotIO v1 = io_mode(MD_LSQR_V, W->am[1][0].p, W->am[1][1].p);
+    E.step(true, true, init0, init1);
+    E.loop([&](int) {
+        E.step(false, true, u0, u1);
+        E.step(true, true, v0, v1);
+    }, kChunk);
+    E.ew(EW_COPY, 0, (int)m, W->am[0][1].p, q1, nullptr, nullptr, nullptr, nullptr, nullptr, -1, 1.0, 0);
+    E.ew(EW_COPY, 1, (int)m, W->am[1][1].p, q2, nullptr, nullptr, nullptr, nullptr, nullptr, -1, 1.0, 0);
+    // p_i = rhs_i - A' q_i : one two-column SpMM
+    if (h->At.nblk) {
+        StepParams P = E.base_n;
+        P.io[0] = io_mode(MD_PLAIN, const_cast<double *>(rhs1));
+        P.io[0].gin = q1; P.io[0].self = p1; P.io[0].c0 = -1.0; P.io[0].c1 = 1.0;
+        P.io[1] = io_mode(MD_PLAIN, const_cast<double *>(rhs2));
+        P.io[1].gin = q2; P.io[1].self = p2; P.io[1].c0 = -1.0; P.io[1].c1 = 1.0;
+        gk_step_kernel<false><<<h->At.nblk, kBlock, 0, h->stream>>>(P, 0);
+        h->launches += 1;
+    }
+    E.fetch(st);
+}
+
+// MINRES on (A A' + lambda I) in slot `slot` (non-pair kernels), result copied to `out`
+static void run_minres(Engine &E, int slot, const double *rhs, double *out) {
+    Handle *h = E.h;
+    IterWs *W = E.W;
+    const int m = (int)h->ncon;
+    double *r1 = W->am[slot][0].p, *r2 = W->am[slot][1].p, *wa = W->am[slot][2].p, *wb = W->am[slot][3].p,
+           *x = W->am[slot][4].p, *y = W->ym.p, *t = W->an[slot][0].p;
+    E.ew(EW_MINRES_INIT, slot, m, rhs, r1, r2, wa, wb, x, nullptr, -1, 1.0);
+    double *w1 = wa, *w2 = wb;
+    SlotIO none = io_none();
+    E.loop([&](int k) {
+        // t = A' r2 ; y = (A t + lambda r2)/beta - (beta/oldbeta) r1 ; alpha = r2'y / beta
+        SlotIO n_io = io_mode(MD_PLAIN);
+        n_io.gin = r2; n_io.self = t; n_io.c0 = 1.0;
+        SlotIO m_io = io_mode(MD_MINRES_M, r2, r1);
+        m_io.gin = t; m_io.self = y;
+        if (slot == 0) { E.step(false, false, n_io, none); E.step(true, false, m_io, none); }
+        else { E.step(false, false, none, n_io); E.step(true, false, none, m_io); }
+        E.ew(EW_MINRES_E1, slot, m, y, r1, r2, w1, w2, nullptr, nullptr, -1, 1.0);
+        double *wcur = (k == 1) ? w2 : w1;
+        E.ew(EW_MINRES_E2, slot, m, nullptr, nullptr, nullptr, wcur, nullptr, x, nullptr, -1, 1.0);
+        if (k >= 2) std::swap(w1, w2);
+    }, 2);
+    E.ew(EW_COPY, slot, m, x, out, nullptr, nullptr, nullptr, nullptr, nullptr, -1, 1.0, 0);
+}
+
+// CGLS on A' (min ||b - A' x||^2 + lambda ||x||^2) in slot `slot`, result copied to `out`
+static void run_cgls(Engine &E, int slot, const double *rhs, double *out) {
+    Handle *h = E.h;
+    IterWs *W = E.W;
+    const int m = (int)h->ncon, n = (int)h->nvar;
+    double *r = W->an[slot][0].p, *q = W->an[slot][1].p;
+    double *x = W->am[slot][0].p, *p = W->am[slot][1].p, *s = W->am[slot][2].p;
+    W->am[slot][0].zero(h->stream);
+    E.ew(EW_CGLS_INIT, slot, n, rhs, r, nullptr, nullptr, nullptr, nullptr, nullptr, -1, 1.0);
+    SlotIO none = io_none();
+    {
+        SlotIO io = io_mode(MD_CGLS_INIT_M);
+        io.gin = r; io.self = p;
+        if (slot == 0) E.step(true, false, io, none); else E.step(true, false, none, io);
+    }
+    E.loop([&](int) {
+        SlotIO n_io = io_mode(MD_CGLS_N);
+        n_io.gin = p; n_io.self = q;
+        if (slot == 0) E.step(false, false, n_io, none); else E.step(false, false, none, n_io);
+        E.ew(EW_CGLS_EN, slot, n, nullptr, r, q, nullptr, nullptr, nullptr, nullptr, -1, 1.0);
+        SlotIO m_io = io_mode(MD_CGLS_M, x, p);
+        m_io.gin = r; m_io.self = s;
+        if (slot == 0) E.step(true, false, m_io, none); else E.step(true, false, none, m_io);
+        E.ew(EW_CGLS_EM, slot, m, nullptr, s, p, nullptr, nullptr, nullptr, nullptr, -1, 1.0);
+    }, 2);
+    E.ew(EW_COPY, slot, m, x, out, nullptr, nullptr, nullptr, nullptr, nullptr, -1, 1.0, 0);
+}
+
+void iter_solve_two_extras(Handle *h, double delta, const double *rhs1, const double *rhs2, double *u1,
+                           double *u2, fpsb_krylov_stats *st, bool ldlt_variant) {
+    iter_setup(h);
+    Engine E(h);
+    IterWs *W = h->iter;
+    const fpsb_iter_opts &o = h->iopts;
+    const int64_t n = h->nvar, m = h->ncon;
+    const double tau = std::max(delta, 1e-14);
+    fpsb_krylov_stats tmp[2];
+    if (!ldlt_variant) {
+        // LSQR(A', rhs1, lambda = sqrt(tau))   src/solve_linear_system.jl:53
+        E.begin(make_lsqr(sqrt(tau), o.ls_atol, o.ls_rtol, o.ls_itmax, n, m), make_none());
+        W->Gn.zero(h->stream); W->Gm.zero(h->stream);
+        W->am[0][1].zero(h->stream);
+        lsqr_init(E, 0, rhs1);
+        SlotIO l_init = io_mode(MD_LSQR_INIT_M), l_u = io_mode(MD_LSQR_U);
+        SlotIO l_v = io_mode(MD_LSQR_V, W->am[0][0].p, W->am[0][1].p);
+        E.step(true, true, l_init, io_none());
+        E.loop([&](int) {
+            E.step(false, true, l_u, io_none());
+            E.step(true, true, l_v, io_none());
+        }, kChunk);
+        E.ew(EW_COPY, 0, (int)m, W->am[0][1].p, u1, nullptr, nullptr, nullptr, nullptr, nullptr, -1, 1.0, 0);
+        E.fetch(tmp);
+        st[0] = tmp[0];
+        // MINRES(A A', rhs2, lambda = tau, ne_*)   src/solve_linear_system.jl:60-70
+        E.begin(make_none(), make_minres(tau, o.ne_atol, o.ne_rtol, o.ne_etol, o.ne_conlim, o.ne_itmax, m));
+        run_minres(E, 1, rhs2, u2);
+        E.fetch(tmp);
+        st[1] = tmp[1];
+    } else {
+        // cgls(A', rhs1, lambda = tau) ; minres(A A', rhs2, lambda = tau) — Krylov.jl defaults
+        E.begin(make_cgls(tau, kSqrtEps, kSqrtEps, 0, n, m), make_none());
+        run_cgls(E, 0, rhs1, u1);
+        E.fetch(tmp);
+        st[0] = tmp[0];
+        E.begin(make_none(), make_minres(tau, kSqrtEps / 100, kSqrtEps / 100, kSqrtEps, 1.0 / kSqrtEps, 0, m));
+        run_minres(E, 1, rhs2, u2);
+        E.fetch(tmp);
+        st[1] = tmp[1];
+    }
+}
+
+}  // namespace fpsb

@@ -1,0 +1,187 @@
+/*
+ * fpsb.h — C ABI of libfpsb200.so: B200-native (sm_100a) 2-right-hand-side quasi-definite solves
+ *
+ *        K = [ I   A' ]      A = J(x) in R^{ncon x nvar}  (the user model's Jacobian)
+ *            [ A  -dI ]
+ *
+ * This is the drop-in boundary for FletcherPenaltySolver.jl's hot path.  Every entry point
+ * replaces one piece of the reference's plugin surface; the Julia shim that binds them with
+ * `ccall` is fletcherpenaltysolver.jl_b200/julia/B200Solver.jl.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ / torch types cross this boundary;
+ *   - every function returns an int: FPSB_OK (0) or a negative FPSB_E* code; numerical failure is
+ *     NEVER an error return: it is reported through `factorized` / `stats[].solved`, exactly like
+ *     the reference (`@warn`, never throw: src/solve_linear_system.jl:54,73,92,101,128,136,197,245);
+ *   - `loc` says where the caller's vectors live: FPSB_HOST (pageable or pinned host memory, the
+ *     copies happen inside the call) or FPSB_DEVICE (device pointers on the handle's GPU; the call
+ *     is stream-ordered on the handle's stream and synchronises before returning stats);
+ *   - vectors are float64; index arrays are int64 (Julia `Int`);
+ *   - a handle is not thread-safe (the reference is single-threaded and non re-entrant);
+ *   - there is no CPU fallback: without a CUDA device every entry point fails with FPSB_ECUDA.
+ */
+#ifndef FPSB_H
+#define FPSB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FPSB_VERSION 100
+
+typedef struct fpsb_handle_s *fpsb_handle;
+
+enum { FPSB_HOST = 0, FPSB_DEVICE = 1 };
+
+enum {
+    FPSB_OK = 0,
+    FPSB_EINVAL = -1,   /* bad argument (NULL, negative size, index out of range) */
+    FPSB_ECUDA = -2,    /* CUDA runtime error (see fpsb_last_error) */
+    FPSB_ESTATE = -3,   /* call order violated (e.g. solve before analyze / set_jac_values) */
+    FPSB_ENOMEM = -4,
+    FPSB_ENCCL = -5
+};
+
+/* Krylov termination status (mirrors Krylov.jl's status strings; same codes as the oracle) */
+enum {
+    FPSB_ST_UNKNOWN = 0, FPSB_ST_ZERO_RHS = 1, FPSB_ST_SOLVED = 2, FPSB_ST_ZERO_RESID = 3,
+    FPSB_ST_FWD_ERR = 4, FPSB_ST_TIRED = 5, FPSB_ST_ILLCOND_MACH = 6, FPSB_ST_ILLCOND_LIM = 7,
+    FPSB_ST_INCONSISTENT = 8, FPSB_ST_ZERO_ATB = 9
+};
+
+/* Krylov.jl `stats` fields the reference reads (`.solved`, src/solve_linear_system.jl:53,72,...) */
+typedef struct {
+    int64_t niter;
+    int32_t solved;
+    int32_t inconsistent;
+    int32_t status;
+    int32_t pad_;
+    double rnorm, arnorm, anorm, acond, xnorm;
+} fpsb_krylov_stats;
+
+/* IterativeSolver fields (src/solve_two_systems_struct.jl:23-73, defaults :99-115).
+   itmax == 0 means "Krylov.jl default" as in the reference. */
+typedef struct {
+    double ls_atol, ls_rtol; int64_t ls_itmax;
+    double ln_atol, ln_rtol, ln_btol, ln_conlim; int64_t ln_itmax;
+    double ne_atol, ne_rtol, ne_etol, ne_conlim; int64_t ne_itmax;
+} fpsb_iter_opts;
+
+/* LDLtSolver keyword arguments (src/solve_two_systems_struct.jl:312-314) */
+typedef struct {
+    double ldlt_tol, ldlt_r1, ldlt_r2;
+} fpsb_ldlt_opts;
+
+/* ---------------------------------------------------------------------------------------------
+ * Library / handle
+ * ------------------------------------------------------------------------------------------- */
+int fpsb_version(void);
+/* last error message of the calling thread ("" when none) */
+const char *fpsb_last_error(void);
+/* number of CUDA devices visible; <= 0 means the library cannot run */
+int fpsb_device_count(void);
+
+/* Replaces the structural part of both QDSolver constructors
+ *   LDLtSolver(nlp, ::T; ...)      src/solve_two_systems_struct.jl:308-353 (jac_structure!, :333-337)
+ *   IterativeSolver(nlp, ::T; ...) src/solve_two_systems_struct.jl:94-160
+ * jrow/jcol: the COO structure returned by jac_structure!(nlp, rows, cols) (length nnzj),
+ * `index_base` 1 for Julia, 0 for C/Python.  Builds on the device: CSR of A and of A' (for
+ * jprod / jtprod without atomics) and the COO->CSR value maps. `device` is the CUDA ordinal. */
+int fpsb_create(int64_t nvar, int64_t ncon, int64_t nnzj, const int64_t *jrow, const int64_t *jcol,
+                int index_base, int device, fpsb_handle *out);
+int fpsb_destroy(fpsb_handle h);
+int fpsb_dims(fpsb_handle h, int64_t *nvar, int64_t *ncon, int64_t *nnzj);
+/* the handle's CUDA stream (cudaStream_t) so callers can order their own work / events on it */
+void *fpsb_stream(fpsb_handle h);
+int fpsb_synchronize(fpsb_handle h);
+/* CUDA-event stopwatch on the handle's stream (used by bench.py for device-side timing) */
+int fpsb_timer_start(fpsb_handle h);
+int fpsb_timer_stop(fpsb_handle h, double *elapsed_ms);
+/* number of kernels launched by this handle since creation (bench.py's gpu_launches) */
+int64_t fpsb_launch_count(fpsb_handle h);
+
+/* Replaces jac_coord!(nlp, x, vals[nvar+1 : nvar+nnzj]) feeding both paths
+ *   src/solve_linear_system.jl:224-228 (LDLt)  and  jac_op! at :119-121 (Iterative).
+ * vals: nnzj values in the COO order given to fpsb_create. */
+int fpsb_set_jac_values(fpsb_handle h, const double *vals, int loc);
+
+/* jprod! / jtprod! of the Jacobian operator (NLPModels jac_op!): out = A v, A' u.
+ * Also used by the caller side for the rho-terms (src/model-Fletcherpenaltynlp.jl:388-395,552-563). */
+int fpsb_jprod(fpsb_handle h, const double *v, double *Av, int loc);
+int fpsb_jtprod(fpsb_handle h, const double *u, double *Atu, int loc);
+/* two-column variants (columns contiguous: v is [v1 | v2], each of the natural length) */
+int fpsb_jprod2(fpsb_handle h, const double *v, double *Av, int loc);
+int fpsb_jtprod2(fpsb_handle h, const double *u, double *Atu, int loc);
+
+/* ---------------------------------------------------------------------------------------------
+ * Iterative path — IterativeSolver (LSQR / CRAIG / MINRES fused iterations)
+ * ------------------------------------------------------------------------------------------- */
+/* defaults of src/solve_two_systems_struct.jl:99-115 for given (nvar, ncon) */
+int fpsb_iter_default_opts(int64_t nvar, int64_t ncon, fpsb_iter_opts *opts);
+/* allocates the Krylov workspaces (LsqrWorkspace/CraigWorkspace/MinresWorkspace equivalents) */
+int fpsb_iter_setup(fpsb_handle h, const fpsb_iter_opts *opts);
+
+/* solve_two_mixed [Iterative]  src/solve_linear_system.jl:107-140
+ *   q1 = LSQR(A', rhs1, lambda = sqrt(delta)), p1 = rhs1 - A' q1
+ *   (x, y) = CRAIG(A, -rhs2 [, M = I/delta, sqd]), p2 = -x, q2 = y
+ * rhs1: nvar, rhs2: ncon; p1, p2: nvar; q1, q2: ncon. stats[0] = LSQR, stats[1] = CRAIG. */
+int fpsb_iter_solve_two_mixed(fpsb_handle h, double delta, const double *rhs1, const double *rhs2,
+                              double *p1, double *q1, double *p2, double *q2, int loc,
+                              fpsb_krylov_stats stats[2]);
+/* solve_two_least_squares [Iterative]  src/solve_linear_system.jl:79-105 (two LSQR on A');
+ * rhs1, rhs2: nvar. (The reference returns q1 aliased to q2; here both are returned.) */
+int fpsb_iter_solve_two_least_squares(fpsb_handle h, double delta, const double *rhs1,
+                                      const double *rhs2, double *p1, double *q1, double *p2,
+                                      double *q2, int loc, fpsb_krylov_stats stats[2]);
+/* solve_two_extras [Iterative]  src/solve_linear_system.jl:45-77
+ *   u1 = LSQR(A', rhs1, lambda = sqrt(tau)); u2 = MINRES(A A', rhs2, lambda = tau), tau = max(delta,1e-14) */
+int fpsb_iter_solve_two_extras(fpsb_handle h, double delta, const double *rhs1, const double *rhs2,
+                               double *u1, double *u2, int loc, fpsb_krylov_stats stats[2]);
+
+/* ---------------------------------------------------------------------------------------------
+ * LDLt path — LDLtSolver (host symbolic analysis + device numeric refactorisation + 2-RHS solves)
+ * ------------------------------------------------------------------------------------------- */
+int fpsb_ldlt_default_opts(fpsb_ldlt_opts *opts);
+/* ldl_analyze(Symmetric(sparse(rows, cols, vals), :U))  src/solve_two_systems_struct.jl:343-348.
+ * P: permutation of size nvar+ncon, P[k] = (index_base-based) index eliminated k-th, or NULL for
+ * the built-in approximate-minimum-degree ordering (LDLFactorizations' default is amd()).
+ * Sets n_d = nvar, tol, r1, r2 from opts. Host work: ordering, elimination tree, column counts,
+ * fill pattern, supernodes, dependency lists; uploads the device plan. */
+int fpsb_ldlt_analyze(fpsb_handle h, const int64_t *P, int index_base, const fpsb_ldlt_opts *opts);
+/* sizes of the symbolic factor: N = nvar + ncon and nnz(L) (strict lower part, like LDLFactorizations) */
+int fpsb_ldlt_symbolic_sizes(fpsb_handle h, int64_t *N, int64_t *lnz);
+/* bit-exact check surface: 0-based P, parent (-1 = root), Lnz, Lp (N+1), Li (lnz). Any may be NULL. */
+int fpsb_ldlt_get_symbolic(fpsb_handle h, int64_t *P, int64_t *parent, int64_t *Lnz, int64_t *Lp,
+                           int64_t *Li);
+/* summary of the supernodal plan: nsuper, nnz stored in panels (incl. relaxed zeros), number of
+ * (descendant -> target) update pairs, flops of the numeric factorisation */
+int fpsb_ldlt_plan_info(fpsb_handle h, int64_t *nsuper, int64_t *panel_nnz, int64_t *npairs,
+                        double *flops);
+/* ldl_factorize!(M, str) with vals = [1..1 | jac values | -delta..-delta]
+ *   src/solve_linear_system.jl:231-234. Uses the values last given to fpsb_set_jac_values.
+ * *factorized mirrors LDLFactorizations.factorized(str). */
+int fpsb_ldlt_factorize(fpsb_handle h, double delta, int *factorized);
+/* numeric factor in LDLFactorizations' layout (Lx aligned with Li above, D of size N), host copies */
+int fpsb_ldlt_get_factor(fpsb_handle h, double *Lx, double *D);
+
+/* solve_two_mixed [LDLt]  src/solve_linear_system.jl:206-252 : refactor + K [p1 p2; q1 q2] = [rhs1 0; 0 rhs2].
+ * On a failed factorisation the outputs hold the right-hand sides (reference behaviour, :242-251). */
+int fpsb_ldlt_solve_two_mixed(fpsb_handle h, double delta, const double *rhs1, const double *rhs2,
+                              double *p1, double *q1, double *p2, double *q2, int loc,
+                              int *factorized);
+/* solve_two_least_squares [LDLt]  src/solve_linear_system.jl:161-204 : no refactor,
+ * K [p1 p2; q1 q2] = [rhs1 rhs2; 0 0] */
+int fpsb_ldlt_solve_two_least_squares(fpsb_handle h, const double *rhs1, const double *rhs2,
+                                      double *p1, double *q1, double *p2, double *q2, int loc,
+                                      int *factorized);
+/* solve_two_extras [LDLt]  src/solve_linear_system.jl:142-159 : cgls(A', rhs1, lambda = tau),
+ * minres(A A', rhs2, lambda = tau) with Krylov.jl default tolerances */
+int fpsb_ldlt_solve_two_extras(fpsb_handle h, double delta, const double *rhs1, const double *rhs2,
+                               double *u1, double *u2, int loc, fpsb_krylov_stats stats[2]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FPSB_H */
