@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py — 2-RHS KKT solves/s at n=1M, nnz(A)=10M (BASELINE.json metric).
+
+A step = one `solve_two_mixed`: refresh the device-resident Jacobian values + the two
+quasi-definite solves K [p1 p2; q1 q2] = [g 0; 0 c] on the Krylov (IterativeSolver) path,
+LSQR and CRAIG advanced in lock-step by the fused two-column SpMM kernels.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU)
+    python bench.py --impl reference --steps K --warmup W    # CPU arm: the oracle port on host cores
+
+value : whole-job solves/s with rhs / Jacobian values already resident in HBM (FPSB_DEVICE)
+e2e   : the same step through the C ABI with HOST buffers (FPSB_HOST: jac values + both rhs
+        copied H2D and the four result vectors copied D2H inside the timed region)
+N > 1 : independent instances sharded across GPUs, no data-path collective ("weak").
+The reference (Julia) cannot run here: the CPU arm is the oracle's C port of the same algorithms
+(kind "port", 1 thread — the reference path is single-threaded).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SQRT_EPS = float(np.sqrt(np.finfo(np.float64).eps))
+
+
+def make_workload(n, m, k, w, seed):
+    from fpsb200 import models
+    A = models.window_random_jacobian(m, n, k, w=w, seed=seed)
+    coo = A.tocoo()
+    rng = np.random.default_rng(seed)
+    rhs1 = rng.standard_normal(n)
+    rhs2 = rng.standard_normal(m)
+    return A, coo.row.astype(np.int64), coo.col.astype(np.int64), coo.data.astype(np.float64), rhs1, rhs2
+
+
+def algorithmic_bytes(n, m, nnz, it0, it1, delta):
+    """SURVEY §8(d) ideal-fusion bytes of one fused LSQR(A') + CRAIG(A) solve: every launch of the
+    step kernel streams the matrix once (12 B/nnz + row pointers); LSQR touches u (n) r/w in the
+    n-space kernel and v, w, x (m) r/w in the m-space kernel; CRAIG touches v, x (+w2 if delta != 0)
+    in n-space and Mu, w, y in m-space.  Gathers (L2/L1 hits) are not counted."""
+    both = min(it0, it1)
+    only0 = max(it0 - it1, 0)
+    only1 = max(it1 - it0, 0)
+    mat_n = 12 * nnz + 4 * (n + 1)     # rows of A' (n-space kernel)
+    mat_m = 12 * nnz + 4 * (m + 1)     # rows of A  (m-space kernel)
+    lsqr_n, lsqr_m = 16 * n, 48 * m
+    craig_n, craig_m = (48 if delta != 0 else 32) * n, 48 * m
+    launches = 1 + 2 * max(it0, it1)
+    total = mat_m + 16 * m             # LSQR init: v1 = A u1 (write v), read u via gather
+    total += both * (mat_n + mat_m + lsqr_n + lsqr_m + craig_n + craig_m)
+    total += only0 * (mat_n + mat_m + lsqr_n + lsqr_m)
+    total += only1 * (mat_n + mat_m + craig_n + craig_m)
+    return total, launches
+
+
+class ClockSampler:
+    """nvidia-smi clock/throttle sampler running during the timed region."""
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def oracle_solve_timer(A, rhs1, rhs2, delta):
+    """Returns a closure running one full solve_two_mixed on the CPU oracle (1 thread)."""
+    from oracle import oracle as O
+    O.build()
+    it = O.IterativeOracle(A)
+
+    def run():
+        t = time.perf_counter()
+        out = it.solve_two_mixed(delta, rhs1, rhs2)
+        return time.perf_counter() - t, out[4]
+    return run
+
+
+def run_reference(args, cfg):
+    """CPU arm: the oracle's C port of LSQR + CRAIG (Krylov.jl restated) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n, m, k, w = cfg["n"], cfg["m"], cfg["nnz_per_row"], cfg["window"]
+    A, jrow, jcol, vals, rhs1, rhs2 = make_workload(n, m, k, w, args.seed)
+    run = oracle_solve_timer(A, rhs1, rhs2, args.delta)
+    for _ in range(min(args.warmup, 1)):
+        run()
+    times, st = [], None
+    for _ in range(args.steps):
+        t, st = run()
+        times.append(t)
+    tot = sum(times)
+    val = args.steps / tot
+    line = {
+        "impl": "reference", "metric": "2-RHS KKT solves/s", "value": val, "unit": "solves/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": cfg,
+        "cpu_baseline": {"value": val, "unit": "solves/s", "cores": 1, "kind": "port",
+                         "sample": f"{args.steps} full-size solve_two_mixed calls (LSQR {st[0]['niter']} it + "
+                                   f"CRAIG {st[1]['niter']} it), oracle/fps_oracle.c, 1 thread of "
+                                   f"{os.cpu_count()} available; the Julia reference is not runnable here"},
+        "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--m", type=int, default=500_000)
+    ap.add_argument("--nnz-per-row", type=int, default=20)
+    ap.add_argument("--window", type=int, default=64)
+    ap.add_argument("--delta", type=float, default=0.0)
+    ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--cpu-baseline-solves", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ldlt", action="store_true", help="skip the LDLt-path extra measurements")
+    args = ap.parse_args()
+
+    n, m, k, w = args.n, args.m, args.nnz_per_row, args.window
+    cfg = {"workload": "C4-shape synthetic sparse equality-constrained problem: window-random Jacobian "
+                       f"n={n} m={m} nnz={m * k} ({k}/row, |j-2i|<={w}), N(0,1) values, seed {args.seed}; "
+                       "step = solve_two_mixed (Jacobian refresh + LSQR/CRAIG 2-RHS solve), Krylov path, "
+                       f"reference tolerances sqrt(eps), delta={args.delta}",
+           "n": n, "m": m, "nnz": m * k, "nnz_per_row": k, "window": w, "delta": args.delta,
+           "l2_policy": "inputs larger than L2 (CSR of A and A' = 240 MB streamed every iteration vs 126 MB L2)",
+           "parallelism": f"{args.gpus} independent instance(s), one per GPU, no collective"}
+    if args.impl == "reference":
+        run_reference(args, cfg)
+        return
+
+    import torch
+    import fpsb200
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    A, jrow, jcol, vals, rhs1, rhs2 = make_workload(n, m, k, w, args.seed + rank)
+    nnz = len(vals)
+    H = fpsb200.B200Handle(n, m, jrow, jcol, device=local_rank)
+    H.iter_setup(None)
+    dev = torch.device("cuda", local_rank)
+    d_vals = torch.tensor(vals, device=dev)
+    d_r1 = torch.tensor(rhs1, device=dev)
+    d_r2 = torch.tensor(rhs2, device=dev)
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        H.set_jac_values(d_vals)
+        return H.iter_solve_two_mixed(args.delta, d_r1, d_r2)
+
+    def step_host():
+        H.set_jac_values(vals)
+        return H.iter_solve_two_mixed(args.delta, rhs1, rhs2)
+
+    # ---- resident (value) -------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        out = step_resident()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    l0 = H.launch_count()
+    loop_ms, step_launches = 0.0, 0
+    H.timer_start()
+    for _ in range(args.steps):
+        out = step_resident()
+        ms, nl = H.iter_last_profile()
+        loop_ms += ms
+        step_launches += nl
+    dev_ms = H.timer_stop()
+    barrier()
+    clocks = sampler.stop()
+    launches = H.launch_count() - l0
+    st = out[4]
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    max_ms = float(t.item())
+
+    # ---- end to end through the C ABI with host buffers ----------------------------------------
+    for _ in range(2):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    H.timer_start()
+    for _ in range(args.steps):
+        step_host()
+    e2e_dev_ms = H.timer_stop()
+    e2e_wall_ms = 1e3 * (time.perf_counter() - t0)
+    barrier()
+    t = torch.tensor([max(e2e_dev_ms, e2e_wall_ms)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+        dist = None
+    if rank != 0:
+        return
+
+    # ---- roofline of the dominant kernel (fused SpMM step) ---------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    tot_bytes, eff_launches = algorithmic_bytes(n, m, nnz, st[0]["niter"], st[1]["niter"], args.delta)
+    loop_ms_per_solve = loop_ms / args.steps
+    achieved = tot_bytes / (loop_ms_per_solve * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": "gk_step_kernel<PAIR=true> (fused 2-column SpMM + Krylov row epilogue)",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "frac_of_nominal_8000": achieved / 8000.0, "peak_source": peak_src,
+        "traffic": None,
+        "bytes_per_launch": tot_bytes / eff_launches,
+        "avg_launch_us": 1e3 * loop_ms_per_solve / eff_launches,
+        "launches_per_solve": eff_launches,
+        "launched_incl_post_convergence_noops": step_launches / args.steps,
+        "iters": {"lsqr": st[0]["niter"], "craig": st[1]["niter"]},
+        "note": "achieved = SURVEY 8(d) algorithmic bytes of the whole Krylov loop / CUDA-event time of "
+                "that loop on the handle's stream (includes host polling gaps and the no-op launches "
+                "queued after convergence)",
+    }
+
+    # ---- extras: SpMV and the LDLt path on the same matrix ------------------------------------------
+    extra = {}
+    if args.gpus > 1:            # scaling runs: headline only (extras / CPU baseline are N=1 work)
+        args.no_ldlt = True
+        args.no_cpu_baseline = True
+    try:
+        if args.gpus > 1:
+            raise RuntimeError("skipped at N>1")
+        H.timer_start()
+        for _ in range(20):
+            y = H.jprod(d_r1)
+        ms = H.timer_stop() / 20
+        b = 12 * nnz + 4 * (m + 1) + 8 * n + 8 * m
+        extra["spmv_A"] = {"us": 1e3 * ms, "GB/s": b / ms / 1e6, "frac_of_measured_peak": b / ms / 1e6 / peak}
+        H.timer_start()
+        for _ in range(20):
+            y = H.jtprod(d_r2)
+        ms = H.timer_stop() / 20
+        b = 12 * nnz + 4 * (n + 1) + 8 * n + 8 * m
+        extra["spmv_At"] = {"us": 1e3 * ms, "GB/s": b / ms / 1e6, "frac_of_measured_peak": b / ms / 1e6 / peak}
+        d_r3 = torch.tensor(np.random.default_rng(7).standard_normal(n), device=dev)
+        H.iter_solve_two_least_squares(args.delta, d_r1, d_r3)
+        H.timer_start()
+        for _ in range(5):
+            o2 = H.iter_solve_two_least_squares(args.delta, d_r1, d_r3)
+        ms = H.timer_stop() / 5
+        extra["iter_solve_two_least_squares"] = {"ms": ms, "solves/s": 1e3 / ms,
+                                                 "iters": [o2[4][0]["niter"], o2[4][1]["niter"]]}
+    except Exception as e:   # extras must never take the headline down
+        extra["error_spmv"] = repr(e)
+    if not args.no_ldlt:
+        try:
+            t0 = time.perf_counter()
+            H.ldlt_analyze()
+            extra["ldlt_analyze_host_s"] = time.perf_counter() - t0
+            info = H.ldlt_plan_info()
+            sym_N = n + m
+            lnz = int(H.ldlt_symbolic()["Lp"][-1])
+            extra["ldlt_plan"] = dict(info, lnz=lnz)
+            H.ldlt_solve_two_mixed(SQRT_EPS, d_r1, d_r2)
+            H.timer_start()
+            for _ in range(3):
+                o3 = H.ldlt_solve_two_mixed(SQRT_EPS, d_r1, d_r2)
+            ms = H.timer_stop() / 3
+            extra["ldlt_solve_two_mixed"] = {"ms": ms, "solves/s": 1e3 / ms, "factorized": bool(o3[4]),
+                                             "delta": SQRT_EPS}
+            H.timer_start()
+            for _ in range(5):
+                o3 = H.ldlt_solve_two_least_squares(d_r1, d_r3)
+            ms = H.timer_stop() / 5
+            sb = 24 * lnz + 88 * sym_N
+            extra["ldlt_solve_two_least_squares"] = {"ms": ms, "solves/s": 1e3 / ms,
+                                                     "GB/s": sb / ms / 1e6,
+                                                     "frac_of_measured_peak": sb / ms / 1e6 / peak}
+        except Exception as e:
+            extra["error_ldlt"] = repr(e)
+
+    # ---- CPU baseline (oracle port, bounded sample) -------------------------------------------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        run = oracle_solve_timer(A, rhs1, rhs2, args.delta)
+        ts, ost = [], None
+        for _ in range(args.cpu_baseline_solves):
+            tt, ost = run()
+            ts.append(tt)
+        cpu = {"value": len(ts) / sum(ts), "unit": "solves/s", "cores": 1, "kind": "port",
+               "sample": f"{len(ts)} full-size solve_two_mixed calls ({sum(ts):.1f} s; LSQR {ost[0]['niter']} it + "
+                         f"CRAIG {ost[1]['niter']} it) with oracle/fps_oracle.c, gcc -O3, 1 thread of "
+                         f"{os.cpu_count()} host cores (the reference path is single-threaded; Julia absent)"}
+
+    value = args.gpus * args.steps / (max_ms * 1e-3)
+    e2e_value = args.gpus * args.steps / (e2e_ms * 1e-3)
+    line = {
+        "metric": "2-RHS KKT solves/s", "value": value, "unit": "solves/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": max_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": cfg, "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "solves/s",
+                "h2d_bytes_per_step": 8 * (nnz + n + m), "d2h_bytes_per_step": 16 * (n + m),
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "solver_stats": {"lsqr": st[0], "craig": st[1]},
+        "extra": extra,
+    }
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

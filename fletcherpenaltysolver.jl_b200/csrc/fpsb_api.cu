@@ -252,6 +252,14 @@ int fpsb_iter_setup(fpsb_handle hh, const fpsb_iter_opts *opts) {
     FPSB_CATCH
 }
 
+int fpsb_iter_last_profile(fpsb_handle hh, double *loop_ms, int64_t *step_launches) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQUIRE(h, FPSB_EINVAL, "NULL handle");
+    if (loop_ms) *loop_ms = h->prof_loop_ms;
+    if (step_launches) *step_launches = h->prof_step_launches;
+    return FPSB_OK;
+}
+
 static int iter_solve(fpsb_handle hh, int kind, double delta, const double *rhs1, const double *rhs2,
                       double *p1, double *q1, double *p2, double *q2, int loc, fpsb_krylov_stats *stats) {
     Handle *h = reinterpret_cast<Handle *>(hh);

@@ -108,6 +108,8 @@ struct Handle {
     LdltPlan *ldlt = nullptr;
     fpsb_iter_opts iopts{};
     bool iopts_set = false;
+    double prof_loop_ms = 0.0;          // CUDA-event time of the last Krylov loop region
+    int64_t prof_step_launches = 0;     // fused SpMM step kernels launched in that region
 };
 
 // krylov.cu

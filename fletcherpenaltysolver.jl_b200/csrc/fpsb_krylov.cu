@@ -759,11 +759,11 @@ __global__ void __launch_bounds__(kBlock) ew_kernel(EwParams P) {
     double acc[1] = {0.0};
     const int stride = gridDim.x * blockDim.x;
     // coefficients
-    double alpha = 0, beta = 0, oldbeta = 0, delta = 0, eps_ = 0, gamma = 1, phi = 0, xi = 0, c1 = 0,
+    double alpha = 0, beta = 0, delta = 0, eps_ = 0, gamma = 1, phi = 0, xi = 0, c1 = 0,
            s1 = 0, sv = 0, lambda = 0, beta_c = 0;
     int iter = 0, pend = 0;
     if (S && !is_init) {
-        alpha = S->alpha; beta = S->beta; oldbeta = S->oldbeta; delta = S->delta; eps_ = S->eps_;
+        alpha = S->alpha; beta = S->beta; delta = S->delta; eps_ = S->eps_;
         gamma = S->gamma; phi = S->phi; xi = S->xi; c1 = S->c1; s1 = S->s1; sv = S->sv;
         lambda = S->lambda; beta_c = S->beta_c; iter = S->iter; pend = S->pend;
     }
@@ -890,6 +890,9 @@ struct IterWs {
     int *h_done = nullptr;               // pinned
     SlotState *h_st = nullptr;           // pinned [2]
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaEvent_t pev[2] = {nullptr, nullptr};   // profile: Krylov loop region
+    int64_t prof_launch0 = 0, prof_launch1 = 0;
+    bool prof_armed = false;
     int ew_grid = 0;
 };
 
@@ -1019,6 +1022,8 @@ void iter_setup(Handle *h) {
     FPSB_CUDA(cudaMallocHost((void **)&W->h_st, 2 * sizeof(SlotState)));
     FPSB_CUDA(cudaEventCreateWithFlags(&W->ev[0], cudaEventDisableTiming));
     FPSB_CUDA(cudaEventCreateWithFlags(&W->ev[1], cudaEventDisableTiming));
+    FPSB_CUDA(cudaEventCreate(&W->pev[0]));
+    FPSB_CUDA(cudaEventCreate(&W->pev[1]));
     FPSB_CUDA(cudaStreamSynchronize(h->stream));
 }
 
@@ -1029,6 +1034,8 @@ void iter_free(Handle *h) {
     if (W->h_st) cudaFreeHost(W->h_st);
     if (W->ev[0]) cudaEventDestroy(W->ev[0]);
     if (W->ev[1]) cudaEventDestroy(W->ev[1]);
+    if (W->pev[0]) cudaEventDestroy(W->pev[0]);
+    if (W->pev[1]) cudaEventDestroy(W->pev[1]);
     delete W;
     h->iter = nullptr;
 }
@@ -1169,11 +1176,28 @@ struct Engine {
             throw CudaFail{FPSB_ECUDA};
         }
     }
+    // CUDA-event bracket around the Krylov loop (first step kernel .. last chunk), for the roofline
+    void mark_begin() {
+        FPSB_CUDA(cudaEventRecord(W->pev[0], h->stream));
+        W->prof_launch0 = h->launches;
+        W->prof_armed = true;
+    }
+    void mark_end() {
+        FPSB_CUDA(cudaEventRecord(W->pev[1], h->stream));
+        W->prof_launch1 = h->launches;
+    }
     void fetch(fpsb_krylov_stats *st) {
         FPSB_CUDA(cudaMemcpyAsync(W->h_st, W->st.p, 2 * sizeof(SlotState), cudaMemcpyDeviceToHost, h->stream));
         FPSB_CUDA(cudaStreamSynchronize(h->stream));
         stats_from(W->h_st[0], st[0]);
         stats_from(W->h_st[1], st[1]);
+        if (W->prof_armed) {
+            float ms = 0.f;
+            FPSB_CUDA(cudaEventElapsedTime(&ms, W->pev[0], W->pev[1]));
+            h->prof_loop_ms = ms;
+            h->prof_step_launches = W->prof_launch1 - W->prof_launch0;
+            W->prof_armed = false;
+        }
     }
 };
 
@@ -1222,18 +1246,16 @@ void iter_solve_two_mixed(Handle *h, double delta, const double *rhs1, const dou
     SlotIO l_v = io_mode(MD_LSQR_V, W->am[0][0].p, W->am[0][1].p);
     SlotIO c_v = io_mode(MD_CRAIG_V, W->an[1][0].p, W->an[1][1].p);
     SlotIO c_u = io_mode(MD_CRAIG_U, W->am[1][0].p, W->am[1][1].p);
+    E.mark_begin();
     E.step(true, true, l_init, io_none());
     E.loop([&](int) {
         E.step(false, true, l_u, c_v);
         E.step(true, true, l_v, c_u);
     }, kChunk);
+    E.mark_end();
     // outputs
     E.ew(EW_COPY, 0, (int)m, W->am[0][1].p, q1, nullptr, nullptr, nullptr, nullptr, nullptr, -1, 1.0, 0);
     residual_p(E, rhs1, q1, p1);
-    {
-        EwParams P{};
-        (void)P;
-    }
     E.ew(EW_CRAIG_FLUSH, 1, (int)n, nullptr, W->an[1][0].p, W->an[1][1].p, p2, nullptr, nullptr, W->Gn.p, 1, 1.0, 1);
     E.ew(EW_COPY, 1, (int)m, W->am[1][1].p, q2, nullptr, nullptr, nullptr, nullptr, nullptr, -1, 1.0, 0);
     E.fetch(st);
@@ -1257,11 +1279,13 @@ void iter_solve_two_least_squares(Handle *h, double delta, const double *rhs1, c
     SlotIO u0 = io_mode(MD_LSQR_U), u1 = io_mode(MD_LSQR_U);
     SlotIO v0 = io_mode(MD_LSQR_V, W->am[0][0].p, W->am[0][1].p);
     SlotIO v1 = io_mode(MD_LSQR_V, W->am[1][0].p, W->am[1][1].p);
+    E.mark_begin();
     E.step(true, true, init0, init1);
     E.loop([&](int) {
         E.step(false, true, u0, u1);
         E.step(true, true, v0, v1);
     }, kChunk);
+    E.mark_end();
     E.ew(EW_COPY, 0, (int)m, W->am[0][1].p, q1, nullptr, nullptr, nullptr, nullptr, nullptr, -1, 1.0, 0);
     E.ew(EW_COPY, 1, (int)m, W->am[1][1].p, q2, nullptr, nullptr, nullptr, nullptr, nullptr, -1, 1.0, 0);
     // p_i = rhs_i - A' q_i : one two-column SpMM

@@ -1,5 +1,737 @@
-// placeholder — replaced by the supernodal LDLt implementation
+// fpsb_ldlt.cu — numeric LDL' refactorisation and 2-RHS triangular solves on the GPU.
+//
+// Reference surface replaced (file:line under /root/reference):
+//   sparse(rows, cols, vals) + ldl_factorize!(M, str)   src/solve_linear_system.jl:231-234
+//   ldiv!(str, sol) on the N x 2 `sol`                  src/solve_linear_system.jl:242-243, :194-195
+//   LDLFactorizations' up-looking numeric LDL' with dynamic regularisation
+//
+// Design (B200): the fill pattern is known from the host analysis (fpsb_symbolic.cpp), so L is
+// stored as dense supernodal panels in HBM.  One persistent kernel factorises everything:
+// CTAs (or single warps for tiny supernodes) take supernodes from a level-ordered ticket queue and
+// pull the updates of their descendants (left-looking, no floating-point atomics => bitwise
+// reproducible), waiting on per-supernode release/acquire flags instead of level barriers.
+// The diagonal block is factorised in shared memory with the reference's pivot rule
+//   |D[k]| < tol  =>  D[k] = sign(r) * max(|D[k] + r|, |r|),  r = (P[k] < n_d ? r1 : r2),
+// and the triangular solves run the same dependency-driven schedule on an interleaved N x 2
+// right-hand side (both columns share every load of L).
 #include "fpsb_internal.h"
+#include "fpsb_symbolic.h"
+#include "fpsb_device.cuh"
+#include <algorithm>
+#include <cstring>
+#include <stdexcept>
+
 namespace fpsb {
-void ldlt_free(Handle *h) { (void)h; }
+
+constexpr int kMaxW = 64;               // == kMaxSuperWidth in fpsb_symbolic.cpp
+constexpr int kLdltBlock = 256;
+constexpr int kWarpsPerBlock = kLdltBlock / 32;
+constexpr int kSmallW = 8;              // warp-level supernodes: w <= kSmallW and w*(w+nr) <= 512
+constexpr int kShDoubles = (kMaxW + 1) * kMaxW + 4 * kMaxW;
+
+struct PlanDev {
+    int N, nsuper, ntasks;
+    const int *sfirst;
+    const int64_t *rptr;
+    const int *rows;
+    const int64_t *poff;
+    const int *order;
+    const int *task_start, *task_cnt;
+    const int64_t *uptr;
+    const int *usrc, *ua, *ub;
+    const int64_t *urel;
+    const int *rel;
+    const int64_t *tptr;
+    const int *ttgt;
+    const int *P;
+    double *panels;
+    double *D;
+    double2 *Y;
+    int *done_f, *done_s, *done_b;
+    int *ticket;        // [3]
+    int *fail;          // 0 ok ; >0 (index+1) zero pivot ; -2 dependency wait timed out
+    int n_d;
+    double tol, r1, r2;
+    int dynamic_reg;
+};
+
+struct LdltPlan {
+    Symbolic S;
+    fpsb_ldlt_opts opts{};
+    DevBuf<int> sfirst, rows, order, task_start, task_cnt, usrc, ua, ub, rel, ttgt, P, pinv, asrc;
+    DevBuf<int64_t> rptr, poff, uptr, urel, tptr, aslot, aptr;
+    DevBuf<double> panels, D;
+    DevBuf<double2> Y;
+    DevBuf<int> done_f, done_s, done_b, ticket, fail;
+    int ntasks = 0;
+    int epoch = 0;
+    int64_t naslot = 0;
+    bool factorized = false;
+    bool have_factor = false;
+    PlanDev dev{};
+};
+
+__device__ __forceinline__ int ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
+__device__ __forceinline__ void st_release(int *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <bool WARP>
+__device__ __forceinline__ void gsync() {
+    if (WARP) __syncwarp();
+    else __syncthreads();
+}
+
+// one thread spins (bounded), the group then synchronises
+template <bool WARP>
+__device__ __forceinline__ void wait_done(const int *flag, int epoch, int tid, int *fail) {
+    if (tid == 0) {
+        int it = 0;
+        while (ld_acquire(flag) != epoch) {
+            __nanosleep(40);
+            ++it;
+            if ((it & 1023) == 0 && ld_acquire(fail) == -2) break;     // someone already gave up
+            if (it > (1 << 24)) { atomicExch(fail, -2); break; }
+        }
+        __threadfence();
+    }
+    gsync<WARP>();
+}
+
+// ------------------------------------------------------------------------------------------------
+// assembly: panels <- [1..1 | jac values | -delta..]  through the precomputed slot map
+// ------------------------------------------------------------------------------------------------
+__global__ void assemble_kernel(int64_t nslot, const int64_t *aslot, const int64_t *aptr, const int *asrc,
+                                const double *jvals, int nvar, int64_t nnzj, double delta, double *panels) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nslot) return;
+    double s = 0.0;
+    for (int64_t p = aptr[i]; p < aptr[i + 1]; ++p) {
+        int id = asrc[p];
+        double v = (id < nvar) ? 1.0 : ((int64_t)id < nvar + nnzj ? jvals[id - nvar] : -delta);
+        s += v;
+    }
+    panels[aslot[i]] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// numeric factorisation of one supernode (left-looking)
+// ------------------------------------------------------------------------------------------------
+template <bool WARP>
+__device__ void factor_supernode(const PlanDev &P, int t, double *sh, int epoch, int tid, int nt) {
+    const int f = P.sfirst[t];
+    const int w = P.sfirst[t + 1] - f;
+    const int nr = (int)(P.rptr[t + 1] - P.rptr[t]);
+    const int ld = w + nr;
+    double *panel = P.panels + P.poff[t];
+
+    // 1. pull the updates of every descendant supernode
+    for (int64_t q = P.uptr[t]; q < P.uptr[t + 1]; ++q) {
+        const int d = P.usrc[q];
+        wait_done<WARP>(&P.done_f[d], epoch, tid, P.fail);
+        const int fd = P.sfirst[d];
+        const int wd = P.sfirst[d + 1] - fd;
+        const int nrd = (int)(P.rptr[d + 1] - P.rptr[d]);
+        const int ldd = wd + nrd;
+        const double *pd = P.panels + P.poff[d] + wd;     // rows below d's block
+        const double *Dd = P.D + fd;
+        const int a = P.ua[q], b = P.ub[q];
+        const int *relq = P.rel + P.urel[q];
+        const int nrow = nrd - a, ncol = b - a;
+        const int total = nrow * ncol;
+        for (int e = tid; e < total; e += nt) {
+            const int j = e / nrow;
+            const int i = e - j * nrow;
+            if (i < j) continue;
+            double s = 0.0;
+            for (int k = 0; k < wd; ++k) {
+                const double lj = __ldcg(pd + (size_t)k * ldd + a + j);
+                const double li = __ldcg(pd + (size_t)k * ldd + a + i);
+                s += li * (lj * __ldcg(Dd + k));
+            }
+            panel[(size_t)relq[j] * ld + relq[i]] -= s;
+        }
+        gsync<WARP>();
+    }
+
+    // 2. dense LDL' of the w x w diagonal block in shared memory (row-major, stride w+1)
+    const int ws = w + 1;
+    double *B = sh;
+    double *yk = sh + (size_t)ws * w;
+    double *dd = yk + w;
+    for (int e = tid; e < w * w; e += nt) {
+        const int j = e / w, i = e - j * w;      // column j, row i
+        if (i >= j) B[i * ws + j] = panel[(size_t)j * ld + i];
+    }
+    gsync<WARP>();
+    for (int k = 0; k < w; ++k) {
+        if (tid == 0) {
+            double dk = B[k * ws + k];
+            if (P.dynamic_reg && fabs(dk) < P.tol) {
+                const double r = (P.P[f + k] < P.n_d) ? P.r1 : P.r2;
+                const double sg = (double)((r > 0.0) - (r < 0.0));
+                dk = sg * fmax(fabs(dk + r), fabs(r));
+            }
+            if (dk == 0.0) { atomicCAS(P.fail, 0, f + k + 1); dk = 1.0; }
+            dd[k] = dk;
+            P.D[f + k] = dk;
+        }
+        gsync<WARP>();
+        const double dk = dd[k];
+        for (int i = k + 1 + tid; i < w; i += nt) {
+            const double y = B[i * ws + k];
+            yk[i] = y;
+            B[i * ws + k] = y / dk;
+        }
+        gsync<WARP>();
+        const int rem = w - k - 1;
+        for (int e = tid; e < rem * rem; e += nt) {
+            const int jj = e / rem, ii = e - jj * rem;
+            if (ii < jj) continue;
+            const int i = k + 1 + ii, j = k + 1 + jj;
+            B[i * ws + j] -= B[i * ws + k] * yk[j];
+        }
+        gsync<WARP>();
+    }
+    for (int e = tid; e < w * w; e += nt) {
+        const int j = e / w, i = e - j * w;
+        if (i > j) panel[(size_t)j * ld + i] = B[i * ws + j];
+    }
+
+    // 3. sub-diagonal block: y_k = a_k - sum_{j<k} y_j L11[k][j] ; L21[i][k] = y_k / d_k
+    for (int i = tid; i < nr; i += nt) {
+        double y[kMaxW];
+        double *row = panel + w + i;
+        for (int k = 0; k < w; ++k) {
+            double s = row[(size_t)k * ld];
+            for (int j = 0; j < k; ++j) s -= y[j] * B[k * ws + j];
+            y[k] = s;
+            row[(size_t)k * ld] = s / dd[k];
+        }
+    }
+    __threadfence();
+    gsync<WARP>();
+    if (tid == 0) st_release(&P.done_f[t], epoch);
+}
+
+template <bool WARP>
+__device__ void fwd_supernode(const PlanDev &P, int t, double *sh, int epoch, int tid, int nt) {
+    const int f = P.sfirst[t];
+    const int w = P.sfirst[t + 1] - f;
+    const int nr = (int)(P.rptr[t + 1] - P.rptr[t]);
+    const int ld = w + nr;
+    const double *panel = P.panels + P.poff[t];
+    double2 *ys = reinterpret_cast<double2 *>(sh);     // w entries
+    for (int k = tid; k < w; k += nt) ys[k] = P.Y[f + k];
+    gsync<WARP>();
+    for (int64_t q = P.uptr[t]; q < P.uptr[t + 1]; ++q) {
+        const int d = P.usrc[q];
+        wait_done<WARP>(&P.done_s[d], epoch, tid, P.fail);
+        const int fd = P.sfirst[d];
+        const int wd = P.sfirst[d + 1] - fd;
+        const int nrd = (int)(P.rptr[d + 1] - P.rptr[d]);
+        const int ldd = wd + nrd;
+        const double *pd = P.panels + P.poff[d] + wd;
+        const int a = P.ua[q], b = P.ub[q];
+        const int *relq = P.rel + P.urel[q];
+        for (int j = a + tid; j < b; j += nt) {
+            double s0 = 0.0, s1 = 0.0;
+            for (int k = 0; k < wd; ++k) {
+                const double l = __ldcg(pd + (size_t)k * ldd + j);
+                const double2 yv = __ldcg(P.Y + fd + k);
+                s0 += l * yv.x; s1 += l * yv.y;
+            }
+            const int lc = relq[j - a];
+            ys[lc].x -= s0; ys[lc].y -= s1;
+        }
+        gsync<WARP>();
+    }
+    // unit lower triangular solve with L11
+    for (int k = 0; k < w; ++k) {
+        const double2 yk = ys[k];
+        for (int i = k + 1 + tid; i < w; i += nt) {
+            const double l = panel[(size_t)k * ld + i];
+            ys[i].x -= l * yk.x; ys[i].y -= l * yk.y;
+        }
+        gsync<WARP>();
+    }
+    for (int k = tid; k < w; k += nt) P.Y[f + k] = ys[k];
+    __threadfence();
+    gsync<WARP>();
+    if (tid == 0) st_release(&P.done_s[t], epoch);
+}
+
+template <bool WARP>
+__device__ void bwd_supernode(const PlanDev &P, int t, double *sh, int epoch, int tid, int nt) {
+    const int f = P.sfirst[t];
+    const int w = P.sfirst[t + 1] - f;
+    const int nr = (int)(P.rptr[t + 1] - P.rptr[t]);
+    const int ld = w + nr;
+    const double *panel = P.panels + P.poff[t];
+    const int *R = P.rows + P.rptr[t];
+    for (int64_t q = P.tptr[t]; q < P.tptr[t + 1]; ++q)
+        wait_done<WARP>(&P.done_b[P.ttgt[q]], epoch, tid, P.fail);
+    double2 *xs = reinterpret_cast<double2 *>(sh);     // w entries
+    // xs[k] = y_k / d_k - sum_r L21[r][k] x[R[r]]
+    const int lane = tid & 31, wid = tid >> 5, nwarp = WARP ? 1 : (nt >> 5);
+    for (int k = wid; k < w; k += nwarp) {
+        double s0 = 0.0, s1 = 0.0;
+        const double *col = panel + (size_t)k * ld + w;
+        for (int r = lane; r < nr; r += 32) {
+            const double l = col[r];
+            const double2 xv = __ldcg(P.Y + R[r]);
+            s0 += l * xv.x; s1 += l * xv.y;
+        }
+        s0 = warp_sum(s0); s1 = warp_sum(s1);
+        if (lane == 0) {
+            const double2 yv = P.Y[f + k];
+            const double dk = P.D[f + k];
+            xs[k] = make_double2(yv.x / dk - s0, yv.y / dk - s1);
+        }
+    }
+    gsync<WARP>();
+    for (int i = w - 1; i > 0; --i) {
+        const double2 xi = xs[i];
+        for (int k = tid; k < i; k += nt) {
+            const double l = panel[(size_t)k * ld + i];
+            xs[k].x -= l * xi.x; xs[k].y -= l * xi.y;
+        }
+        gsync<WARP>();
+    }
+    for (int k = tid; k < w; k += nt) P.Y[f + k] = xs[k];
+    __threadfence();
+    gsync<WARP>();
+    if (tid == 0) st_release(&P.done_b[t], epoch);
+}
+
+// phase: 0 factor, 1 forward, 2 backward (tasks taken in reverse)
+template <int PHASE>
+__global__ void __launch_bounds__(kLdltBlock) ldlt_phase_kernel(PlanDev P, int epoch) {
+    __shared__ double sh[kShDoubles];
+    __shared__ int s_task;
+    const int tid = threadIdx.x;
+    for (;;) {
+        if (tid == 0) s_task = atomicAdd(&P.ticket[PHASE], 1);
+        __syncthreads();
+        int task = s_task;
+        __syncthreads();
+        if (task >= P.ntasks) break;
+        if (PHASE == 2) task = P.ntasks - 1 - task;
+        const int t0 = P.task_start[task], cnt = P.task_cnt[task];
+        if (cnt == 0) {
+            const int t = P.order[t0];
+            if (PHASE == 0) factor_supernode<false>(P, t, sh, epoch, tid, kLdltBlock);
+            else if (PHASE == 1) fwd_supernode<false>(P, t, sh, epoch, tid, kLdltBlock);
+            else bwd_supernode<false>(P, t, sh, epoch, tid, kLdltBlock);
+        } else {
+            const int wid = tid >> 5, lane = tid & 31;
+            if (wid < cnt) {
+                // in the backward phase the bundle is walked in reverse as well
+                const int t = P.order[PHASE == 2 ? t0 + cnt - 1 - wid : t0 + wid];
+                double *wsh = sh + wid * ((kSmallW + 1) * kSmallW + 4 * kSmallW);
+                if (PHASE == 0) factor_supernode<true>(P, t, wsh, epoch, lane, 32);
+                else if (PHASE == 1) fwd_supernode<true>(P, t, wsh, epoch, lane, 32);
+                else bwd_supernode<true>(P, t, wsh, epoch, lane, 32);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Y[k] = (B0[P[k]], B1[P[k]]) with B0 = [rhs1; 0], B1 = kind == 0 ? [0; rhs2] : [rhs2; 0]
+__global__ void load_rhs_kernel(int N, int nvar, int kind, const int *P, const double *rhs1,
+                                const double *rhs2, double2 *Y) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= N) return;
+    const int i = P[k];
+    double2 v;
+    v.x = (i < nvar) ? rhs1[i] : 0.0;
+    if (kind == 0) v.y = (i < nvar) ? 0.0 : rhs2[i - nvar];
+    else v.y = (i < nvar) ? rhs2[i] : 0.0;
+    Y[k] = v;
+}
+__global__ void store_sol_kernel(int N, int nvar, const int *pinv, const double2 *Y, double *p1, double *q1,
+                                 double *p2, double *q2) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const double2 v = Y[pinv[i]];
+    if (i < nvar) { p1[i] = v.x; p2[i] = v.y; }
+    else { q1[i - nvar] = v.x; q2[i - nvar] = v.y; }
+}
+// reference behaviour on a failed factorisation: `sol` still holds the right-hand sides
+__global__ void passthrough_kernel(int nvar, int ncon, int kind, const double *rhs1, const double *rhs2,
+                                   double *p1, double *q1, double *p2, double *q2) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nvar) { p1[i] = rhs1[i]; p2[i] = (kind == 0) ? 0.0 : rhs2[i]; }
+    if (i < ncon) { q1[i] = 0.0; q2[i] = (kind == 0) ? rhs2[i] : 0.0; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+template <class T>
+static void up(DevBuf<T> &b, const std::vector<T> &v, cudaStream_t s) { b.from(v, s); }
+
+void ldlt_analyze(Handle *h, const int64_t *Puser, const fpsb_ldlt_opts *opts) {
+    ldlt_free(h);
+    LdltPlan *L = new LdltPlan();
+    h->ldlt = L;
+    if (opts) L->opts = *opts;
+    else fpsb_ldlt_default_opts(&L->opts);
+    try {
+        analyze((int)h->nvar, (int)h->ncon, h->nnzj, h->jrow.data(), h->jcol.data(), Puser, L->S);
+    } catch (const std::invalid_argument &e) {
+        set_error("fpsb_ldlt_analyze: %s", e.what());
+        throw CudaFail{FPSB_EINVAL};
+    } catch (const std::exception &e) {
+        set_error("fpsb_ldlt_analyze: %s", e.what());
+        throw CudaFail{FPSB_ESTATE};
+    }
+    Symbolic &S = L->S;
+    // tasks: big supernodes alone, small ones bundled one per warp
+    std::vector<int> tstart, tcnt;
+    {
+        auto small = [&](int s) {
+            int w = S.sfirst[(size_t)s + 1] - S.sfirst[(size_t)s];
+            int nr = (int)(S.rptr[(size_t)s + 1] - S.rptr[(size_t)s]);
+            return w <= kSmallW && (int64_t)w * (w + nr) <= 512;
+        };
+        int i = 0;
+        while (i < S.nsuper) {
+            if (small(S.order[(size_t)i])) {
+                int j = i;
+                while (j < S.nsuper && j - i < kWarpsPerBlock && small(S.order[(size_t)j])) j++;
+                tstart.push_back(i); tcnt.push_back(j - i);
+                i = j;
+            } else {
+                tstart.push_back(i); tcnt.push_back(0);
+                i++;
+            }
+        }
+    }
+    L->ntasks = (int)tstart.size();
+    cudaStream_t s = h->stream;
+    up(L->sfirst, S.sfirst, s); up(L->rows, S.rows, s); up(L->order, S.order, s);
+    up(L->task_start, tstart, s); up(L->task_cnt, tcnt, s);
+    up(L->usrc, S.usrc, s); up(L->ua, S.ua, s); up(L->ub, S.ub, s); up(L->rel, S.rel, s);
+    up(L->ttgt, S.ttgt, s); up(L->P, S.P, s); up(L->pinv, S.pinv, s); up(L->asrc, S.asrc, s);
+    up(L->rptr, S.rptr, s); up(L->poff, S.poff, s); up(L->uptr, S.uptr, s); up(L->urel, S.urel, s);
+    up(L->tptr, S.tptr, s); up(L->aslot, S.aslot, s); up(L->aptr, S.aptr, s);
+    L->naslot = (int64_t)S.aslot.size();
+    L->panels.alloc((size_t)S.panel_size + 8);
+    L->D.alloc((size_t)S.N + 8);
+    L->Y.alloc((size_t)S.N + 8);
+    L->done_f.alloc((size_t)S.nsuper + 8); L->done_s.alloc((size_t)S.nsuper + 8); L->done_b.alloc((size_t)S.nsuper + 8);
+    L->done_f.zero(s); L->done_s.zero(s); L->done_b.zero(s);
+    L->ticket.alloc(8); L->fail.alloc(8);
+    L->ticket.zero(s); L->fail.zero(s);
+    FPSB_CUDA(cudaStreamSynchronize(s));
+    PlanDev &D = L->dev;
+    D.N = S.N; D.nsuper = S.nsuper; D.ntasks = L->ntasks;
+    D.sfirst = L->sfirst.p; D.rptr = L->rptr.p; D.rows = L->rows.p; D.poff = L->poff.p; D.order = L->order.p;
+    D.task_start = L->task_start.p; D.task_cnt = L->task_cnt.p;
+    D.uptr = L->uptr.p; D.usrc = L->usrc.p; D.ua = L->ua.p; D.ub = L->ub.p; D.urel = L->urel.p; D.rel = L->rel.p;
+    D.tptr = L->tptr.p; D.ttgt = L->ttgt.p; D.P = L->P.p;
+    D.panels = L->panels.p; D.D = L->D.p; D.Y = L->Y.p;
+    D.done_f = L->done_f.p; D.done_s = L->done_s.p; D.done_b = L->done_b.p;
+    D.ticket = L->ticket.p; D.fail = L->fail.p;
+    D.n_d = (int)h->nvar;
+    D.tol = L->opts.ldlt_tol; D.r1 = L->opts.ldlt_r1; D.r2 = L->opts.ldlt_r2;
+    D.dynamic_reg = (D.r1 != 0.0) || (D.r2 != 0.0);
+}
+
+void ldlt_free(Handle *h) {
+    if (h->ldlt) { delete h->ldlt; h->ldlt = nullptr; }
+}
+
+static int phase_grid(const LdltPlan *L) { return std::max(1, std::min(L->ntasks, 148 * 6)); }
+
+void ldlt_factorize(Handle *h, double delta, int *factorized) {
+    LdltPlan *L = h->ldlt;
+    cudaStream_t s = h->stream;
+    L->factorized = false;
+    L->have_factor = false;
+    L->epoch += 1;
+    FPSB_CUDA(cudaMemsetAsync(L->panels.p, 0, (size_t)(L->S.panel_size + 8) * sizeof(double), s));
+    FPSB_CUDA(cudaMemsetAsync(L->ticket.p, 0, 8 * sizeof(int), s));
+    FPSB_CUDA(cudaMemsetAsync(L->fail.p, 0, sizeof(int), s));
+    if (L->naslot) {
+        int grid = (int)((L->naslot + 255) / 256);
+        assemble_kernel<<<grid, 256, 0, s>>>(L->naslot, L->aslot.p, L->aptr.p, L->asrc.p, h->coo_vals.p,
+                                             (int)h->nvar, h->nnzj, delta, L->panels.p);
+        h->launches += 1;
+    }
+    if (L->ntasks) {
+        ldlt_phase_kernel<0><<<phase_grid(L), kLdltBlock, 0, s>>>(L->dev, L->epoch);
+        h->launches += 1;
+    }
+    int fail = 0;
+    FPSB_CUDA(cudaMemcpyAsync(&fail, L->fail.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    FPSB_CUDA(cudaStreamSynchronize(s));
+    FPSB_CUDA(cudaGetLastError());
+    if (fail == -2) {
+        set_error("ldlt_factorize: dependency wait timed out (internal scheduling error)");
+        throw CudaFail{FPSB_ECUDA};
+    }
+    L->have_factor = true;
+    L->factorized = (fail == 0);
+    if (factorized) *factorized = L->factorized ? 1 : 0;
+}
+
+// kind 0: mixed right-hand sides, 1: least squares
+void ldlt_solve2(Handle *h, int kind, const double *rhs1, const double *rhs2, double *p1, double *q1,
+                 double *p2, double *q2, int *factorized) {
+    LdltPlan *L = h->ldlt;
+    cudaStream_t s = h->stream;
+    const int N = L->S.N, nvar = (int)h->nvar, ncon = (int)h->ncon;
+    if (factorized) *factorized = L->factorized ? 1 : 0;
+    if (N == 0) return;
+    const int grid = (N + 255) / 256;
+    if (!L->factorized) {
+        passthrough_kernel<<<(std::max(nvar, ncon) + 255) / 256, 256, 0, s>>>(nvar, ncon, kind, rhs1, rhs2, p1, q1, p2, q2);
+        h->launches += 1;
+        return;
+    }
+    L->epoch += 1;
+    FPSB_CUDA(cudaMemsetAsync(L->ticket.p, 0, 8 * sizeof(int), s));
+    load_rhs_kernel<<<grid, 256, 0, s>>>(N, nvar, kind, L->P.p, rhs1, rhs2, L->Y.p);
+    ldlt_phase_kernel<1><<<phase_grid(L), kLdltBlock, 0, s>>>(L->dev, L->epoch);
+    ldlt_phase_kernel<2><<<phase_grid(L), kLdltBlock, 0, s>>>(L->dev, L->epoch);
+    store_sol_kernel<<<grid, 256, 0, s>>>(N, nvar, L->pinv.p, L->Y.p, p1, q1, p2, q2);
+    h->launches += 4;
+    FPSB_CUDA(cudaGetLastError());
+}
+
+}  // namespace fpsb
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: LDLt entry points
+// ------------------------------------------------------------------------------------------------
+using namespace fpsb;
+
+#define REQ(cond, code, msg) do { if (!(cond)) { fpsb::set_error(msg); return code; } } while (0)
+#define TRY_ try {
+#define CATCH_ } catch (const fpsb::CudaFail &f) { return f.code; } \
+    catch (const std::bad_alloc &) { fpsb::set_error("out of memory"); return FPSB_ENOMEM; } \
+    catch (const std::exception &e) { fpsb::set_error("%s", e.what()); return FPSB_ECUDA; } \
+    catch (...) { fpsb::set_error("unexpected C++ exception"); return FPSB_ECUDA; }
+
+struct fpsb_symbolic_s { Symbolic S; };
+
+extern "C" {
+
+int fpsb_ldlt_default_opts(fpsb_ldlt_opts *o) {
+    REQ(o, FPSB_EINVAL, "NULL opts");
+    const double se = 1.4901161193847656e-08;
+    o->ldlt_tol = se; o->ldlt_r1 = se; o->ldlt_r2 = -se;
+    return FPSB_OK;
+}
+
+// host-only symbolic analysis (no CUDA needed): used by fpsb_ldlt_analyze and by the CPU tests
+int fpsb_symbolic_create(int64_t nvar, int64_t ncon, int64_t nnzj, const int64_t *jrow, const int64_t *jcol,
+                         int index_base, const int64_t *P, fpsb_symbolic *out) {
+    REQ(out, FPSB_EINVAL, "NULL out");
+    *out = nullptr;
+    REQ(nvar >= 0 && ncon >= 0 && nnzj >= 0 && (nnzj == 0 || (jrow && jcol)), FPSB_EINVAL, "bad arguments");
+    TRY_
+    std::vector<int64_t> r((size_t)nnzj), c((size_t)nnzj), Pz;
+    for (int64_t k = 0; k < nnzj; ++k) {
+        r[(size_t)k] = jrow[k] - index_base; c[(size_t)k] = jcol[k] - index_base;
+        REQ(r[(size_t)k] >= 0 && r[(size_t)k] < ncon && c[(size_t)k] >= 0 && c[(size_t)k] < nvar, FPSB_EINVAL,
+            "Jacobian index out of range");
+    }
+    if (P) { Pz.resize((size_t)(nvar + ncon)); for (int64_t k = 0; k < nvar + ncon; ++k) Pz[(size_t)k] = P[k] - index_base; }
+    fpsb_symbolic_s *S = new fpsb_symbolic_s();
+    try {
+        analyze((int)nvar, (int)ncon, nnzj, r.data(), c.data(), P ? Pz.data() : nullptr, S->S);
+    } catch (const std::invalid_argument &e) {
+        delete S;
+        fpsb::set_error("fpsb_symbolic_create: %s", e.what());
+        return FPSB_EINVAL;
+    } catch (...) { delete S; throw; }
+    *out = S;
+    return FPSB_OK;
+    CATCH_
+}
+int fpsb_symbolic_destroy(fpsb_symbolic s) { delete s; return FPSB_OK; }
+
+static void sym_sizes(const Symbolic &S, int64_t *N, int64_t *lnz) {
+    if (N) *N = S.N;
+    if (lnz) *lnz = S.Lp.empty() ? 0 : S.Lp[(size_t)S.N];
+}
+static void sym_get(const Symbolic &S, int64_t *P, int64_t *parent, int64_t *Lnz, int64_t *Lp, int64_t *Li) {
+    const int N = S.N;
+    for (int k = 0; k < N; ++k) {
+        if (P) P[k] = S.P[(size_t)k];
+        if (parent) parent[k] = S.parent[(size_t)k];
+        if (Lnz) Lnz[k] = S.Lp[(size_t)k + 1] - S.Lp[(size_t)k];
+    }
+    if (Lp) for (int k = 0; k <= N; ++k) Lp[k] = S.Lp[(size_t)k];
+    if (Li) for (size_t p = 0; p < S.Li.size(); ++p) Li[p] = S.Li[p];
+}
+static void sym_plan(const Symbolic &S, int64_t *nsuper, int64_t *panel_nnz, int64_t *npairs, double *flops) {
+    if (nsuper) *nsuper = S.nsuper;
+    if (panel_nnz) *panel_nnz = S.panel_size;
+    if (npairs) *npairs = (int64_t)S.usrc.size();
+    if (flops) *flops = S.flops;
+}
+int fpsb_symbolic_sizes(fpsb_symbolic s, int64_t *N, int64_t *lnz) {
+    REQ(s, FPSB_EINVAL, "NULL symbolic");
+    sym_sizes(s->S, N, lnz);
+    return FPSB_OK;
+}
+int fpsb_symbolic_get(fpsb_symbolic s, int64_t *P, int64_t *parent, int64_t *Lnz, int64_t *Lp, int64_t *Li) {
+    REQ(s, FPSB_EINVAL, "NULL symbolic");
+    sym_get(s->S, P, parent, Lnz, Lp, Li);
+    return FPSB_OK;
+}
+int fpsb_symbolic_plan_info(fpsb_symbolic s, int64_t *nsuper, int64_t *panel_nnz, int64_t *npairs, double *flops) {
+    REQ(s, FPSB_EINVAL, "NULL symbolic");
+    sym_plan(s->S, nsuper, panel_nnz, npairs, flops);
+    return FPSB_OK;
+}
+
+int fpsb_ldlt_analyze(fpsb_handle hh, const int64_t *P, int index_base, const fpsb_ldlt_opts *opts) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQ(h, FPSB_EINVAL, "NULL handle");
+    REQ(index_base == 0 || index_base == 1, FPSB_EINVAL, "index_base must be 0 or 1");
+    TRY_
+    FPSB_CUDA(cudaSetDevice(h->device));
+    std::vector<int64_t> Pz;
+    if (P) { Pz.resize((size_t)(h->nvar + h->ncon)); for (size_t k = 0; k < Pz.size(); ++k) Pz[k] = P[k] - index_base; }
+    ldlt_analyze(h, P ? Pz.data() : nullptr, opts);
+    return FPSB_OK;
+    CATCH_
+}
+int fpsb_ldlt_symbolic_sizes(fpsb_handle hh, int64_t *N, int64_t *lnz) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQ(h && h->ldlt, FPSB_ESTATE, "fpsb_ldlt_analyze has not been called");
+    sym_sizes(h->ldlt->S, N, lnz);
+    return FPSB_OK;
+}
+int fpsb_ldlt_get_symbolic(fpsb_handle hh, int64_t *P, int64_t *parent, int64_t *Lnz, int64_t *Lp, int64_t *Li) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQ(h && h->ldlt, FPSB_ESTATE, "fpsb_ldlt_analyze has not been called");
+    sym_get(h->ldlt->S, P, parent, Lnz, Lp, Li);
+    return FPSB_OK;
+}
+int fpsb_ldlt_plan_info(fpsb_handle hh, int64_t *nsuper, int64_t *panel_nnz, int64_t *npairs, double *flops) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQ(h && h->ldlt, FPSB_ESTATE, "fpsb_ldlt_analyze has not been called");
+    sym_plan(h->ldlt->S, nsuper, panel_nnz, npairs, flops);
+    return FPSB_OK;
+}
+int fpsb_ldlt_factorize(fpsb_handle hh, double delta, int *factorized) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQ(h && h->ldlt, FPSB_ESTATE, "fpsb_ldlt_analyze has not been called");
+    REQ(h->have_vals, FPSB_ESTATE, "Jacobian values not set (call fpsb_set_jac_values first)");
+    TRY_
+    FPSB_CUDA(cudaSetDevice(h->device));
+    ldlt_factorize(h, delta, factorized);
+    return FPSB_OK;
+    CATCH_
+}
+int fpsb_ldlt_get_factor(fpsb_handle hh, double *Lx, double *D) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQ(h && h->ldlt, FPSB_ESTATE, "fpsb_ldlt_analyze has not been called");
+    REQ(h->ldlt->have_factor, FPSB_ESTATE, "no numeric factorisation available");
+    TRY_
+    FPSB_CUDA(cudaSetDevice(h->device));
+    LdltPlan *L = h->ldlt;
+    const Symbolic &S = L->S;
+    std::vector<double> panels((size_t)S.panel_size + 1), Dh((size_t)S.N + 1);
+    FPSB_CUDA(cudaMemcpy(panels.data(), L->panels.p, (size_t)S.panel_size * sizeof(double), cudaMemcpyDeviceToHost));
+    FPSB_CUDA(cudaMemcpy(Dh.data(), L->D.p, (size_t)S.N * sizeof(double), cudaMemcpyDeviceToHost));
+    if (D) memcpy(D, Dh.data(), (size_t)S.N * sizeof(double));
+    if (Lx) {
+        for (int s = 0; s < S.nsuper; ++s) {
+            const int f = S.sfirst[(size_t)s], l = S.sfirst[(size_t)s + 1] - 1, w = l - f + 1;
+            const int nr = (int)(S.rptr[(size_t)s + 1] - S.rptr[(size_t)s]);
+            const int ld = w + nr;
+            const int *R = S.rows.data() + S.rptr[(size_t)s];
+            const double *pan = panels.data() + S.poff[(size_t)s];
+            for (int j = f; j <= l; ++j) {
+                for (int64_t p = S.Lp[(size_t)j]; p < S.Lp[(size_t)j + 1]; ++p) {
+                    const int r = S.Li[(size_t)p];
+                    int lr;
+                    if (r <= l) lr = r - f;
+                    else lr = w + (int)(std::lower_bound(R, R + nr, r) - R);
+                    Lx[p] = pan[(size_t)(j - f) * ld + lr];
+                }
+            }
+        }
+    }
+    return FPSB_OK;
+    CATCH_
+}
+
+static int ldlt_solve_api(fpsb_handle hh, int kind, bool refactor, double delta, const double *rhs1,
+                          const double *rhs2, double *p1, double *q1, double *p2, double *q2, int loc,
+                          int *factorized) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQ(h && h->ldlt, FPSB_ESTATE, "fpsb_ldlt_analyze has not been called");
+    REQ(rhs1 && rhs2 && p1 && q1 && p2 && q2, FPSB_EINVAL, "NULL argument");
+    REQ(!refactor || h->have_vals, FPSB_ESTATE, "Jacobian values not set (call fpsb_set_jac_values first)");
+    TRY_
+    FPSB_CUDA(cudaSetDevice(h->device));
+    const size_t n = (size_t)h->nvar, m = (size_t)h->ncon;
+    const size_t n2 = kind == 0 ? m : n;
+    int ok = 0;
+    if (refactor) ldlt_factorize(h, delta, &ok);
+    // host staging (same scheme as the iterative path)
+    double *d_in = nullptr, *d_out = nullptr, *pinned = nullptr;
+    const double *d1 = rhs1, *d2 = rhs2;
+    double *o1 = p1, *o2 = q1, *o3 = p2, *o4 = q2;
+    if (loc == FPSB_HOST) {
+        if (h->stage_in.n < n + n2 + 8) h->stage_in.alloc(n + n2 + 8);
+        if (h->stage_out.n < 2 * (n + m) + 8) h->stage_out.alloc(2 * (n + m) + 8);
+        const size_t need = n + n2 + 2 * (n + m) + 8;
+        if (h->pin_count < need) {
+            if (h->pin) cudaFreeHost(h->pin);
+            h->pin = nullptr; h->pin_count = 0;
+            FPSB_CUDA(cudaMallocHost((void **)&h->pin, need * sizeof(double)));
+            h->pin_count = need;
+        }
+        pinned = h->pin;
+        memcpy(pinned, rhs1, n * sizeof(double));
+        memcpy(pinned + n, rhs2, n2 * sizeof(double));
+        d_in = h->stage_in.p; d_out = h->stage_out.p;
+        FPSB_CUDA(cudaMemcpyAsync(d_in, pinned, (n + n2) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        d1 = d_in; d2 = d_in + n;
+        o1 = d_out; o2 = d_out + n; o3 = d_out + n + m; o4 = d_out + 2 * n + m;
+    }
+    ldlt_solve2(h, kind, d1, d2, o1, o2, o3, o4, &ok);
+    if (loc == FPSB_HOST) {
+        double *res = pinned + n + n2;
+        FPSB_CUDA(cudaMemcpyAsync(res, d_out, 2 * (n + m) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        FPSB_CUDA(cudaStreamSynchronize(h->stream));
+        memcpy(p1, res, n * sizeof(double));
+        memcpy(q1, res + n, m * sizeof(double));
+        memcpy(p2, res + n + m, n * sizeof(double));
+        memcpy(q2, res + 2 * n + m, m * sizeof(double));
+    } else {
+        FPSB_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    FPSB_CUDA(cudaGetLastError());
+    int fail = 0;
+    FPSB_CUDA(cudaMemcpy(&fail, h->ldlt->fail.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (fail == -2) { fpsb::set_error("ldlt solve: dependency wait timed out"); return FPSB_ECUDA; }
+    if (factorized) *factorized = ok;
+    return FPSB_OK;
+    CATCH_
+}
+
+int fpsb_ldlt_solve_two_mixed(fpsb_handle h, double delta, const double *rhs1, const double *rhs2, double *p1,
+                              double *q1, double *p2, double *q2, int loc, int *factorized) {
+    return ldlt_solve_api(h, 0, true, delta, rhs1, rhs2, p1, q1, p2, q2, loc, factorized);
+}
+int fpsb_ldlt_solve_two_least_squares(fpsb_handle h, const double *rhs1, const double *rhs2, double *p1,
+                                      double *q1, double *p2, double *q2, int loc, int *factorized) {
+    return ldlt_solve_api(h, 1, false, 0.0, rhs1, rhs2, p1, q1, p2, q2, loc, factorized);
+}
+
+}  // extern "C"

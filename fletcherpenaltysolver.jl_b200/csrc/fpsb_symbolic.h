@@ -1,0 +1,46 @@
+// fpsb_symbolic.h — host-side symbolic analysis of K = [I A'; A -dI] (ldl_analyze equivalent)
+#pragma once
+#include <stdint.h>
+#include <vector>
+
+namespace fpsb {
+
+struct Symbolic {
+    int N = 0;
+    std::vector<int> P, pinv;         // P[k] = original index eliminated k-th
+    std::vector<int> parent;          // elimination tree (-1 = root)
+    std::vector<int64_t> Lp;          // N+1, strict lower column pointers
+    std::vector<int> Li;              // row indices (ascending per column)
+    // supernodal plan
+    int nsuper = 0;
+    std::vector<int> sfirst;          // nsuper+1 : first column of each supernode
+    std::vector<int> sn_of;           // N : supernode of each column
+    std::vector<int64_t> rptr;        // nsuper+1 : offsets into rows[]
+    std::vector<int> rows;            // below-block row structure of each supernode (ascending)
+    std::vector<int64_t> poff;        // nsuper+1 : panel offsets (doubles); ld = w + nr
+    std::vector<int> level;           // nsuper : height from the leaves of the supernodal tree
+    std::vector<int> order;           // nsuper : supernodes sorted by (level, index) — task order
+    // update pairs, grouped by target (ascending source): source d contributes rows[a..b) of d
+    std::vector<int64_t> uptr;        // nsuper+1
+    std::vector<int> usrc, ua, ub;    // per pair
+    std::vector<int64_t> urel;        // per pair: offset into rel[]
+    std::vector<int> rel;             // local row index in the target panel of d's rows a..nr_d
+    // pairs grouped by source (for the backward solve dependency waits): targets of each source
+    std::vector<int64_t> tptr;        // nsuper+1
+    std::vector<int> ttgt;            // distinct target supernodes of each source
+    // assembly map: panel slot <- sources (index into [1..1 | jvals | -delta..])
+    std::vector<int64_t> aslot;       // distinct target slots (panel offsets)
+    std::vector<int64_t> aptr;        // naslot+1
+    std::vector<int> asrc;            // source ids
+    int64_t panel_size = 0;
+    double flops = 0;
+};
+
+// approximate minimum degree ordering of a symmetric pattern (Ap/Ai: full pattern, no diagonal)
+void amd_order(int n, const std::vector<int64_t> &Ap, const std::vector<int> &Ai, std::vector<int> &P);
+
+// full analysis; Puser may be null (-> amd_order). jrow/jcol are 0-based.
+void analyze(int nvar, int ncon, int64_t nnzj, const int64_t *jrow, const int64_t *jcol,
+             const int64_t *Puser, Symbolic &S);
+
+}  // namespace fpsb

@@ -141,6 +141,11 @@ class B200Handle:
         check(_lib.lib().fpsb_iter_setup(self.h, C.byref(opts) if opts is not None else None),
               "fpsb_iter_setup")
 
+    def iter_last_profile(self):
+        ms, nl = C.c_double(), C.c_int64()
+        check(_lib.lib().fpsb_iter_last_profile(self.h, C.byref(ms), C.byref(nl)), "fpsb_iter_last_profile")
+        return ms.value, nl.value
+
     def iter_solve_two_mixed(self, delta, rhs1, rhs2):
         return self._two(_lib.lib().fpsb_iter_solve_two_mixed, "fpsb_iter_solve_two_mixed",
                          (C.c_double(delta),), rhs1, rhs2, True)

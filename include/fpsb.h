@@ -135,10 +135,28 @@ int fpsb_iter_solve_two_mixed(fpsb_handle h, double delta, const double *rhs1, c
 int fpsb_iter_solve_two_least_squares(fpsb_handle h, double delta, const double *rhs1,
                                       const double *rhs2, double *p1, double *q1, double *p2,
                                       double *q2, int loc, fpsb_krylov_stats stats[2]);
+/* CUDA-event time (ms) of the Krylov loop region of the last solve_two_mixed/_least_squares call
+ * on this handle and the number of fused SpMM step kernels launched in it (bench.py roofline). */
+int fpsb_iter_last_profile(fpsb_handle h, double *loop_ms, int64_t *step_launches);
 /* solve_two_extras [Iterative]  src/solve_linear_system.jl:45-77
  *   u1 = LSQR(A', rhs1, lambda = sqrt(tau)); u2 = MINRES(A A', rhs2, lambda = tau), tau = max(delta,1e-14) */
 int fpsb_iter_solve_two_extras(fpsb_handle h, double delta, const double *rhs1, const double *rhs2,
                                double *u1, double *u2, int loc, fpsb_krylov_stats stats[2]);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host-only symbolic analysis (no CUDA device needed) — the `ldl_analyze` half of the LDLtSolver
+ * constructor, src/solve_two_systems_struct.jl:343-344. fpsb_ldlt_analyze runs exactly this and
+ * uploads the plan; exposing it lets the bit-exact symbolic check run on a CPU-only machine.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct fpsb_symbolic_s *fpsb_symbolic;
+int fpsb_symbolic_create(int64_t nvar, int64_t ncon, int64_t nnzj, const int64_t *jrow,
+                         const int64_t *jcol, int index_base, const int64_t *P, fpsb_symbolic *out);
+int fpsb_symbolic_destroy(fpsb_symbolic s);
+int fpsb_symbolic_sizes(fpsb_symbolic s, int64_t *N, int64_t *lnz);
+int fpsb_symbolic_get(fpsb_symbolic s, int64_t *P, int64_t *parent, int64_t *Lnz, int64_t *Lp,
+                      int64_t *Li);
+int fpsb_symbolic_plan_info(fpsb_symbolic s, int64_t *nsuper, int64_t *panel_nnz, int64_t *npairs,
+                            double *flops);
 
 /* ---------------------------------------------------------------------------------------------
  * LDLt path — LDLtSolver (host symbolic analysis + device numeric refactorisation + 2-RHS solves)
