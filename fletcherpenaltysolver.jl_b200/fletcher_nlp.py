@@ -104,11 +104,18 @@ class FletcherPenaltyNLP:
         return fx, gx
 
     def _jprod(self, x, v):
-        """jprod! on the device-resident Jacobian (refreshed by the last solve_two_mixed at x)."""
-        return self.qdsolver.handle.jprod(np.ascontiguousarray(v, dtype=np.float64))
+        """jprod! on the device-resident Jacobian (refreshed by the last solve_two_mixed at x);
+        QDSolver subtypes without a device handle fall back to the user model's jprod!."""
+        h = getattr(self.qdsolver, "handle", None)
+        if h is None:
+            return self.nlp.jprod(x, v)
+        return h.jprod(np.ascontiguousarray(v, dtype=np.float64))
 
     def _jtprod(self, x, u):
-        return self.qdsolver.handle.jtprod(np.ascontiguousarray(u, dtype=np.float64))
+        h = getattr(self.qdsolver, "handle", None)
+        if h is None:
+            return self.nlp.jtprod(x, u)
+        return h.jtprod(np.ascontiguousarray(u, dtype=np.float64))
 
     def hprod(self, x, v, obj_weight=1.0):
         self.neval["hprod"] += 1

@@ -301,6 +301,8 @@ def solve_two_mixed(fpnlp, x, rhs1, rhs2):
     rhs1 has size nvar, rhs2 size ncon.  Refreshes the Jacobian at x (jac_coord! / jac_op!),
     then solves K [p1 p2; q1 q2] = [rhs1 0; 0 rhs2]."""
     qds = fpnlp.qdsolver
+    if hasattr(qds, "solve_two_mixed"):          # user-defined QDSolver subtype (dispatch on type)
+        return qds.solve_two_mixed(fpnlp, x, rhs1, rhs2)
     H = qds.handle
     H.set_jac_values(_jac_values(fpnlp, x))
     if isinstance(qds, IterativeSolver):
@@ -326,6 +328,8 @@ def solve_two_least_squares(fpnlp, x, rhs1, rhs2):
     Both right-hand sides have size nvar.  The Jacobian / factorisation of the last
     solve_two_mixed call is trusted (reference comments at :86 and :178)."""
     qds = fpnlp.qdsolver
+    if hasattr(qds, "solve_two_least_squares"):
+        return qds.solve_two_least_squares(fpnlp, x, rhs1, rhs2)
     H = qds.handle
     if isinstance(qds, IterativeSolver):
         p1, q1, p2, q2, st = H.iter_solve_two_least_squares(float(fpnlp.delta), rhs1, rhs2)
@@ -346,6 +350,8 @@ def solve_two_least_squares(fpnlp, x, rhs1, rhs2):
 def solve_two_extras(fpnlp, x, rhs1, rhs2):
     """invJtJJv, invJtJSsv = solve_two_extras(nlp, x, rhs1, rhs2)  (src/solve_linear_system.jl:1-10)"""
     qds = fpnlp.qdsolver
+    if hasattr(qds, "solve_two_extras"):
+        return qds.solve_two_extras(fpnlp, x, rhs1, rhs2)
     H = qds.handle
     if isinstance(qds, IterativeSolver):
         u1, u2, st = H.iter_solve_two_extras(float(fpnlp.delta), rhs1, rhs2)
