@@ -86,9 +86,13 @@ def test_oracle_vs_dense_solve(oracle, delta):
         lo = oracle.LDLtOracle(n, m, coo.row, coo.col, P)
         p1, q1, p2, q2, ok = lo.solve_two_mixed(coo.data, delta, r1, r2)
         assert ok
-        assert _rel(np.r_[p1, q1], s1) < 1e-11 and _rel(np.r_[p2, q2], s2) < 1e-11
+        # delta = 0: a constraint pivoted before all of its variables has D = -0 and is replaced by
+        # -sqrt(eps) (dynamic regularisation) => O(sqrt(eps)) perturbation of the solution
+        _, D = lo.numeric()
+        bar = 1e-6 if np.any(np.abs(np.abs(D) - SQRT_EPS) < 1e-12) else 1e-11
+        assert _rel(np.r_[p1, q1], s1) < bar and _rel(np.r_[p2, q2], s2) < bar
         p1, q1, p2, q2, ok = lo.solve_two_least_squares(r1, r3)
-        assert _rel(np.r_[p1, q1], s1) < 1e-11 and _rel(np.r_[p2, q2], s3) < 1e-11
+        assert _rel(np.r_[p1, q1], s1) < bar and _rel(np.r_[p2, q2], s3) < bar
     it = oracle.IterativeOracle(A)
     p1, q1, p2, q2, st = it.solve_two_mixed(delta, r1, r2)
     assert st[0]["solved"] and st[1]["solved"]
