@@ -220,7 +220,7 @@ static int do_spmv(fpsb_handle hh, bool transpose, const double *x, double *y, i
     const double *dx = S.in(x, nin);
     double *dy = S.out(y, nout);
     if (nout) {
-        if ((transpose ? h->At.nblk : h->A.nblk) == 0) FPSB_CUDA(cudaMemsetAsync(dy, 0, nout * sizeof(double), h->stream));
+        if ((transpose ? h->At.grid : h->A.grid) == 0) FPSB_CUDA(cudaMemsetAsync(dy, 0, nout * sizeof(double), h->stream));
         spmv_plain(h, transpose, dx, dy, ncols);
     }
     S.finish();

@@ -48,17 +48,21 @@ struct DevBuf {
 // ------------------------------------------------------------------------------------------------
 // CSR operator on the device with its row-block tiling (one CTA per row block)
 // ------------------------------------------------------------------------------------------------
-constexpr int kTile = 2048;       // nnz staged per CTA (TMA bulk copy into shared memory)
-constexpr int kBlock = 256;       // threads per CTA == max rows per row block
+constexpr int kBlock = 256;       // threads per CTA (8 warps, one SELL slice per warp at a time)
 
+// Operator stored as SELL-32-sigma (+ CSR of the few long rows)
 struct CsrDev {
     int nrows = 0, ncols = 0;
     int64_t nnz = 0;
-    DevBuf<int> rp, ci, perm;     // perm: CSR slot -> COO index (value refresh)
-    DevBuf<double> vx;
-    DevBuf<int> blk;              // row-block boundaries (nblk + 1)
-    int nblk = 0;
-    int lanes = 8;                // sub-warp width used for the per-row reduction
+    int nslice = 0;
+    int64_t padded = 0;           // stored entries including padding
+    int nlong = 0;
+    DevBuf<int> sl_off, rowidx, scol, sperm;   // sperm: slot -> COO index (-1 = padding)
+    DevBuf<double> sval;
+    DevBuf<int> long_row, long_rp, long_col, long_perm;
+    DevBuf<double> long_val;
+    int grid_sell = 0;            // persistent CTAs over the slices
+    int grid = 0;                 // grid_sell + nlong
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -92,6 +96,7 @@ struct LdltPlan;   // defined in fpsb_ldlt.cu
 
 struct Handle {
     int device = 0;
+    int num_sms = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t nvar = 0, ncon = 0, nnzj = 0;

@@ -63,12 +63,19 @@ struct SlotIO {
 };
 
 struct StepParams {
-    const int *rp;
-    const int *ci;
-    const double *vx;
-    const int *blk;
+    // SELL-32-sigma operator
+    const int *sl_off;     // nslice + 1 : element offsets (multiples of 32)
+    const int *rowidx;     // nslice * 32 : original row of each lane, -1 for padding lanes
+    const int *scol;
+    const double *sval;
+    int nslice;
+    int grid_sell;         // CTAs working on slices; CTAs beyond handle one long row each
+    // long rows (CSR)
+    const int *long_row;
+    const int *long_rp;
+    const int *long_col;
+    const double *long_val;
     int nrows;
-    int lanes;
     const double2 *gin2;   // interleaved gather pair (PAIR kernels)
     double2 *self2;        // interleaved recurred pair of this row space (PAIR kernels)
     SlotIO io[2];
@@ -481,6 +488,8 @@ __device__ void finish_ew(SlotState &S, int op, double a0) {
 // ------------------------------------------------------------------------------------------------
 struct Coef {
     int mode, first, pend, iter;
+    int rd0, rd1, wr0, wr1;      // which aux vectors (a0 / a1) the row epilogue reads / writes
+    int rdself;
     double gsc, ssc, alpha, beta, sigma, tr_prev, lambda;
     double xi, c1, s1, s2g, trw, xr, mscale, oldbeta, c0, c1h;
 };
@@ -489,30 +498,45 @@ __device__ __forceinline__ void load_coef(Coef &C, const SlotIO &io, const SlotS
     C.mode = io.mode;
     C.c0 = io.c0; C.c1h = io.c1;
     C.gsc = 1.0; C.ssc = 1.0;
-    if (!use_state || io.mode == MD_NONE || io.mode == MD_PLAIN) return;
+    C.rd0 = C.rd1 = C.wr0 = C.wr1 = C.rdself = 0;
+    C.first = 0; C.pend = 0; C.iter = 0; C.lambda = 0.0;
+    if (io.mode == MD_NONE) return;
+    if (io.mode == MD_PLAIN) { C.rd0 = io.a0 != nullptr; return; }
+    if (!use_state) return;
     C.first = st->first; C.pend = st->pend; C.iter = st->iter;
     C.alpha = st->alpha; C.beta = st->beta; C.sigma = st->sigma; C.tr_prev = st->tr_prev;
     C.lambda = st->lambda; C.xi = st->xi; C.c1 = st->c1; C.s1 = st->s1; C.s2g = st->s2g;
     C.trw = st->trw; C.xr = st->xr; C.mscale = st->mscale; C.oldbeta = st->oldbeta;
     switch (io.mode) {
         case MD_LSQR_INIT_M: C.gsc = st->su; break;
-        case MD_LSQR_U: C.gsc = st->sv; C.ssc = st->su; break;
-        case MD_LSQR_V: C.gsc = st->su; C.ssc = st->sv; break;
-        case MD_CRAIG_V: C.gsc = st->mscale * st->su; C.ssc = st->sv; break;
-        case MD_CRAIG_U: C.gsc = st->sv; C.ssc = st->su; break;
-        case MD_CGLS_M: case MD_CGLS_N: case MD_CGLS_INIT_M: case MD_MINRES_M: break;
+        case MD_LSQR_U: C.gsc = st->sv; C.ssc = st->su; C.rdself = 1; break;
+        case MD_LSQR_V:
+            C.gsc = st->su; C.ssc = st->sv; C.rdself = 1;
+            C.rd0 = C.rd1 = !C.first; C.wr0 = C.wr1 = 1;
+            break;
+        case MD_CRAIG_V:
+            C.gsc = st->mscale * st->su; C.ssc = st->sv; C.rdself = 1;
+            C.rd0 = C.wr0 = C.pend;
+            C.rd1 = C.wr1 = C.pend && (C.lambda > 0);
+            break;
+        case MD_CRAIG_U:
+            C.gsc = st->sv; C.ssc = st->su; C.rdself = 1;
+            C.rd0 = C.rd1 = C.wr0 = C.wr1 = 1;
+            break;
+        case MD_MINRES_M: C.rd0 = 1; C.rd1 = (C.iter + 1 >= 2); break;
+        case MD_CGLS_M: C.rd0 = C.rd1 = 1; C.wr0 = 1; break;
         default: break;
     }
 }
 
-// row epilogue: returns the new value of the recurred ("self") vector entry
-__device__ __forceinline__ double row_epilogue(const Coef &C, const SlotIO &io, int row, double sraw,
-                                               double selfold, double &acc0, double &acc1) {
+// row epilogue on values: (sraw, selfold, a0, a1) -> returns new self; a0 / a1 updated in place
+__device__ __forceinline__ double row_epilogue(const Coef &C, double sraw, double selfold, double &a0,
+                                               double &a1, double &acc0, double &acc1) {
     double out = 0.0;
     switch (C.mode) {
         case MD_PLAIN: {
             out = C.c0 * sraw;
-            if (io.a0) out += C.c1h * io.a0[row];
+            if (C.rd0) out += C.c1h * a0;
             acc0 += out * out;
         } break;
         case MD_LSQR_INIT_M: {
@@ -524,47 +548,47 @@ __device__ __forceinline__ double row_epilogue(const Coef &C, const SlotIO &io, 
             acc0 += out * out;
         } break;
         case MD_LSQR_V: {
-            double vj = selfold * C.ssc;
-            double wj = C.first ? vj : (vj - C.tr_prev * io.a0[row]);
+            const double vj = selfold * C.ssc;
+            const double wj = C.first ? vj : (vj - C.tr_prev * a0);
             acc1 += wj * wj;
-            io.a0[row] = wj;
-            io.a1[row] = (C.first ? 0.0 : io.a1[row]) + C.sigma * wj;
+            a0 = wj;
+            a1 = (C.first ? 0.0 : a1) + C.sigma * wj;
             out = C.gsc * sraw - C.beta * vj;
             acc0 += out * out;
         } break;
         case MD_CRAIG_V: {
-            double vp = selfold * C.ssc;
+            const double vp = selfold * C.ssc;
             if (C.pend) {
                 if (C.lambda > 0) {
-                    double w2 = io.a1[row];
-                    double x = io.a0[row] + (C.xi * C.c1) * vp;
+                    const double w2 = a1;
+                    double x = a0 + (C.xi * C.c1) * vp;
                     x = x + (C.xi * C.s1) * w2;
-                    io.a0[row] = x;
-                    io.a1[row] = C.s2g * (C.s1 * vp - C.c1 * w2);
+                    a0 = x;
+                    a1 = C.s2g * (C.s1 * vp - C.c1 * w2);
                 } else {
-                    io.a0[row] += C.xi * vp;
+                    a0 += C.xi * vp;
                 }
             }
             out = C.gsc * sraw - C.beta * vp;
             acc0 += out * out;
         } break;
         case MD_CRAIG_U: {
-            double mu = selfold * C.ssc;
-            double uj = C.mscale * mu;
-            double wj = uj - C.trw * io.a0[row];
-            io.a0[row] = wj;
-            io.a1[row] += C.xr * wj;
+            const double mu = selfold * C.ssc;
+            const double uj = C.mscale * mu;
+            const double wj = uj - C.trw * a0;
+            a0 = wj;
+            a1 += C.xr * wj;
             acc1 += wj * wj;
             out = C.gsc * sraw - C.alpha * mu;
             acc0 += out * out;
         } break;
         case MD_MINRES_M: {
             // a0 = r2 (= v), a1 = r1 ; self = y
-            double r2 = io.a0[row];
+            const double r2 = a0;
             double y = sraw;
             if (C.lambda != 0.0) y += C.lambda * r2;
             y *= (1.0 / C.beta);
-            if (C.iter + 1 >= 2) y -= (C.beta / C.oldbeta) * io.a1[row];
+            if (C.rd1) y -= (C.beta / C.oldbeta) * a1;
             out = y;
             acc0 += r2 * y;
         } break;
@@ -578,8 +602,8 @@ __device__ __forceinline__ double row_epilogue(const Coef &C, const SlotIO &io, 
         } break;
         case MD_CGLS_M: {
             // a0 = x, a1 = p ; self = s
-            double x = io.a0[row] + C.alpha * io.a1[row];
-            io.a0[row] = x;
+            const double x = a0 + C.alpha * a1;
+            a0 = x;
             double sv = sraw;
             if (C.lambda > 0) sv -= C.lambda * x;
             out = sv;
@@ -591,83 +615,128 @@ __device__ __forceinline__ double row_epilogue(const Coef &C, const SlotIO &io, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// the fused SpMM step kernel
+// the fused SpMM step kernel — SELL-32-sigma: one warp per slice of 32 rows, lane == row.
+// Values / column indices of a slice are stored column-major (32 consecutive entries per slice
+// column), so every load of the matrix stream is a fully coalesced 256 B / 128 B warp access, the
+// row sum lives in two registers (one per right-hand-side column) and the Krylov row epilogue runs
+// in the same lane: no shuffles, no shared memory, no block barrier on the streaming path.
+// Rows longer than kLongRow are handled by extra CTAs (one per row, block reduction).
 // ------------------------------------------------------------------------------------------------
+constexpr int kUnroll = 4;
+
 template <bool PAIR>
-__global__ void __launch_bounds__(kBlock) gk_step_kernel(StepParams P, int use_state) {
-    __shared__ alignas(16) double s_val[kTile + 8];
-    __shared__ alignas(16) int s_col[kTile + 8];
-    __shared__ int s_rp[kBlock + 1];
-    __shared__ double s_sum[2][kBlock];
+__global__ void __launch_bounds__(kBlock, 3) gk_step_kernel(StepParams P, int use_state) {
     __shared__ double s_red[4 * 8];
-    __shared__ alignas(8) uint64_t s_bar;
     __shared__ int s_last;
 
     const int tid = threadIdx.x;
-    bool act0 = P.io[0].mode != MD_NONE && (!use_state || P.st[0].active);
-    bool act1 = P.io[1].mode != MD_NONE && (!use_state || P.st[1].active);
+    const bool act0 = P.io[0].mode != MD_NONE && (!use_state || P.st[0].active);
+    const bool act1 = P.io[1].mode != MD_NONE && (!use_state || P.st[1].active);
     if (!act0 && !act1) return;
 
-    Coef C0, C1;
-    C0.mode = MD_NONE; C1.mode = MD_NONE;
-    if (act0) load_coef(C0, P.io[0], &P.st[0], use_state);
-    if (act1) load_coef(C1, P.io[1], &P.st[1], use_state);
-
-    const int b = blockIdx.x;
-    const int row_lo = P.blk[b], row_hi = P.blk[b + 1];
-    const int nr = row_hi - row_lo;
-    for (int i = tid; i <= nr; i += kBlock) s_rp[i] = P.rp[row_lo + i];
-    if (tid == 0) { mbar_init(&s_bar, 1); mbar_fence_init(); }
+    // per-slot coefficients live in shared memory (broadcast reads) to keep registers for the
+    // loads in flight
+    __shared__ Coef sC[2];
+    if (tid == 0) {
+        load_coef(sC[0], P.io[0], &P.st[0], use_state);
+        load_coef(sC[1], P.io[1], &P.st[1], use_state);
+        if (!act0) { sC[0].mode = MD_NONE; sC[0].rd0 = sC[0].rd1 = sC[0].wr0 = sC[0].wr1 = sC[0].rdself = 0; }
+        if (!act1) { sC[1].mode = MD_NONE; sC[1].rd0 = sC[1].rd1 = sC[1].wr0 = sC[1].wr1 = sC[1].rdself = 0; }
+    }
     __syncthreads();
-    const int e0 = s_rp[0], e1 = s_rp[nr];
-    const int cnt = e1 - e0;
-    const int L = P.lanes;
+    const Coef &C0 = sC[0];
+    const Coef &C1 = sC[1];
 
-    if (cnt <= kTile) {
-        const int ea = e0 & ~3;
-        const int len = ((e1 - ea) + 3) & ~3;
-        if (len > 0) {
-            if (tid == 0) {
-                mbar_expect_tx(&s_bar, (uint32_t)len * 12u);
-                tma_bulk_g2s(s_val, P.vx + ea, (uint32_t)len * 8u, &s_bar);
-                tma_bulk_g2s(s_col, P.ci + ea, (uint32_t)len * 4u, &s_bar);
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    const int cta = blockIdx.x;
+
+    if (cta < P.grid_sell) {
+        const int lane = tid & 31, wid = tid >> 5;
+        const int s_begin = (int)(((int64_t)P.nslice * cta) / P.grid_sell);
+        const int s_end = (int)(((int64_t)P.nslice * (cta + 1)) / P.grid_sell);
+        for (int sl = s_begin + wid; sl < s_end; sl += kBlock / 32) {
+            const int off = P.sl_off[sl];
+            const int width = (P.sl_off[sl + 1] - off) >> 5;
+            const int row = P.rowidx[sl * 32 + lane];
+            // row-epilogue operands first: their DRAM latency hides behind the matrix stream
+            double2 old2 = make_double2(0.0, 0.0);
+            double so0 = 0.0, so1 = 0.0, a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+            if (row >= 0) {
+                if (PAIR) old2 = __ldcs(P.self2 + row);
+                else {
+                    if (C0.rdself) so0 = __ldcs(P.io[0].self + row);
+                    if (C1.rdself) so1 = __ldcs(P.io[1].self + row);
+                }
+                if (C0.rd0) a00 = __ldcs(P.io[0].a0 + row);
+                if (C0.rd1) a01 = __ldcs(P.io[0].a1 + row);
+                if (C1.rd0) a10 = __ldcs(P.io[1].a0 + row);
+                if (C1.rd1) a11 = __ldcs(P.io[1].a1 + row);
             }
-            if (!mbar_wait(&s_bar, 0)) { if (tid == 0) atomicExch(P.done_flag, -1); return; }
-        }
-        const int g = tid / L, l = tid - g * L, ng = kBlock / L;
-        for (int r0 = 0; r0 < nr; r0 += ng) {
-            const int r = r0 + g;
-            double a0 = 0.0, a1 = 0.0;
-            if (r < nr) {
-                const int rs = s_rp[r] - ea, re = s_rp[r + 1] - ea;
+            const double *vp = P.sval + off + lane;
+            const int *cp = P.scol + off + lane;
+            double s0 = 0.0, s1 = 0.0;
+            int j = 0;
+            for (; j + kUnroll <= width; j += kUnroll) {
+                double v[kUnroll];
+                int c[kUnroll];
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                    v[u] = __ldcs(vp + (size_t)(j + u) * 32);
+                    c[u] = __ldcs(cp + (size_t)(j + u) * 32);
+                }
                 if (PAIR) {
-                    for (int k = rs + l; k < re; k += L) {
-                        const double v = s_val[k];
-                        const double2 x = __ldg(P.gin2 + s_col[k]);
-                        a0 += v * x.x;
-                        a1 += v * x.y;
-                    }
+                    double2 x[kUnroll];
+#pragma unroll
+                    for (int u = 0; u < kUnroll; ++u) x[u] = __ldg(P.gin2 + c[u]);
+#pragma unroll
+                    for (int u = 0; u < kUnroll; ++u) { s0 += v[u] * x[u].x; s1 += v[u] * x[u].y; }
                 } else {
-                    for (int k = rs + l; k < re; k += L) {
-                        const double v = s_val[k];
-                        const int c = s_col[k];
-                        if (act0) a0 += v * __ldg(P.io[0].gin + c);
-                        if (act1) a1 += v * __ldg(P.io[1].gin + c);
+                    double x0[kUnroll], x1[kUnroll];
+#pragma unroll
+                    for (int u = 0; u < kUnroll; ++u) {
+                        x0[u] = act0 ? __ldg(P.io[0].gin + c[u]) : 0.0;
+                        x1[u] = act1 ? __ldg(P.io[1].gin + c[u]) : 0.0;
                     }
+#pragma unroll
+                    for (int u = 0; u < kUnroll; ++u) { s0 += v[u] * x0[u]; s1 += v[u] * x1[u]; }
                 }
             }
-            for (int o = L >> 1; o > 0; o >>= 1) {
-                a0 += __shfl_down_sync(0xffffffffu, a0, o, L);
-                a1 += __shfl_down_sync(0xffffffffu, a1, o, L);
+            for (; j < width; ++j) {
+                const double v = __ldcs(vp + (size_t)j * 32);
+                const int c = __ldcs(cp + (size_t)j * 32);
+                if (PAIR) {
+                    const double2 x = __ldg(P.gin2 + c);
+                    s0 += v * x.x; s1 += v * x.y;
+                } else {
+                    if (act0) s0 += v * __ldg(P.io[0].gin + c);
+                    if (act1) s1 += v * __ldg(P.io[1].gin + c);
+                }
             }
-            if (l == 0 && r < nr) { s_sum[0][r] = a0; s_sum[1][r] = a1; }
+            if (row >= 0) {
+                if (PAIR) {
+                    double2 nw = old2;
+                    if (act0) nw.x = row_epilogue(C0, s0, old2.x, a00, a01, acc[0], acc[1]);
+                    if (act1) nw.y = row_epilogue(C1, s1, old2.y, a10, a11, acc[2], acc[3]);
+                    __stcs(P.self2 + row, nw);
+                } else {
+                    if (act0) __stcs(P.io[0].self + row, row_epilogue(C0, s0, so0, a00, a01, acc[0], acc[1]));
+                    if (act1) __stcs(P.io[1].self + row, row_epilogue(C1, s1, so1, a10, a11, acc[2], acc[3]));
+                }
+                if (C0.wr0) __stcs(P.io[0].a0 + row, a00);
+                if (C0.wr1) __stcs(P.io[0].a1 + row, a01);
+                if (C1.wr0) __stcs(P.io[1].a0 + row, a10);
+                if (C1.wr1) __stcs(P.io[1].a1 + row, a11);
+            }
         }
     } else {
-        // a single long row: the whole CTA strides over it (plain coalesced loads)
+        // one long row per CTA: strided over the whole block, fixed-tree block reduction
+        const int lr = cta - P.grid_sell;
+        const int row = P.long_row[lr];
+        const int e0 = P.long_rp[lr], e1 = P.long_rp[lr + 1];
         double a[2] = {0.0, 0.0};
         for (int k = e0 + tid; k < e1; k += kBlock) {
-            const double v = P.vx[k];
-            const int c = P.ci[k];
+            const double v = P.long_val[k];
+            const int c = P.long_col[k];
             if (PAIR) {
                 const double2 x = __ldg(P.gin2 + c);
                 a[0] += v * x.x; a[1] += v * x.y;
@@ -677,37 +746,40 @@ __global__ void __launch_bounds__(kBlock) gk_step_kernel(StepParams P, int use_s
             }
         }
         block_sum<2>(a, s_red);
-        if (tid == 0) { s_sum[0][0] = a[0]; s_sum[1][0] = a[1]; }
-    }
-    __syncthreads();
-
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    if (tid < nr) {
-        const int row = row_lo + tid;
-        const double s0 = s_sum[0][tid], s1 = s_sum[1][tid];
-        if (PAIR) {
-            double2 old = P.self2[row];
-            double2 nw = old;
-            if (act0) nw.x = row_epilogue(C0, P.io[0], row, s0, old.x, acc[0], acc[1]);
-            if (act1) nw.y = row_epilogue(C1, P.io[1], row, s1, old.y, acc[2], acc[3]);
-            P.self2[row] = nw;
-        } else {
-            if (act0) {
-                double old = (C0.mode == MD_PLAIN || C0.mode >= MD_MINRES_M) ? 0.0 : P.io[0].self[row];
-                P.io[0].self[row] = row_epilogue(C0, P.io[0], row, s0, old, acc[0], acc[1]);
+        if (tid == 0) {
+            double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+            if (C0.rd0) a00 = P.io[0].a0[row];
+            if (C0.rd1) a01 = P.io[0].a1[row];
+            if (C1.rd0) a10 = P.io[1].a0[row];
+            if (C1.rd1) a11 = P.io[1].a1[row];
+            if (PAIR) {
+                const double2 old2 = P.self2[row];
+                double2 nw = old2;
+                if (act0) nw.x = row_epilogue(C0, a[0], old2.x, a00, a01, acc[0], acc[1]);
+                if (act1) nw.y = row_epilogue(C1, a[1], old2.y, a10, a11, acc[2], acc[3]);
+                P.self2[row] = nw;
+            } else {
+                if (act0) {
+                    const double so = C0.rdself ? P.io[0].self[row] : 0.0;
+                    P.io[0].self[row] = row_epilogue(C0, a[0], so, a00, a01, acc[0], acc[1]);
+                }
+                if (act1) {
+                    const double so = C1.rdself ? P.io[1].self[row] : 0.0;
+                    P.io[1].self[row] = row_epilogue(C1, a[1], so, a10, a11, acc[2], acc[3]);
+                }
             }
-            if (act1) {
-                double old = (C1.mode == MD_PLAIN || C1.mode >= MD_MINRES_M) ? 0.0 : P.io[1].self[row];
-                P.io[1].self[row] = row_epilogue(C1, P.io[1], row, s1, old, acc[2], acc[3]);
-            }
+            if (C0.wr0) P.io[0].a0[row] = a00;
+            if (C0.wr1) P.io[0].a1[row] = a01;
+            if (C1.wr0) P.io[1].a0[row] = a10;
+            if (C1.wr1) P.io[1].a1[row] = a11;
         }
     }
     if (!use_state) return;
 
-    // deterministic norms: per-CTA partials, the last CTA reduces them in a fixed order
+    // deterministic norms: one partial per CTA, the last CTA reduces them in a fixed order
     block_sum<4>(acc, s_red);
     if (tid == 0) {
-        double *pp = P.partials + (size_t)b * 4;
+        double *pp = P.partials + (size_t)cta * 4;
         pp[0] = acc[0]; pp[1] = acc[1]; pp[2] = acc[2]; pp[3] = acc[3];
         __threadfence();
         unsigned t = atomicAdd(P.counter, 1u);
@@ -872,7 +944,7 @@ __global__ void __launch_bounds__(kBlock) ew_kernel(EwParams P) {
 
 __global__ void gather_vals_kernel(int nnz, const int *perm, const double *coo, double *vx) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nnz) vx[i] = coo[perm[i]];
+    if (i < nnz) { const int p = perm[i]; vx[i] = (p >= 0) ? coo[p] : 0.0; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -918,73 +990,119 @@ static void build_csr_host(int nrows, int ncols, int64_t nnz, const int64_t *ri,
     }
 }
 
-static void build_blocks(const std::vector<int> &rp, int nrows, std::vector<int> &blk) {
-    blk.clear();
-    blk.push_back(0);
-    int r = 0;
-    while (r < nrows) {
-        int start = r;
-        int base = rp[r];
-        // always take at least one row (a long row gets a block of its own)
-        r++;
-        if (rp[r] - base <= kTile) {
-            while (r < nrows && (r - start) < kBlock && rp[r + 1] - base <= kTile) r++;
-        }
-        blk.push_back(r);
-    }
-}
+constexpr int kLongRow = 1024;   // rows longer than this leave the SELL part
+constexpr int kSigma = 2048;     // sorting window (rows) of SELL-32-sigma
 
-static int pick_lanes(int64_t nnz, int nrows) {
-    double avg = nrows > 0 ? (double)nnz / nrows : 1.0;
-    int L = 2;
-    while (L < 32 && L * 2 <= avg) L *= 2;     // largest power of two <= avg nnz per row
-    return std::max(2, std::min(32, L));
-}
-
-static void upload_csr(Handle *h, CsrDev &M, int nrows, int ncols, const std::vector<int> &rp,
-                       const std::vector<int> &ci, const std::vector<int> &perm) {
+// CSR -> SELL-32-sigma (+ CSR of the long rows) and upload
+static void upload_sell(Handle *h, CsrDev &M, int nrows, int ncols, const std::vector<int> &rp,
+                        const std::vector<int> &ci, const std::vector<int> &perm) {
     M.nrows = nrows; M.ncols = ncols; M.nnz = (int64_t)ci.size();
-    M.rp.from(rp, h->stream);
-    M.ci.from(ci, h->stream);
-    M.perm.from(perm, h->stream);
-    M.vx.alloc(ci.size() + 8);
-    M.vx.zero(h->stream);
-    std::vector<int> blk;
-    build_blocks(rp, nrows, blk);
-    M.nblk = (int)blk.size() - 1;
-    M.blk.from(blk, h->stream);
-    M.lanes = pick_lanes(M.nnz, nrows);
+    std::vector<int> rowidx, sl_off(1, 0), long_row, long_rp(1, 0), long_col, long_perm;
+    std::vector<int> order;
+    for (int w0 = 0; w0 < nrows; w0 += kSigma) {
+        const int w1 = std::min(nrows, w0 + kSigma);
+        order.clear();
+        for (int r = w0; r < w1; ++r) {
+            const int len = rp[(size_t)r + 1] - rp[(size_t)r];
+            if (len > kLongRow) {
+                long_row.push_back(r);
+                for (int p = rp[(size_t)r]; p < rp[(size_t)r + 1]; ++p) { long_col.push_back(ci[(size_t)p]); long_perm.push_back(perm[(size_t)p]); }
+                long_rp.push_back((int)long_col.size());
+            } else order.push_back(r);
+        }
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            return (rp[(size_t)a + 1] - rp[(size_t)a]) > (rp[(size_t)b + 1] - rp[(size_t)b]);
+        });
+        for (size_t i = 0; i < order.size(); i += 32) {
+            int width = 0;
+            for (size_t l = 0; l < 32; ++l) {
+                const int r = (i + l < order.size()) ? order[i + l] : -1;
+                rowidx.push_back(r);
+                if (r >= 0) width = std::max(width, rp[(size_t)r + 1] - rp[(size_t)r]);
+            }
+            sl_off.push_back(sl_off.back() + width * 32);
+        }
+    }
+    const int nslice = (int)sl_off.size() - 1;
+    const size_t padded = (size_t)sl_off.back();
+    std::vector<int> scol(padded, 0), sperm(padded, -1);
+    for (int sidx = 0; sidx < nslice; ++sidx) {
+        const int off = sl_off[(size_t)sidx], width = (sl_off[(size_t)sidx + 1] - off) / 32;
+        for (int l = 0; l < 32; ++l) {
+            const int r = rowidx[(size_t)sidx * 32 + l];
+            int len = 0, base = 0;
+            if (r >= 0) { base = rp[(size_t)r]; len = rp[(size_t)r + 1] - base; }
+            int lastc = (len > 0) ? ci[(size_t)(base + len - 1)] : 0;
+            for (int j = 0; j < width; ++j) {
+                const size_t q = (size_t)off + (size_t)j * 32 + l;
+                if (j < len) { scol[q] = ci[(size_t)(base + j)]; sperm[q] = perm[(size_t)(base + j)]; }
+                else { scol[q] = lastc; sperm[q] = -1; }     // padding: value 0, local column
+            }
+        }
+    }
+    M.nslice = nslice;
+    M.padded = (int64_t)padded;
+    M.nlong = (int)long_row.size();
+    M.sl_off.from(sl_off, h->stream);
+    M.rowidx.from(rowidx, h->stream);
+    M.scol.from(scol, h->stream);
+    M.sperm.from(sperm, h->stream);
+    M.sval.alloc(padded + 8);
+    M.sval.zero(h->stream);
+    M.long_row.from(long_row, h->stream);
+    M.long_rp.from(long_rp, h->stream);
+    M.long_col.from(long_col, h->stream);
+    M.long_perm.from(long_perm, h->stream);
+    M.long_val.alloc(long_col.size() + 8);
+    M.long_val.zero(h->stream);
+    M.grid_sell = nslice > 0 ? std::max(1, std::min((nslice + 7) / 8, 3 * h->num_sms)) : 0;
+    M.grid = M.grid_sell + M.nlong;
 }
 
 void csr_build(Handle *h) {
     const int m = (int)h->ncon, n = (int)h->nvar;
+    {
+        int dev = 0, sms = 148;
+        FPSB_CUDA(cudaGetDevice(&dev));
+        FPSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        h->num_sms = sms;
+    }
     std::vector<int> rp, ci, perm;
     build_csr_host(m, n, h->nnzj, h->jrow.data(), h->jcol.data(), rp, ci, perm);
-    upload_csr(h, h->A, m, n, rp, ci, perm);
+    upload_sell(h, h->A, m, n, rp, ci, perm);
     build_csr_host(n, m, h->nnzj, h->jcol.data(), h->jrow.data(), rp, ci, perm);
-    upload_csr(h, h->At, n, m, rp, ci, perm);
+    upload_sell(h, h->At, n, m, rp, ci, perm);
     h->coo_vals.alloc((size_t)h->nnzj + 8);
     FPSB_CUDA(cudaStreamSynchronize(h->stream));
 }
 
 void csr_refresh_values(Handle *h) {
-    int nnz = (int)h->nnzj;
-    if (nnz == 0) return;
-    int grid = (nnz + 255) / 256;
-    gather_vals_kernel<<<grid, 256, 0, h->stream>>>(nnz, h->A.perm.p, h->coo_vals.p, h->A.vx.p);
-    gather_vals_kernel<<<grid, 256, 0, h->stream>>>(nnz, h->At.perm.p, h->coo_vals.p, h->At.vx.p);
-    h->launches += 2;
+    for (CsrDev *M : {&h->A, &h->At}) {
+        if (M->padded > 0) {
+            int grid = (int)((M->padded + 255) / 256);
+            gather_vals_kernel<<<grid, 256, 0, h->stream>>>((int)M->padded, M->sperm.p, h->coo_vals.p, M->sval.p);
+            h->launches += 1;
+        }
+        const int nl = (int)(M->long_col.n > 8 ? M->long_col.n - 8 : 0);
+        if (M->nlong > 0 && nl > 0) {
+            gather_vals_kernel<<<(nl + 255) / 256, 256, 0, h->stream>>>(nl, M->long_perm.p, h->coo_vals.p, M->long_val.p);
+            h->launches += 1;
+        }
+    }
     FPSB_CUDA(cudaGetLastError());
 }
 
 static void fill_csr(StepParams &P, const CsrDev &M) {
-    P.rp = M.rp.p; P.ci = M.ci.p; P.vx = M.vx.p; P.blk = M.blk.p; P.nrows = M.nrows; P.lanes = M.lanes;
+    P.sl_off = M.sl_off.p; P.rowidx = M.rowidx.p; P.scol = M.scol.p; P.sval = M.sval.p;
+    P.nslice = M.nslice; P.grid_sell = M.grid_sell;
+    P.long_row = M.long_row.p; P.long_rp = M.long_rp.p; P.long_col = M.long_col.p; P.long_val = M.long_val.p;
+    P.nrows = M.nrows;
 }
 
 // y = Op x for 1 or 2 plain columns (columns contiguous in memory)
 void spmv_plain(Handle *h, bool transpose, const double *x, double *y, int ncols_rhs) {
     const CsrDev &M = transpose ? h->At : h->A;
-    if (M.nrows == 0) return;
+    if (M.nrows == 0 || M.grid == 0) return;
     StepParams P{};
     fill_csr(P, M);
     for (int s = 0; s < 2; ++s) {
@@ -994,7 +1112,7 @@ void spmv_plain(Handle *h, bool transpose, const double *x, double *y, int ncols
         P.io[s].a0 = nullptr;
         P.io[s].c0 = 1.0; P.io[s].c1 = 0.0;
     }
-    gk_step_kernel<false><<<M.nblk, kBlock, 0, h->stream>>>(P, 0);
+    gk_step_kernel<false><<<M.grid, kBlock, 0, h->stream>>>(P, 0);
     h->launches += 1;
     FPSB_CUDA(cudaGetLastError());
 }
@@ -1011,7 +1129,7 @@ void iter_setup(Handle *h) {
     }
     W->ym.alloc(m + 4);
     W->st.alloc(2);
-    int maxblk = std::max(h->A.nblk, h->At.nblk);
+    int maxblk = std::max(h->A.grid, h->At.grid);
     W->ew_grid = 148 * 4;
     W->partials.alloc((size_t)std::max(maxblk, W->ew_grid) * 4 + 16);
     W->counter.alloc(4);
@@ -1133,9 +1251,9 @@ struct Engine {
         StepParams P = mspace ? base_m : base_n;
         P.io[0] = io0; P.io[1] = io1;
         const CsrDev &M = mspace ? h->A : h->At;
-        if (M.nblk == 0) return;
-        if (pair) gk_step_kernel<true><<<M.nblk, kBlock, 0, h->stream>>>(P, 1);
-        else gk_step_kernel<false><<<M.nblk, kBlock, 0, h->stream>>>(P, 1);
+        if (M.grid == 0) return;
+        if (pair) gk_step_kernel<true><<<M.grid, kBlock, 0, h->stream>>>(P, 1);
+        else gk_step_kernel<false><<<M.grid, kBlock, 0, h->stream>>>(P, 1);
         h->launches += 1;
     }
     void ew(int op, int slot, int n, const double *in0, double *v0, double *v1, double *v2, double *v3,
@@ -1211,12 +1329,12 @@ static SlotIO io_mode(int mode, double *a0 = nullptr, double *a1 = nullptr, doub
 // p = rhs - A' q  (n-space), plain kernel
 static void residual_p(Engine &E, const double *rhs, const double *q, double *p) {
     Handle *h = E.h;
-    if (h->At.nblk == 0) return;
+    if (h->At.grid == 0) return;
     StepParams P = E.base_n;
     P.io[0] = io_mode(MD_PLAIN, const_cast<double *>(rhs));
     P.io[0].gin = q; P.io[0].self = p; P.io[0].c0 = -1.0; P.io[0].c1 = 1.0;
     P.io[1] = io_none();
-    gk_step_kernel<false><<<h->At.nblk, kBlock, 0, h->stream>>>(P, 0);
+    gk_step_kernel<false><<<h->At.grid, kBlock, 0, h->stream>>>(P, 0);
     h->launches += 1;
 }
 
@@ -1289,13 +1407,13 @@ void iter_solve_two_least_squares(Handle *h, double delta, const double *rhs1, c
     E.ew(EW_COPY, 0, (int)m, W->am[0][1].p, q1, nullptr, nullptr, nullptr, nullptr, nullptr, -1, 1.0, 0);
     E.ew(EW_COPY, 1, (int)m, W->am[1][1].p, q2, nullptr, nullptr, nullptr, nullptr, nullptr, -1, 1.0, 0);
     // p_i = rhs_i - A' q_i : one two-column SpMM
-    if (h->At.nblk) {
+    if (h->At.grid) {
         StepParams P = E.base_n;
         P.io[0] = io_mode(MD_PLAIN, const_cast<double *>(rhs1));
         P.io[0].gin = q1; P.io[0].self = p1; P.io[0].c0 = -1.0; P.io[0].c1 = 1.0;
         P.io[1] = io_mode(MD_PLAIN, const_cast<double *>(rhs2));
         P.io[1].gin = q2; P.io[1].self = p2; P.io[1].c0 = -1.0; P.io[1].c1 = 1.0;
-        gk_step_kernel<false><<<h->At.nblk, kBlock, 0, h->stream>>>(P, 0);
+        gk_step_kernel<false><<<h->At.grid, kBlock, 0, h->stream>>>(P, 0);
         h->launches += 1;
     }
     E.fetch(st);

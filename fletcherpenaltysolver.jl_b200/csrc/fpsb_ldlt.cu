@@ -38,12 +38,18 @@ struct PlanDev {
     const int *order;
     const int *task_start, *task_cnt;
     const int64_t *uptr;
+    const int64_t *umid;      // pairs [uptr[t], umid[t]) come from non-leaf sources
     const int *usrc, *ua, *ub;
     const int64_t *urel;
     const int *rel;
     const int64_t *tptr;
     const int *ttgt;
     const int *P;
+    const int *sn_of;
+    // leaf contributions grouped by target column
+    const int64_t *lcptr, *lc_src, *lc_rel;
+    const int *lc_cnt, *lc_ldd, *lc_wd, *lc_fd;
+    int ntasks_leaf;          // tasks [0, ntasks_leaf) are leaf supernodes (no incoming update)
     double *panels;
     double *D;
     double2 *Y;
@@ -58,8 +64,10 @@ struct PlanDev {
 struct LdltPlan {
     Symbolic S;
     fpsb_ldlt_opts opts{};
-    DevBuf<int> sfirst, rows, order, task_start, task_cnt, usrc, ua, ub, rel, ttgt, P, pinv, asrc;
-    DevBuf<int64_t> rptr, poff, uptr, urel, tptr, aslot, aptr;
+    DevBuf<int> sfirst, rows, order, task_start, task_cnt, usrc, ua, ub, rel, ttgt, P, pinv, asrc, sn_of;
+    DevBuf<int> lc_cnt, lc_ldd, lc_wd, lc_fd;
+    DevBuf<int64_t> rptr, poff, uptr, umid, urel, tptr, aslot, aptr, lcptr, lc_src, lc_rel;
+    int ntasks_leaf = 0;
     DevBuf<double> panels, D;
     DevBuf<double2> Y;
     DevBuf<int> done_f, done_s, done_b, ticket, fail;
@@ -129,8 +137,9 @@ __device__ void factor_supernode(const PlanDev &P, int t, double *sh, int epoch,
     const int ld = w + nr;
     double *panel = P.panels + P.poff[t];
 
-    // 1. pull the updates of every descendant supernode
-    for (int64_t q = P.uptr[t]; q < P.uptr[t + 1]; ++q) {
+    // 1. pull the updates of every non-leaf descendant supernode (leaf contributions were applied
+    //    by leaf_update_kernel before this launch)
+    for (int64_t q = P.uptr[t]; q < P.umid[t]; ++q) {
         const int d = P.usrc[q];
         wait_done<WARP>(&P.done_f[d], epoch, tid, P.fail);
         const int fd = P.sfirst[d];
@@ -228,7 +237,7 @@ __device__ void fwd_supernode(const PlanDev &P, int t, double *sh, int epoch, in
     double2 *ys = reinterpret_cast<double2 *>(sh);     // w entries
     for (int k = tid; k < w; k += nt) ys[k] = P.Y[f + k];
     gsync<WARP>();
-    for (int64_t q = P.uptr[t]; q < P.uptr[t + 1]; ++q) {
+    for (int64_t q = P.uptr[t]; q < P.umid[t]; ++q) {
         const int d = P.usrc[q];
         wait_done<WARP>(&P.done_s[d], epoch, tid, P.fail);
         const int fd = P.sfirst[d];
@@ -266,15 +275,16 @@ __device__ void fwd_supernode(const PlanDev &P, int t, double *sh, int epoch, in
 }
 
 template <bool WARP>
-__device__ void bwd_supernode(const PlanDev &P, int t, double *sh, int epoch, int tid, int nt) {
+__device__ void bwd_supernode(const PlanDev &P, int t, double *sh, int epoch, int tid, int nt, bool nowait) {
     const int f = P.sfirst[t];
     const int w = P.sfirst[t + 1] - f;
     const int nr = (int)(P.rptr[t + 1] - P.rptr[t]);
     const int ld = w + nr;
     const double *panel = P.panels + P.poff[t];
     const int *R = P.rows + P.rptr[t];
-    for (int64_t q = P.tptr[t]; q < P.tptr[t + 1]; ++q)
-        wait_done<WARP>(&P.done_b[P.ttgt[q]], epoch, tid, P.fail);
+    if (!nowait)
+        for (int64_t q = P.tptr[t]; q < P.tptr[t + 1]; ++q)
+            wait_done<WARP>(&P.done_b[P.ttgt[q]], epoch, tid, P.fail);
     double2 *xs = reinterpret_cast<double2 *>(sh);     // w entries
     // xs[k] = y_k / d_k - sum_r L21[r][k] x[R[r]]
     const int lane = tid & 31, wid = tid >> 5, nwarp = WARP ? 1 : (nt >> 5);
@@ -309,24 +319,27 @@ __device__ void bwd_supernode(const PlanDev &P, int t, double *sh, int epoch, in
 }
 
 // phase: 0 factor, 1 forward, 2 backward (tasks taken in reverse)
+// tasks [task_lo, task_hi) are taken through ticket counter `tk`; `nowait`: every dependency is
+// known to be complete (an earlier launch), so the backward phase skips its flag waits
 template <int PHASE>
-__global__ void __launch_bounds__(kLdltBlock) ldlt_phase_kernel(PlanDev P, int epoch) {
+__global__ void __launch_bounds__(kLdltBlock) ldlt_phase_kernel(PlanDev P, int epoch, int task_lo, int task_hi,
+                                                                int tk, int nowait) {
     __shared__ double sh[kShDoubles];
     __shared__ int s_task;
     const int tid = threadIdx.x;
     for (;;) {
-        if (tid == 0) s_task = atomicAdd(&P.ticket[PHASE], 1);
+        if (tid == 0) s_task = atomicAdd(&P.ticket[tk], 1);
         __syncthreads();
-        int task = s_task;
+        int task = task_lo + s_task;
         __syncthreads();
-        if (task >= P.ntasks) break;
-        if (PHASE == 2) task = P.ntasks - 1 - task;
+        if (task >= task_hi) break;
+        if (PHASE == 2) task = task_hi - 1 - (task - task_lo);
         const int t0 = P.task_start[task], cnt = P.task_cnt[task];
         if (cnt == 0) {
             const int t = P.order[t0];
             if (PHASE == 0) factor_supernode<false>(P, t, sh, epoch, tid, kLdltBlock);
             else if (PHASE == 1) fwd_supernode<false>(P, t, sh, epoch, tid, kLdltBlock);
-            else bwd_supernode<false>(P, t, sh, epoch, tid, kLdltBlock);
+            else bwd_supernode<false>(P, t, sh, epoch, tid, kLdltBlock, nowait != 0);
         } else {
             const int wid = tid >> 5, lane = tid & 31;
             if (wid < cnt) {
@@ -335,11 +348,61 @@ __global__ void __launch_bounds__(kLdltBlock) ldlt_phase_kernel(PlanDev P, int e
                 double *wsh = sh + wid * ((kSmallW + 1) * kSmallW + 4 * kSmallW);
                 if (PHASE == 0) factor_supernode<true>(P, t, wsh, epoch, lane, 32);
                 else if (PHASE == 1) fwd_supernode<true>(P, t, wsh, epoch, lane, 32);
-                else bwd_supernode<true>(P, t, wsh, epoch, lane, 32);
+                else bwd_supernode<true>(P, t, wsh, epoch, lane, 32, nowait != 0);
             }
         }
         __syncthreads();
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// leaf contributions: embarrassingly parallel over TARGET columns (each column is owned by one
+// 8-lane group, sources applied in ascending order => deterministic, no floating-point atomics)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) leaf_update_kernel(PlanDev P) {
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = gt >> 3, l8 = gt & 7;
+    if (j >= P.N) return;
+    const int64_t e0 = P.lcptr[j], e1 = P.lcptr[j + 1];
+    if (e0 == e1) return;
+    const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~7);
+    const int t = P.sn_of[j];
+    const int ft = P.sfirst[t];
+    const int ldt = P.sfirst[t + 1] - ft + (int)(P.rptr[t + 1] - P.rptr[t]);
+    double *col = P.panels + P.poff[t] + (size_t)(j - ft) * ldt;
+    for (int64_t e = e0; e < e1; ++e) {
+        const double *src = P.panels + P.lc_src[e];
+        const int cnt = P.lc_cnt[e], ldd = P.lc_ldd[e], wd = P.lc_wd[e];
+        const double *Dd = P.D + P.lc_fd[e];
+        const int *relp = P.rel + P.lc_rel[e];
+        for (int i = l8; i < cnt; i += 8) {
+            double s = 0.0;
+            for (int k = 0; k < wd; ++k) s += src[(size_t)k * ldd + i] * (src[(size_t)k * ldd] * Dd[k]);
+            col[relp[i]] -= s;
+        }
+        __syncwarp(gmask);
+    }
+}
+
+// forward solve: y[j] -= sum over leaf sources d containing row j of L_d(j, :) . y_d
+__global__ void __launch_bounds__(256) leaf_fwd_update_kernel(PlanDev P) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.N) return;
+    const int64_t e0 = P.lcptr[j], e1 = P.lcptr[j + 1];
+    if (e0 == e1) return;
+    double s0 = 0.0, s1 = 0.0;
+    for (int64_t e = e0; e < e1; ++e) {
+        const double *src = P.panels + P.lc_src[e];
+        const int ldd = P.lc_ldd[e], wd = P.lc_wd[e], fd = P.lc_fd[e];
+        for (int k = 0; k < wd; ++k) {
+            const double l = src[(size_t)k * ldd];
+            const double2 yv = P.Y[fd + k];
+            s0 += l * yv.x; s1 += l * yv.y;
+        }
+    }
+    double2 y = P.Y[j];
+    y.x -= s0; y.y -= s1;
+    P.Y[j] = y;
 }
 
 // Y[k] = (B0[P[k]], B1[P[k]]) with B0 = [rhs1; 0], B1 = kind == 0 ? [0; rhs2] : [rhs2; 0]
@@ -400,17 +463,23 @@ void ldlt_analyze(Handle *h, const int64_t *Puser, const fpsb_ldlt_opts *opts) {
             int nr = (int)(S.rptr[(size_t)s + 1] - S.rptr[(size_t)s]);
             return w <= kSmallW && (int64_t)w * (w + nr) <= 512;
         };
-        int i = 0;
-        while (i < S.nsuper) {
-            if (small(S.order[(size_t)i])) {
-                int j = i;
-                while (j < S.nsuper && j - i < kWarpsPerBlock && small(S.order[(size_t)j])) j++;
-                tstart.push_back(i); tcnt.push_back(j - i);
-                i = j;
-            } else {
-                tstart.push_back(i); tcnt.push_back(0);
-                i++;
+        // `order` is sorted by level: the first nleaf entries are the leaf supernodes; bundles never
+        // straddle the leaf / non-leaf boundary (they are processed by different launches)
+        for (int part = 0; part < 2; part++) {
+            int i = part == 0 ? 0 : S.nleaf;
+            const int end = part == 0 ? S.nleaf : S.nsuper;
+            while (i < end) {
+                if (small(S.order[(size_t)i])) {
+                    int j = i;
+                    while (j < end && j - i < kWarpsPerBlock && small(S.order[(size_t)j])) j++;
+                    tstart.push_back(i); tcnt.push_back(j - i);
+                    i = j;
+                } else {
+                    tstart.push_back(i); tcnt.push_back(0);
+                    i++;
+                }
             }
+            if (part == 0) L->ntasks_leaf = (int)tstart.size();
         }
     }
     L->ntasks = (int)tstart.size();
@@ -421,6 +490,9 @@ void ldlt_analyze(Handle *h, const int64_t *Puser, const fpsb_ldlt_opts *opts) {
     up(L->ttgt, S.ttgt, s); up(L->P, S.P, s); up(L->pinv, S.pinv, s); up(L->asrc, S.asrc, s);
     up(L->rptr, S.rptr, s); up(L->poff, S.poff, s); up(L->uptr, S.uptr, s); up(L->urel, S.urel, s);
     up(L->tptr, S.tptr, s); up(L->aslot, S.aslot, s); up(L->aptr, S.aptr, s);
+    up(L->umid, S.umid, s); up(L->sn_of, S.sn_of, s);
+    up(L->lcptr, S.lcptr, s); up(L->lc_src, S.lc_src, s); up(L->lc_rel, S.lc_rel, s);
+    up(L->lc_cnt, S.lc_cnt, s); up(L->lc_ldd, S.lc_ldd, s); up(L->lc_wd, S.lc_wd, s); up(L->lc_fd, S.lc_fd, s);
     L->naslot = (int64_t)S.aslot.size();
     L->panels.alloc((size_t)S.panel_size + 8);
     L->D.alloc((size_t)S.N + 8);
@@ -436,6 +508,10 @@ void ldlt_analyze(Handle *h, const int64_t *Puser, const fpsb_ldlt_opts *opts) {
     D.task_start = L->task_start.p; D.task_cnt = L->task_cnt.p;
     D.uptr = L->uptr.p; D.usrc = L->usrc.p; D.ua = L->ua.p; D.ub = L->ub.p; D.urel = L->urel.p; D.rel = L->rel.p;
     D.tptr = L->tptr.p; D.ttgt = L->ttgt.p; D.P = L->P.p;
+    D.umid = L->umid.p; D.sn_of = L->sn_of.p;
+    D.lcptr = L->lcptr.p; D.lc_src = L->lc_src.p; D.lc_rel = L->lc_rel.p;
+    D.lc_cnt = L->lc_cnt.p; D.lc_ldd = L->lc_ldd.p; D.lc_wd = L->lc_wd.p; D.lc_fd = L->lc_fd.p;
+    D.ntasks_leaf = L->ntasks_leaf;
     D.panels = L->panels.p; D.D = L->D.p; D.Y = L->Y.p;
     D.done_f = L->done_f.p; D.done_s = L->done_s.p; D.done_b = L->done_b.p;
     D.ticket = L->ticket.p; D.fail = L->fail.p;
@@ -448,7 +524,7 @@ void ldlt_free(Handle *h) {
     if (h->ldlt) { delete h->ldlt; h->ldlt = nullptr; }
 }
 
-static int phase_grid(const LdltPlan *L) { return std::max(1, std::min(L->ntasks, 148 * 6)); }
+static int phase_grid(int ntasks) { return std::max(1, std::min(ntasks, 148 * 6)); }
 
 void ldlt_factorize(Handle *h, double delta, int *factorized) {
     LdltPlan *L = h->ldlt;
@@ -465,8 +541,17 @@ void ldlt_factorize(Handle *h, double delta, int *factorized) {
                                              (int)h->nvar, h->nnzj, delta, L->panels.p);
         h->launches += 1;
     }
-    if (L->ntasks) {
-        ldlt_phase_kernel<0><<<phase_grid(L), kLdltBlock, 0, s>>>(L->dev, L->epoch);
+    const int nl = L->ntasks_leaf, nn = L->ntasks - L->ntasks_leaf, N = L->S.N;
+    if (nl) {     // leaves: no dependencies at all
+        ldlt_phase_kernel<0><<<phase_grid(nl), kLdltBlock, 0, s>>>(L->dev, L->epoch, 0, nl, 0, 1);
+        h->launches += 1;
+    }
+    if (nn) {
+        if (nl) {
+            leaf_update_kernel<<<(int)(((int64_t)N * 8 + 255) / 256), 256, 0, s>>>(L->dev);
+            h->launches += 1;
+        }
+        ldlt_phase_kernel<0><<<phase_grid(nn), kLdltBlock, 0, s>>>(L->dev, L->epoch, nl, L->ntasks, 1, 0);
         h->launches += 1;
     }
     int fail = 0;
@@ -499,10 +584,19 @@ void ldlt_solve2(Handle *h, int kind, const double *rhs1, const double *rhs2, do
     L->epoch += 1;
     FPSB_CUDA(cudaMemsetAsync(L->ticket.p, 0, 8 * sizeof(int), s));
     load_rhs_kernel<<<grid, 256, 0, s>>>(N, nvar, kind, L->P.p, rhs1, rhs2, L->Y.p);
-    ldlt_phase_kernel<1><<<phase_grid(L), kLdltBlock, 0, s>>>(L->dev, L->epoch);
-    ldlt_phase_kernel<2><<<phase_grid(L), kLdltBlock, 0, s>>>(L->dev, L->epoch);
+    const int nl = L->ntasks_leaf, nn = L->ntasks - L->ntasks_leaf;
+    // forward: leaves (independent) -> leaf contributions by target row -> the rest (dependency driven)
+    if (nl) { ldlt_phase_kernel<1><<<phase_grid(nl), kLdltBlock, 0, s>>>(L->dev, L->epoch, 0, nl, 0, 1); h->launches += 1; }
+    if (nn) {
+        if (nl) { leaf_fwd_update_kernel<<<grid, 256, 0, s>>>(L->dev); h->launches += 1; }
+        ldlt_phase_kernel<1><<<phase_grid(nn), kLdltBlock, 0, s>>>(L->dev, L->epoch, nl, L->ntasks, 1, 0);
+        // backward: the non-leaf part in reverse dependency order, then all leaves at once
+        ldlt_phase_kernel<2><<<phase_grid(nn), kLdltBlock, 0, s>>>(L->dev, L->epoch, nl, L->ntasks, 2, 0);
+        h->launches += 2;
+    }
+    if (nl) { ldlt_phase_kernel<2><<<phase_grid(nl), kLdltBlock, 0, s>>>(L->dev, L->epoch, 0, nl, 3, 1); h->launches += 1; }
     store_sol_kernel<<<grid, 256, 0, s>>>(N, nvar, L->pinv.p, L->Y.p, p1, q1, p2, q2);
-    h->launches += 4;
+    h->launches += 2;
     FPSB_CUDA(cudaGetLastError());
 }
 
@@ -573,7 +667,10 @@ static void sym_get(const Symbolic &S, int64_t *P, int64_t *parent, int64_t *Lnz
     if (Lp) for (int k = 0; k <= N; ++k) Lp[k] = S.Lp[(size_t)k];
     if (Li) for (size_t p = 0; p < S.Li.size(); ++p) Li[p] = S.Li[p];
 }
-static void sym_plan(const Symbolic &S, int64_t *nsuper, int64_t *panel_nnz, int64_t *npairs, double *flops) {
+static void sym_plan(const Symbolic &S, int64_t *nsuper, int64_t *panel_nnz, int64_t *npairs, double *flops,
+                     int64_t *nlevels, int64_t *nleaf) {
+    if (nlevels) *nlevels = S.nlevels;
+    if (nleaf) *nleaf = S.nleaf;
     if (nsuper) *nsuper = S.nsuper;
     if (panel_nnz) *panel_nnz = S.panel_size;
     if (npairs) *npairs = (int64_t)S.usrc.size();
@@ -589,9 +686,10 @@ int fpsb_symbolic_get(fpsb_symbolic s, int64_t *P, int64_t *parent, int64_t *Lnz
     sym_get(s->S, P, parent, Lnz, Lp, Li);
     return FPSB_OK;
 }
-int fpsb_symbolic_plan_info(fpsb_symbolic s, int64_t *nsuper, int64_t *panel_nnz, int64_t *npairs, double *flops) {
+int fpsb_symbolic_plan_info(fpsb_symbolic s, int64_t *nsuper, int64_t *panel_nnz, int64_t *npairs, double *flops,
+                            int64_t *nlevels, int64_t *nleaf) {
     REQ(s, FPSB_EINVAL, "NULL symbolic");
-    sym_plan(s->S, nsuper, panel_nnz, npairs, flops);
+    sym_plan(s->S, nsuper, panel_nnz, npairs, flops, nlevels, nleaf);
     return FPSB_OK;
 }
 
@@ -619,10 +717,11 @@ int fpsb_ldlt_get_symbolic(fpsb_handle hh, int64_t *P, int64_t *parent, int64_t 
     sym_get(h->ldlt->S, P, parent, Lnz, Lp, Li);
     return FPSB_OK;
 }
-int fpsb_ldlt_plan_info(fpsb_handle hh, int64_t *nsuper, int64_t *panel_nnz, int64_t *npairs, double *flops) {
+int fpsb_ldlt_plan_info(fpsb_handle hh, int64_t *nsuper, int64_t *panel_nnz, int64_t *npairs, double *flops,
+                        int64_t *nlevels, int64_t *nleaf) {
     Handle *h = reinterpret_cast<Handle *>(hh);
     REQ(h && h->ldlt, FPSB_ESTATE, "fpsb_ldlt_analyze has not been called");
-    sym_plan(h->ldlt->S, nsuper, panel_nnz, npairs, flops);
+    sym_plan(h->ldlt->S, nsuper, panel_nnz, npairs, flops, nlevels, nleaf);
     return FPSB_OK;
 }
 int fpsb_ldlt_factorize(fpsb_handle hh, double delta, int *factorized) {

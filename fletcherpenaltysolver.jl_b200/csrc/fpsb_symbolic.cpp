@@ -566,21 +566,25 @@ void analyze(int nvar, int ncon, int64_t nnzj, const int64_t *jrow, const int64_
     S.ttgt.resize(pairs.size());
     for (size_t k = 0; k < pairs.size(); k++) { S.tptr[(size_t)pairs[k].d + 1]++; S.ttgt[k] = pairs[k].t; }
     for (int s = 0; s < S.nsuper; s++) S.tptr[(size_t)s + 1] += S.tptr[(size_t)s];
-    // by-target list: stable counting sort by t keeps ascending d
+    // by-target list: non-leaf sources first, then leaf sources; ascending d inside each group
     S.uptr.assign((size_t)S.nsuper + 1, 0);
     for (auto &p : pairs) S.uptr[(size_t)p.t + 1]++;
     for (int s = 0; s < S.nsuper; s++) S.uptr[(size_t)s + 1] += S.uptr[(size_t)s];
+    S.umid.assign((size_t)S.nsuper, 0);
     S.usrc.resize(pairs.size()); S.ua.resize(pairs.size()); S.ub.resize(pairs.size());
     S.urel.resize(pairs.size());
     {
         std::vector<int64_t> pos(S.uptr.begin(), S.uptr.end() - 1);
-        int64_t relsz = 0;
-        std::vector<int64_t> slot_of(pairs.size());
-        for (size_t k = 0; k < pairs.size(); k++) {
-            int64_t q = pos[(size_t)pairs[k].t]++;
-            slot_of[k] = q;
-            S.usrc[(size_t)q] = pairs[k].d; S.ua[(size_t)q] = pairs[k].a; S.ub[(size_t)q] = pairs[k].b;
+        for (int pass = 0; pass < 2; pass++) {
+            for (size_t k = 0; k < pairs.size(); k++) {
+                const bool leaf = S.level[(size_t)pairs[k].d] == 0;
+                if ((pass == 0) == leaf) continue;
+                int64_t q = pos[(size_t)pairs[k].t]++;
+                S.usrc[(size_t)q] = pairs[k].d; S.ua[(size_t)q] = pairs[k].a; S.ub[(size_t)q] = pairs[k].b;
+            }
+            if (pass == 0) for (int t = 0; t < S.nsuper; t++) S.umid[(size_t)t] = pos[(size_t)t];
         }
+        int64_t relsz = 0;
         for (size_t q = 0; q < pairs.size(); q++) {
             int d = S.usrc[q];
             int nr = (int)(S.rptr[(size_t)d + 1] - S.rptr[(size_t)d]);
@@ -610,6 +614,42 @@ void analyze(int nvar, int ncon, int64_t nnzj, const int64_t *jrow, const int64_
                 }
             }
         }
+        // leaf contributions grouped by target column (counting sort by column; ascending d kept
+        // because targets are visited in ascending t and their leaf pairs in ascending d... the
+        // order inside a column is made explicit by sorting on d below)
+        S.lcptr.assign((size_t)N + 1, 0);
+        for (int t = 0; t < S.nsuper; t++)
+            for (int64_t q = S.umid[(size_t)t]; q < S.uptr[(size_t)t + 1]; q++) {
+                const int d = S.usrc[(size_t)q];
+                const int *Rd = S.rows.data() + S.rptr[(size_t)d];
+                for (int jp = S.ua[(size_t)q]; jp < S.ub[(size_t)q]; jp++) S.lcptr[(size_t)Rd[jp] + 1]++;
+            }
+        for (int j = 0; j < N; j++) S.lcptr[(size_t)j + 1] += S.lcptr[(size_t)j];
+        const size_t nlc = (size_t)S.lcptr[(size_t)N];
+        S.lc_src.resize(nlc); S.lc_rel.resize(nlc); S.lc_cnt.resize(nlc);
+        S.lc_ldd.resize(nlc); S.lc_wd.resize(nlc); S.lc_fd.resize(nlc);
+        std::vector<int64_t> cpos(S.lcptr.begin(), S.lcptr.end() - 1);
+        for (int t = 0; t < S.nsuper; t++)
+            for (int64_t q = S.umid[(size_t)t]; q < S.uptr[(size_t)t + 1]; q++) {
+                const int d = S.usrc[(size_t)q];
+                const int *Rd = S.rows.data() + S.rptr[(size_t)d];
+                const int fd = first[(size_t)d], wd = first[(size_t)d + 1] - fd;
+                const int nrd = (int)(S.rptr[(size_t)d + 1] - S.rptr[(size_t)d]);
+                for (int jp = S.ua[(size_t)q]; jp < S.ub[(size_t)q]; jp++) {
+                    const size_t e = (size_t)cpos[(size_t)Rd[jp]]++;
+                    S.lc_src[e] = S.poff[(size_t)d] + wd + jp;
+                    S.lc_rel[e] = S.urel[(size_t)q] + (jp - S.ua[(size_t)q]);
+                    S.lc_cnt[e] = nrd - jp;
+                    S.lc_ldd[e] = wd + nrd;
+                    S.lc_wd[e] = wd;
+                    S.lc_fd[e] = fd;
+                }
+            }
+    }
+    S.nlevels = 0; S.nleaf = 0;
+    for (int t = 0; t < S.nsuper; t++) {
+        S.nlevels = std::max(S.nlevels, S.level[(size_t)t] + 1);
+        if (S.level[(size_t)t] == 0) S.nleaf++;
     }
     // task order: by (level, index)
     S.order.resize((size_t)S.nsuper);

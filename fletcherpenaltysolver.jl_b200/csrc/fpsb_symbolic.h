@@ -22,18 +22,29 @@ struct Symbolic {
     std::vector<int> order;           // nsuper : supernodes sorted by (level, index) — task order
     // update pairs, grouped by target (ascending source): source d contributes rows[a..b) of d
     std::vector<int64_t> uptr;        // nsuper+1
+    std::vector<int64_t> umid;        // nsuper : pairs [uptr[t], umid[t]) have non-leaf sources,
+                                      //          [umid[t], uptr[t+1]) have leaf (level-0) sources
     std::vector<int> usrc, ua, ub;    // per pair
     std::vector<int64_t> urel;        // per pair: offset into rel[]
     std::vector<int> rel;             // local row index in the target panel of d's rows a..nr_d
     // pairs grouped by source (for the backward solve dependency waits): targets of each source
     std::vector<int64_t> tptr;        // nsuper+1
     std::vector<int> ttgt;            // distinct target supernodes of each source
+    // leaf contributions by target column: for permuted column j, entries [lcptr[j], lcptr[j+1])
+    // describe the leaf supernodes d whose row structure contains j (ascending d)
+    std::vector<int64_t> lcptr;       // N+1
+    std::vector<int64_t> lc_src;      // panel offset of L_d(jp, 0)
+    std::vector<int64_t> lc_rel;      // offset into rel[] of the local row index of row jp
+    std::vector<int> lc_cnt;          // rows jp..nr_d-1 of d
+    std::vector<int> lc_ldd, lc_wd, lc_fd;
     // assembly map: panel slot <- sources (index into [1..1 | jvals | -delta..])
     std::vector<int64_t> aslot;       // distinct target slots (panel offsets)
     std::vector<int64_t> aptr;        // naslot+1
     std::vector<int> asrc;            // source ids
     int64_t panel_size = 0;
     double flops = 0;
+    int nlevels = 0;                  // height of the supernodal dependency DAG
+    int nleaf = 0;                    // supernodes with no incoming update (level 0)
 };
 
 // approximate minimum degree ordering of a symmetric pattern (Ap/Ai: full pattern, no diagonal)

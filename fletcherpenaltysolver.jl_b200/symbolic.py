@@ -37,10 +37,11 @@ class SymbolicAnalysis:
         return dict(P=P, parent=parent, Lnz=Lnz, Lp=Lp, Li=Li[:lnz])
 
     def plan_info(self):
-        ns, pn, npairs, fl = C.c_int64(), C.c_int64(), C.c_int64(), C.c_double()
+        ns, pn, npairs, fl, nl, nf = C.c_int64(), C.c_int64(), C.c_int64(), C.c_double(), C.c_int64(), C.c_int64()
         check(_lib.lib().fpsb_symbolic_plan_info(self.h, C.byref(ns), C.byref(pn), C.byref(npairs),
-                                                 C.byref(fl)), "fpsb_symbolic_plan_info")
-        return dict(nsuper=ns.value, panel_nnz=pn.value, npairs=npairs.value, flops=fl.value)
+                                                 C.byref(fl), C.byref(nl), C.byref(nf)), "fpsb_symbolic_plan_info")
+        return dict(nsuper=ns.value, panel_nnz=pn.value, npairs=npairs.value, flops=fl.value,
+                    nlevels=nl.value, nleaf=nf.value)
 
     def __del__(self):
         try:

@@ -156,7 +156,7 @@ int fpsb_symbolic_sizes(fpsb_symbolic s, int64_t *N, int64_t *lnz);
 int fpsb_symbolic_get(fpsb_symbolic s, int64_t *P, int64_t *parent, int64_t *Lnz, int64_t *Lp,
                       int64_t *Li);
 int fpsb_symbolic_plan_info(fpsb_symbolic s, int64_t *nsuper, int64_t *panel_nnz, int64_t *npairs,
-                            double *flops);
+                            double *flops, int64_t *nlevels, int64_t *nleaf);
 
 /* ---------------------------------------------------------------------------------------------
  * LDLt path — LDLtSolver (host symbolic analysis + device numeric refactorisation + 2-RHS solves)
@@ -174,9 +174,10 @@ int fpsb_ldlt_symbolic_sizes(fpsb_handle h, int64_t *N, int64_t *lnz);
 int fpsb_ldlt_get_symbolic(fpsb_handle h, int64_t *P, int64_t *parent, int64_t *Lnz, int64_t *Lp,
                            int64_t *Li);
 /* summary of the supernodal plan: nsuper, nnz stored in panels (incl. relaxed zeros), number of
- * (descendant -> target) update pairs, flops of the numeric factorisation */
+ * (descendant -> target) update pairs, flops of the numeric factorisation, height of the supernodal
+ * dependency DAG (critical path, in supernodes) and number of leaf supernodes */
 int fpsb_ldlt_plan_info(fpsb_handle h, int64_t *nsuper, int64_t *panel_nnz, int64_t *npairs,
-                        double *flops);
+                        double *flops, int64_t *nlevels, int64_t *nleaf);
 /* ldl_factorize!(M, str) with vals = [1..1 | jac values | -delta..-delta]
  *   src/solve_linear_system.jl:231-234. Uses the values last given to fpsb_set_jac_values.
  * *factorized mirrors LDLFactorizations.factorized(str). */
