@@ -30,6 +30,13 @@ static double *pin(Handle *h, size_t count) {
     return h->pin;
 }
 
+// true when `p` is page-locked host memory (cudaHostRegister / cudaMallocHost): DMA straight from it
+static bool is_pinned_host(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 struct Staged {
     // device views of the caller's vectors; for FPSB_HOST they live in the handle's stage buffers
     Handle *h;
@@ -45,10 +52,14 @@ struct Staged {
     }
     const double *in(const double *p, size_t count) {
         if (loc == FPSB_DEVICE) return p;
-        double *hp = h->pin + in_off;
-        memcpy(hp, p, count * sizeof(double));
         double *d = h->stage_in.p + in_off;
-        FPSB_CUDA(cudaMemcpyAsync(d, hp, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        if (is_pinned_host(p)) {
+            FPSB_CUDA(cudaMemcpyAsync(d, p, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        } else {
+            double *hp = h->pin + in_off;
+            memcpy(hp, p, count * sizeof(double));
+            FPSB_CUDA(cudaMemcpyAsync(d, hp, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        }
         in_off += count;
         return d;
     }
@@ -61,11 +72,21 @@ struct Staged {
     }
     void finish() {
         if (loc == FPSB_DEVICE) { FPSB_CUDA(cudaStreamSynchronize(h->stream)); return; }
-        double *hp = h->pin + in_off;   // place results after the inputs in the pinned area
-        if (out_off)
-            FPSB_CUDA(cudaMemcpyAsync(hp, h->stage_out.p, out_off * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        double *hp = h->pin + in_off;   // staged results go after the inputs in the pinned area
+        std::vector<char> direct(outs.size(), 0);
+        for (size_t i = 0; i < outs.size(); ++i) {
+            auto &o = outs[i];
+            const size_t bytes = o.second.second * sizeof(double);
+            if (is_pinned_host(o.first)) {
+                direct[i] = 1;
+                FPSB_CUDA(cudaMemcpyAsync(o.first, h->stage_out.p + o.second.first, bytes, cudaMemcpyDeviceToHost, h->stream));
+            } else {
+                FPSB_CUDA(cudaMemcpyAsync(hp + o.second.first, h->stage_out.p + o.second.first, bytes, cudaMemcpyDeviceToHost, h->stream));
+            }
+        }
         FPSB_CUDA(cudaStreamSynchronize(h->stream));
-        for (auto &o : outs) memcpy(o.first, hp + o.second.first, o.second.second * sizeof(double));
+        for (size_t i = 0; i < outs.size(); ++i)
+            if (!direct[i]) memcpy(outs[i].first, hp + outs[i].second.first, outs[i].second.second * sizeof(double));
     }
 };
 
@@ -144,6 +165,21 @@ int fpsb_destroy(fpsb_handle hh) {
     return FPSB_OK;
 }
 
+// page-lock / unlock a caller-owned host buffer so FPSB_HOST calls DMA directly from / into it
+int fpsb_pin_host(void *ptr, int64_t bytes) {
+    REQUIRE(ptr && bytes > 0, FPSB_EINVAL, "fpsb_pin_host: bad arguments");
+    cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return FPSB_OK; }
+    if (e != cudaSuccess) { fpsb::set_error("cudaHostRegister: %s", cudaGetErrorString(e)); cudaGetLastError(); return FPSB_ECUDA; }
+    return FPSB_OK;
+}
+int fpsb_unpin_host(void *ptr) {
+    REQUIRE(ptr, FPSB_EINVAL, "fpsb_unpin_host: NULL");
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); }
+    return FPSB_OK;
+}
+
 int fpsb_dims(fpsb_handle hh, int64_t *nvar, int64_t *ncon, int64_t *nnzj) {
     Handle *h = reinterpret_cast<Handle *>(hh);
     REQUIRE(h, FPSB_EINVAL, "NULL handle");
@@ -194,7 +230,9 @@ int fpsb_set_jac_values(fpsb_handle hh, const double *vals, int loc) {
     FPSB_CUDA(cudaSetDevice(h->device));
     size_t nz = (size_t)h->nnzj;
     if (nz) {
-        if (loc == FPSB_HOST) {
+        if (loc == FPSB_HOST && is_pinned_host(vals)) {
+            FPSB_CUDA(cudaMemcpyAsync(h->coo_vals.p, vals, nz * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        } else if (loc == FPSB_HOST) {
             double *hp = pin(h, nz);
             memcpy(hp, vals, nz * sizeof(double));
             FPSB_CUDA(cudaMemcpyAsync(h->coo_vals.p, hp, nz * sizeof(double), cudaMemcpyHostToDevice, h->stream));

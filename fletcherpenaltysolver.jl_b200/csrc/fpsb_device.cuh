@@ -51,21 +51,21 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// fixed-tree block reduction of NV values per thread (blockDim.x == 256); result valid in thread 0
+// fixed-tree block reduction of NV values per thread (<= 16 warps); result valid in thread 0
 template <int NV>
-__device__ __forceinline__ void block_sum(double (&v)[NV], double *scratch /* NV*8 */) {
+__device__ __forceinline__ void block_sum(double (&v)[NV], double *scratch /* NV*16 */) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
         double x = warp_sum(v[k]);
-        if (lane == 0) scratch[k * 8 + w] = x;
+        if (lane == 0) scratch[k * 16 + w] = x;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
             double x = 0.0;
-            for (int i = 0; i < (int)(blockDim.x >> 5); ++i) x += scratch[k * 8 + i];
+            for (int i = 0; i < (int)((blockDim.x + 31) >> 5); ++i) x += scratch[k * 16 + i];
             v[k] = x;
         }
     }

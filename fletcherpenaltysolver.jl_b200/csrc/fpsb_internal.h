@@ -58,6 +58,7 @@ struct CsrDev {
     int64_t padded = 0;           // stored entries including padding
     int nlong = 0;
     DevBuf<int> sl_off, rowidx, scol, sperm;   // sperm: slot -> COO index (-1 = padding)
+    DevBuf<int> wchunk;                        // first slice of every warp's contiguous chunk
     DevBuf<double> sval;
     DevBuf<int> long_row, long_rp, long_col, long_perm;
     DevBuf<double> long_val;

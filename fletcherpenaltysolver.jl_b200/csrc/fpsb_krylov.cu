@@ -64,6 +64,7 @@ struct SlotIO {
 
 struct StepParams {
     // SELL-32-sigma operator
+    const int *wchunk;     // grid_sell * 8 + 1 : first slice of every warp's contiguous chunk
     const int *sl_off;     // nslice + 1 : element offsets (multiples of 32)
     const int *rowidx;     // nslice * 32 : original row of each lane, -1 for padding lanes
     const int *scol;
@@ -615,18 +616,39 @@ __device__ __forceinline__ double row_epilogue(const Coef &C, double sraw, doubl
 }
 
 // ------------------------------------------------------------------------------------------------
-// the fused SpMM step kernel — SELL-32-sigma: one warp per slice of 32 rows, lane == row.
-// Values / column indices of a slice are stored column-major (32 consecutive entries per slice
-// column), so every load of the matrix stream is a fully coalesced 256 B / 128 B warp access, the
-// row sum lives in two registers (one per right-hand-side column) and the Krylov row epilogue runs
-// in the same lane: no shuffles, no shared memory, no block barrier on the streaming path.
+// the fused SpMM step kernel — SELL-32-sigma streamed through a TMA ring.
+//
+// Layout: a slice is 32 rows, stored column-major (32 consecutive entries per slice column), lane ==
+// row.  A CTA owns a contiguous range of slices, i.e. one contiguous stream of 32-entry "stream
+// rows" of sval / scol.  Warp 8 is the producer: one lane moves the stream into an 8-stage ring in
+// shared memory with cp.async.bulk (TMA), 32 stream rows (8 KB of values + 4 KB of indices) per
+// stage, signalled by mbarriers — 96 KB of loads in flight per CTA, none of it held in registers.
+// Warps 0-7 are consumers: they take the CTA's slices round-robin (adjacent slices => the 8 gather
+// windows overlap in L1), read values / indices conflict-free from the ring, keep only the
+// x-gathers in flight, accumulate the two row sums in registers and run the Krylov row epilogue in
+// the same lane (operands prefetched at slice start).  Every consumer walks every stage (waits
+// full, arrives empty), so a stage is recycled exactly when all 8 warps are past it.
 // Rows longer than kLongRow are handled by extra CTAs (one per row, block reduction).
 // ------------------------------------------------------------------------------------------------
 constexpr int kUnroll = 4;
+constexpr int kConsumers = 8;
+constexpr int kStepThreads = (kConsumers + 1) * 32;
+constexpr int kRingStages = 8;
+constexpr int kStageRows = 32;
+constexpr int kStageElems = kStageRows * 32;
+constexpr int kRingBytes = kRingStages * kStageElems * 12;
+static_assert(kStageRows == 32 && kStageElems == 1024 && (kRingStages & (kRingStages - 1)) == 0, "ring indexing uses shifts");
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
 template <bool PAIR>
-__global__ void __launch_bounds__(kBlock, 3) gk_step_kernel(StepParams P, int use_state) {
-    __shared__ double s_red[4 * 8];
+__global__ void __launch_bounds__(kStepThreads, 2) gk_step_kernel(StepParams P, int use_state) {
+    extern __shared__ __align__(128) unsigned char ring[];
+    __shared__ double s_red[4 * 16];
+    __shared__ alignas(8) uint64_t full_bar[kRingStages];
+    __shared__ alignas(8) uint64_t empty_bar[kRingStages];
     __shared__ int s_last;
 
     const int tid = threadIdx.x;
@@ -642,6 +664,8 @@ __global__ void __launch_bounds__(kBlock, 3) gk_step_kernel(StepParams P, int us
         load_coef(sC[1], P.io[1], &P.st[1], use_state);
         if (!act0) { sC[0].mode = MD_NONE; sC[0].rd0 = sC[0].rd1 = sC[0].wr0 = sC[0].wr1 = sC[0].rdself = 0; }
         if (!act1) { sC[1].mode = MD_NONE; sC[1].rd0 = sC[1].rd1 = sC[1].wr0 = sC[1].wr1 = sC[1].rdself = 0; }
+        for (int s = 0; s < kRingStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kConsumers); }
+        mbar_fence_init();
     }
     __syncthreads();
     const Coef &C0 = sC[0];
@@ -654,87 +678,120 @@ __global__ void __launch_bounds__(kBlock, 3) gk_step_kernel(StepParams P, int us
         const int lane = tid & 31, wid = tid >> 5;
         const int s_begin = (int)(((int64_t)P.nslice * cta) / P.grid_sell);
         const int s_end = (int)(((int64_t)P.nslice * (cta + 1)) / P.grid_sell);
-        for (int sl = s_begin + wid; sl < s_end; sl += kBlock / 32) {
-            const int off = P.sl_off[sl];
-            const int width = (P.sl_off[sl + 1] - off) >> 5;
-            const int row = P.rowidx[sl * 32 + lane];
-            // row-epilogue operands first: their DRAM latency hides behind the matrix stream
-            double2 old2 = make_double2(0.0, 0.0);
-            double so0 = 0.0, so1 = 0.0, a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
-            if (row >= 0) {
-                if (PAIR) old2 = __ldcs(P.self2 + row);
-                else {
-                    if (C0.rdself) so0 = __ldcs(P.io[0].self + row);
-                    if (C1.rdself) so1 = __ldcs(P.io[1].self + row);
+        const int R0 = P.sl_off[s_begin] >> 5, R1 = P.sl_off[s_end] >> 5;
+        const int nstage = (R1 - R0 + kStageRows - 1) / kStageRows;
+        double *ring_val = reinterpret_cast<double *>(ring);
+        int *ring_col = reinterpret_cast<int *>(ring + (size_t)kRingStages * kStageElems * 8);
+        bool ok = true;
+        if (wid == kConsumers) {
+            // ---------------- producer ----------------
+            if (lane == 0) {
+                for (int k = 0; k < nstage && ok; ++k) {
+                    const int slot = k % kRingStages;
+                    if (k >= kRingStages) ok = mbar_wait(&empty_bar[slot], (uint32_t)(((k / kRingStages) & 1) ^ 1));
+                    if (!ok) break;
+                    const int rows = min(kStageRows, R1 - R0 - k * kStageRows);
+                    const size_t e = ((size_t)R0 + (size_t)k * kStageRows) * 32;
+                    mbar_expect_tx(&full_bar[slot], (uint32_t)rows * 32u * 12u);
+                    tma_bulk_g2s(ring_val + (size_t)slot * kStageElems, P.sval + e, (uint32_t)rows * 256u, &full_bar[slot]);
+                    tma_bulk_g2s(ring_col + (size_t)slot * kStageElems, P.scol + e, (uint32_t)rows * 128u, &full_bar[slot]);
                 }
-                if (C0.rd0) a00 = __ldcs(P.io[0].a0 + row);
-                if (C0.rd1) a01 = __ldcs(P.io[0].a1 + row);
-                if (C1.rd0) a10 = __ldcs(P.io[1].a0 + row);
-                if (C1.rd1) a11 = __ldcs(P.io[1].a1 + row);
             }
-            const double *vp = P.sval + off + lane;
-            const int *cp = P.scol + off + lane;
-            double s0 = 0.0, s1 = 0.0;
-            int j = 0;
-            for (; j + kUnroll <= width; j += kUnroll) {
-                double v[kUnroll];
-                int c[kUnroll];
-#pragma unroll
-                for (int u = 0; u < kUnroll; ++u) {
-                    v[u] = __ldcs(vp + (size_t)(j + u) * 32);
-                    c[u] = __ldcs(cp + (size_t)(j + u) * 32);
+        } else {
+            // ---------------- consumers ----------------
+            int kcur = -1;
+            auto advance_to = [&](int k) {
+                while (kcur < k && ok) {
+                    if (kcur >= 0) { __syncwarp(); if (lane == 0) mbar_arrive(&empty_bar[kcur % kRingStages]); }
+                    ++kcur;
+                    ok = mbar_wait(&full_bar[kcur % kRingStages], (uint32_t)((kcur / kRingStages) & 1));
                 }
-                if (PAIR) {
-                    double2 x[kUnroll];
-#pragma unroll
-                    for (int u = 0; u < kUnroll; ++u) x[u] = __ldg(P.gin2 + c[u]);
-#pragma unroll
-                    for (int u = 0; u < kUnroll; ++u) { s0 += v[u] * x[u].x; s1 += v[u] * x[u].y; }
-                } else {
-                    double x0[kUnroll], x1[kUnroll];
-#pragma unroll
-                    for (int u = 0; u < kUnroll; ++u) {
-                        x0[u] = act0 ? __ldg(P.io[0].gin + c[u]) : 0.0;
-                        x1[u] = act1 ? __ldg(P.io[1].gin + c[u]) : 0.0;
+            };
+            for (int sl = s_begin + wid; sl < s_end && ok; sl += kConsumers) {
+                const int ra = (P.sl_off[sl] >> 5) - R0, rb = (P.sl_off[sl + 1] >> 5) - R0;
+                const int row = P.rowidx[sl * 32 + lane];
+                // row-epilogue operands first: their DRAM latency hides behind the slice
+                double2 old2 = make_double2(0.0, 0.0);
+                double so0 = 0.0, so1 = 0.0, a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+                if (row >= 0) {
+                    if (PAIR) old2 = __ldcs(P.self2 + row);
+                    else {
+                        if (C0.rdself) so0 = __ldcs(P.io[0].self + row);
+                        if (C1.rdself) so1 = __ldcs(P.io[1].self + row);
                     }
+                    if (C0.rd0) a00 = __ldcs(P.io[0].a0 + row);
+                    if (C0.rd1) a01 = __ldcs(P.io[0].a1 + row);
+                    if (C1.rd0) a10 = __ldcs(P.io[1].a0 + row);
+                    if (C1.rd1) a11 = __ldcs(P.io[1].a1 + row);
+                }
+                double s0 = 0.0, s1 = 0.0;
+                // the slice's rows, one ring stage at a time (a 20-row slice touches 1-2 stages)
+                int r = ra;
+                while (r < rb && ok) {
+                    const int k = r >> 5;                               // kStageRows == 32
+                    advance_to(k);
+                    const int seg_end = min(rb, (k + 1) << 5);
+                    const int nrows = seg_end - r;
+                    const int q0 = ((k & (kRingStages - 1)) << 10) + ((r & 31) << 5) + lane;
+                    const double *vp = ring_val + q0;
+                    const int *cp = ring_col + q0;
+                    for (int j = 0; j < nrows; j += kUnroll) {
+                        double v[kUnroll];
+                        int c[kUnroll];
 #pragma unroll
-                    for (int u = 0; u < kUnroll; ++u) { s0 += v[u] * x0[u]; s1 += v[u] * x1[u]; }
+                        for (int u = 0; u < kUnroll; ++u) {
+                            const bool in = (j + u) < nrows;
+                            v[u] = in ? vp[(j + u) * 32] : 0.0;
+                            c[u] = in ? cp[(j + u) * 32] : -1;
+                        }
+                        if (PAIR) {
+                            double2 x[kUnroll];
+#pragma unroll
+                            for (int u = 0; u < kUnroll; ++u)
+                                x[u] = (c[u] >= 0) ? __ldg(P.gin2 + c[u]) : make_double2(0.0, 0.0);
+#pragma unroll
+                            for (int u = 0; u < kUnroll; ++u) { s0 = fma(v[u], x[u].x, s0); s1 = fma(v[u], x[u].y, s1); }
+                        } else {
+                            double x0[kUnroll], x1[kUnroll];
+#pragma unroll
+                            for (int u = 0; u < kUnroll; ++u) {
+                                x0[u] = (act0 && c[u] >= 0) ? __ldg(P.io[0].gin + c[u]) : 0.0;
+                                x1[u] = (act1 && c[u] >= 0) ? __ldg(P.io[1].gin + c[u]) : 0.0;
+                            }
+#pragma unroll
+                            for (int u = 0; u < kUnroll; ++u) { s0 = fma(v[u], x0[u], s0); s1 = fma(v[u], x1[u], s1); }
+                        }
+                    }
+                    r = seg_end;
+                }
+                if (row >= 0 && ok) {
+                    if (PAIR) {
+                        double2 nw = old2;
+                        if (act0) nw.x = row_epilogue(C0, s0, old2.x, a00, a01, acc[0], acc[1]);
+                        if (act1) nw.y = row_epilogue(C1, s1, old2.y, a10, a11, acc[2], acc[3]);
+                        __stcs(P.self2 + row, nw);
+                    } else {
+                        if (act0) __stcs(P.io[0].self + row, row_epilogue(C0, s0, so0, a00, a01, acc[0], acc[1]));
+                        if (act1) __stcs(P.io[1].self + row, row_epilogue(C1, s1, so1, a10, a11, acc[2], acc[3]));
+                    }
+                    if (C0.wr0) __stcs(P.io[0].a0 + row, a00);
+                    if (C0.wr1) __stcs(P.io[0].a1 + row, a01);
+                    if (C1.wr0) __stcs(P.io[1].a0 + row, a10);
+                    if (C1.wr1) __stcs(P.io[1].a1 + row, a11);
                 }
             }
-            for (; j < width; ++j) {
-                const double v = __ldcs(vp + (size_t)j * 32);
-                const int c = __ldcs(cp + (size_t)j * 32);
-                if (PAIR) {
-                    const double2 x = __ldg(P.gin2 + c);
-                    s0 += v * x.x; s1 += v * x.y;
-                } else {
-                    if (act0) s0 += v * __ldg(P.io[0].gin + c);
-                    if (act1) s1 += v * __ldg(P.io[1].gin + c);
-                }
-            }
-            if (row >= 0) {
-                if (PAIR) {
-                    double2 nw = old2;
-                    if (act0) nw.x = row_epilogue(C0, s0, old2.x, a00, a01, acc[0], acc[1]);
-                    if (act1) nw.y = row_epilogue(C1, s1, old2.y, a10, a11, acc[2], acc[3]);
-                    __stcs(P.self2 + row, nw);
-                } else {
-                    if (act0) __stcs(P.io[0].self + row, row_epilogue(C0, s0, so0, a00, a01, acc[0], acc[1]));
-                    if (act1) __stcs(P.io[1].self + row, row_epilogue(C1, s1, so1, a10, a11, acc[2], acc[3]));
-                }
-                if (C0.wr0) __stcs(P.io[0].a0 + row, a00);
-                if (C0.wr1) __stcs(P.io[0].a1 + row, a01);
-                if (C1.wr0) __stcs(P.io[1].a0 + row, a10);
-                if (C1.wr1) __stcs(P.io[1].a1 + row, a11);
-            }
+            // walk (and release) the remaining stages so the producer can finish
+            advance_to(nstage - 1);
+            if (kcur >= 0 && ok) { __syncwarp(); if (lane == 0) mbar_arrive(&empty_bar[kcur % kRingStages]); }
         }
+        if (!ok && lane == 0) atomicExch(P.done_flag, -1);
     } else {
         // one long row per CTA: strided over the whole block, fixed-tree block reduction
         const int lr = cta - P.grid_sell;
         const int row = P.long_row[lr];
         const int e0 = P.long_rp[lr], e1 = P.long_rp[lr + 1];
         double a[2] = {0.0, 0.0};
-        for (int k = e0 + tid; k < e1; k += kBlock) {
+        for (int k = e0 + tid; k < e1; k += kStepThreads) {
             const double v = P.long_val[k];
             const int c = P.long_col[k];
             if (PAIR) {
@@ -789,7 +846,7 @@ __global__ void __launch_bounds__(kBlock, 3) gk_step_kernel(StepParams P, int us
     if (!s_last) return;
     __threadfence();
     double tot[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int i = tid; i < (int)gridDim.x; i += kBlock) {
+    for (int i = tid; i < (int)gridDim.x; i += kStepThreads) {
         const double *pp = P.partials + (size_t)i * 4;
         tot[0] += __ldcg(pp + 0); tot[1] += __ldcg(pp + 1);
         tot[2] += __ldcg(pp + 2); tot[3] += __ldcg(pp + 3);
@@ -821,7 +878,7 @@ struct EwParams {
 };
 
 __global__ void __launch_bounds__(kBlock) ew_kernel(EwParams P) {
-    __shared__ double s_red[8];
+    __shared__ double s_red[16];
     __shared__ int s_last;
     SlotState *S = P.st ? &P.st[P.slot] : nullptr;
     const bool is_init = (P.op == EW_INIT_LSQR || P.op == EW_INIT_CRAIG || P.op == EW_MINRES_INIT ||
@@ -1055,8 +1112,25 @@ static void upload_sell(Handle *h, CsrDev &M, int nrows, int ncols, const std::v
     M.long_perm.from(long_perm, h->stream);
     M.long_val.alloc(long_col.size() + 8);
     M.long_val.zero(h->stream);
-    M.grid_sell = nslice > 0 ? std::max(1, std::min((nslice + 7) / 8, 3 * h->num_sms)) : 0;
+    M.grid_sell = nslice > 0 ? std::max(1, std::min((nslice + 7) / 8, 2 * h->num_sms)) : 0;
     M.grid = M.grid_sell + M.nlong;
+    {
+        // contiguous chunks of slices per warp, balanced by streamed rows (+1 per slice for the
+        // epilogue); wchunk[w] = first slice of warp w
+        const int nw = M.grid_sell * (kBlock / 32);
+        std::vector<int> wchunk((size_t)nw + 1, nslice);
+        std::vector<int64_t> cost((size_t)nslice + 1, 0);
+        for (int i = 0; i < nslice; ++i) cost[(size_t)i + 1] = cost[(size_t)i] + (sl_off[(size_t)i + 1] - sl_off[(size_t)i]) / 32 + 2;
+        int cur = 0;
+        for (int w = 0; w < nw; ++w) {
+            wchunk[(size_t)w] = cur;
+            const int64_t target = nw > 0 ? cost[(size_t)nslice] * (w + 1) / nw : 0;
+            while (cur < nslice && cost[(size_t)cur + 1] <= target) cur++;
+        }
+        wchunk[(size_t)nw] = nslice;
+        if (nw > 0) wchunk[0] = 0;
+        M.wchunk.from(wchunk, h->stream);
+    }
 }
 
 void csr_build(Handle *h) {
@@ -1066,6 +1140,8 @@ void csr_build(Handle *h) {
         FPSB_CUDA(cudaGetDevice(&dev));
         FPSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         h->num_sms = sms;
+        FPSB_CUDA(cudaFuncSetAttribute(gk_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes));
+        FPSB_CUDA(cudaFuncSetAttribute(gk_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes));
     }
     std::vector<int> rp, ci, perm;
     build_csr_host(m, n, h->nnzj, h->jrow.data(), h->jcol.data(), rp, ci, perm);
@@ -1093,6 +1169,7 @@ void csr_refresh_values(Handle *h) {
 }
 
 static void fill_csr(StepParams &P, const CsrDev &M) {
+    P.wchunk = M.wchunk.p;
     P.sl_off = M.sl_off.p; P.rowidx = M.rowidx.p; P.scol = M.scol.p; P.sval = M.sval.p;
     P.nslice = M.nslice; P.grid_sell = M.grid_sell;
     P.long_row = M.long_row.p; P.long_rp = M.long_rp.p; P.long_col = M.long_col.p; P.long_val = M.long_val.p;
@@ -1112,7 +1189,7 @@ void spmv_plain(Handle *h, bool transpose, const double *x, double *y, int ncols
         P.io[s].a0 = nullptr;
         P.io[s].c0 = 1.0; P.io[s].c1 = 0.0;
     }
-    gk_step_kernel<false><<<M.grid, kBlock, 0, h->stream>>>(P, 0);
+    gk_step_kernel<false><<<M.grid, kStepThreads, kRingBytes, h->stream>>>(P, 0);
     h->launches += 1;
     FPSB_CUDA(cudaGetLastError());
 }
@@ -1252,8 +1329,8 @@ struct Engine {
         P.io[0] = io0; P.io[1] = io1;
         const CsrDev &M = mspace ? h->A : h->At;
         if (M.grid == 0) return;
-        if (pair) gk_step_kernel<true><<<M.grid, kBlock, 0, h->stream>>>(P, 1);
-        else gk_step_kernel<false><<<M.grid, kBlock, 0, h->stream>>>(P, 1);
+        if (pair) gk_step_kernel<true><<<M.grid, kStepThreads, kRingBytes, h->stream>>>(P, 1);
+        else gk_step_kernel<false><<<M.grid, kStepThreads, kRingBytes, h->stream>>>(P, 1);
         h->launches += 1;
     }
     void ew(int op, int slot, int n, const double *in0, double *v0, double *v1, double *v2, double *v3,
@@ -1334,7 +1411,7 @@ static void residual_p(Engine &E, const double *rhs, const double *q, double *p)
     P.io[0] = io_mode(MD_PLAIN, const_cast<double *>(rhs));
     P.io[0].gin = q; P.io[0].self = p; P.io[0].c0 = -1.0; P.io[0].c1 = 1.0;
     P.io[1] = io_none();
-    gk_step_kernel<false><<<h->At.grid, kBlock, 0, h->stream>>>(P, 0);
+    gk_step_kernel<false><<<h->At.grid, kStepThreads, kRingBytes, h->stream>>>(P, 0);
     h->launches += 1;
 }
 
@@ -1413,7 +1490,7 @@ void iter_solve_two_least_squares(Handle *h, double delta, const double *rhs1, c
         P.io[0].gin = q1; P.io[0].self = p1; P.io[0].c0 = -1.0; P.io[0].c1 = 1.0;
         P.io[1] = io_mode(MD_PLAIN, const_cast<double *>(rhs2));
         P.io[1].gin = q2; P.io[1].self = p2; P.io[1].c0 = -1.0; P.io[1].c1 = 1.0;
-        gk_step_kernel<false><<<h->At.grid, kBlock, 0, h->stream>>>(P, 0);
+        gk_step_kernel<false><<<h->At.grid, kStepThreads, kRingBytes, h->stream>>>(P, 0);
         h->launches += 1;
     }
     E.fetch(st);

@@ -653,6 +653,26 @@ int fpsb_symbolic_create(int64_t nvar, int64_t ncon, int64_t nnzj, const int64_t
 }
 int fpsb_symbolic_destroy(fpsb_symbolic s) { delete s; return FPSB_OK; }
 
+// host-only: dissection ordering of K (P_out: nvar+ncon entries, index_base-based)
+int fpsb_order_dissection(int64_t nvar, int64_t ncon, int64_t nnzj, const int64_t *jrow, const int64_t *jcol,
+                          int index_base, int nparts, int64_t *P_out) {
+    REQ(P_out && nvar >= 0 && ncon >= 0 && nnzj >= 0 && (nnzj == 0 || (jrow && jcol)), FPSB_EINVAL, "bad arguments");
+    TRY_
+    std::vector<int64_t> r((size_t)nnzj), c((size_t)nnzj);
+    for (int64_t k = 0; k < nnzj; ++k) {
+        r[(size_t)k] = jrow[k] - index_base; c[(size_t)k] = jcol[k] - index_base;
+        REQ(r[(size_t)k] >= 0 && r[(size_t)k] < ncon && c[(size_t)k] >= 0 && c[(size_t)k] < nvar, FPSB_EINVAL,
+            "Jacobian index out of range");
+    }
+    std::vector<int64_t> Gp;
+    std::vector<int> Gi, P;
+    build_kkt_graph((int)nvar, (int)ncon, nnzj, r.data(), c.data(), Gp, Gi);
+    dissection_order((int)(nvar + ncon), Gp, Gi, nparts, P);
+    for (size_t k = 0; k < P.size(); ++k) P_out[k] = P[k] + index_base;
+    return FPSB_OK;
+    CATCH_
+}
+
 static void sym_sizes(const Symbolic &S, int64_t *N, int64_t *lnz) {
     if (N) *N = S.N;
     if (lnz) *lnz = S.Lp.empty() ? 0 : S.Lp[(size_t)S.N];

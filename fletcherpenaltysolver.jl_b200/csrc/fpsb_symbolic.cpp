@@ -352,12 +352,176 @@ void amd_order(int n, const std::vector<int64_t> &Ap, const std::vector<int> &Ai
 }
 
 // ------------------------------------------------------------------------------------------------
+// One-way dissection by BFS level sets + cyclic-reduction order of the separators.
+// A B200-oriented alternative to the minimum-degree default: AMD minimises fill but, on band-like
+// KKT structure, yields an elimination tree that is one long chain (14 000+ dependent supernodes at
+// n = 1M), which serialises the GPU factorisation.  Here the graph is cut into `nparts` pieces by
+// single BFS levels (each level is a vertex separator), piece interiors are ordered independently
+// (minimum degree on the induced subgraph) and the separators are ordered like cyclic reduction
+// (odd ones first, then those = 2 mod 4, ...), so the dependency depth is
+// O(depth of one piece + log2(nparts)) instead of O(N / supernode width).
+// Passed to the analysis as an explicit P (the `ldl_analyze(A, P)` form).
+// ------------------------------------------------------------------------------------------------
+void dissection_order(int n, const std::vector<int64_t> &Ap, const std::vector<int> &Ai, int nparts_target,
+                      std::vector<int> &Pout) {
+    Pout.clear();
+    Pout.reserve((size_t)n);
+    if (n == 0) return;
+    if (nparts_target <= 0) nparts_target = std::max(1, std::min(1024, n / 6000));
+    const int part_size = std::max(64, n / std::max(1, nparts_target));
+    std::vector<int> level((size_t)n, -1), comp_nodes, queue((size_t)n);
+    std::vector<char> visited((size_t)n, 0);
+    std::vector<int> local((size_t)n, -1);
+    std::vector<std::vector<int>> separators_all;   // separators of all components, in CR order at the end
+    std::vector<std::pair<int, int>> sep_rank;       // (trailing zeros, running id)
+    auto bfs = [&](int start, std::vector<int> &order, std::vector<int> &lvl_ptr, int stamp_base) {
+        // levels written as stamp_base + level into `level` (re-used across sweeps via negative marks)
+        order.clear(); lvl_ptr.clear();
+        int head = 0, tail = 0;
+        queue[(size_t)tail++] = start;
+        level[(size_t)start] = stamp_base;
+        lvl_ptr.push_back(0);
+        int cur = stamp_base;
+        while (head < tail) {
+            int v = queue[(size_t)head++];
+            if (level[(size_t)v] != cur) { cur = level[(size_t)v]; lvl_ptr.push_back((int)order.size()); }
+            order.push_back(v);
+            for (int64_t p = Ap[(size_t)v]; p < Ap[(size_t)v + 1]; p++) {
+                int u = Ai[(size_t)p];
+                if (level[(size_t)u] < stamp_base) { level[(size_t)u] = level[(size_t)v] + 1; queue[(size_t)tail++] = u; }
+            }
+        }
+        lvl_ptr.push_back((int)order.size());
+    };
+    auto order_interior = [&](const std::vector<int> &nodes) {
+        // minimum degree on the induced subgraph
+        const int k = (int)nodes.size();
+        if (k == 0) return;
+        for (int i = 0; i < k; i++) local[(size_t)nodes[(size_t)i]] = i;
+        std::vector<int64_t> sp((size_t)k + 1, 0);
+        std::vector<int> si;
+        for (int i = 0; i < k; i++) {
+            int v = nodes[(size_t)i];
+            for (int64_t p = Ap[(size_t)v]; p < Ap[(size_t)v + 1]; p++) {
+                int u = local[(size_t)Ai[(size_t)p]];
+                if (u >= 0) si.push_back(u);
+            }
+            sp[(size_t)i + 1] = (int64_t)si.size();
+        }
+        std::vector<int> lp;
+        amd_order(k, sp, si, lp);
+        for (int i = 0; i < k; i++) Pout.push_back(nodes[(size_t)lp[(size_t)i]]);
+        for (int i = 0; i < k; i++) local[(size_t)nodes[(size_t)i]] = -1;
+    };
+    int stamp = 0;
+    std::vector<int> order, lvl_ptr;
+    for (int root = 0; root < n; root++) {
+        if (visited[(size_t)root]) continue;
+        // pseudo-peripheral start: a few BFS sweeps, restarting from a min-degree node of the last level
+        int start = root;
+        int nlev = 0;
+        for (int sweep = 0; sweep < 4; sweep++) {
+            stamp += n + 2;
+            bfs(start, order, lvl_ptr, stamp);
+            int nl = (int)lvl_ptr.size() - 1;
+            if (sweep > 0 && nl <= nlev) break;
+            nlev = nl;
+            int best = -1;
+            int64_t bestdeg = INT64_MAX;
+            for (int q = lvl_ptr[(size_t)nl - 1]; q < lvl_ptr[(size_t)nl]; q++) {
+                int v = order[(size_t)q];
+                int64_t d = Ap[(size_t)v + 1] - Ap[(size_t)v];
+                if (d < bestdeg) { bestdeg = d; best = v; }
+            }
+            if (best < 0 || best == start) break;
+            if (sweep < 3) start = best;
+        }
+        // final level structure from `start`
+        stamp += n + 2;
+        bfs(start, order, lvl_ptr, stamp);
+        const int nc = (int)order.size();
+        const int nl = (int)lvl_ptr.size() - 1;
+        for (int v : order) visited[(size_t)v] = 1;
+        int p = std::max(1, nc / part_size);
+        std::vector<int> seps;     // separator levels (ascending)
+        if (p >= 2 && nl >= 5) {
+            int last = 0;
+            for (int k = 1; k < p; k++) {
+                const int64_t target = (int64_t)nc * k / p;
+                int l = (int)(std::upper_bound(lvl_ptr.begin(), lvl_ptr.end(), (int)target) - lvl_ptr.begin()) - 1;
+                l = std::max(l, last + 2);
+                if (l >= nl - 1) break;
+                // the thinnest of the neighbouring levels
+                int bestl = l;
+                for (int c = l - 1; c <= l + 1; c++) {
+                    if (c < last + 2 || c >= nl - 1) continue;
+                    if (lvl_ptr[(size_t)c + 1] - lvl_ptr[(size_t)c] < lvl_ptr[(size_t)bestl + 1] - lvl_ptr[(size_t)bestl]) bestl = c;
+                }
+                seps.push_back(bestl);
+                last = bestl;
+            }
+        }
+        // interiors
+        int lo = 0;
+        std::vector<int> nodes;
+        for (size_t k = 0; k <= seps.size(); k++) {
+            const int hi = (k < seps.size()) ? seps[k] : nl;     // levels [lo, hi)
+            nodes.assign(order.begin() + lvl_ptr[(size_t)lo], order.begin() + lvl_ptr[(size_t)hi]);
+            order_interior(nodes);
+            lo = hi + 1;
+        }
+        // separators of this component, ranked like cyclic reduction
+        for (size_t k = 0; k < seps.size(); k++) {
+            const int l = seps[k];
+            std::vector<int> sn(order.begin() + lvl_ptr[(size_t)l], order.begin() + lvl_ptr[(size_t)l + 1]);
+            int idx = (int)k + 1, tz = 0;
+            while ((idx & 1) == 0) { idx >>= 1; tz++; }
+            sep_rank.push_back({tz, (int)separators_all.size()});
+            separators_all.push_back(std::move(sn));
+        }
+    }
+    std::stable_sort(sep_rank.begin(), sep_rank.end(),
+                     [](const std::pair<int, int> &a, const std::pair<int, int> &b) { return a.first < b.first; });
+    for (auto &r : sep_rank)
+        for (int v : separators_all[(size_t)r.second]) Pout.push_back(v);
+    if ((int)Pout.size() != n) throw std::runtime_error("dissection_order: internal error");
+}
+
+// ------------------------------------------------------------------------------------------------
 static bool relax_ok(int W, int64_t stored, int64_t zeros) {
     double z = stored > 0 ? (double)zeros / (double)stored : 0.0;
     if (W <= 4) return true;
     if (W <= 16) return z < 0.5;
     if (W <= 48) return z < 0.12;
     return z < 0.05;
+}
+
+// symmetric pattern of K without the diagonal (variables <-> constraints), sorted, de-duplicated
+void build_kkt_graph(int nvar, int ncon, int64_t nnzj, const int64_t *jrow, const int64_t *jcol,
+                     std::vector<int64_t> &Gp, std::vector<int> &Gi) {
+    const int N = nvar + ncon;
+    Gp.assign((size_t)N + 1, 0);
+    for (int64_t e = 0; e < nnzj; e++) { Gp[(size_t)jcol[e] + 1]++; Gp[(size_t)(nvar + jrow[e]) + 1]++; }
+    for (int i = 0; i < N; i++) Gp[i + 1] += Gp[i];
+    Gi.assign((size_t)Gp[N], 0);
+    std::vector<int64_t> pos(Gp.begin(), Gp.end() - 1);
+    for (int64_t e = 0; e < nnzj; e++) {
+        int v = (int)jcol[e], c = nvar + (int)jrow[e];
+        Gi[(size_t)pos[v]++] = c;
+        Gi[(size_t)pos[c]++] = v;
+    }
+    std::vector<int64_t> Np((size_t)N + 1, 0);
+    int64_t out = 0;
+    for (int i = 0; i < N; i++) {
+        int64_t a = Gp[i], b = Gp[i + 1];
+        std::sort(Gi.begin() + a, Gi.begin() + b);
+        int64_t start = out;
+        for (int64_t p = a; p < b; p++)
+            if (out == start || Gi[(size_t)(out - 1)] != Gi[(size_t)p]) Gi[(size_t)out++] = Gi[(size_t)p];
+        Np[i + 1] = out;
+    }
+    Gp = Np;
+    Gi.resize((size_t)out);
 }
 
 constexpr int kMaxSuperWidth = 64;
@@ -367,32 +531,9 @@ void analyze(int nvar, int ncon, int64_t nnzj, const int64_t *jrow, const int64_
     const int N = nvar + ncon;
     S = Symbolic();
     S.N = N;
-    // ---- symmetric pattern of K without the diagonal (variables <-> constraints) --------------
-    std::vector<int64_t> Gp((size_t)N + 1, 0);
-    for (int64_t e = 0; e < nnzj; e++) { Gp[(size_t)jcol[e] + 1]++; Gp[(size_t)(nvar + jrow[e]) + 1]++; }
-    for (int i = 0; i < N; i++) Gp[i + 1] += Gp[i];
-    std::vector<int> Gi((size_t)Gp[N]);
-    {
-        std::vector<int64_t> pos(Gp.begin(), Gp.end() - 1);
-        for (int64_t e = 0; e < nnzj; e++) {
-            int v = (int)jcol[e], c = nvar + (int)jrow[e];
-            Gi[(size_t)pos[v]++] = c;
-            Gi[(size_t)pos[c]++] = v;
-        }
-        // sort + dedupe each list
-        std::vector<int64_t> Np((size_t)N + 1, 0);
-        int64_t out = 0;
-        for (int i = 0; i < N; i++) {
-            int64_t a = Gp[i], b = Gp[i + 1];
-            std::sort(Gi.begin() + a, Gi.begin() + b);
-            int64_t start = out;
-            for (int64_t p = a; p < b; p++)
-                if (out == start || Gi[(size_t)(out - 1)] != Gi[(size_t)p]) Gi[(size_t)out++] = Gi[(size_t)p];
-            Np[i + 1] = out;
-        }
-        Gp = Np;
-        Gi.resize((size_t)out);
-    }
+    std::vector<int64_t> Gp;
+    std::vector<int> Gi;
+    build_kkt_graph(nvar, ncon, nnzj, jrow, jcol, Gp, Gi);
     // ---- ordering ---------------------------------------------------------------------------
     S.P.resize((size_t)N);
     if (Puser) {

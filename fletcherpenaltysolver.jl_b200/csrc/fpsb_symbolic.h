@@ -50,6 +50,12 @@ struct Symbolic {
 // approximate minimum degree ordering of a symmetric pattern (Ap/Ai: full pattern, no diagonal)
 void amd_order(int n, const std::vector<int64_t> &Ap, const std::vector<int> &Ai, std::vector<int> &P);
 
+// BFS level-set dissection + cyclic-reduction separator order (nparts_target <= 0: automatic)
+void dissection_order(int n, const std::vector<int64_t> &Ap, const std::vector<int> &Ai, int nparts_target,
+                      std::vector<int> &P);
+void build_kkt_graph(int nvar, int ncon, int64_t nnzj, const int64_t *jrow, const int64_t *jcol,
+                     std::vector<int64_t> &Gp, std::vector<int> &Gi);
+
 // full analysis; Puser may be null (-> amd_order). jrow/jcol are 0-based.
 void analyze(int nvar, int ncon, int64_t nnzj, const int64_t *jrow, const int64_t *jcol,
              const int64_t *Puser, Symbolic &S);

@@ -68,6 +68,15 @@ class B200Handle:
             return C.c_void_p(a.data_ptr()), (FPSB_DEVICE if a.is_cuda else FPSB_HOST)
         raise TypeError("expected a numpy array or a torch tensor")
 
+    @staticmethod
+    def pin_host(a):
+        """Page-lock a long-lived numpy array so FPSB_HOST calls DMA directly from / into it."""
+        check(_lib.lib().fpsb_pin_host(_ptr(a), C.c_int64(a.nbytes)), "fpsb_pin_host")
+
+    @staticmethod
+    def unpin_host(a):
+        _lib.lib().fpsb_unpin_host(_ptr(a))
+
     def stream(self):
         return _lib.lib().fpsb_stream(self.h)
 
@@ -123,11 +132,11 @@ class B200Handle:
         import torch
         return [torch.empty(s, dtype=torch.float64, device=like.device) for s in sizes]
 
-    def _two(self, fn, name, pre, rhs1, rhs2, with_stats):
+    def _two(self, fn, name, pre, rhs1, rhs2, with_stats, out=None):
         if isinstance(rhs1, np.ndarray):
             rhs1, rhs2 = _f64(rhs1), _f64(rhs2)
         n, m = self.nvar, self.ncon
-        p1, q1, p2, q2 = self._outs(rhs1, [n, m, n, m])
+        p1, q1, p2, q2 = out if out is not None else self._outs(rhs1, [n, m, n, m])
         a1, loc = self._arg(rhs1)
         a2, _ = self._arg(rhs2)
         tail = (KrylovStats * 2)() if with_stats else C.c_int(0)
@@ -146,9 +155,9 @@ class B200Handle:
         check(_lib.lib().fpsb_iter_last_profile(self.h, C.byref(ms), C.byref(nl)), "fpsb_iter_last_profile")
         return ms.value, nl.value
 
-    def iter_solve_two_mixed(self, delta, rhs1, rhs2):
+    def iter_solve_two_mixed(self, delta, rhs1, rhs2, out=None):
         return self._two(_lib.lib().fpsb_iter_solve_two_mixed, "fpsb_iter_solve_two_mixed",
-                         (C.c_double(delta),), rhs1, rhs2, True)
+                         (C.c_double(delta),), rhs1, rhs2, True, out)
 
     def iter_solve_two_least_squares(self, delta, rhs1, rhs2):
         return self._two(_lib.lib().fpsb_iter_solve_two_least_squares,
@@ -272,7 +281,7 @@ class LDLtSolver(QDSolver):
     """
 
     def __init__(self, nlp, _zero=0.0, *, explicit_linear_constraints=False, ldlt_tol=SQRT_EPS,
-                 ldlt_r1=SQRT_EPS, ldlt_r2=-SQRT_EPS, P=None, device=0, **kwargs):
+                 ldlt_r1=SQRT_EPS, ldlt_r2=-SQRT_EPS, P=None, ordering="amd", device=0, **kwargs):
         ncon = _npen(nlp, explicit_linear_constraints)
         nvar = nlp.meta.nvar
         self.explicit_linear_constraints = explicit_linear_constraints
@@ -282,6 +291,13 @@ class LDLtSolver(QDSolver):
         o = LdltOpts()
         o.ldlt_tol, o.ldlt_r1, o.ldlt_r2 = ldlt_tol, ldlt_r1, ldlt_r2
         self.opts = o
+        if P is None and ordering == "dissection":
+            # B200-oriented ordering: same fill class as minimum degree on band-like structure but a
+            # dependency depth of O(log) instead of O(N) (see fpsb_order_dissection in include/fpsb.h)
+            from .symbolic import order_dissection
+            P = order_dissection(nvar, ncon, rows, cols)
+        elif ordering not in ("amd", "dissection"):
+            raise ValueError("ordering must be 'amd' or 'dissection'")
         self.handle.ldlt_analyze(P, 0, o)
         self.factorized = False
         self.last_stats = None

@@ -50,3 +50,15 @@ class SymbolicAnalysis:
                 self.h = None
         except Exception:
             pass
+
+
+def order_dissection(nvar, ncon, jrow, jcol, nparts=0, index_base=0):
+    """BFS level-set dissection ordering of K (binding of fpsb_order_dissection); returns P."""
+    jrow = np.ascontiguousarray(jrow, dtype=np.int64)
+    jcol = np.ascontiguousarray(jcol, dtype=np.int64)
+    P = np.zeros(nvar + ncon, np.int64)
+    check(_lib.lib().fpsb_order_dissection(C.c_int64(nvar), C.c_int64(ncon), C.c_int64(len(jrow)),
+                                           jrow.ctypes.data_as(C.c_void_p), jcol.ctypes.data_as(C.c_void_p),
+                                           C.c_int(index_base), C.c_int(nparts),
+                                           P.ctypes.data_as(C.c_void_p)), "fpsb_order_dissection")
+    return P

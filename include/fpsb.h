@@ -93,6 +93,11 @@ int fpsb_create(int64_t nvar, int64_t ncon, int64_t nnzj, const int64_t *jrow, c
                 int index_base, int device, fpsb_handle *out);
 int fpsb_destroy(fpsb_handle h);
 int fpsb_dims(fpsb_handle h, int64_t *nvar, int64_t *ncon, int64_t *nnzj);
+/* Optional: page-lock a caller-owned host buffer (cudaHostRegister) so that FPSB_HOST calls DMA
+ * straight from / into it instead of staging through the handle's pinned area. Meant for the
+ * solver-owned, long-lived vectors of the Julia shim (jvals, p1, q1, p2, q2). Unpin before freeing. */
+int fpsb_pin_host(void *ptr, int64_t bytes);
+int fpsb_unpin_host(void *ptr);
 /* the handle's CUDA stream (cudaStream_t) so callers can order their own work / events on it */
 void *fpsb_stream(fpsb_handle h);
 int fpsb_synchronize(fpsb_handle h);
@@ -152,6 +157,13 @@ typedef struct fpsb_symbolic_s *fpsb_symbolic;
 int fpsb_symbolic_create(int64_t nvar, int64_t ncon, int64_t nnzj, const int64_t *jrow,
                          const int64_t *jcol, int index_base, const int64_t *P, fpsb_symbolic *out);
 int fpsb_symbolic_destroy(fpsb_symbolic s);
+/* B200-oriented alternative ordering (host only): BFS level-set dissection of the KKT graph into
+ * `nparts` pieces (<= 0: automatic) with cyclic-reduction order of the separators. It trades some
+ * fill for a dependency depth of O(piece depth + log2 nparts) instead of the O(N / 64) chain that
+ * minimum degree produces on band-like structure. Pass the result as P to fpsb_ldlt_analyze /
+ * fpsb_symbolic_create (the `ldl_analyze(A, P)` form of LDLFactorizations). */
+int fpsb_order_dissection(int64_t nvar, int64_t ncon, int64_t nnzj, const int64_t *jrow,
+                          const int64_t *jcol, int index_base, int nparts, int64_t *P_out);
 int fpsb_symbolic_sizes(fpsb_symbolic s, int64_t *N, int64_t *lnz);
 int fpsb_symbolic_get(fpsb_symbolic s, int64_t *P, int64_t *parent, int64_t *Lnz, int64_t *Lp,
                       int64_t *Li);

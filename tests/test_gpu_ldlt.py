@@ -165,3 +165,43 @@ def test_qdsolver_surface_golden(oracle):
         assert abs(f.obj(x) - G["G3"]["obj"]) < 10 * tol
         assert np.allclose(f.gx, G["G3"]["gx"], atol=1e-12)
         assert np.allclose(f.ys, G["G3"]["ys"], atol=10 * tol)
+
+
+def test_ldlt_dissection_ordering_and_pinned_host(oracle):
+    """The B200-oriented ordering through the plugin surface (LDLtSolver(..., ordering="dissection"))
+    gives the same solution as the oracle run with the same P; host buffers page-locked with
+    fpsb_pin_host take the direct-DMA path and give identical results."""
+    import fpsb200
+    from fpsb200 import models
+    mdl = models.sparse_qp(40000, 20000, nnz_per_row=10, w=32, seed=9)
+    qds = fpsb200.LDLtSolver(mdl, 0.0, ordering="dissection")
+    H = qds.handle
+    info = H.ldlt_plan_info()
+    assert info["nlevels"] < 400
+    rows, cols = mdl.jac_structure()
+    vals = mdl.jac_coord(None)
+    H.set_jac_values(vals)
+    rng = np.random.default_rng(2)
+    r1 = rng.standard_normal(40000); r2 = rng.standard_normal(20000)
+    p1, q1, p2, q2, ok = H.ldlt_solve_two_mixed(1e-3, r1, r2)
+    assert ok
+    sym = H.ldlt_symbolic()
+    lo = oracle.LDLtOracle(40000, 20000, rows, cols, sym["P"])
+    op1, oq1, op2, oq2, ook = lo.solve_two_mixed(vals, 1e-3, r1, r2)
+    for a, b in ((p1, op1), (q1, oq1), (p2, op2), (q2, oq2)):
+        assert _rel(a, b) < 1e-8
+    A = mdl.A
+    e1, e2 = _residuals(A, 1e-3, r1, r2, p1, q1, p2, q2, "mixed")
+    assert e1 < 1e-10 and e2 < 1e-10
+    # pinned host buffers: same numbers through the direct-DMA path
+    bufs = [np.array(vals), np.array(r1), np.array(r2)]
+    for b in bufs:
+        H.pin_host(b)
+    H.set_jac_values(bufs[0])
+    pp1, qq1, pp2, qq2, ok = H.ldlt_solve_two_mixed(1e-3, bufs[1], bufs[2])
+    assert ok and np.array_equal(pp1, p1) and np.array_equal(qq2, q2)
+    got = H.iter_solve_two_mixed(1e-3, bufs[1], bufs[2])
+    ref = H.iter_solve_two_mixed(1e-3, r1, r2)
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[3], ref[3])
+    for b in bufs:
+        H.unpin_host(b)

@@ -9,7 +9,7 @@ import pytest
 
 import fpsb200
 from fpsb200 import _lib, models, sharding
-from fpsb200.symbolic import SymbolicAnalysis
+from fpsb200.symbolic import SymbolicAnalysis, order_dissection
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -119,3 +119,28 @@ def test_instance_sharding_gloo_world2():
     for r in res:
         assert r[2] == [[float(i)] * 3 for i in range(7)]
         assert r[3] == 11.0
+
+
+def test_dissection_ordering_cuts_dependency_depth(oracle):
+    """fpsb_order_dissection: a valid permutation whose supernodal dependency depth is far below
+    minimum degree's on band-like KKT structure, at comparable fill; the analysis stays bit-exact
+    against the oracle for this P as for any other."""
+    m, n = 30000, 60000
+    A = models.window_random_jacobian(m, n, 10, w=32, seed=5)
+    coo = A.tocoo()
+    P = order_dissection(n, m, coo.row, coo.col, nparts=32)
+    assert sorted(P.tolist()) == list(range(n + m))
+    Sd = SymbolicAnalysis(n, m, coo.row, coo.col, P)
+    Sa = SymbolicAnalysis(n, m, coo.row, coo.col)
+    d, a = Sd.plan_info(), Sa.plan_info()
+    assert d["nlevels"] * 4 < a["nlevels"]
+    assert Sd.lnz < 2.5 * Sa.lnz
+    g = Sd.get()
+    lo = oracle.LDLtOracle(n, m, coo.row, coo.col, g["P"])
+    assert lo.solve_two_mixed(coo.data, 1e-2, np.ones(n), np.ones(m))[4]
+    s = lo.symbolic()
+    for key in ("parent", "Lnz", "Lp", "Li"):
+        assert np.array_equal(g[key], s[key]), key
+    # small / disconnected graphs fall back gracefully
+    P = order_dissection(6, 2, [0, 1], [0, 3])
+    assert sorted(P.tolist()) == list(range(8))
