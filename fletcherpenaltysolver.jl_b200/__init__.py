@@ -6,11 +6,11 @@ libfpsb200.so (hand-written CUDA for sm_100a, C ABI in include/fpsb.h).
 """
 from . import _lib
 from ._lib import FPSB_DEVICE, FPSB_HOST, FpsbError, IterOpts, KrylovStats, LdltOpts
-from .qdsolver import (B200Handle, IterativeSolver, LDLtSolver, QDSolver, qdsolver_correspondence,
+from .qdsolver import (B200Handle, IterativeSolver, LDLtSolver, QDSolver, batch_solve_two, qdsolver_correspondence,
                        solve_two_extras, solve_two_least_squares, solve_two_mixed)
 from .fletcher_nlp import FletcherPenaltyNLP
 from . import models
 
 __all__ = ["B200Handle", "IterativeSolver", "LDLtSolver", "QDSolver", "qdsolver_correspondence",
            "solve_two_extras", "solve_two_least_squares", "solve_two_mixed", "FletcherPenaltyNLP",
-           "models", "FPSB_HOST", "FPSB_DEVICE", "FpsbError", "IterOpts", "KrylovStats", "LdltOpts"]
+           "models", "batch_solve_two", "FPSB_HOST", "FPSB_DEVICE", "FpsbError", "IterOpts", "KrylovStats", "LdltOpts"]

@@ -8,7 +8,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libfpsb200.so")
+SO_PATH = os.environ.get("FPSB200_LIB", os.path.join(_HERE, "libfpsb200.so"))
 
 FPSB_HOST, FPSB_DEVICE = 0, 1
 
@@ -53,7 +53,7 @@ EXPORTS = [
     "fpsb_ldlt_plan_info", "fpsb_ldlt_factorize", "fpsb_ldlt_get_factor",
     "fpsb_ldlt_solve_two_mixed", "fpsb_ldlt_solve_two_least_squares", "fpsb_ldlt_solve_two_extras",
     "fpsb_symbolic_create", "fpsb_symbolic_destroy", "fpsb_symbolic_sizes", "fpsb_symbolic_get",
-    "fpsb_symbolic_plan_info", "fpsb_order_dissection",
+    "fpsb_symbolic_plan_info", "fpsb_order_dissection", "fpsb_batch_solve_two",
 ]
 
 _lib = None

@@ -636,7 +636,12 @@ constexpr int kStepThreads = (kConsumers + 1) * 32;
 constexpr int kRingStages = 8;
 constexpr int kStageRows = 32;
 constexpr int kStageElems = kStageRows * 32;
+#ifdef FPSB_STEP_PLAIN
+constexpr int kRingBytes = 0;
+#else
 constexpr int kRingBytes = kRingStages * kStageElems * 12;
+#endif
+constexpr int kMaxSlicesPerCta = 96;     // slice metadata staged in shared memory (12.4 KB)
 static_assert(kStageRows == 32 && kStageElems == 1024 && (kRingStages & (kRingStages - 1)) == 0, "ring indexing uses shifts");
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
@@ -647,6 +652,8 @@ template <bool PAIR>
 __global__ void __launch_bounds__(kStepThreads, 2) gk_step_kernel(StepParams P, int use_state) {
     extern __shared__ __align__(128) unsigned char ring[];
     __shared__ double s_red[4 * 16];
+    __shared__ int s_off[kMaxSlicesPerCta + 1];
+    __shared__ int s_row[kMaxSlicesPerCta * 32];
     __shared__ alignas(8) uint64_t full_bar[kRingStages];
     __shared__ alignas(8) uint64_t empty_bar[kRingStages];
     __shared__ int s_last;
@@ -678,11 +685,105 @@ __global__ void __launch_bounds__(kStepThreads, 2) gk_step_kernel(StepParams P, 
         const int lane = tid & 31, wid = tid >> 5;
         const int s_begin = (int)(((int64_t)P.nslice * cta) / P.grid_sell);
         const int s_end = (int)(((int64_t)P.nslice * (cta + 1)) / P.grid_sell);
-        const int R0 = P.sl_off[s_begin] >> 5, R1 = P.sl_off[s_end] >> 5;
+        // stage this CTA's slice metadata (row offsets and the lane -> row map) in shared memory
+        for (int i = tid; i <= s_end - s_begin; i += kStepThreads) s_off[i] = P.sl_off[s_begin + i] >> 5;
+        for (int i = tid; i < (s_end - s_begin) * 32; i += kStepThreads) s_row[i] = P.rowidx[s_begin * 32 + i];
+        __syncthreads();
+        const int R0 = s_off[0], R1 = s_off[s_end - s_begin];
         const int nstage = (R1 - R0 + kStageRows - 1) / kStageRows;
+        const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
         double *ring_val = reinterpret_cast<double *>(ring);
         int *ring_col = reinterpret_cast<int *>(ring + (size_t)kRingStages * kStageElems * 8);
         bool ok = true;
+#ifdef FPSB_STEP_PLAIN
+        // A/B variant: no TMA ring — all 9 warps stream their slices with plain coalesced loads
+        // (two register batches in flight), same L2 policies, staged metadata and operand prefetch
+        {
+            (void)pol_stream; (void)ring_val; (void)ring_col; (void)nstage;
+            struct Ops { double2 old2; double so0, so1, a00, a01, a10, a11; };
+            auto load_ops = [&](int row, Ops &o) {
+                o.old2 = make_double2(0.0, 0.0);
+                o.so0 = o.so1 = o.a00 = o.a01 = o.a10 = o.a11 = 0.0;
+                if (row >= 0) {
+                    if (PAIR) o.old2 = __ldcs(P.self2 + row);
+                    else {
+                        if (C0.rdself) o.so0 = __ldcs(P.io[0].self + row);
+                        if (C1.rdself) o.so1 = __ldcs(P.io[1].self + row);
+                    }
+                    if (C0.rd0) o.a00 = __ldcs(P.io[0].a0 + row);
+                    if (C0.rd1) o.a01 = __ldcs(P.io[0].a1 + row);
+                    if (C1.rd0) o.a10 = __ldcs(P.io[1].a0 + row);
+                    if (C1.rd1) o.a11 = __ldcs(P.io[1].a1 + row);
+                }
+            };
+            constexpr int NW = kConsumers + 1;
+            const int ns = s_end - s_begin;
+            Ops nxt;
+            if (wid < ns) load_ops(s_row[wid * 32 + lane], nxt);
+            for (int ls = wid; ls < ns; ls += NW) {
+                const int width = s_off[ls + 1] - s_off[ls];
+                const int row = s_row[ls * 32 + lane];
+                Ops o = nxt;
+                if (ls + NW < ns) load_ops(s_row[(ls + NW) * 32 + lane], nxt);
+                const double *vp = P.sval + (size_t)s_off[ls] * 32 + lane;
+                const int *cp = P.scol + (size_t)s_off[ls] * 32 + lane;
+                double s0 = 0.0, s1 = 0.0;
+                const int nb = (width + kUnroll - 1) / kUnroll;
+                double vA[kUnroll], vB[kUnroll];
+                int cA[kUnroll], cB[kUnroll];
+                auto load_batch = [&](int bidx, double (&v)[kUnroll], int (&c)[kUnroll]) {
+#pragma unroll
+                    for (int u = 0; u < kUnroll; ++u) {
+                        const int j = bidx * kUnroll + u;
+                        const bool in = j < width;
+                        v[u] = in ? __ldcs(vp + (size_t)j * 32) : 0.0;
+                        c[u] = in ? __ldcs(cp + (size_t)j * 32) : -1;
+                    }
+                };
+                auto consume = [&](const double (&v)[kUnroll], const int (&c)[kUnroll]) {
+                    if (PAIR) {
+                        double2 x[kUnroll];
+#pragma unroll
+                        for (int u = 0; u < kUnroll; ++u)
+                            x[u] = (c[u] >= 0) ? ldg_evict_last(P.gin2 + c[u], pol_keep) : make_double2(0.0, 0.0);
+#pragma unroll
+                        for (int u = 0; u < kUnroll; ++u) { s0 = fma(v[u], x[u].x, s0); s1 = fma(v[u], x[u].y, s1); }
+                    } else {
+                        double x0[kUnroll], x1[kUnroll];
+#pragma unroll
+                        for (int u = 0; u < kUnroll; ++u) {
+                            x0[u] = (act0 && c[u] >= 0) ? ldg_evict_last(P.io[0].gin + c[u], pol_keep) : 0.0;
+                            x1[u] = (act1 && c[u] >= 0) ? ldg_evict_last(P.io[1].gin + c[u], pol_keep) : 0.0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < kUnroll; ++u) { s0 = fma(v[u], x0[u], s0); s1 = fma(v[u], x1[u], s1); }
+                    }
+                };
+                load_batch(0, vA, cA);
+                load_batch(1, vB, cB);
+                for (int bb = 0; bb < nb; bb += 2) {
+                    consume(vA, cA);
+                    load_batch(bb + 2, vA, cA);
+                    if (bb + 1 < nb) { consume(vB, cB); load_batch(bb + 3, vB, cB); }
+                }
+                if (row >= 0) {
+                    if (PAIR) {
+                        double2 nw = o.old2;
+                        if (act0) nw.x = row_epilogue(C0, s0, o.old2.x, o.a00, o.a01, acc[0], acc[1]);
+                        if (act1) nw.y = row_epilogue(C1, s1, o.old2.y, o.a10, o.a11, acc[2], acc[3]);
+                        stg_evict_last(P.self2 + row, nw, pol_keep);
+                    } else {
+                        if (act0) __stcs(P.io[0].self + row, row_epilogue(C0, s0, o.so0, o.a00, o.a01, acc[0], acc[1]));
+                        if (act1) __stcs(P.io[1].self + row, row_epilogue(C1, s1, o.so1, o.a10, o.a11, acc[2], acc[3]));
+                    }
+                    if (C0.wr0) __stcs(P.io[0].a0 + row, o.a00);
+                    if (C0.wr1) __stcs(P.io[0].a1 + row, o.a01);
+                    if (C1.wr0) __stcs(P.io[1].a0 + row, o.a10);
+                    if (C1.wr1) __stcs(P.io[1].a1 + row, o.a11);
+                }
+            }
+        }
+#else
         if (wid == kConsumers) {
             // ---------------- producer ----------------
             if (lane == 0) {
@@ -693,8 +794,8 @@ __global__ void __launch_bounds__(kStepThreads, 2) gk_step_kernel(StepParams P, 
                     const int rows = min(kStageRows, R1 - R0 - k * kStageRows);
                     const size_t e = ((size_t)R0 + (size_t)k * kStageRows) * 32;
                     mbar_expect_tx(&full_bar[slot], (uint32_t)rows * 32u * 12u);
-                    tma_bulk_g2s(ring_val + (size_t)slot * kStageElems, P.sval + e, (uint32_t)rows * 256u, &full_bar[slot]);
-                    tma_bulk_g2s(ring_col + (size_t)slot * kStageElems, P.scol + e, (uint32_t)rows * 128u, &full_bar[slot]);
+                    tma_bulk_g2s_hint(ring_val + (size_t)slot * kStageElems, P.sval + e, (uint32_t)rows * 256u, &full_bar[slot], pol_stream);
+                    tma_bulk_g2s_hint(ring_col + (size_t)slot * kStageElems, P.scol + e, (uint32_t)rows * 128u, &full_bar[slot], pol_stream);
                 }
             }
         } else {
@@ -707,23 +808,32 @@ __global__ void __launch_bounds__(kStepThreads, 2) gk_step_kernel(StepParams P, 
                     ok = mbar_wait(&full_bar[kcur % kRingStages], (uint32_t)((kcur / kRingStages) & 1));
                 }
             };
-            for (int sl = s_begin + wid; sl < s_end && ok; sl += kConsumers) {
-                const int ra = (P.sl_off[sl] >> 5) - R0, rb = (P.sl_off[sl + 1] >> 5) - R0;
-                const int row = P.rowidx[sl * 32 + lane];
-                // row-epilogue operands first: their DRAM latency hides behind the slice
-                double2 old2 = make_double2(0.0, 0.0);
-                double so0 = 0.0, so1 = 0.0, a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+            // row-epilogue operands of a slice (registers); loaded one slice ahead so that neither
+            // the row map nor these DRAM reads sit on the slice's critical path
+            struct Ops { double2 old2; double so0, so1, a00, a01, a10, a11; };
+            auto load_ops = [&](int row, Ops &o) {
+                o.old2 = make_double2(0.0, 0.0);
+                o.so0 = o.so1 = o.a00 = o.a01 = o.a10 = o.a11 = 0.0;
                 if (row >= 0) {
-                    if (PAIR) old2 = __ldcs(P.self2 + row);
+                    if (PAIR) o.old2 = __ldcs(P.self2 + row);
                     else {
-                        if (C0.rdself) so0 = __ldcs(P.io[0].self + row);
-                        if (C1.rdself) so1 = __ldcs(P.io[1].self + row);
+                        if (C0.rdself) o.so0 = __ldcs(P.io[0].self + row);
+                        if (C1.rdself) o.so1 = __ldcs(P.io[1].self + row);
                     }
-                    if (C0.rd0) a00 = __ldcs(P.io[0].a0 + row);
-                    if (C0.rd1) a01 = __ldcs(P.io[0].a1 + row);
-                    if (C1.rd0) a10 = __ldcs(P.io[1].a0 + row);
-                    if (C1.rd1) a11 = __ldcs(P.io[1].a1 + row);
+                    if (C0.rd0) o.a00 = __ldcs(P.io[0].a0 + row);
+                    if (C0.rd1) o.a01 = __ldcs(P.io[0].a1 + row);
+                    if (C1.rd0) o.a10 = __ldcs(P.io[1].a0 + row);
+                    if (C1.rd1) o.a11 = __ldcs(P.io[1].a1 + row);
                 }
+            };
+            const int ns = s_end - s_begin;
+            Ops nxt;
+            if (wid < ns) load_ops(s_row[wid * 32 + lane], nxt);
+            for (int ls = wid; ls < ns && ok; ls += kConsumers) {
+                const int ra = s_off[ls] - R0, rb = s_off[ls + 1] - R0;
+                const int row = s_row[ls * 32 + lane];
+                Ops o = nxt;
+                if (ls + kConsumers < ns) load_ops(s_row[(ls + kConsumers) * 32 + lane], nxt);
                 double s0 = 0.0, s1 = 0.0;
                 // the slice's rows, one ring stage at a time (a 20-row slice touches 1-2 stages)
                 int r = ra;
@@ -748,15 +858,15 @@ __global__ void __launch_bounds__(kStepThreads, 2) gk_step_kernel(StepParams P, 
                             double2 x[kUnroll];
 #pragma unroll
                             for (int u = 0; u < kUnroll; ++u)
-                                x[u] = (c[u] >= 0) ? __ldg(P.gin2 + c[u]) : make_double2(0.0, 0.0);
+                                x[u] = (c[u] >= 0) ? ldg_evict_last(P.gin2 + c[u], pol_keep) : make_double2(0.0, 0.0);
 #pragma unroll
                             for (int u = 0; u < kUnroll; ++u) { s0 = fma(v[u], x[u].x, s0); s1 = fma(v[u], x[u].y, s1); }
                         } else {
                             double x0[kUnroll], x1[kUnroll];
 #pragma unroll
                             for (int u = 0; u < kUnroll; ++u) {
-                                x0[u] = (act0 && c[u] >= 0) ? __ldg(P.io[0].gin + c[u]) : 0.0;
-                                x1[u] = (act1 && c[u] >= 0) ? __ldg(P.io[1].gin + c[u]) : 0.0;
+                                x0[u] = (act0 && c[u] >= 0) ? ldg_evict_last(P.io[0].gin + c[u], pol_keep) : 0.0;
+                                x1[u] = (act1 && c[u] >= 0) ? ldg_evict_last(P.io[1].gin + c[u], pol_keep) : 0.0;
                             }
 #pragma unroll
                             for (int u = 0; u < kUnroll; ++u) { s0 = fma(v[u], x0[u], s0); s1 = fma(v[u], x1[u], s1); }
@@ -766,24 +876,25 @@ __global__ void __launch_bounds__(kStepThreads, 2) gk_step_kernel(StepParams P, 
                 }
                 if (row >= 0 && ok) {
                     if (PAIR) {
-                        double2 nw = old2;
-                        if (act0) nw.x = row_epilogue(C0, s0, old2.x, a00, a01, acc[0], acc[1]);
-                        if (act1) nw.y = row_epilogue(C1, s1, old2.y, a10, a11, acc[2], acc[3]);
-                        __stcs(P.self2 + row, nw);
+                        double2 nw = o.old2;
+                        if (act0) nw.x = row_epilogue(C0, s0, o.old2.x, o.a00, o.a01, acc[0], acc[1]);
+                        if (act1) nw.y = row_epilogue(C1, s1, o.old2.y, o.a10, o.a11, acc[2], acc[3]);
+                        stg_evict_last(P.self2 + row, nw, pol_keep);      // gathered by the next launch
                     } else {
-                        if (act0) __stcs(P.io[0].self + row, row_epilogue(C0, s0, so0, a00, a01, acc[0], acc[1]));
-                        if (act1) __stcs(P.io[1].self + row, row_epilogue(C1, s1, so1, a10, a11, acc[2], acc[3]));
+                        if (act0) __stcs(P.io[0].self + row, row_epilogue(C0, s0, o.so0, o.a00, o.a01, acc[0], acc[1]));
+                        if (act1) __stcs(P.io[1].self + row, row_epilogue(C1, s1, o.so1, o.a10, o.a11, acc[2], acc[3]));
                     }
-                    if (C0.wr0) __stcs(P.io[0].a0 + row, a00);
-                    if (C0.wr1) __stcs(P.io[0].a1 + row, a01);
-                    if (C1.wr0) __stcs(P.io[1].a0 + row, a10);
-                    if (C1.wr1) __stcs(P.io[1].a1 + row, a11);
+                    if (C0.wr0) __stcs(P.io[0].a0 + row, o.a00);
+                    if (C0.wr1) __stcs(P.io[0].a1 + row, o.a01);
+                    if (C1.wr0) __stcs(P.io[1].a0 + row, o.a10);
+                    if (C1.wr1) __stcs(P.io[1].a1 + row, o.a11);
                 }
             }
             // walk (and release) the remaining stages so the producer can finish
             advance_to(nstage - 1);
             if (kcur >= 0 && ok) { __syncwarp(); if (lane == 0) mbar_arrive(&empty_bar[kcur % kRingStages]); }
         }
+#endif
         if (!ok && lane == 0) atomicExch(P.done_flag, -1);
     } else {
         // one long row per CTA: strided over the whole block, fixed-tree block reduction
@@ -1008,7 +1119,10 @@ __global__ void gather_vals_kernel(int nnz, const int *perm, const double *coo, 
 // host side
 // ------------------------------------------------------------------------------------------------
 struct IterWs {
-    DevBuf<double2> Gn, Gm;              // interleaved Golub-Kahan pairs (n-space, m-space)
+    DevBuf<double2> Gnm;                 // one allocation: [Gn | Gm] so a single L2 persisting window covers both
+    struct View { double2 *p = nullptr; size_t n = 0;
+                  void zero(cudaStream_t s) { if (p) FPSB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(double2), s)); } };
+    View Gn, Gm;                         // interleaved Golub-Kahan pairs (n-space, m-space)
     DevBuf<double> an[2][2];             // n-space aux per slot (CRAIG x, w2 ; CGLS r, q ; MINRES t)
     DevBuf<double> am[2][5];             // m-space aux per slot
     DevBuf<double> ym;                   // MINRES y / CGLS s
@@ -1113,6 +1227,13 @@ static void upload_sell(Handle *h, CsrDev &M, int nrows, int ncols, const std::v
     M.long_val.alloc(long_col.size() + 8);
     M.long_val.zero(h->stream);
     M.grid_sell = nslice > 0 ? std::max(1, std::min((nslice + 7) / 8, 2 * h->num_sms)) : 0;
+    {
+        // slice metadata of a CTA must fit its shared-memory staging area; keep whole waves of
+        // resident CTAs (2 per SM) so there is no ragged tail wave
+        const int resident = 2 * h->num_sms;
+        const int need = (nslice + kMaxSlicesPerCta - 1) / kMaxSlicesPerCta;
+        if (need > M.grid_sell) M.grid_sell = ((need + resident - 1) / resident) * resident;
+    }
     M.grid = M.grid_sell + M.nlong;
     {
         // contiguous chunks of slices per warp, balanced by streamed rows (+1 per slice for the
@@ -1199,7 +1320,31 @@ void iter_setup(Handle *h) {
     IterWs *W = new IterWs();
     h->iter = W;
     const size_t n = (size_t)h->nvar, m = (size_t)h->ncon;
-    W->Gn.alloc(n + 4); W->Gm.alloc(m + 4);
+    {
+        const size_t gn = (n + 4 + 7) & ~(size_t)7, gm = (m + 4 + 7) & ~(size_t)7;
+        W->Gnm.alloc(gn + gm);
+        W->Gn.p = W->Gnm.p; W->Gn.n = gn;
+        W->Gm.p = W->Gnm.p + gn; W->Gm.n = gm;
+        // keep the gathered vectors resident in L2 across the 240 MB matrix stream of every iteration
+        int dev = 0, maxp = 0, maxw = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        cudaDeviceGetAttribute(&maxw, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        const size_t bytes = (gn + gm) * sizeof(double2);
+        if (maxp > 0 && maxw > 0) {
+            const size_t want = std::min(bytes, (size_t)maxp);
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+            cudaStreamAttrValue attr;
+            memset(&attr, 0, sizeof(attr));
+            attr.accessPolicyWindow.base_ptr = (void *)W->Gnm.p;
+            attr.accessPolicyWindow.num_bytes = std::min(bytes, (size_t)maxw);
+            attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)std::max<size_t>(bytes, 1));
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            if (cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+        }
+        cudaGetLastError();
+    }
     for (int s = 0; s < 2; ++s) {
         for (int k = 0; k < 2; ++k) W->an[s][k].alloc(n + 4);
         for (int k = 0; k < 5; ++k) W->am[s][k].alloc(m + 4);

@@ -385,3 +385,24 @@ def solve_two_extras(fpnlp, x, rhs1, rhs2):
         qds.last_stats = st
         return u1, u2
     raise TypeError(f"solve_two_extras: no method for {type(qds).__name__}")
+
+
+def batch_solve_two(A, delta, rhs1, rhs2, kind="mixed", opts=None, device=0):
+    """Throughput mode (BASELINE config C5): `ninst` independent small instances sharing
+    (nvar, ncon).  A: (ninst, ncon, nvar); rhs1: (ninst, nvar); rhs2: (ninst, ncon) for
+    kind="mixed" or (ninst, nvar) for kind="least_squares".  numpy in -> numpy out.
+    Returns p1, q1, p2, q2, factorized (bool array)."""
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    ninst, m, n = A.shape
+    rhs1 = np.ascontiguousarray(rhs1, dtype=np.float64)
+    rhs2 = np.ascontiguousarray(rhs2, dtype=np.float64)
+    k = 0 if kind == "mixed" else 1
+    assert rhs1.shape == (ninst, n) and rhs2.shape == (ninst, m if k == 0 else n)
+    p1 = np.empty((ninst, n)); q1 = np.empty((ninst, m)); p2 = np.empty((ninst, n)); q2 = np.empty((ninst, m))
+    fac = np.zeros(ninst, dtype=np.int32)
+    check(_lib.lib().fpsb_batch_solve_two(C.c_int64(ninst), C.c_int(n), C.c_int(m), C.c_int(k), _ptr(A),
+                                          C.c_double(delta), _ptr(rhs1), _ptr(rhs2), _ptr(p1), _ptr(q1),
+                                          _ptr(p2), _ptr(q2), _ptr(fac),
+                                          C.byref(opts) if opts is not None else None, C.c_int(FPSB_HOST),
+                                          C.c_int(device)), "fpsb_batch_solve_two")
+    return p1, q1, p2, q2, fac.astype(bool)

@@ -212,6 +212,18 @@ int fpsb_ldlt_solve_two_least_squares(fpsb_handle h, const double *rhs1, const d
 int fpsb_ldlt_solve_two_extras(fpsb_handle h, double delta, const double *rhs1, const double *rhs2,
                                double *u1, double *u2, int loc, fpsb_krylov_stats stats[2]);
 
+/* ---------------------------------------------------------------------------------------------
+ * Throughput mode — many independent SMALL instances (BASELINE config C5): the LDLt path of
+ * solve_two_mixed (kind 0, src/solve_linear_system.jl:206-252) or solve_two_least_squares (kind 1,
+ * :161-204) for `ninst` instances that share (nvar, ncon), nvar + ncon <= 32, natural ordering.
+ * A: [ninst][ncon][nvar] dense row-major Jacobians; rhs / outputs instance-major; factorized[i]
+ * mirrors LDLFactorizations.factorized (outputs hold the right-hand sides when it is 0).
+ * Multi-GPU: shard the instances across ranks (one call per rank, `device` = local GPU); no
+ * communication is involved. */
+int fpsb_batch_solve_two(int64_t ninst, int nvar, int ncon, int kind, const double *A, double delta,
+                         const double *rhs1, const double *rhs2, double *p1, double *q1, double *p2,
+                         double *q2, int *factorized, const fpsb_ldlt_opts *opts, int loc, int device);
+
 #ifdef __cplusplus
 }
 #endif
