@@ -15,7 +15,9 @@ EXTRA=""
 for f in "$HERE"/fpsb_symbolic.cpp "$HERE"/fpsb_batch.cu; do
   if [ -f "$f" ]; then
     o="$HERE/build/$(basename "${f%.*}").o"
-    "$NVCC" $COMMON -c "$f" -o "$o"
+    # the batch kernel mirrors the reference's scalar LDL' operation by operation: no FMA contraction
+    FM=""; case "$f" in *fpsb_batch.cu) FM="-fmad=false";; esac
+    "$NVCC" $COMMON $FM -c "$f" -o "$o"
     EXTRA="$EXTRA $o"
   fi
 done

@@ -30,6 +30,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // bounded wait: a mis-programmed transaction count must not hang the GPU box
 __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity) {
     for (int it = 0; it < (1 << 22); ++it)

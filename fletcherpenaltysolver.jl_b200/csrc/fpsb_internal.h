@@ -50,20 +50,21 @@ struct DevBuf {
 // ------------------------------------------------------------------------------------------------
 constexpr int kBlock = 256;       // threads per CTA (8 warps, one SELL slice per warp at a time)
 
-// Operator stored as SELL-32-sigma (+ CSR of the few long rows)
+// Operator stored as tiled SELL-32 (+ CSR of the few long rows)
 struct CsrDev {
     int nrows = 0, ncols = 0;
     int64_t nnz = 0;
     int nslice = 0;
     int64_t padded = 0;           // stored entries including padding
     int nlong = 0;
-    DevBuf<int> sl_off, rowidx, scol, sperm;   // sperm: slot -> COO index (-1 = padding)
-    DevBuf<int> wchunk;                        // first slice of every warp's contiguous chunk
+    DevBuf<int> rowloc, scol, sperm;           // sperm: slot -> COO index (-1 = padding)
+    DevBuf<unsigned char> tiles;               // TileMeta[ntiles] (fpsb_krylov.cu)
+    DevBuf<unsigned char> rowflag;             // 1 = long row
+    int ntiles = 0, win_cap = 0, val_cap = 0, stage_bytes = 0, nstage = 0;
     DevBuf<double> sval;
     DevBuf<int> long_row, long_rp, long_col, long_perm;
     DevBuf<double> long_val;
-    int grid_sell = 0;            // persistent CTAs over the slices
-    int grid = 0;                 // grid_sell + nlong
+    int grid = 0;                 // persistent CTAs of the tile kernel (long rows: nlong extra CTAs of their own kernel)
 };
 
 // ------------------------------------------------------------------------------------------------

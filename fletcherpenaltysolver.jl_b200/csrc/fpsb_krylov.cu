@@ -62,15 +62,20 @@ struct SlotIO {
     double c0, c1;
 };
 
+struct TileMeta;
+
 struct StepParams {
-    // SELL-32-sigma operator
-    const int *wchunk;     // grid_sell * 8 + 1 : first slice of every warp's contiguous chunk
-    const int *sl_off;     // nslice + 1 : element offsets (multiples of 32)
-    const int *rowidx;     // nslice * 32 : original row of each lane, -1 for padding lanes
-    const int *scol;
+    // tiled SELL-32 operator (see the kernel comment)
+    const TileMeta *tiles;
+    int ntiles;
+    int win_cap;           // capacity of the shared-memory gather window (16-byte entries)
+    int val_cap;           // capacity of a ring stage (entries)
+    int stage_bytes, nstage;   // ring geometry
+    int nlong;
+    const int *rowloc;     // nslice * 32 : row of each lane relative to its tile, -1 for padding lanes
+    const int *scol;       // window-relative columns (windowed tiles) or global columns
     const double *sval;
-    int nslice;
-    int grid_sell;         // CTAs working on slices; CTAs beyond handle one long row each
+    const unsigned char *rowflag;   // nrows : 1 for long rows (nullptr when there are none)
     // long rows (CSR)
     const int *long_row;
     const int *long_rp;
@@ -616,332 +621,295 @@ __device__ __forceinline__ double row_epilogue(const Coef &C, double sraw, doubl
 }
 
 // ------------------------------------------------------------------------------------------------
-// the fused SpMM step kernel — SELL-32-sigma streamed through a TMA ring.
+// the fused SpMM step kernel — tiled SELL-32 streamed through a TMA ring by persistent CTAs.
 //
-// Layout: a slice is 32 rows, stored column-major (32 consecutive entries per slice column), lane ==
-// row.  A CTA owns a contiguous range of slices, i.e. one contiguous stream of 32-entry "stream
-// rows" of sval / scol.  Warp 8 is the producer: one lane moves the stream into an 8-stage ring in
-// shared memory with cp.async.bulk (TMA), 32 stream rows (8 KB of values + 4 KB of indices) per
-// stage, signalled by mbarriers — 96 KB of loads in flight per CTA, none of it held in registers.
-// Warps 0-7 are consumers: they take the CTA's slices round-robin (adjacent slices => the 8 gather
-// windows overlap in L1), read values / indices conflict-free from the ring, keep only the
-// x-gathers in flight, accumulate the two row sums in registers and run the Krylov row epilogue in
-// the same lane (operands prefetched at slice start).  Every consumer walks every stage (waits
-// full, arrives empty), so a stage is recycled exactly when all 8 warps are past it.
-// Rows longer than kLongRow are handled by extra CTAs (one per row, block reduction).
+// Layout: the rows of the operator are cut into tiles of up to kTileRows consecutive rows (fewer
+// when the rows are long, so that a tile always fits a ring stage); inside a tile the rows are
+// sorted by length and packed into slices of 32 (lane == row).  A slice stores its entries as
+// "pair rows": entries 2p and 2p+1 of the 32 lanes are interleaved, so one 16-byte access brings
+// two values and one 8-byte access two column indices per lane (an odd last entry is stored as a
+// plain 32-entry row).  All values of a tile are contiguous in HBM, and so are its indices.
+//
+// One persistent CTA per SM walks the tiles b, b + grid, b + 2 grid, ... :
+//   producer  (warp 0, one lane) keeps the ring full: per tile four TMA bulk copies (cp.async.bulk +
+//             mbarrier) bring the tile's values, its column indices, its lane -> row map and the
+//             slice of the gathered vector(s) the tile can touch — columns [cmin, cmin + ccnt) —
+//             into one ring stage.  Every byte the SM needs from HBM is requested as large
+//             contiguous reads several tiles ahead of its use, none of it held in registers.
+//   consumers kGroups groups of 4 warps; group g takes the CTA's tiles g, g + kGroups, ...
+//     phase 1  one warp per slice: values / indices are read conflict-free from the stage, the
+//              gathers cost shared-memory bank cycles instead of one L1 wavefront per distinct
+//              128-byte line; the two row sums of every row go to a small per-group buffer indexed
+//              by the row's position in the tile, and the stage is handed back to the producer.
+//     phase 2  the Krylov row epilogue runs over the tile's rows in natural order (one thread per
+//              row), so every vector it reads and writes is accessed fully coalesced even though
+//              SELL permuted the rows; its operands were requested before phase 1.
+//   Groups are in different phases at any time, so the shared-memory pipe, the HBM stream and the
+//   epilogue traffic overlap inside one SM.
+// Tiles whose column span exceeds the window capacity gather from global memory instead.
+// Rows longer than kLongRow are handled by a small separate kernel (one CTA per row) launched
+// before this one; its per-row norm partials join the fixed-order reduction below.
+// Norms: per-thread partial sums over the CTA's tiles (fixed order) -> fixed-tree CTA sum -> the
+// grid's last CTA adds the per-CTA partials in index order and runs the scalar recurrences.  The
+// result does not depend on the order in which CTAs finish.
 // ------------------------------------------------------------------------------------------------
-constexpr int kUnroll = 4;
-constexpr int kConsumers = 8;
-constexpr int kStepThreads = (kConsumers + 1) * 32;
-constexpr int kRingStages = 8;
-constexpr int kStageRows = 32;
-constexpr int kStageElems = kStageRows * 32;
-#ifdef FPSB_STEP_PLAIN
-constexpr int kRingBytes = 0;
-#else
-constexpr int kRingBytes = kRingStages * kStageElems * 12;
-#endif
-constexpr int kMaxSlicesPerCta = 96;     // slice metadata staged in shared memory (12.4 KB)
-static_assert(kStageRows == 32 && kStageElems == 1024 && (kRingStages & (kRingStages - 1)) == 0, "ring indexing uses shifts");
+constexpr int kTileRows = 128;
+constexpr int kTileSlices = kTileRows / 32;
+constexpr int kGroups = 3;
+constexpr int kGroupThreads = kTileRows;                       // one thread per tile row in phase 2
+constexpr int kStepThreads = 32 + kGroups * kGroupThreads;     // producer warp + consumer groups
+constexpr int kStageBytesMax = 40 * 1024;                      // values + indices + row map + window
+constexpr int kMaxStages = 8;
+constexpr int kRingBudget = 200 * 1024;
+constexpr int kWinCapMax = 1536;          // window capacity (entries of 16 bytes) a tile may ask for
+constexpr int kLongThreads = 256;
 
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+struct __align__(16) TileMeta {
+    int rmap;            // first entry of the tile's lane -> row map (rowloc[rmap .. rmap + ns * 32))
+    int ns;              // slices in the tile, ns <= kTileSlices (one warp each)
+    int cmin, ccnt;      // gather window (ccnt == 0: gather from global memory, scol holds global columns)
+    int row0, nrows;     // rows [row0, row0 + nrows) of the operator
+    int eoff, elems;     // the tile's entries: sval / scol [eoff, eoff + elems)
+    int width[kTileSlices];   // entries per row of each slice
+};
+static_assert(sizeof(TileMeta) == 48, "TileMeta is loaded as three int4");
+
+__device__ __forceinline__ TileMeta load_tile(const TileMeta *tiles, int t) {
+    const int4 *tp = reinterpret_cast<const int4 *>(tiles + t);
+    const int4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+    TileMeta T;
+    T.rmap = a.x; T.ns = a.y; T.cmin = a.z; T.ccnt = a.w;
+    T.row0 = b.x; T.nrows = b.y; T.eoff = b.z; T.elems = b.w;
+    T.width[0] = c.x; T.width[1] = c.y; T.width[2] = c.z; T.width[3] = c.w;
+    return T;
+}
+
+__device__ __forceinline__ void group_bar(int g) {
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(kGroupThreads) : "memory");
 }
 
 template <bool PAIR>
-__global__ void __launch_bounds__(kStepThreads, 2) gk_step_kernel(StepParams P, int use_state) {
-    extern __shared__ __align__(128) unsigned char ring[];
+__global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, int use_state) {
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    __shared__ double2 s_sum[kGroups][2][kTileRows];
     __shared__ double s_red[4 * 16];
-    __shared__ int s_off[kMaxSlicesPerCta + 1];
-    __shared__ int s_row[kMaxSlicesPerCta * 32];
-    __shared__ alignas(8) uint64_t full_bar[kRingStages];
-    __shared__ alignas(8) uint64_t empty_bar[kRingStages];
+    __shared__ alignas(8) uint64_t full_bar[kMaxStages];
+    __shared__ alignas(8) uint64_t empty_bar[kMaxStages];
+    __shared__ SlotState sS[2];
+    __shared__ Coef sC[2];
     __shared__ int s_last;
 
     const int tid = threadIdx.x;
-    const bool act0 = P.io[0].mode != MD_NONE && (!use_state || P.st[0].active);
-    const bool act1 = P.io[1].mode != MD_NONE && (!use_state || P.st[1].active);
-    if (!act0 && !act1) return;
-
-    // per-slot coefficients live in shared memory (broadcast reads) to keep registers for the
-    // loads in flight
-    __shared__ Coef sC[2];
+    const int cta = blockIdx.x, nstage = P.nstage;
+    // ---- prologue: one round trip brings both slot states into shared memory ----
+    if (use_state) {
+        const double *g = reinterpret_cast<const double *>(P.st);
+        double *d = reinterpret_cast<double *>(sS);
+        for (int i = tid; i < (int)(2 * sizeof(SlotState) / sizeof(double)); i += kStepThreads) d[i] = __ldcg(g + i);
+    }
     if (tid == 0) {
-        load_coef(sC[0], P.io[0], &P.st[0], use_state);
-        load_coef(sC[1], P.io[1], &P.st[1], use_state);
+        for (int s = 0; s < nstage; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kTileSlices); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const bool act0 = P.io[0].mode != MD_NONE && (!use_state || sS[0].active);
+    const bool act1 = P.io[1].mode != MD_NONE && (!use_state || sS[1].active);
+    if (!act0 && !act1) return;
+    if (tid == 0) {
+        load_coef(sC[0], P.io[0], &sS[0], use_state);
+        load_coef(sC[1], P.io[1], &sS[1], use_state);
         if (!act0) { sC[0].mode = MD_NONE; sC[0].rd0 = sC[0].rd1 = sC[0].wr0 = sC[0].wr1 = sC[0].rdself = 0; }
         if (!act1) { sC[1].mode = MD_NONE; sC[1].rd0 = sC[1].rd1 = sC[1].wr0 = sC[1].wr1 = sC[1].rdself = 0; }
-        for (int s = 0; s < kRingStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kConsumers); }
-        mbar_fence_init();
     }
     __syncthreads();
     const Coef &C0 = sC[0];
     const Coef &C1 = sC[1];
-
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    const int cta = blockIdx.x;
+    // stage layout: [values val_cap*8 | indices val_cap*4 | row map kTileRows*4 | window win_cap*16]
+    const size_t stage_bytes = (size_t)P.stage_bytes;
+    // vectors of doubles need 16-byte aligned sources for the TMA path (the pairs always are)
+    const bool win_tma = PAIR || ((((uintptr_t)P.io[0].gin | (uintptr_t)P.io[1].gin) & 15) == 0);
+    bool ok = true;
 
-    if (cta < P.grid_sell) {
-        const int lane = tid & 31, wid = tid >> 5;
-        const int s_begin = (int)(((int64_t)P.nslice * cta) / P.grid_sell);
-        const int s_end = (int)(((int64_t)P.nslice * (cta + 1)) / P.grid_sell);
-        // stage this CTA's slice metadata (row offsets and the lane -> row map) in shared memory
-        for (int i = tid; i <= s_end - s_begin; i += kStepThreads) s_off[i] = P.sl_off[s_begin + i] >> 5;
-        for (int i = tid; i < (s_end - s_begin) * 32; i += kStepThreads) s_row[i] = P.rowidx[s_begin * 32 + i];
-        __syncthreads();
-        const int R0 = s_off[0], R1 = s_off[s_end - s_begin];
-        const int nstage = (R1 - R0 + kStageRows - 1) / kStageRows;
-        const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
-        double *ring_val = reinterpret_cast<double *>(ring);
-        int *ring_col = reinterpret_cast<int *>(ring + (size_t)kRingStages * kStageElems * 8);
-        bool ok = true;
-#ifdef FPSB_STEP_PLAIN
-        // A/B variant: no TMA ring — all 9 warps stream their slices with plain coalesced loads
-        // (two register batches in flight), same L2 policies, staged metadata and operand prefetch
-        {
-            (void)pol_stream; (void)ring_val; (void)ring_col; (void)nstage;
-            struct Ops { double2 old2; double so0, so1, a00, a01, a10, a11; };
-            auto load_ops = [&](int row, Ops &o) {
-                o.old2 = make_double2(0.0, 0.0);
-                o.so0 = o.so1 = o.a00 = o.a01 = o.a10 = o.a11 = 0.0;
-                if (row >= 0) {
-                    if (PAIR) o.old2 = __ldcs(P.self2 + row);
-                    else {
-                        if (C0.rdself) o.so0 = __ldcs(P.io[0].self + row);
-                        if (C1.rdself) o.so1 = __ldcs(P.io[1].self + row);
-                    }
-                    if (C0.rd0) o.a00 = __ldcs(P.io[0].a0 + row);
-                    if (C0.rd1) o.a01 = __ldcs(P.io[0].a1 + row);
-                    if (C1.rd0) o.a10 = __ldcs(P.io[1].a0 + row);
-                    if (C1.rd1) o.a11 = __ldcs(P.io[1].a1 + row);
-                }
-            };
-            constexpr int NW = kConsumers + 1;
-            const int ns = s_end - s_begin;
-            Ops nxt;
-            if (wid < ns) load_ops(s_row[wid * 32 + lane], nxt);
-            for (int ls = wid; ls < ns; ls += NW) {
-                const int width = s_off[ls + 1] - s_off[ls];
-                const int row = s_row[ls * 32 + lane];
-                Ops o = nxt;
-                if (ls + NW < ns) load_ops(s_row[(ls + NW) * 32 + lane], nxt);
-                const double *vp = P.sval + (size_t)s_off[ls] * 32 + lane;
-                const int *cp = P.scol + (size_t)s_off[ls] * 32 + lane;
-                double s0 = 0.0, s1 = 0.0;
-                const int nb = (width + kUnroll - 1) / kUnroll;
-                double vA[kUnroll], vB[kUnroll];
-                int cA[kUnroll], cB[kUnroll];
-                auto load_batch = [&](int bidx, double (&v)[kUnroll], int (&c)[kUnroll]) {
-#pragma unroll
-                    for (int u = 0; u < kUnroll; ++u) {
-                        const int j = bidx * kUnroll + u;
-                        const bool in = j < width;
-                        v[u] = in ? __ldcs(vp + (size_t)j * 32) : 0.0;
-                        c[u] = in ? __ldcs(cp + (size_t)j * 32) : -1;
-                    }
-                };
-                auto consume = [&](const double (&v)[kUnroll], const int (&c)[kUnroll]) {
-                    if (PAIR) {
-                        double2 x[kUnroll];
-#pragma unroll
-                        for (int u = 0; u < kUnroll; ++u)
-                            x[u] = (c[u] >= 0) ? ldg_evict_last(P.gin2 + c[u], pol_keep) : make_double2(0.0, 0.0);
-#pragma unroll
-                        for (int u = 0; u < kUnroll; ++u) { s0 = fma(v[u], x[u].x, s0); s1 = fma(v[u], x[u].y, s1); }
-                    } else {
-                        double x0[kUnroll], x1[kUnroll];
-#pragma unroll
-                        for (int u = 0; u < kUnroll; ++u) {
-                            x0[u] = (act0 && c[u] >= 0) ? ldg_evict_last(P.io[0].gin + c[u], pol_keep) : 0.0;
-                            x1[u] = (act1 && c[u] >= 0) ? ldg_evict_last(P.io[1].gin + c[u], pol_keep) : 0.0;
-                        }
-#pragma unroll
-                        for (int u = 0; u < kUnroll; ++u) { s0 = fma(v[u], x0[u], s0); s1 = fma(v[u], x1[u], s1); }
-                    }
-                };
-                load_batch(0, vA, cA);
-                load_batch(1, vB, cB);
-                for (int bb = 0; bb < nb; bb += 2) {
-                    consume(vA, cA);
-                    load_batch(bb + 2, vA, cA);
-                    if (bb + 1 < nb) { consume(vB, cB); load_batch(bb + 3, vB, cB); }
-                }
-                if (row >= 0) {
-                    if (PAIR) {
-                        double2 nw = o.old2;
-                        if (act0) nw.x = row_epilogue(C0, s0, o.old2.x, o.a00, o.a01, acc[0], acc[1]);
-                        if (act1) nw.y = row_epilogue(C1, s1, o.old2.y, o.a10, o.a11, acc[2], acc[3]);
-                        stg_evict_last(P.self2 + row, nw, pol_keep);
-                    } else {
-                        if (act0) __stcs(P.io[0].self + row, row_epilogue(C0, s0, o.so0, o.a00, o.a01, acc[0], acc[1]));
-                        if (act1) __stcs(P.io[1].self + row, row_epilogue(C1, s1, o.so1, o.a10, o.a11, acc[2], acc[3]));
-                    }
-                    if (C0.wr0) __stcs(P.io[0].a0 + row, o.a00);
-                    if (C0.wr1) __stcs(P.io[0].a1 + row, o.a01);
-                    if (C1.wr0) __stcs(P.io[1].a0 + row, o.a10);
-                    if (C1.wr1) __stcs(P.io[1].a1 + row, o.a11);
-                }
-            }
-        }
-#else
-        if (wid == kConsumers) {
-            // ---------------- producer ----------------
-            if (lane == 0) {
-                for (int k = 0; k < nstage && ok; ++k) {
-                    const int slot = k % kRingStages;
-                    if (k >= kRingStages) ok = mbar_wait(&empty_bar[slot], (uint32_t)(((k / kRingStages) & 1) ^ 1));
-                    if (!ok) break;
-                    const int rows = min(kStageRows, R1 - R0 - k * kStageRows);
-                    const size_t e = ((size_t)R0 + (size_t)k * kStageRows) * 32;
-                    mbar_expect_tx(&full_bar[slot], (uint32_t)rows * 32u * 12u);
-                    tma_bulk_g2s_hint(ring_val + (size_t)slot * kStageElems, P.sval + e, (uint32_t)rows * 256u, &full_bar[slot], pol_stream);
-                    tma_bulk_g2s_hint(ring_col + (size_t)slot * kStageElems, P.scol + e, (uint32_t)rows * 128u, &full_bar[slot], pol_stream);
-                }
-            }
-        } else {
-            // ---------------- consumers ----------------
-            int kcur = -1;
-            auto advance_to = [&](int k) {
-                while (kcur < k && ok) {
-                    if (kcur >= 0) { __syncwarp(); if (lane == 0) mbar_arrive(&empty_bar[kcur % kRingStages]); }
-                    ++kcur;
-                    ok = mbar_wait(&full_bar[kcur % kRingStages], (uint32_t)((kcur / kRingStages) & 1));
-                }
-            };
-            // row-epilogue operands of a slice (registers); loaded one slice ahead so that neither
-            // the row map nor these DRAM reads sit on the slice's critical path
-            struct Ops { double2 old2; double so0, so1, a00, a01, a10, a11; };
-            auto load_ops = [&](int row, Ops &o) {
-                o.old2 = make_double2(0.0, 0.0);
-                o.so0 = o.so1 = o.a00 = o.a01 = o.a10 = o.a11 = 0.0;
-                if (row >= 0) {
-                    if (PAIR) o.old2 = __ldcs(P.self2 + row);
-                    else {
-                        if (C0.rdself) o.so0 = __ldcs(P.io[0].self + row);
-                        if (C1.rdself) o.so1 = __ldcs(P.io[1].self + row);
-                    }
-                    if (C0.rd0) o.a00 = __ldcs(P.io[0].a0 + row);
-                    if (C0.rd1) o.a01 = __ldcs(P.io[0].a1 + row);
-                    if (C1.rd0) o.a10 = __ldcs(P.io[1].a0 + row);
-                    if (C1.rd1) o.a11 = __ldcs(P.io[1].a1 + row);
-                }
-            };
-            const int ns = s_end - s_begin;
-            Ops nxt;
-            if (wid < ns) load_ops(s_row[wid * 32 + lane], nxt);
-            for (int ls = wid; ls < ns && ok; ls += kConsumers) {
-                const int ra = s_off[ls] - R0, rb = s_off[ls + 1] - R0;
-                const int row = s_row[ls * 32 + lane];
-                Ops o = nxt;
-                if (ls + kConsumers < ns) load_ops(s_row[(ls + kConsumers) * 32 + lane], nxt);
-                double s0 = 0.0, s1 = 0.0;
-                // the slice's rows, one ring stage at a time (a 20-row slice touches 1-2 stages)
-                int r = ra;
-                while (r < rb && ok) {
-                    const int k = r >> 5;                               // kStageRows == 32
-                    advance_to(k);
-                    const int seg_end = min(rb, (k + 1) << 5);
-                    const int nrows = seg_end - r;
-                    const int q0 = ((k & (kRingStages - 1)) << 10) + ((r & 31) << 5) + lane;
-                    const double *vp = ring_val + q0;
-                    const int *cp = ring_col + q0;
-                    for (int j = 0; j < nrows; j += kUnroll) {
-                        double v[kUnroll];
-                        int c[kUnroll];
-#pragma unroll
-                        for (int u = 0; u < kUnroll; ++u) {
-                            const bool in = (j + u) < nrows;
-                            v[u] = in ? vp[(j + u) * 32] : 0.0;
-                            c[u] = in ? cp[(j + u) * 32] : -1;
-                        }
-                        if (PAIR) {
-                            double2 x[kUnroll];
-#pragma unroll
-                            for (int u = 0; u < kUnroll; ++u)
-                                x[u] = (c[u] >= 0) ? ldg_evict_last(P.gin2 + c[u], pol_keep) : make_double2(0.0, 0.0);
-#pragma unroll
-                            for (int u = 0; u < kUnroll; ++u) { s0 = fma(v[u], x[u].x, s0); s1 = fma(v[u], x[u].y, s1); }
-                        } else {
-                            double x0[kUnroll], x1[kUnroll];
-#pragma unroll
-                            for (int u = 0; u < kUnroll; ++u) {
-                                x0[u] = (act0 && c[u] >= 0) ? ldg_evict_last(P.io[0].gin + c[u], pol_keep) : 0.0;
-                                x1[u] = (act1 && c[u] >= 0) ? ldg_evict_last(P.io[1].gin + c[u], pol_keep) : 0.0;
-                            }
-#pragma unroll
-                            for (int u = 0; u < kUnroll; ++u) { s0 = fma(v[u], x0[u], s0); s1 = fma(v[u], x1[u], s1); }
-                        }
-                    }
-                    r = seg_end;
-                }
-                if (row >= 0 && ok) {
-                    if (PAIR) {
-                        double2 nw = o.old2;
-                        if (act0) nw.x = row_epilogue(C0, s0, o.old2.x, o.a00, o.a01, acc[0], acc[1]);
-                        if (act1) nw.y = row_epilogue(C1, s1, o.old2.y, o.a10, o.a11, acc[2], acc[3]);
-                        stg_evict_last(P.self2 + row, nw, pol_keep);      // gathered by the next launch
-                    } else {
-                        if (act0) __stcs(P.io[0].self + row, row_epilogue(C0, s0, o.so0, o.a00, o.a01, acc[0], acc[1]));
-                        if (act1) __stcs(P.io[1].self + row, row_epilogue(C1, s1, o.so1, o.a10, o.a11, acc[2], acc[3]));
-                    }
-                    if (C0.wr0) __stcs(P.io[0].a0 + row, o.a00);
-                    if (C0.wr1) __stcs(P.io[0].a1 + row, o.a01);
-                    if (C1.wr0) __stcs(P.io[1].a0 + row, o.a10);
-                    if (C1.wr1) __stcs(P.io[1].a1 + row, o.a11);
-                }
-            }
-            // walk (and release) the remaining stages so the producer can finish
-            advance_to(nstage - 1);
-            if (kcur >= 0 && ok) { __syncwarp(); if (lane == 0) mbar_arrive(&empty_bar[kcur % kRingStages]); }
-        }
-#endif
-        if (!ok && lane == 0) atomicExch(P.done_flag, -1);
-    } else {
-        // one long row per CTA: strided over the whole block, fixed-tree block reduction
-        const int lr = cta - P.grid_sell;
-        const int row = P.long_row[lr];
-        const int e0 = P.long_rp[lr], e1 = P.long_rp[lr + 1];
-        double a[2] = {0.0, 0.0};
-        for (int k = e0 + tid; k < e1; k += kStepThreads) {
-            const double v = P.long_val[k];
-            const int c = P.long_col[k];
-            if (PAIR) {
-                const double2 x = __ldg(P.gin2 + c);
-                a[0] += v * x.x; a[1] += v * x.y;
-            } else {
-                if (act0) a[0] += v * __ldg(P.io[0].gin + c);
-                if (act1) a[1] += v * __ldg(P.io[1].gin + c);
-            }
-        }
-        block_sum<2>(a, s_red);
+    if (tid < 32) {
+        // ------------------------------- producer -------------------------------
         if (tid == 0) {
-            double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
-            if (C0.rd0) a00 = P.io[0].a0[row];
-            if (C0.rd1) a01 = P.io[0].a1[row];
-            if (C1.rd0) a10 = P.io[1].a0[row];
-            if (C1.rd1) a11 = P.io[1].a1[row];
-            if (PAIR) {
-                const double2 old2 = P.self2[row];
-                double2 nw = old2;
-                if (act0) nw.x = row_epilogue(C0, a[0], old2.x, a00, a01, acc[0], acc[1]);
-                if (act1) nw.y = row_epilogue(C1, a[1], old2.y, a10, a11, acc[2], acc[3]);
-                P.self2[row] = nw;
-            } else {
-                if (act0) {
-                    const double so = C0.rdself ? P.io[0].self[row] : 0.0;
-                    P.io[0].self[row] = row_epilogue(C0, a[0], so, a00, a01, acc[0], acc[1]);
+            // tile descriptors are fetched two tiles ahead of their use
+            const int gsz = (int)gridDim.x;
+            int k = 0, tile = cta, t1 = cta + gsz;
+            TileMeta T{}, T1{};
+            if (tile < P.ntiles) T = load_tile(P.tiles, tile);
+            if (t1 < P.ntiles) T1 = load_tile(P.tiles, t1);
+            for (; tile < P.ntiles; ++k) {
+                const int t2 = t1 + gsz;
+                TileMeta T2{};
+                if (t2 < P.ntiles) T2 = load_tile(P.tiles, t2);
+                const int s = k % nstage;
+                if (k >= nstage) ok = mbar_wait(&empty_bar[s], (uint32_t)((k / nstage - 1) & 1)) && ok;
+                unsigned char *st = s_dyn + (size_t)s * stage_bytes;
+                double *s_val = reinterpret_cast<double *>(st);
+                int *s_col = reinterpret_cast<int *>(st + (size_t)P.val_cap * 8);
+                int *s_map = reinterpret_cast<int *>(st + (size_t)P.val_cap * 12);
+                unsigned char *s_win = st + (size_t)P.val_cap * 12 + kTileRows * 4;
+                uint32_t tot = (uint32_t)T.elems * 12u + (uint32_t)T.ns * 128u;
+                uint32_t wbytes = 0;
+                if (T.ccnt > 0) {
+                    if (PAIR) { wbytes = (uint32_t)T.ccnt * 16u; tot += wbytes; }
+                    else if (win_tma && !(T.ccnt & 1)) { wbytes = (uint32_t)T.ccnt * 8u; tot += wbytes * ((act0 ? 1u : 0u) + (act1 ? 1u : 0u)); }
                 }
-                if (act1) {
-                    const double so = C1.rdself ? P.io[1].self[row] : 0.0;
-                    P.io[1].self[row] = row_epilogue(C1, a[1], so, a10, a11, acc[2], acc[3]);
+                mbar_expect_tx(&full_bar[s], tot);
+                if (T.elems > 0) {
+                    tma_bulk_g2s(s_val, P.sval + T.eoff, (uint32_t)T.elems * 8u, &full_bar[s]);
+                    tma_bulk_g2s(s_col, P.scol + T.eoff, (uint32_t)T.elems * 4u, &full_bar[s]);
+                }
+                if (T.ns > 0) tma_bulk_g2s(s_map, P.rowloc + T.rmap, (uint32_t)T.ns * 128u, &full_bar[s]);
+                if (wbytes) {
+                    if (PAIR) tma_bulk_g2s(s_win, P.gin2 + T.cmin, wbytes, &full_bar[s]);
+                    else {
+                        double *w0 = reinterpret_cast<double *>(s_win);
+                        if (act0) tma_bulk_g2s(w0, P.io[0].gin + T.cmin, wbytes, &full_bar[s]);
+                        if (act1) tma_bulk_g2s(w0 + P.win_cap, P.io[1].gin + T.cmin, wbytes, &full_bar[s]);
+                    }
+                }
+                T = T1; T1 = T2; tile = t1; t1 = t2;
+            }
+        }
+    } else {
+        // ------------------------------- consumers -------------------------------
+        const int ct = tid - 32;
+        const int g = ct / kGroupThreads, t = ct % kGroupThreads;
+        const int lane = t & 31, wid = t >> 5;
+        int k = g;
+        int tile = cta + k * (int)gridDim.x;
+        TileMeta T{};
+        if (tile < P.ntiles) T = load_tile(P.tiles, tile);
+        for (; tile < P.ntiles; k += kGroups) {
+            const int s = k % nstage;
+            // row-epilogue operands of this thread's row: in flight during the wait and phase 1
+            const int row = T.row0 + t;
+            const bool has_row = t < T.nrows && !(P.rowflag != nullptr && P.rowflag[row]);
+            double2 old2 = make_double2(0.0, 0.0);
+            double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+            if (has_row) {
+                if (PAIR) old2 = P.self2[row];
+                else {
+                    if (C0.rdself) old2.x = P.io[0].self[row];
+                    if (C1.rdself) old2.y = P.io[1].self[row];
+                }
+                if (C0.rd0) a00 = __ldcs(P.io[0].a0 + row);
+                if (C0.rd1) a01 = __ldcs(P.io[0].a1 + row);
+                if (C1.rd0) a10 = __ldcs(P.io[1].a0 + row);
+                if (C1.rd1) a11 = __ldcs(P.io[1].a1 + row);
+            }
+            // next tile's descriptor (prefetched a whole tile ahead)
+            const int ntile = cta + (k + kGroups) * (int)gridDim.x;
+            TileMeta Tn{};
+            if (ntile < P.ntiles) Tn = load_tile(P.tiles, ntile);
+
+            const unsigned char *st = s_dyn + (size_t)s * stage_bytes;
+            const double *s_val = reinterpret_cast<const double *>(st);
+            const int *s_col = reinterpret_cast<const int *>(st + (size_t)P.val_cap * 8);
+            const int *s_map = reinterpret_cast<const int *>(st + (size_t)P.val_cap * 12);
+            unsigned char *s_win = const_cast<unsigned char *>(st) + (size_t)P.val_cap * 12 + kTileRows * 4;
+            const double2 *win2 = reinterpret_cast<const double2 *>(s_win);
+            double *win0 = reinterpret_cast<double *>(s_win);
+            double *win1 = win0 + P.win_cap;
+            const bool windowed = T.ccnt > 0;
+
+            ok = mbar_wait(&full_bar[s], (uint32_t)((k / nstage) & 1)) && ok;
+            if (!PAIR && windowed && !(win_tma && !(T.ccnt & 1))) {
+                // unaligned / odd-sized caller vectors: the group stages the window itself
+                for (int i = t; i < T.ccnt; i += kGroupThreads) {
+                    if (act0) win0[i] = P.io[0].gin[T.cmin + i];
+                    if (act1) win1[i] = P.io[1].gin[T.cmin + i];
+                }
+                group_bar(g);
+            }
+            // ---------------- phase 1: row sums of this warp's slice ----------------
+            double s0 = 0.0, s1 = 0.0;
+            int lrow = -1;
+            if (wid < T.ns) {
+                int off = 0, width = T.width[0];
+#pragma unroll
+                for (int i = 1; i < kTileSlices; ++i) if (i <= wid) { off += T.width[i - 1] * 32; width = T.width[i]; }
+                const int npair = width >> 1;
+                lrow = s_map[wid * 32 + lane];
+                const double2 *sv = reinterpret_cast<const double2 *>(s_val + off) + lane;
+                const int2 *sc = reinterpret_cast<const int2 *>(s_col + off) + lane;
+                if (PAIR) {
+                    if (windowed) {
+#pragma unroll 5
+                        for (int p = 0; p < npair; ++p) {
+                            const double2 v = sv[p * 32];
+                            const int2 c = sc[p * 32];
+                            const double2 x0 = win2[c.x], x1 = win2[c.y];
+                            s0 = fma(v.x, x0.x, s0); s1 = fma(v.x, x0.y, s1);
+                            s0 = fma(v.y, x1.x, s0); s1 = fma(v.y, x1.y, s1);
+                        }
+                        if (width & 1) {
+                            const double v = s_val[off + npair * 64 + lane];
+                            const double2 x = win2[s_col[off + npair * 64 + lane]];
+                            s0 = fma(v, x.x, s0); s1 = fma(v, x.y, s1);
+                        }
+                    } else {
+#pragma unroll 5
+                        for (int p = 0; p < npair; ++p) {
+                            const double2 v = sv[p * 32];
+                            const int2 c = sc[p * 32];
+                            const double2 x0 = __ldg(P.gin2 + c.x), x1 = __ldg(P.gin2 + c.y);
+                            s0 = fma(v.x, x0.x, s0); s1 = fma(v.x, x0.y, s1);
+                            s0 = fma(v.y, x1.x, s0); s1 = fma(v.y, x1.y, s1);
+                        }
+                        if (width & 1) {
+                            const double v = s_val[off + npair * 64 + lane];
+                            const double2 x = __ldg(P.gin2 + s_col[off + npair * 64 + lane]);
+                            s0 = fma(v, x.x, s0); s1 = fma(v, x.y, s1);
+                        }
+                    }
+                } else {
+                    auto gather_fma = [&](double v, int c) {
+                        if (act0) s0 = fma(v, windowed ? win0[c] : __ldg(P.io[0].gin + c), s0);
+                        if (act1) s1 = fma(v, windowed ? win1[c] : __ldg(P.io[1].gin + c), s1);
+                    };
+#pragma unroll 5
+                    for (int p = 0; p < npair; ++p) {
+                        const double2 v = sv[p * 32];
+                        const int2 c = sc[p * 32];
+                        gather_fma(v.x, c.x);
+                        gather_fma(v.y, c.y);
+                    }
+                    if (width & 1) gather_fma(s_val[off + npair * 64 + lane], s_col[off + npair * 64 + lane]);
                 }
             }
-            if (C0.wr0) P.io[0].a0[row] = a00;
-            if (C0.wr1) P.io[0].a1[row] = a01;
-            if (C1.wr0) P.io[1].a0[row] = a10;
-            if (C1.wr1) P.io[1].a1[row] = a11;
+            // the stage is consumed: hand it back to the producer (one arrival per warp)
+            if (!PAIR) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // group-staged windows
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+            double2 *sum = s_sum[g][(k / kGroups) & 1];
+            if (lrow >= 0) sum[lrow] = make_double2(s0, s1);
+            group_bar(g);
+            // ---------------- phase 2: row epilogue in natural row order ----------------
+            if (has_row) {
+                const double2 sm = sum[t];
+                if (PAIR) {
+                    double2 nw = old2;
+                    if (act0) nw.x = row_epilogue(C0, sm.x, old2.x, a00, a01, acc[0], acc[1]);
+                    if (act1) nw.y = row_epilogue(C1, sm.y, old2.y, a10, a11, acc[2], acc[3]);
+                    P.self2[row] = nw;
+                } else {
+                    if (act0) P.io[0].self[row] = row_epilogue(C0, sm.x, old2.x, a00, a01, acc[0], acc[1]);
+                    if (act1) P.io[1].self[row] = row_epilogue(C1, sm.y, old2.y, a10, a11, acc[2], acc[3]);
+                }
+                if (C0.wr0) __stcs(P.io[0].a0 + row, a00);
+                if (C0.wr1) __stcs(P.io[0].a1 + row, a01);
+                if (C1.wr0) __stcs(P.io[1].a0 + row, a10);
+                if (C1.wr1) __stcs(P.io[1].a1 + row, a11);
+            }
+            T = Tn;
+            tile = ntile;
         }
     }
+    if (!ok) atomicExch(P.done_flag, -1);
     if (!use_state) return;
 
     // deterministic norms: one partial per CTA, the last CTA reduces them in a fixed order
@@ -950,14 +918,15 @@ __global__ void __launch_bounds__(kStepThreads, 2) gk_step_kernel(StepParams P, 
         double *pp = P.partials + (size_t)cta * 4;
         pp[0] = acc[0]; pp[1] = acc[1]; pp[2] = acc[2]; pp[3] = acc[3];
         __threadfence();
-        unsigned t = atomicAdd(P.counter, 1u);
-        s_last = (t == gridDim.x - 1);
+        unsigned tk = atomicAdd(P.counter, 1u);
+        s_last = (tk == gridDim.x - 1);
     }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
     double tot[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int i = tid; i < (int)gridDim.x; i += kStepThreads) {
+    const int nparts = (int)gridDim.x + P.nlong;       // long-row partials follow the CTA partials
+    for (int i = tid; i < nparts; i += kStepThreads) {
         const double *pp = P.partials + (size_t)i * 4;
         tot[0] += __ldcg(pp + 0); tot[1] += __ldcg(pp + 1);
         tot[2] += __ldcg(pp + 2); tot[3] += __ldcg(pp + 3);
@@ -969,6 +938,75 @@ __global__ void __launch_bounds__(kStepThreads, 2) gk_step_kernel(StepParams P, 
         if (!P.st[0].active && !P.st[1].active) *P.done_flag = 1;
         *P.counter = 0;
         __threadfence();
+    }
+}
+
+// rows longer than kLongRow: one CTA per row, strided over the row, fixed-tree block reduction.
+// Launched before gk_step_kernel of the same step; leaves its norm partials at partials[pbase + row#].
+template <bool PAIR>
+__global__ void __launch_bounds__(kLongThreads) long_rows_kernel(StepParams P, int use_state, int pbase) {
+    __shared__ double s_red[4 * 16];
+    __shared__ Coef sC[2];
+    const int tid = threadIdx.x;
+    const bool act0 = P.io[0].mode != MD_NONE && (!use_state || P.st[0].active);
+    const bool act1 = P.io[1].mode != MD_NONE && (!use_state || P.st[1].active);
+    if (!act0 && !act1) return;
+    if (tid == 0) {
+        load_coef(sC[0], P.io[0], &P.st[0], use_state);
+        load_coef(sC[1], P.io[1], &P.st[1], use_state);
+        if (!act0) { sC[0].mode = MD_NONE; sC[0].rd0 = sC[0].rd1 = sC[0].wr0 = sC[0].wr1 = sC[0].rdself = 0; }
+        if (!act1) { sC[1].mode = MD_NONE; sC[1].rd0 = sC[1].rd1 = sC[1].wr0 = sC[1].wr1 = sC[1].rdself = 0; }
+    }
+    __syncthreads();
+    const Coef &C0 = sC[0];
+    const Coef &C1 = sC[1];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    const int lr = blockIdx.x;
+    const int row = P.long_row[lr];
+    const int e0 = P.long_rp[lr], e1 = P.long_rp[lr + 1];
+    double a[2] = {0.0, 0.0};
+    for (int k = e0 + tid; k < e1; k += kLongThreads) {
+        const double v = P.long_val[k];
+        const int c = P.long_col[k];
+        if (PAIR) {
+            const double2 x = __ldg(P.gin2 + c);
+            a[0] += v * x.x; a[1] += v * x.y;
+        } else {
+            if (act0) a[0] += v * __ldg(P.io[0].gin + c);
+            if (act1) a[1] += v * __ldg(P.io[1].gin + c);
+        }
+    }
+    block_sum<2>(a, s_red);
+    if (tid == 0) {
+        double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+        if (C0.rd0) a00 = P.io[0].a0[row];
+        if (C0.rd1) a01 = P.io[0].a1[row];
+        if (C1.rd0) a10 = P.io[1].a0[row];
+        if (C1.rd1) a11 = P.io[1].a1[row];
+        if (PAIR) {
+            const double2 old2 = P.self2[row];
+            double2 nw = old2;
+            if (act0) nw.x = row_epilogue(C0, a[0], old2.x, a00, a01, acc[0], acc[1]);
+            if (act1) nw.y = row_epilogue(C1, a[1], old2.y, a10, a11, acc[2], acc[3]);
+            P.self2[row] = nw;
+        } else {
+            if (act0) {
+                const double so = C0.rdself ? P.io[0].self[row] : 0.0;
+                P.io[0].self[row] = row_epilogue(C0, a[0], so, a00, a01, acc[0], acc[1]);
+            }
+            if (act1) {
+                const double so = C1.rdself ? P.io[1].self[row] : 0.0;
+                P.io[1].self[row] = row_epilogue(C1, a[1], so, a10, a11, acc[2], acc[3]);
+            }
+        }
+        if (C0.wr0) P.io[0].a0[row] = a00;
+        if (C0.wr1) P.io[0].a1[row] = a01;
+        if (C1.wr0) P.io[1].a0[row] = a10;
+        if (C1.wr1) P.io[1].a1[row] = a11;
+        if (use_state) {
+            double *pp = P.partials + (size_t)(pbase + lr) * 4;
+            pp[0] = acc[0]; pp[1] = acc[1]; pp[2] = acc[2]; pp[3] = acc[3];
+        }
     }
 }
 
@@ -1161,97 +1199,140 @@ static void build_csr_host(int nrows, int ncols, int64_t nnz, const int64_t *ri,
     }
 }
 
-constexpr int kLongRow = 1024;   // rows longer than this leave the SELL part
-constexpr int kSigma = 2048;     // sorting window (rows) of SELL-32-sigma
+constexpr int kLongRow = 96;     // rows longer than this leave the SELL part (a 32-row slice must fit a stage)
 
-// CSR -> SELL-32-sigma (+ CSR of the long rows) and upload
+// CSR -> tiled SELL-32 (+ CSR of the long rows) and upload
 static void upload_sell(Handle *h, CsrDev &M, int nrows, int ncols, const std::vector<int> &rp,
                         const std::vector<int> &ci, const std::vector<int> &perm) {
     M.nrows = nrows; M.ncols = ncols; M.nnz = (int64_t)ci.size();
-    std::vector<int> rowidx, sl_off(1, 0), long_row, long_rp(1, 0), long_col, long_perm;
-    std::vector<int> order;
-    for (int w0 = 0; w0 < nrows; w0 += kSigma) {
-        const int w1 = std::min(nrows, w0 + kSigma);
-        order.clear();
-        for (int r = w0; r < w1; ++r) {
-            const int len = rp[(size_t)r + 1] - rp[(size_t)r];
-            if (len > kLongRow) {
-                long_row.push_back(r);
-                for (int p = rp[(size_t)r]; p < rp[(size_t)r + 1]; ++p) { long_col.push_back(ci[(size_t)p]); long_perm.push_back(perm[(size_t)p]); }
-                long_rp.push_back((int)long_col.size());
-            } else order.push_back(r);
+    std::vector<int> rowloc, sl_off(1, 0), long_row, long_rp(1, 0), long_col, long_perm;
+    std::vector<unsigned char> rowflag((size_t)nrows + 8, 0);
+    std::vector<TileMeta> tiles;
+    std::vector<int> slice_rows;      // global row per lane (host only)
+    std::vector<int> order, widths;
+    int win_cap = 0, val_cap = 32;
+    auto rlen = [&](int r) { return rp[(size_t)r + 1] - rp[(size_t)r]; };
+    for (int r = 0; r < nrows; ++r) {
+        if (rlen(r) > kLongRow) {
+            long_row.push_back(r);
+            rowflag[(size_t)r] = 1;
+            for (int p = rp[(size_t)r]; p < rp[(size_t)r + 1]; ++p) { long_col.push_back(ci[(size_t)p]); long_perm.push_back(perm[(size_t)p]); }
+            long_rp.push_back((int)long_col.size());
         }
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-            return (rp[(size_t)a + 1] - rp[(size_t)a]) > (rp[(size_t)b + 1] - rp[(size_t)b]);
-        });
+    }
+    const size_t budget = (size_t)kStageBytesMax - kTileRows * 4;
+    for (int w0 = 0; w0 < nrows;) {
+        // largest tile (multiple of 32 rows, at most kTileRows) whose values + indices + window fit a stage
+        int R = std::min(kTileRows, nrows - w0);
+        int cnt = 0, c0 = 0, elems = 0;
+        for (;;) {
+            order.clear();
+            int cmin = ncols, cmax = -1;
+            for (int r = w0; r < w0 + R; ++r) {
+                if (rowflag[(size_t)r]) continue;
+                order.push_back(r);
+                if (rlen(r) > 0) {      // columns ascend within a row
+                    cmin = std::min(cmin, ci[(size_t)rp[(size_t)r]]);
+                    cmax = std::max(cmax, ci[(size_t)rp[(size_t)r + 1] - 1]);
+                }
+            }
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return rlen(a) > rlen(b); });
+            widths.clear();
+            elems = 0;
+            for (size_t i = 0; i < order.size(); i += 32) { widths.push_back(rlen(order[i])); elems += widths.back() * 32; }
+            c0 = 0; cnt = 0;
+            if (cmax >= 0) {
+                c0 = cmin & ~1;               // 16-byte aligned start for vectors of doubles
+                cnt = cmax - c0 + 1;
+                if (cnt > kWinCapMax) cnt = 0;
+            }
+            if ((size_t)elems * 12 + (size_t)cnt * 16 <= budget) break;
+            if (R > 32) { R = std::max(32, ((R / 2) + 31) & ~31); continue; }
+            cnt = 0;     // a single slice (at most kLongRow wide, 36 KB): drop the window
+            break;
+        }
+        TileMeta T{};
+        T.rmap = (int)rowloc.size();
+        T.row0 = w0; T.nrows = R;
+        T.cmin = cnt > 0 ? c0 : 0; T.ccnt = cnt;
+        T.eoff = sl_off.back(); T.elems = elems;
+        win_cap = std::max(win_cap, cnt);
+        val_cap = std::max(val_cap, elems);
+        T.ns = (int)widths.size();
+        for (int i = 0; i < kTileSlices; ++i) T.width[i] = i < T.ns ? widths[(size_t)i] : 0;
         for (size_t i = 0; i < order.size(); i += 32) {
-            int width = 0;
             for (size_t l = 0; l < 32; ++l) {
                 const int r = (i + l < order.size()) ? order[i + l] : -1;
-                rowidx.push_back(r);
-                if (r >= 0) width = std::max(width, rp[(size_t)r + 1] - rp[(size_t)r]);
+                slice_rows.push_back(r);
+                rowloc.push_back(r >= 0 ? r - w0 : -1);
             }
-            sl_off.push_back(sl_off.back() + width * 32);
+            sl_off.push_back(sl_off.back() + widths[i / 32] * 32);
         }
+        tiles.push_back(T);
+        w0 += R;
     }
     const int nslice = (int)sl_off.size() - 1;
     const size_t padded = (size_t)sl_off.back();
     std::vector<int> scol(padded, 0), sperm(padded, -1);
-    for (int sidx = 0; sidx < nslice; ++sidx) {
-        const int off = sl_off[(size_t)sidx], width = (sl_off[(size_t)sidx + 1] - off) / 32;
-        for (int l = 0; l < 32; ++l) {
-            const int r = rowidx[(size_t)sidx * 32 + l];
-            int len = 0, base = 0;
-            if (r >= 0) { base = rp[(size_t)r]; len = rp[(size_t)r + 1] - base; }
-            int lastc = (len > 0) ? ci[(size_t)(base + len - 1)] : 0;
-            for (int j = 0; j < width; ++j) {
-                const size_t q = (size_t)off + (size_t)j * 32 + l;
-                if (j < len) { scol[q] = ci[(size_t)(base + j)]; sperm[q] = perm[(size_t)(base + j)]; }
-                else { scol[q] = lastc; sperm[q] = -1; }     // padding: value 0, local column
+    for (const TileMeta &T : tiles) {
+        const int cbase = T.ccnt > 0 ? T.cmin : 0;
+        const int s0 = T.rmap / 32;
+        for (int sidx = s0; sidx < s0 + T.ns; ++sidx) {
+            const int off = sl_off[(size_t)sidx], width = (sl_off[(size_t)sidx + 1] - off) / 32;
+            const int npair = width / 2;
+            for (int l = 0; l < 32; ++l) {
+                const int r = slice_rows[(size_t)sidx * 32 + l];
+                int len = 0, base = 0;
+                if (r >= 0) { base = rp[(size_t)r]; len = rp[(size_t)r + 1] - base; }
+                for (int j = 0; j < width; ++j) {
+                    // pair rows: entries 2p, 2p+1 of a lane are adjacent; an odd last entry is a plain row
+                    const size_t q = (j < 2 * npair) ? (size_t)off + ((size_t)(j >> 1) * 32 + l) * 2 + (j & 1)
+                                                     : (size_t)off + (size_t)npair * 64 + l;
+                    if (j < len) { scol[q] = ci[(size_t)(base + j)] - cbase; sperm[q] = perm[(size_t)(base + j)]; }
+                    else { scol[q] = 0; sperm[q] = -1; }     // padding: value 0, valid column
+                }
             }
         }
     }
     M.nslice = nslice;
     M.padded = (int64_t)padded;
     M.nlong = (int)long_row.size();
-    M.sl_off.from(sl_off, h->stream);
-    M.rowidx.from(rowidx, h->stream);
+    M.ntiles = (int)tiles.size();
+    M.win_cap = (win_cap + 7) & ~7;
+    M.val_cap = (val_cap + 31) & ~31;
+    M.stage_bytes = (int)((((size_t)M.val_cap * 12 + kTileRows * 4 + (size_t)M.win_cap * 16) + 127) & ~(size_t)127);
+    M.nstage = std::max(2, std::min(kMaxStages, kRingBudget / M.stage_bytes));
+    M.rowloc.from(rowloc, h->stream);
     M.scol.from(scol, h->stream);
     M.sperm.from(sperm, h->stream);
     M.sval.alloc(padded + 8);
     M.sval.zero(h->stream);
+    M.tiles.alloc((tiles.size() + 1) * sizeof(TileMeta));
+    if (!tiles.empty()) FPSB_CUDA(cudaMemcpyAsync(M.tiles.p, tiles.data(), tiles.size() * sizeof(TileMeta), cudaMemcpyHostToDevice, h->stream));
+    M.rowflag.from(rowflag, h->stream);
     M.long_row.from(long_row, h->stream);
     M.long_rp.from(long_rp, h->stream);
     M.long_col.from(long_col, h->stream);
     M.long_perm.from(long_perm, h->stream);
     M.long_val.alloc(long_col.size() + 8);
     M.long_val.zero(h->stream);
-    M.grid_sell = nslice > 0 ? std::max(1, std::min((nslice + 7) / 8, 2 * h->num_sms)) : 0;
-    {
-        // slice metadata of a CTA must fit its shared-memory staging area; keep whole waves of
-        // resident CTAs (2 per SM) so there is no ragged tail wave
-        const int resident = 2 * h->num_sms;
-        const int need = (nslice + kMaxSlicesPerCta - 1) / kMaxSlicesPerCta;
-        if (need > M.grid_sell) M.grid_sell = ((need + resident - 1) / resident) * resident;
+    M.grid = nrows > 0 ? std::max(1, std::min(h->num_sms, M.ntiles)) : 0;
+    FPSB_CUDA(cudaStreamSynchronize(h->stream));     // the host vectors above die with this scope
+}
+
+// one step of the fused operator: the long rows first (their norm partials are picked up by the
+// last CTA of the main kernel), then the persistent tile kernel
+static void launch_step(Handle *h, const CsrDev &M, const StepParams &P, bool pair, int use_state) {
+    if (M.grid == 0) return;
+    if (M.nlong > 0) {
+        if (pair) long_rows_kernel<true><<<M.nlong, kLongThreads, 0, h->stream>>>(P, use_state, M.grid);
+        else long_rows_kernel<false><<<M.nlong, kLongThreads, 0, h->stream>>>(P, use_state, M.grid);
+        h->launches += 1;
     }
-    M.grid = M.grid_sell + M.nlong;
-    {
-        // contiguous chunks of slices per warp, balanced by streamed rows (+1 per slice for the
-        // epilogue); wchunk[w] = first slice of warp w
-        const int nw = M.grid_sell * (kBlock / 32);
-        std::vector<int> wchunk((size_t)nw + 1, nslice);
-        std::vector<int64_t> cost((size_t)nslice + 1, 0);
-        for (int i = 0; i < nslice; ++i) cost[(size_t)i + 1] = cost[(size_t)i] + (sl_off[(size_t)i + 1] - sl_off[(size_t)i]) / 32 + 2;
-        int cur = 0;
-        for (int w = 0; w < nw; ++w) {
-            wchunk[(size_t)w] = cur;
-            const int64_t target = nw > 0 ? cost[(size_t)nslice] * (w + 1) / nw : 0;
-            while (cur < nslice && cost[(size_t)cur + 1] <= target) cur++;
-        }
-        wchunk[(size_t)nw] = nslice;
-        if (nw > 0) wchunk[0] = 0;
-        M.wchunk.from(wchunk, h->stream);
-    }
+    const size_t smem = (size_t)M.nstage * (size_t)M.stage_bytes;
+    if (pair) gk_step_kernel<true><<<M.grid, kStepThreads, smem, h->stream>>>(P, use_state);
+    else gk_step_kernel<false><<<M.grid, kStepThreads, smem, h->stream>>>(P, use_state);
+    h->launches += 1;
 }
 
 void csr_build(Handle *h) {
@@ -1261,8 +1342,8 @@ void csr_build(Handle *h) {
         FPSB_CUDA(cudaGetDevice(&dev));
         FPSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         h->num_sms = sms;
-        FPSB_CUDA(cudaFuncSetAttribute(gk_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes));
-        FPSB_CUDA(cudaFuncSetAttribute(gk_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes));
+        FPSB_CUDA(cudaFuncSetAttribute(gk_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBudget + 8 * 1024));
+        FPSB_CUDA(cudaFuncSetAttribute(gk_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBudget + 8 * 1024));
     }
     std::vector<int> rp, ci, perm;
     build_csr_host(m, n, h->nnzj, h->jrow.data(), h->jcol.data(), rp, ci, perm);
@@ -1290,9 +1371,10 @@ void csr_refresh_values(Handle *h) {
 }
 
 static void fill_csr(StepParams &P, const CsrDev &M) {
-    P.wchunk = M.wchunk.p;
-    P.sl_off = M.sl_off.p; P.rowidx = M.rowidx.p; P.scol = M.scol.p; P.sval = M.sval.p;
-    P.nslice = M.nslice; P.grid_sell = M.grid_sell;
+    P.tiles = reinterpret_cast<const TileMeta *>(M.tiles.p); P.ntiles = M.ntiles; P.win_cap = M.win_cap; P.val_cap = M.val_cap;
+    P.rowloc = M.rowloc.p; P.scol = M.scol.p; P.sval = M.sval.p;
+    P.stage_bytes = M.stage_bytes; P.nstage = M.nstage; P.nlong = M.nlong;
+    P.rowflag = M.nlong > 0 ? M.rowflag.p : nullptr;
     P.long_row = M.long_row.p; P.long_rp = M.long_rp.p; P.long_col = M.long_col.p; P.long_val = M.long_val.p;
     P.nrows = M.nrows;
 }
@@ -1310,8 +1392,7 @@ void spmv_plain(Handle *h, bool transpose, const double *x, double *y, int ncols
         P.io[s].a0 = nullptr;
         P.io[s].c0 = 1.0; P.io[s].c1 = 0.0;
     }
-    gk_step_kernel<false><<<M.grid, kStepThreads, kRingBytes, h->stream>>>(P, 0);
-    h->launches += 1;
+    launch_step(h, M, P, false, 0);
     FPSB_CUDA(cudaGetLastError());
 }
 
@@ -1351,7 +1432,7 @@ void iter_setup(Handle *h) {
     }
     W->ym.alloc(m + 4);
     W->st.alloc(2);
-    int maxblk = std::max(h->A.grid, h->At.grid);
+    int maxblk = std::max(h->A.grid + h->A.nlong, h->At.grid + h->At.nlong);
     W->ew_grid = 148 * 4;
     W->partials.alloc((size_t)std::max(maxblk, W->ew_grid) * 4 + 16);
     W->counter.alloc(4);
@@ -1467,16 +1548,13 @@ struct Engine {
         memcpy(W->h_st, hs, sizeof(hs));
         FPSB_CUDA(cudaMemcpyAsync(W->st.p, W->h_st, sizeof(hs), cudaMemcpyHostToDevice, h->stream));
         FPSB_CUDA(cudaMemsetAsync(W->done.p, 0, sizeof(int), h->stream));
-        FPSB_CUDA(cudaMemsetAsync(W->counter.p, 0, sizeof(unsigned), h->stream));
+        W->counter.zero(h->stream);
     }
     void step(bool mspace, bool pair, const SlotIO &io0, const SlotIO &io1) {
         StepParams P = mspace ? base_m : base_n;
         P.io[0] = io0; P.io[1] = io1;
         const CsrDev &M = mspace ? h->A : h->At;
-        if (M.grid == 0) return;
-        if (pair) gk_step_kernel<true><<<M.grid, kStepThreads, kRingBytes, h->stream>>>(P, 1);
-        else gk_step_kernel<false><<<M.grid, kStepThreads, kRingBytes, h->stream>>>(P, 1);
-        h->launches += 1;
+        launch_step(h, M, P, pair, 1);
     }
     void ew(int op, int slot, int n, const double *in0, double *v0, double *v1, double *v2, double *v3,
             double *v4, double2 *pair, int pair_slot, double c0, int use_state = 1) {
@@ -1556,8 +1634,7 @@ static void residual_p(Engine &E, const double *rhs, const double *q, double *p)
     P.io[0] = io_mode(MD_PLAIN, const_cast<double *>(rhs));
     P.io[0].gin = q; P.io[0].self = p; P.io[0].c0 = -1.0; P.io[0].c1 = 1.0;
     P.io[1] = io_none();
-    gk_step_kernel<false><<<h->At.grid, kStepThreads, kRingBytes, h->stream>>>(P, 0);
-    h->launches += 1;
+    launch_step(h, h->At, P, false, 0);
 }
 
 static const int kChunk = 4;
@@ -1635,8 +1712,7 @@ void iter_solve_two_least_squares(Handle *h, double delta, const double *rhs1, c
         P.io[0].gin = q1; P.io[0].self = p1; P.io[0].c0 = -1.0; P.io[0].c1 = 1.0;
         P.io[1] = io_mode(MD_PLAIN, const_cast<double *>(rhs2));
         P.io[1].gin = q2; P.io[1].self = p2; P.io[1].c0 = -1.0; P.io[1].c1 = 1.0;
-        gk_step_kernel<false><<<h->At.grid, kStepThreads, kRingBytes, h->stream>>>(P, 0);
-        h->launches += 1;
+        launch_step(h, h->At, P, false, 0);
     }
     E.fetch(st);
 }
