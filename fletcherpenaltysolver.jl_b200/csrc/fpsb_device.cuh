@@ -91,23 +91,21 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// fixed-tree block reduction of NV values per thread (<= 16 warps); result valid in thread 0
+// fixed-tree block reduction of NV values per thread (<= 32 warps); result valid in thread 0
 template <int NV>
-__device__ __forceinline__ void block_sum(double (&v)[NV], double *scratch /* NV*16 */) {
+__device__ __forceinline__ void block_sum(double (&v)[NV], double *scratch /* NV*32 */) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nw = (int)((blockDim.x + 31) >> 5);
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
         double x = warp_sum(v[k]);
-        if (lane == 0) scratch[k * 16 + w] = x;
+        if (lane == 0) scratch[k * 32 + w] = x;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (w == 0) {
+        // second level: one lane per warp, same shuffle tree
 #pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            double x = 0.0;
-            for (int i = 0; i < (int)((blockDim.x + 31) >> 5); ++i) x += scratch[k * 16 + i];
-            v[k] = x;
-        }
+        for (int k = 0; k < NV; ++k) v[k] = warp_sum(lane < nw ? scratch[k * 32 + lane] : 0.0);
     }
     __syncthreads();
 }

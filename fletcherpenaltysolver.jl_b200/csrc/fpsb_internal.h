@@ -54,14 +54,13 @@ constexpr int kBlock = 256;       // threads per CTA (8 warps, one SELL slice pe
 struct CsrDev {
     int nrows = 0, ncols = 0;
     int64_t nnz = 0;
-    int nslice = 0;
     int64_t padded = 0;           // stored entries including padding
     int nlong = 0;
-    DevBuf<int> rowloc, scol, sperm;           // sperm: slot -> COO index (-1 = padding)
+    DevBuf<int> sperm, tperm0;                 // sperm: stored entry -> COO index (-1 = padding); first entry per tile
+    DevBuf<unsigned char> tbuf;                // tile blocks [values | indices | lane -> row map], back to back
     DevBuf<unsigned char> tiles;               // TileMeta[ntiles] (fpsb_krylov.cu)
     DevBuf<unsigned char> rowflag;             // 1 = long row
-    int ntiles = 0, win_cap = 0, val_cap = 0, stage_bytes = 0, nstage = 0;
-    DevBuf<double> sval;
+    int ntiles = 0, win_cap = 0, blk_cap = 0, stage_bytes = 0, nstage = 0;
     DevBuf<int> long_row, long_rp, long_col, long_perm;
     DevBuf<double> long_val;
     int grid = 0;                 // persistent CTAs of the tile kernel (long rows: nlong extra CTAs of their own kernel)
@@ -123,6 +122,7 @@ struct Handle {
 void csr_build(Handle *h);
 void csr_refresh_values(Handle *h);
 void spmv_plain(Handle *h, bool transpose, const double *x, double *y, int ncols_rhs);
+void phase_timers(unsigned long long *out, int reset);   // debug builds (-DFPSB_PHASE_TIMERS)
 void iter_setup(Handle *h);
 void iter_free(Handle *h);
 void iter_solve_two_mixed(Handle *h, double delta, const double *rhs1, const double *rhs2, double *p1,

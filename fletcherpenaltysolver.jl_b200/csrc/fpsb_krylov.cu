@@ -21,6 +21,11 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
+
+#ifndef FPSB_EXP
+#define FPSB_EXP 0     /* > 0: timing experiments that deliberately break the numerics (never shipped) */
+#endif
 
 namespace fpsb {
 
@@ -69,12 +74,11 @@ struct StepParams {
     const TileMeta *tiles;
     int ntiles;
     int win_cap;           // capacity of the shared-memory gather window (16-byte entries)
-    int val_cap;           // capacity of a ring stage (entries)
     int stage_bytes, nstage;   // ring geometry
+    int inflight;          // tiles a producer may have in flight (bounds the HBM queueing delay of every other load)
     int nlong;
-    const int *rowloc;     // nslice * 32 : row of each lane relative to its tile, -1 for padding lanes
-    const int *scol;       // window-relative columns (windowed tiles) or global columns
-    const double *sval;
+    const unsigned char *tbuf;   // the tiles' blocks, back to back
+    int blk_cap;           // capacity of the block part of a ring stage (bytes)
     const unsigned char *rowflag;   // nrows : 1 for long rows (nullptr when there are none)
     // long rows (CSR)
     const int *long_row;
@@ -474,6 +478,10 @@ __device__ void finish_step(SlotState &S, int mode, double a0, double a1) {
         case MD_CGLS_M: fin_cgls_m(S, a0); break;
         default: break;
     }
+#if defined(FPSB_EXP) && FPSB_EXP > 0
+    // experiments that break the numerics still run a fixed number of iterations
+    if (S.algo != ALGO_NONE) { if (S.iter < S.itmax) S.active = 1; else S.active = 0; }
+#endif
 }
 __device__ void finish_ew(SlotState &S, int op, double a0) {
     switch (op) {
@@ -493,108 +501,151 @@ __device__ void finish_ew(SlotState &S, int op, double a0) {
 // per-slot coefficients loaded once per CTA
 // ------------------------------------------------------------------------------------------------
 struct Coef {
-    int mode, first, pend, iter;
+    int mode;
+    int first, pend, lampos;     // LSQR first iteration / CRAIG pending x update / lambda > 0 (MINRES: != 0)
     int rd0, rd1, wr0, wr1;      // which aux vectors (a0 / a1) the row epilogue reads / writes
     int rdself;
-    double gsc, ssc, alpha, beta, sigma, tr_prev, lambda;
-    double xi, c1, s1, s2g, trw, xr, mscale, oldbeta, c0, c1h;
+    int pad_;
+    double k[7];                 // mode-specific scalars, see load_coef
 };
 
+// compact form kept in registers by the step kernel's epilogue threads
+struct CoefR {
+    int mode, flags;             // flags: bit0 first, bit1 pend, bit2 lampos, bit3 rd0, bit4 rd1, bit5 wr0, bit6 wr1, bit7 rdself
+    double k[7];
+    __device__ __forceinline__ bool first() const { return flags & 1; }
+    __device__ __forceinline__ bool pend() const { return flags & 2; }
+    __device__ __forceinline__ bool lampos() const { return flags & 4; }
+    __device__ __forceinline__ bool rd0() const { return flags & 8; }
+    __device__ __forceinline__ bool rd1() const { return flags & 16; }
+    __device__ __forceinline__ bool wr0() const { return flags & 32; }
+    __device__ __forceinline__ bool wr1() const { return flags & 64; }
+    __device__ __forceinline__ bool rdself() const { return flags & 128; }
+};
+__device__ __forceinline__ CoefR to_regs(const Coef &C) {
+    CoefR R;
+    R.mode = C.mode;
+    R.flags = (C.first ? 1 : 0) | (C.pend ? 2 : 0) | (C.lampos ? 4 : 0) | (C.rd0 ? 8 : 0) | (C.rd1 ? 16 : 0) |
+              (C.wr0 ? 32 : 0) | (C.wr1 ? 64 : 0) | (C.rdself ? 128 : 0);
+#pragma unroll
+    for (int i = 0; i < 7; ++i) R.k[i] = C.k[i];
+    return R;
+}
+
+// k[] per mode:
+//   PLAIN        c0, c1h
+//   LSQR_INIT_M  gsc
+//   LSQR_U       gsc, alpha, ssc
+//   LSQR_V       gsc, beta, ssc, tr_prev, sigma
+//   CRAIG_V      gsc, beta, ssc, xi, c1, s1, s2g
+//   CRAIG_U      gsc, alpha, ssc, mscale, trw, xr
+//   MINRES_M     lambda, beta, oldbeta
+//   CGLS_M       alpha, lambda
 __device__ __forceinline__ void load_coef(Coef &C, const SlotIO &io, const SlotState *st, bool use_state) {
     C.mode = io.mode;
-    C.c0 = io.c0; C.c1h = io.c1;
-    C.gsc = 1.0; C.ssc = 1.0;
     C.rd0 = C.rd1 = C.wr0 = C.wr1 = C.rdself = 0;
-    C.first = 0; C.pend = 0; C.iter = 0; C.lambda = 0.0;
+    C.first = 0; C.pend = 0; C.lampos = 0; C.pad_ = 0;
+    for (int i = 0; i < 7; ++i) C.k[i] = 0.0;
     if (io.mode == MD_NONE) return;
-    if (io.mode == MD_PLAIN) { C.rd0 = io.a0 != nullptr; return; }
+    if (io.mode == MD_PLAIN) { C.k[0] = io.c0; C.k[1] = io.c1; C.rd0 = io.a0 != nullptr; return; }
     if (!use_state) return;
-    C.first = st->first; C.pend = st->pend; C.iter = st->iter;
-    C.alpha = st->alpha; C.beta = st->beta; C.sigma = st->sigma; C.tr_prev = st->tr_prev;
-    C.lambda = st->lambda; C.xi = st->xi; C.c1 = st->c1; C.s1 = st->s1; C.s2g = st->s2g;
-    C.trw = st->trw; C.xr = st->xr; C.mscale = st->mscale; C.oldbeta = st->oldbeta;
     switch (io.mode) {
-        case MD_LSQR_INIT_M: C.gsc = st->su; break;
-        case MD_LSQR_U: C.gsc = st->sv; C.ssc = st->su; C.rdself = 1; break;
+        case MD_LSQR_INIT_M: C.k[0] = st->su; break;
+        case MD_LSQR_U:
+            C.k[0] = st->sv; C.k[1] = st->alpha; C.k[2] = st->su; C.rdself = 1;
+            break;
         case MD_LSQR_V:
-            C.gsc = st->su; C.ssc = st->sv; C.rdself = 1;
+            C.first = st->first;
+            C.k[0] = st->su; C.k[1] = st->beta; C.k[2] = st->sv; C.k[3] = st->tr_prev; C.k[4] = st->sigma;
+            C.rdself = 1;
             C.rd0 = C.rd1 = !C.first; C.wr0 = C.wr1 = 1;
             break;
         case MD_CRAIG_V:
-            C.gsc = st->mscale * st->su; C.ssc = st->sv; C.rdself = 1;
+            C.pend = st->pend; C.lampos = st->lambda > 0;
+            C.k[0] = st->mscale * st->su; C.k[1] = st->beta; C.k[2] = st->sv; C.k[3] = st->xi;
+            C.k[4] = st->c1; C.k[5] = st->s1; C.k[6] = st->s2g;
+            C.rdself = 1;
             C.rd0 = C.wr0 = C.pend;
-            C.rd1 = C.wr1 = C.pend && (C.lambda > 0);
+            C.rd1 = C.wr1 = C.pend && C.lampos;
             break;
         case MD_CRAIG_U:
-            C.gsc = st->sv; C.ssc = st->su; C.rdself = 1;
+            C.k[0] = st->sv; C.k[1] = st->alpha; C.k[2] = st->su; C.k[3] = st->mscale; C.k[4] = st->trw; C.k[5] = st->xr;
+            C.rdself = 1;
             C.rd0 = C.rd1 = C.wr0 = C.wr1 = 1;
             break;
-        case MD_MINRES_M: C.rd0 = 1; C.rd1 = (C.iter + 1 >= 2); break;
-        case MD_CGLS_M: C.rd0 = C.rd1 = 1; C.wr0 = 1; break;
+        case MD_MINRES_M:
+            C.k[0] = st->lambda; C.k[1] = st->beta; C.k[2] = st->oldbeta; C.lampos = st->lambda != 0.0;
+            C.rd0 = 1; C.rd1 = (st->iter + 1 >= 2);
+            break;
+        case MD_CGLS_M:
+            C.k[0] = st->alpha; C.k[1] = st->lambda; C.lampos = st->lambda > 0;
+            C.rd0 = C.rd1 = 1; C.wr0 = 1;
+            break;
         default: break;
     }
 }
 
 // row epilogue on values: (sraw, selfold, a0, a1) -> returns new self; a0 / a1 updated in place
-__device__ __forceinline__ double row_epilogue(const Coef &C, double sraw, double selfold, double &a0,
-                                               double &a1, double &acc0, double &acc1) {
+template <class CT>
+__device__ __forceinline__ double row_epilogue_t(const CT &C, int mode, bool first, bool pend, bool lampos, bool rd0, bool rd1,
+                                                 double sraw, double selfold, double &a0, double &a1, double &acc0, double &acc1) {
     double out = 0.0;
-    switch (C.mode) {
+    switch (mode) {
         case MD_PLAIN: {
-            out = C.c0 * sraw;
-            if (C.rd0) out += C.c1h * a0;
+            out = C.k[0] * sraw;
+            if (rd0) out += C.k[1] * a0;
             acc0 += out * out;
         } break;
         case MD_LSQR_INIT_M: {
-            out = C.gsc * sraw;
+            out = C.k[0] * sraw;
             acc0 += out * out;
         } break;
         case MD_LSQR_U: {
-            out = C.gsc * sraw - C.alpha * (selfold * C.ssc);
+            out = C.k[0] * sraw - C.k[1] * (selfold * C.k[2]);
             acc0 += out * out;
         } break;
         case MD_LSQR_V: {
-            const double vj = selfold * C.ssc;
-            const double wj = C.first ? vj : (vj - C.tr_prev * a0);
+            const double vj = selfold * C.k[2];
+            const double wj = first ? vj : (vj - C.k[3] * a0);
             acc1 += wj * wj;
             a0 = wj;
-            a1 = (C.first ? 0.0 : a1) + C.sigma * wj;
-            out = C.gsc * sraw - C.beta * vj;
+            a1 = (first ? 0.0 : a1) + C.k[4] * wj;
+            out = C.k[0] * sraw - C.k[1] * vj;
             acc0 += out * out;
         } break;
         case MD_CRAIG_V: {
-            const double vp = selfold * C.ssc;
-            if (C.pend) {
-                if (C.lambda > 0) {
+            const double vp = selfold * C.k[2];
+            if (pend) {
+                if (lampos) {
                     const double w2 = a1;
-                    double x = a0 + (C.xi * C.c1) * vp;
-                    x = x + (C.xi * C.s1) * w2;
+                    double x = a0 + (C.k[3] * C.k[4]) * vp;
+                    x = x + (C.k[3] * C.k[5]) * w2;
                     a0 = x;
-                    a1 = C.s2g * (C.s1 * vp - C.c1 * w2);
+                    a1 = C.k[6] * (C.k[5] * vp - C.k[4] * w2);
                 } else {
-                    a0 += C.xi * vp;
+                    a0 += C.k[3] * vp;
                 }
             }
-            out = C.gsc * sraw - C.beta * vp;
+            out = C.k[0] * sraw - C.k[1] * vp;
             acc0 += out * out;
         } break;
         case MD_CRAIG_U: {
-            const double mu = selfold * C.ssc;
-            const double uj = C.mscale * mu;
-            const double wj = uj - C.trw * a0;
+            const double mu = selfold * C.k[2];
+            const double uj = C.k[3] * mu;
+            const double wj = uj - C.k[4] * a0;
             a0 = wj;
-            a1 += C.xr * wj;
+            a1 += C.k[5] * wj;
             acc1 += wj * wj;
-            out = C.gsc * sraw - C.alpha * mu;
+            out = C.k[0] * sraw - C.k[1] * mu;
             acc0 += out * out;
         } break;
         case MD_MINRES_M: {
             // a0 = r2 (= v), a1 = r1 ; self = y
             const double r2 = a0;
             double y = sraw;
-            if (C.lambda != 0.0) y += C.lambda * r2;
-            y *= (1.0 / C.beta);
-            if (C.rd1) y -= (C.beta / C.oldbeta) * a1;
+            if (lampos) y += C.k[0] * r2;
+            y *= (1.0 / C.k[1]);
+            if (rd1) y -= (C.k[1] / C.k[2]) * a1;
             out = y;
             acc0 += r2 * y;
         } break;
@@ -608,10 +659,10 @@ __device__ __forceinline__ double row_epilogue(const Coef &C, double sraw, doubl
         } break;
         case MD_CGLS_M: {
             // a0 = x, a1 = p ; self = s
-            const double x = a0 + C.alpha * a1;
+            const double x = a0 + C.k[0] * a1;
             a0 = x;
             double sv = sraw;
-            if (C.lambda > 0) sv -= C.lambda * x;
+            if (lampos) sv -= C.k[1] * x;
             out = sv;
             acc0 += sv * sv;
         } break;
@@ -619,31 +670,42 @@ __device__ __forceinline__ double row_epilogue(const Coef &C, double sraw, doubl
     }
     return out;
 }
+__device__ __forceinline__ double row_epilogue(const Coef &C, double sraw, double selfold, double &a0, double &a1,
+                                               double &acc0, double &acc1) {
+    return row_epilogue_t(C, C.mode, C.first != 0, C.pend != 0, C.lampos != 0, C.rd0 != 0, C.rd1 != 0, sraw, selfold, a0, a1, acc0, acc1);
+}
+__device__ __forceinline__ double row_epilogue(const CoefR &C, double sraw, double selfold, double &a0, double &a1,
+                                               double &acc0, double &acc1) {
+    return row_epilogue_t(C, C.mode, C.first(), C.pend(), C.lampos(), C.rd0(), C.rd1(), sraw, selfold, a0, a1, acc0, acc1);
+}
 
 // ------------------------------------------------------------------------------------------------
 // the fused SpMM step kernel — tiled SELL-32 streamed through a TMA ring by persistent CTAs.
 //
-// Layout: the rows of the operator are cut into tiles of up to kTileRows consecutive rows (fewer
-// when the rows are long, so that a tile always fits a ring stage); inside a tile the rows are
-// sorted by length and packed into slices of 32 (lane == row).  A slice stores its entries as
-// "pair rows": entries 2p and 2p+1 of the 32 lanes are interleaved, so one 16-byte access brings
-// two values and one 8-byte access two column indices per lane (an odd last entry is stored as a
-// plain 32-entry row).  All values of a tile are contiguous in HBM, and so are its indices.
+// Layout: the rows of the operator are cut into tiles of up to kTileRows consecutive rows (as many
+// rows as fit a ring stage); inside a tile the rows are sorted by length and packed into slices of
+// 32 (lane == row).  A slice stores its entries as "pair rows": entries 2p and 2p+1 of the 32 lanes
+// are interleaved, so one 16-byte access brings two values and one 8-byte access two column indices
+// per lane (an odd last entry is stored as a plain 32-entry row).  Everything a tile needs from the
+// operator — [values | column indices | lane -> row map] — is ONE contiguous block in HBM.
 //
 // One persistent CTA per SM walks the tiles b, b + grid, b + 2 grid, ... :
-//   producer  (warp 0, one lane) keeps the ring full: per tile four TMA bulk copies (cp.async.bulk +
-//             mbarrier) bring the tile's values, its column indices, its lane -> row map and the
-//             slice of the gathered vector(s) the tile can touch — columns [cmin, cmin + ccnt) —
-//             into one ring stage.  Every byte the SM needs from HBM is requested as large
-//             contiguous reads several tiles ahead of its use, none of it held in registers.
+//   producers (warps 0 and 1, one lane each) keep the ring full with cp.async.bulk (TMA) + mbarrier:
+//             warp 0 copies the tile's block, warp 1 the slice of the gathered vector(s) the tile
+//             can touch — columns [cmin, cmin + ccnt) — into the same ring stage.  Measured on
+//             B200 (tools/micro/tma_bw.cu): a bulk copy costs its issuing thread ~0.35 us whatever
+//             its size and an SM sustains one per ~0.17 us, so full HBM bandwidth needs >= 16 KB
+//             per copy: hence one big block per tile and two issuing warps.
+//             Every byte the SM needs from HBM is requested as large contiguous reads several
+//             tiles ahead of its use, none of it held in registers.
 //   consumers kGroups groups of 4 warps; group g takes the CTA's tiles g, g + kGroups, ...
-//     phase 1  one warp per slice: values / indices are read conflict-free from the stage, the
+//     phase 1  a warp per slice: values / indices are read conflict-free from the stage, the
 //              gathers cost shared-memory bank cycles instead of one L1 wavefront per distinct
 //              128-byte line; the two row sums of every row go to a small per-group buffer indexed
-//              by the row's position in the tile, and the stage is handed back to the producer.
-//     phase 2  the Krylov row epilogue runs over the tile's rows in natural order (one thread per
-//              row), so every vector it reads and writes is accessed fully coalesced even though
-//              SELL permuted the rows; its operands were requested before phase 1.
+//              by the row's position in the tile, and the stage is handed back to the producers.
+//     phase 2  the Krylov row epilogue runs over the tile's rows in natural order, so every
+//              vector it reads and writes is accessed fully coalesced even though SELL permuted
+//              the rows; its operands were requested before phase 1.
 //   Groups are in different phases at any time, so the shared-memory pipe, the HBM stream and the
 //   epilogue traffic overlap inside one SM.
 // Tiles whose column span exceeds the window capacity gather from global memory instead.
@@ -656,43 +718,80 @@ __device__ __forceinline__ double row_epilogue(const Coef &C, double sraw, doubl
 constexpr int kTileRows = 128;
 constexpr int kTileSlices = kTileRows / 32;
 constexpr int kGroups = 3;
-constexpr int kGroupThreads = kTileRows;                       // one thread per tile row in phase 2
-constexpr int kStepThreads = 32 + kGroups * kGroupThreads;     // producer warp + consumer groups
-constexpr int kStageBytesMax = 40 * 1024;                      // values + indices + row map + window
+constexpr int kGroupThreads = kTileRows;                      // phase 1: a warp per slice ; phase 2: a thread per row
+constexpr int kGroupWarps = kGroupThreads / 32;
+constexpr int kProducerThreads = 64;                           // warp 0: tile blocks, warp 1: gather windows
+constexpr int kStepThreads = kProducerThreads + kGroups * kGroupThreads;
+constexpr int kStageBytesMax = 40 * 1024;                      // tile block + window
 constexpr int kMaxStages = 8;
-constexpr int kRingBudget = 200 * 1024;
+constexpr int kRingBudget = 188 * 1024;
 constexpr int kWinCapMax = 1536;          // window capacity (entries of 16 bytes) a tile may ask for
 constexpr int kLongThreads = 256;
 
 struct __align__(16) TileMeta {
-    int rmap;            // first entry of the tile's lane -> row map (rowloc[rmap .. rmap + ns * 32))
-    int ns;              // slices in the tile, ns <= kTileSlices (one warp each)
-    int cmin, ccnt;      // gather window (ccnt == 0: gather from global memory, scol holds global columns)
+    long long boff;      // byte offset of the tile's block [values elems*8 | indices elems*4 | row map ns*128]
+    int elems;           // stored entries (multiple of 32)
+    int ns;              // slices in the tile, ns <= kTileSlices
+    int cmin, ccnt;      // gather window (ccnt == 0: gather from global memory, indices are global columns)
     int row0, nrows;     // rows [row0, row0 + nrows) of the operator
-    int eoff, elems;     // the tile's entries: sval / scol [eoff, eoff + elems)
     int width[kTileSlices];   // entries per row of each slice
 };
-static_assert(sizeof(TileMeta) == 48, "TileMeta is loaded as three int4");
+static_assert(sizeof(TileMeta) == 48 && kTileSlices == 4, "TileMeta is loaded as three int4");
+static_assert(kGroupWarps == kTileSlices, "phase 1 maps one warp to one slice");
 
 __device__ __forceinline__ TileMeta load_tile(const TileMeta *tiles, int t) {
     const int4 *tp = reinterpret_cast<const int4 *>(tiles + t);
     const int4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
     TileMeta T;
-    T.rmap = a.x; T.ns = a.y; T.cmin = a.z; T.ccnt = a.w;
-    T.row0 = b.x; T.nrows = b.y; T.eoff = b.z; T.elems = b.w;
+    T.boff = (long long)(((unsigned long long)(unsigned)a.y << 32) | (unsigned)a.x);
+    T.elems = a.z; T.ns = a.w;
+    T.cmin = b.x; T.ccnt = b.y; T.row0 = b.z; T.nrows = b.w;
     T.width[0] = c.x; T.width[1] = c.y; T.width[2] = c.z; T.width[3] = c.w;
+    return T;
+}
+
+// what a consumer keeps of a tile descriptor (registers): everything but the block offset
+struct CTile {
+    int elems, cmin, ccnt, row0;
+    int pk;              // ns | nrows << 8
+    int wpk;             // the four slice widths, one byte each (widths <= kLongRow < 256)
+    __device__ __forceinline__ int ns() const { return pk & 0xff; }
+    __device__ __forceinline__ int nrows() const { return pk >> 8; }
+    __device__ __forceinline__ int width(int i) const { return (wpk >> (8 * i)) & 0xff; }
+};
+__device__ __forceinline__ CTile load_ctile(const TileMeta *tiles, int t) {
+    const int4 *tp = reinterpret_cast<const int4 *>(tiles + t);
+    const int4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+    CTile T;
+    T.elems = a.z; T.cmin = b.x; T.ccnt = b.y; T.row0 = b.z;
+    T.pk = a.w | (b.w << 8);
+    T.wpk = c.x | (c.y << 8) | (c.z << 16) | (c.w << 24);
     return T;
 }
 
 __device__ __forceinline__ void group_bar(int g) {
     asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(kGroupThreads) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+#ifdef FPSB_PHASE_TIMERS
+__device__ unsigned long long g_phase_cycles[16];
+#define PT_DECL long long pt_t0 = clock64(), pt_acc[6] = {0, 0, 0, 0, 0, 0}
+#define PT_MARK(i) do { const long long pt_t1 = clock64(); pt_acc[i] += pt_t1 - pt_t0; pt_t0 = pt_t1; } while (0)
+#define PT_FLUSH(base, n) do { for (int pt_i = 0; pt_i < (n); ++pt_i) atomicAdd(&g_phase_cycles[(base) + pt_i], (unsigned long long)pt_acc[pt_i]); } while (0)
+#else
+#define PT_DECL
+#define PT_MARK(i)
+#define PT_FLUSH(base, n)
+#endif
 
 template <bool PAIR>
 __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, int use_state) {
     extern __shared__ __align__(128) unsigned char s_dyn[];
-    __shared__ double2 s_sum[kGroups][2][kTileRows];
-    __shared__ double s_red[4 * 16];
+    __shared__ double2 s_sum[kGroups][2][kTileRows];        // [group][double buffer][row]
+    __shared__ double s_red[4 * 32];
     __shared__ alignas(8) uint64_t full_bar[kMaxStages];
     __shared__ alignas(8) uint64_t empty_bar[kMaxStages];
     __shared__ SlotState sS[2];
@@ -700,7 +799,10 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, 
     __shared__ int s_last;
 
     const int tid = threadIdx.x;
-    const int cta = blockIdx.x, nstage = P.nstage;
+    const int cta = blockIdx.x, nstage = P.nstage, gsz = (int)gridDim.x;
+#if FPSB_EXP >= 9 && FPSB_EXP <= 11
+    P.ntiles = 0;        // experiment: launch overhead only (prologue + reduction + scalar recurrences)
+#endif
     // ---- prologue: one round trip brings both slot states into shared memory ----
     if (use_state) {
         const double *g = reinterpret_cast<const double *>(P.st);
@@ -708,7 +810,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, 
         for (int i = tid; i < (int)(2 * sizeof(SlotState) / sizeof(double)); i += kStepThreads) d[i] = __ldcg(g + i);
     }
     if (tid == 0) {
-        for (int s = 0; s < nstage; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kTileSlices); }
+        for (int s = 0; s < nstage; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], kGroupWarps); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -722,21 +824,20 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, 
         if (!act1) { sC[1].mode = MD_NONE; sC[1].rd0 = sC[1].rd1 = sC[1].wr0 = sC[1].wr1 = sC[1].rdself = 0; }
     }
     __syncthreads();
-    const Coef &C0 = sC[0];
-    const Coef &C1 = sC[1];
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    // stage layout: [values val_cap*8 | indices val_cap*4 | row map kTileRows*4 | window win_cap*16]
+    // stage layout: [tile block, blk_cap bytes | window win_cap*16 bytes]
     const size_t stage_bytes = (size_t)P.stage_bytes;
     // vectors of doubles need 16-byte aligned sources for the TMA path (the pairs always are)
     const bool win_tma = PAIR || ((((uintptr_t)P.io[0].gin | (uintptr_t)P.io[1].gin) & 15) == 0);
     bool ok = true;
 
-    if (tid < 32) {
-        // ------------------------------- producer -------------------------------
-        if (tid == 0) {
+    if (tid < kProducerThreads) {
+        // ------------------------------- producers -------------------------------
+        if ((tid & 31) == 0) {
+            const bool blocks = tid == 0;      // warp 0: tile blocks ; warp 1: gather windows
             // tile descriptors are fetched two tiles ahead of their use
-            const int gsz = (int)gridDim.x;
             int k = 0, tile = cta, t1 = cta + gsz;
+            PT_DECL;
             TileMeta T{}, T1{};
             if (tile < P.ntiles) T = load_tile(P.tiles, tile);
             if (t1 < P.ntiles) T1 = load_tile(P.tiles, t1);
@@ -745,78 +846,111 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, 
                 TileMeta T2{};
                 if (t2 < P.ntiles) T2 = load_tile(P.tiles, t2);
                 const int s = k % nstage;
+                PT_MARK(0);
                 if (k >= nstage) ok = mbar_wait(&empty_bar[s], (uint32_t)((k / nstage - 1) & 1)) && ok;
+                // bounded run-ahead: tile k - inflight must have landed.  Everything an SM requests is
+                // served in order, so a deep TMA backlog is pure latency for the epilogue's own loads
+                if (k >= P.inflight) {
+                    const int kb = k - P.inflight;
+                    ok = mbar_wait(&full_bar[kb % nstage], (uint32_t)((kb / nstage) & 1)) && ok;
+                }
+                PT_MARK(1);
                 unsigned char *st = s_dyn + (size_t)s * stage_bytes;
-                double *s_val = reinterpret_cast<double *>(st);
-                int *s_col = reinterpret_cast<int *>(st + (size_t)P.val_cap * 8);
-                int *s_map = reinterpret_cast<int *>(st + (size_t)P.val_cap * 12);
-                unsigned char *s_win = st + (size_t)P.val_cap * 12 + kTileRows * 4;
-                uint32_t tot = (uint32_t)T.elems * 12u + (uint32_t)T.ns * 128u;
-                uint32_t wbytes = 0;
-                if (T.ccnt > 0) {
-                    if (PAIR) { wbytes = (uint32_t)T.ccnt * 16u; tot += wbytes; }
-                    else if (win_tma && !(T.ccnt & 1)) { wbytes = (uint32_t)T.ccnt * 8u; tot += wbytes * ((act0 ? 1u : 0u) + (act1 ? 1u : 0u)); }
-                }
-                mbar_expect_tx(&full_bar[s], tot);
-                if (T.elems > 0) {
-                    tma_bulk_g2s(s_val, P.sval + T.eoff, (uint32_t)T.elems * 8u, &full_bar[s]);
-                    tma_bulk_g2s(s_col, P.scol + T.eoff, (uint32_t)T.elems * 4u, &full_bar[s]);
-                }
-                if (T.ns > 0) tma_bulk_g2s(s_map, P.rowloc + T.rmap, (uint32_t)T.ns * 128u, &full_bar[s]);
-                if (wbytes) {
-                    if (PAIR) tma_bulk_g2s(s_win, P.gin2 + T.cmin, wbytes, &full_bar[s]);
-                    else {
-                        double *w0 = reinterpret_cast<double *>(s_win);
-                        if (act0) tma_bulk_g2s(w0, P.io[0].gin + T.cmin, wbytes, &full_bar[s]);
-                        if (act1) tma_bulk_g2s(w0 + P.win_cap, P.io[1].gin + T.cmin, wbytes, &full_bar[s]);
+                if (blocks) {
+                    const uint32_t bytes = (uint32_t)T.elems * 12u + (uint32_t)T.ns * 128u;
+                    mbar_expect_tx(&full_bar[s], bytes);
+                    if (bytes) tma_bulk_g2s(st, P.tbuf + T.boff, bytes, &full_bar[s]);
+                } else {
+                    unsigned char *s_win = st + (size_t)P.blk_cap;
+                    uint32_t wbytes = 0, tot = 0;
+                    if (T.ccnt > 0 && FPSB_EXP != 12) {
+                        if (PAIR) { wbytes = (uint32_t)T.ccnt * 16u; tot = wbytes; }
+                        else if (win_tma && !(T.ccnt & 1)) { wbytes = (uint32_t)T.ccnt * 8u; tot = wbytes * ((act0 ? 1u : 0u) + (act1 ? 1u : 0u)); }
+                    }
+                    mbar_expect_tx(&full_bar[s], tot);
+                    if (wbytes) {
+                        if (PAIR) tma_bulk_g2s(s_win, P.gin2 + T.cmin, wbytes, &full_bar[s]);
+                        else {
+                            double *w0 = reinterpret_cast<double *>(s_win);
+                            if (act0) tma_bulk_g2s(w0, P.io[0].gin + T.cmin, wbytes, &full_bar[s]);
+                            if (act1) tma_bulk_g2s(w0 + P.win_cap, P.io[1].gin + T.cmin, wbytes, &full_bar[s]);
+                        }
                     }
                 }
                 T = T1; T1 = T2; tile = t1; t1 = t2;
+                PT_MARK(2);
             }
+            PT_FLUSH(blocks ? 0 : 3, 3);
         }
     } else {
         // ------------------------------- consumers -------------------------------
-        const int ct = tid - 32;
+        // (1 CTA per SM with a 215 KB ring leaves almost no L1: a register spill costs an L2 round
+        //  trip, so this kernel must stay spill-free — hence 4-warp groups and <= 146 registers)
+        const int ct = tid - kProducerThreads;
         const int g = ct / kGroupThreads, t = ct % kGroupThreads;
         const int lane = t & 31, wid = t >> 5;
+        const CoefR C0 = to_regs(sC[0]), C1 = to_regs(sC[1]);
+        double *const self0 = PAIR ? reinterpret_cast<double *>(P.self2) : P.io[0].self;
+        double *const self1 = PAIR ? reinterpret_cast<double *>(P.self2) + 1 : P.io[1].self;
+        const int self_stride = PAIR ? 2 : 1;
         int k = g;
-        int tile = cta + k * (int)gridDim.x;
-        TileMeta T{};
-        if (tile < P.ntiles) T = load_tile(P.tiles, tile);
+        int tile = cta + k * gsz;
+        PT_DECL;
+        // tile descriptors are fetched two tiles ahead of their use; the row-epilogue operands of the
+        // group's next tile are pulled into L2 one tile ahead (no registers held)
+        CTile T{}, Tn{}, Tnn{};
+        if (tile < P.ntiles) T = load_ctile(P.tiles, tile);
+        if (tile + kGroups * gsz < P.ntiles) Tn = load_ctile(P.tiles, tile + kGroups * gsz);
         for (; tile < P.ntiles; k += kGroups) {
             const int s = k % nstage;
+            PT_MARK(0);
+            const int ntile = cta + (k + kGroups) * gsz, nntile = cta + (k + 2 * kGroups) * gsz;
+            if (nntile < P.ntiles) Tnn = load_ctile(P.tiles, nntile);
             // row-epilogue operands of this thread's row: in flight during the wait and phase 1
             const int row = T.row0 + t;
-            const bool has_row = t < T.nrows && !(P.rowflag != nullptr && P.rowflag[row]);
+            const bool has_row = FPSB_EXP != 4 && FPSB_EXP != 7 && FPSB_EXP != 12 && t < T.nrows() &&
+                                 !(P.rowflag != nullptr && P.rowflag[row]);
             double2 old2 = make_double2(0.0, 0.0);
             double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
-            if (has_row) {
+            if (has_row && FPSB_EXP != 5) {
                 if (PAIR) old2 = P.self2[row];
                 else {
-                    if (C0.rdself) old2.x = P.io[0].self[row];
-                    if (C1.rdself) old2.y = P.io[1].self[row];
+                    if (C0.rdself()) old2.x = self0[row];
+                    if (C1.rdself()) old2.y = self1[row];
                 }
-                if (C0.rd0) a00 = __ldcs(P.io[0].a0 + row);
-                if (C0.rd1) a01 = __ldcs(P.io[0].a1 + row);
-                if (C1.rd0) a10 = __ldcs(P.io[1].a0 + row);
-                if (C1.rd1) a11 = __ldcs(P.io[1].a1 + row);
+                if (C0.rd0()) a00 = __ldcs(P.io[0].a0 + row);
+                if (C0.rd1()) a01 = __ldcs(P.io[0].a1 + row);
+                if (C1.rd0()) a10 = __ldcs(P.io[1].a0 + row);
+                if (C1.rd1()) a11 = __ldcs(P.io[1].a1 + row);
             }
-            // next tile's descriptor (prefetched a whole tile ahead)
-            const int ntile = cta + (k + kGroups) * (int)gridDim.x;
-            TileMeta Tn{};
-            if (ntile < P.ntiles) Tn = load_tile(P.tiles, ntile);
+            if (ntile < P.ntiles && t < Tn.nrows()) {
+                const int r2 = Tn.row0 + t;
+                if (PAIR) { if ((t & 7) == 0) prefetch_l2(P.self2 + r2); }
+                else if ((t & 15) == 0) {
+                    if (C0.rdself()) prefetch_l2(self0 + r2);
+                    if (C1.rdself()) prefetch_l2(self1 + r2);
+                }
+                if ((t & 15) == 0) {
+                    if (C0.rd0()) prefetch_l2(P.io[0].a0 + r2);
+                    if (C0.rd1()) prefetch_l2(P.io[0].a1 + r2);
+                    if (C1.rd0()) prefetch_l2(P.io[1].a0 + r2);
+                    if (C1.rd1()) prefetch_l2(P.io[1].a1 + r2);
+                }
+            }
 
             const unsigned char *st = s_dyn + (size_t)s * stage_bytes;
             const double *s_val = reinterpret_cast<const double *>(st);
-            const int *s_col = reinterpret_cast<const int *>(st + (size_t)P.val_cap * 8);
-            const int *s_map = reinterpret_cast<const int *>(st + (size_t)P.val_cap * 12);
-            unsigned char *s_win = const_cast<unsigned char *>(st) + (size_t)P.val_cap * 12 + kTileRows * 4;
+            const int *s_col = reinterpret_cast<const int *>(st + (size_t)T.elems * 8);
+            const int *s_map = reinterpret_cast<const int *>(st + (size_t)T.elems * 12);
+            unsigned char *s_win = const_cast<unsigned char *>(st) + (size_t)P.blk_cap;
             const double2 *win2 = reinterpret_cast<const double2 *>(s_win);
             double *win0 = reinterpret_cast<double *>(s_win);
             double *win1 = win0 + P.win_cap;
             const bool windowed = T.ccnt > 0;
 
+            PT_MARK(1);
             ok = mbar_wait(&full_bar[s], (uint32_t)((k / nstage) & 1)) && ok;
+            PT_MARK(2);
             if (!PAIR && windowed && !(win_tma && !(T.ccnt & 1))) {
                 // unaligned / odd-sized caller vectors: the group stages the window itself
                 for (int i = t; i < T.ccnt; i += kGroupThreads) {
@@ -825,92 +959,103 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, 
                 }
                 group_bar(g);
             }
-            // ---------------- phase 1: row sums of this warp's slice ----------------
-            double s0 = 0.0, s1 = 0.0;
-            int lrow = -1;
-            if (wid < T.ns) {
-                int off = 0, width = T.width[0];
+            // ---------------- phase 1: row sums, a warp per slice ----------------
+            double2 *sum = s_sum[g][(k / kGroups) & 1];
+            {
+                int off = 0, width = T.width(0);
 #pragma unroll
-                for (int i = 1; i < kTileSlices; ++i) if (i <= wid) { off += T.width[i - 1] * 32; width = T.width[i]; }
+                for (int i = 1; i < kTileSlices; ++i) if (i <= wid) { off += T.width(i - 1) * 32; width = T.width(i); }
                 const int npair = width >> 1;
-                lrow = s_map[wid * 32 + lane];
-                const double2 *sv = reinterpret_cast<const double2 *>(s_val + off) + lane;
-                const int2 *sc = reinterpret_cast<const int2 *>(s_col + off) + lane;
-                if (PAIR) {
-                    if (windowed) {
+                double s0 = 0.0, s1 = 0.0, u0 = 0.0, u1 = 0.0;     // two accumulator pairs: shorter DFMA chains
+                int lrow = -1;
+                if (wid < T.ns() && FPSB_EXP != 3 && FPSB_EXP != 7 && FPSB_EXP != 12) {
+                    lrow = s_map[wid * 32 + lane];
+                    const double2 *sv = reinterpret_cast<const double2 *>(s_val + off) + lane;
+                    const int2 *sc = reinterpret_cast<const int2 *>(s_col + off) + lane;
+                    const bool tail = (width & 1) != 0;
+                    if (PAIR) {
+                        if (windowed) {
 #pragma unroll 5
-                        for (int p = 0; p < npair; ++p) {
-                            const double2 v = sv[p * 32];
-                            const int2 c = sc[p * 32];
-                            const double2 x0 = win2[c.x], x1 = win2[c.y];
-                            s0 = fma(v.x, x0.x, s0); s1 = fma(v.x, x0.y, s1);
-                            s0 = fma(v.y, x1.x, s0); s1 = fma(v.y, x1.y, s1);
-                        }
-                        if (width & 1) {
-                            const double v = s_val[off + npair * 64 + lane];
-                            const double2 x = win2[s_col[off + npair * 64 + lane]];
-                            s0 = fma(v, x.x, s0); s1 = fma(v, x.y, s1);
+                            for (int p = 0; p < npair; ++p) {
+                                const double2 v = sv[p * 32];
+                                const int2 c = sc[p * 32];
+                                const double2 x0 = win2[c.x], x1 = win2[c.y];
+                                s0 = fma(v.x, x0.x, s0); s1 = fma(v.x, x0.y, s1);
+                                u0 = fma(v.y, x1.x, u0); u1 = fma(v.y, x1.y, u1);
+                            }
+                            if (tail) {
+                                const double v = s_val[off + npair * 64 + lane];
+                                const double2 x = win2[s_col[off + npair * 64 + lane]];
+                                s0 = fma(v, x.x, s0); s1 = fma(v, x.y, s1);
+                            }
+                        } else {
+#pragma unroll 5
+                            for (int p = 0; p < npair; ++p) {
+                                const double2 v = sv[p * 32];
+                                const int2 c = sc[p * 32];
+                                const double2 x0 = __ldg(P.gin2 + c.x), x1 = __ldg(P.gin2 + c.y);
+                                s0 = fma(v.x, x0.x, s0); s1 = fma(v.x, x0.y, s1);
+                                u0 = fma(v.y, x1.x, u0); u1 = fma(v.y, x1.y, u1);
+                            }
+                            if (tail) {
+                                const double v = s_val[off + npair * 64 + lane];
+                                const double2 x = __ldg(P.gin2 + s_col[off + npair * 64 + lane]);
+                                s0 = fma(v, x.x, s0); s1 = fma(v, x.y, s1);
+                            }
                         }
                     } else {
+                        auto gather_fma = [&](double v, int c, double &r0, double &r1) {
+                            if (act0) r0 = fma(v, windowed ? win0[c] : __ldg(P.io[0].gin + c), r0);
+                            if (act1) r1 = fma(v, windowed ? win1[c] : __ldg(P.io[1].gin + c), r1);
+                        };
 #pragma unroll 5
                         for (int p = 0; p < npair; ++p) {
                             const double2 v = sv[p * 32];
                             const int2 c = sc[p * 32];
-                            const double2 x0 = __ldg(P.gin2 + c.x), x1 = __ldg(P.gin2 + c.y);
-                            s0 = fma(v.x, x0.x, s0); s1 = fma(v.x, x0.y, s1);
-                            s0 = fma(v.y, x1.x, s0); s1 = fma(v.y, x1.y, s1);
+                            gather_fma(v.x, c.x, s0, s1);
+                            gather_fma(v.y, c.y, u0, u1);
                         }
-                        if (width & 1) {
-                            const double v = s_val[off + npair * 64 + lane];
-                            const double2 x = __ldg(P.gin2 + s_col[off + npair * 64 + lane]);
-                            s0 = fma(v, x.x, s0); s1 = fma(v, x.y, s1);
-                        }
+                        if (tail) gather_fma(s_val[off + npair * 64 + lane], s_col[off + npair * 64 + lane], s0, s1);
                     }
-                } else {
-                    auto gather_fma = [&](double v, int c) {
-                        if (act0) s0 = fma(v, windowed ? win0[c] : __ldg(P.io[0].gin + c), s0);
-                        if (act1) s1 = fma(v, windowed ? win1[c] : __ldg(P.io[1].gin + c), s1);
-                    };
-#pragma unroll 5
-                    for (int p = 0; p < npair; ++p) {
-                        const double2 v = sv[p * 32];
-                        const int2 c = sc[p * 32];
-                        gather_fma(v.x, c.x);
-                        gather_fma(v.y, c.y);
-                    }
-                    if (width & 1) gather_fma(s_val[off + npair * 64 + lane], s_col[off + npair * 64 + lane]);
                 }
+                if (lrow >= 0) sum[lrow] = make_double2(s0 + u0, s1 + u1);
             }
-            // the stage is consumed: hand it back to the producer (one arrival per warp)
+            // the stage is consumed: hand it back to the producers (one arrival per warp)
             if (!PAIR) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // group-staged windows
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
-            double2 *sum = s_sum[g][(k / kGroups) & 1];
-            if (lrow >= 0) sum[lrow] = make_double2(s0, s1);
+            PT_MARK(3);
             group_bar(g);
-            // ---------------- phase 2: row epilogue in natural row order ----------------
+            PT_MARK(4);
+            // ---------------- phase 2: row epilogue in natural row order, a thread per row ----------------
             if (has_row) {
                 const double2 sm = sum[t];
-                if (PAIR) {
-                    double2 nw = old2;
-                    if (act0) nw.x = row_epilogue(C0, sm.x, old2.x, a00, a01, acc[0], acc[1]);
-                    if (act1) nw.y = row_epilogue(C1, sm.y, old2.y, a10, a11, acc[2], acc[3]);
-                    P.self2[row] = nw;
-                } else {
-                    if (act0) P.io[0].self[row] = row_epilogue(C0, sm.x, old2.x, a00, a01, acc[0], acc[1]);
-                    if (act1) P.io[1].self[row] = row_epilogue(C1, sm.y, old2.y, a10, a11, acc[2], acc[3]);
-                }
-                if (C0.wr0) __stcs(P.io[0].a0 + row, a00);
-                if (C0.wr1) __stcs(P.io[0].a1 + row, a01);
-                if (C1.wr0) __stcs(P.io[1].a0 + row, a10);
-                if (C1.wr1) __stcs(P.io[1].a1 + row, a11);
+                double n0 = old2.x, n1 = old2.y;
+                if (act0) n0 = row_epilogue(C0, sm.x, old2.x, a00, a01, acc[0], acc[1]);
+                if (act1) n1 = row_epilogue(C1, sm.y, old2.y, a10, a11, acc[2], acc[3]);
+                if (FPSB_EXP != 6) {
+                    if (PAIR) P.self2[row] = make_double2(n0, n1);
+                    else {
+                        if (act0) self0[row] = n0;
+                        if (act1) self1[row] = n1;
+                    }
+                    if (C0.wr0()) __stcs(P.io[0].a0 + row, a00);
+                    if (C0.wr1()) __stcs(P.io[0].a1 + row, a01);
+                    if (C1.wr0()) __stcs(P.io[1].a0 + row, a10);
+                    if (C1.wr1()) __stcs(P.io[1].a1 + row, a11);
+                } else acc[1] += n0 + n1;
             }
-            T = Tn;
+            T = Tn; Tn = Tnn;
             tile = ntile;
+            PT_MARK(5);
         }
+        if (t == 0 && g == 0) PT_FLUSH(6, 6);
     }
     if (!ok) atomicExch(P.done_flag, -1);
     if (!use_state) return;
+#if FPSB_EXP == 10
+    return;
+#endif
 
     // deterministic norms: one partial per CTA, the last CTA reduces them in a fixed order
     block_sum<4>(acc, s_red);
@@ -932,12 +1077,21 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, 
         tot[2] += __ldcg(pp + 2); tot[3] += __ldcg(pp + 3);
     }
     block_sum<4>(tot, s_red);
+    // scalar recurrences on the shared-memory copy of the slot states (global memory would cost one
+    // L2 round trip per field), then one coalesced write-back
     if (tid == 0) {
-        if (act0) finish_step(P.st[0], P.io[0].mode, tot[0], tot[1]);
-        if (act1) finish_step(P.st[1], P.io[1].mode, tot[2], tot[3]);
-        if (!P.st[0].active && !P.st[1].active) *P.done_flag = 1;
+#if FPSB_EXP != 11
+        if (act0) finish_step(sS[0], P.io[0].mode, tot[0], tot[1]);
+        if (act1) finish_step(sS[1], P.io[1].mode, tot[2], tot[3]);
+        if (!sS[0].active && !sS[1].active) *P.done_flag = 1;
+#endif
         *P.counter = 0;
-        __threadfence();
+    }
+    __syncthreads();
+    {
+        const double *src = reinterpret_cast<const double *>(sS);
+        double *dst = reinterpret_cast<double *>(P.st);
+        for (int i = tid; i < (int)(2 * sizeof(SlotState) / sizeof(double)); i += kStepThreads) dst[i] = src[i];
     }
 }
 
@@ -945,7 +1099,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, 
 // Launched before gk_step_kernel of the same step; leaves its norm partials at partials[pbase + row#].
 template <bool PAIR>
 __global__ void __launch_bounds__(kLongThreads) long_rows_kernel(StepParams P, int use_state, int pbase) {
-    __shared__ double s_red[4 * 16];
+    __shared__ double s_red[4 * 32];
     __shared__ Coef sC[2];
     const int tid = threadIdx.x;
     const bool act0 = P.io[0].mode != MD_NONE && (!use_state || P.st[0].active);
@@ -1027,7 +1181,7 @@ struct EwParams {
 };
 
 __global__ void __launch_bounds__(kBlock) ew_kernel(EwParams P) {
-    __shared__ double s_red[16];
+    __shared__ double s_red[32];
     __shared__ int s_last;
     SlotState *S = P.st ? &P.st[P.slot] : nullptr;
     const bool is_init = (P.op == EW_INIT_LSQR || P.op == EW_INIT_CRAIG || P.op == EW_MINRES_INIT ||
@@ -1148,6 +1302,18 @@ __global__ void __launch_bounds__(kBlock) ew_kernel(EwParams P) {
     }
 }
 
+// Jacobian value refresh of the tiled operator: one CTA per tile, values land in the tile's block
+__global__ void refresh_tiles_kernel(const TileMeta *tiles, const int *tperm0, const int *perm, const double *coo,
+                                     unsigned char *tbuf) {
+    const TileMeta T = load_tile(tiles, blockIdx.x);
+    const int p0 = tperm0[blockIdx.x];
+    double *v = reinterpret_cast<double *>(tbuf + T.boff);
+    for (int e = threadIdx.x; e < T.elems; e += blockDim.x) {
+        const int p = perm[p0 + e];
+        v[e] = (p >= 0) ? coo[p] : 0.0;
+    }
+}
+
 __global__ void gather_vals_kernel(int nnz, const int *perm, const double *coo, double *vx) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nnz) { const int p = perm[i]; vx[i] = (p >= 0) ? coo[p] : 0.0; }
@@ -1205,12 +1371,14 @@ constexpr int kLongRow = 96;     // rows longer than this leave the SELL part (a
 static void upload_sell(Handle *h, CsrDev &M, int nrows, int ncols, const std::vector<int> &rp,
                         const std::vector<int> &ci, const std::vector<int> &perm) {
     M.nrows = nrows; M.ncols = ncols; M.nnz = (int64_t)ci.size();
-    std::vector<int> rowloc, sl_off(1, 0), long_row, long_rp(1, 0), long_col, long_perm;
+    std::vector<int> long_row, long_rp(1, 0), long_col, long_perm;
     std::vector<unsigned char> rowflag((size_t)nrows + 8, 0);
     std::vector<TileMeta> tiles;
-    std::vector<int> slice_rows;      // global row per lane (host only)
+    std::vector<int> tperm0;              // first entry of every tile in sperm
+    std::vector<std::vector<int>> tile_rows;   // rows per lane of every tile's slices (host only)
     std::vector<int> order, widths;
-    int win_cap = 0, val_cap = 32;
+    int win_cap = 0;
+    size_t blk_cap = 128, total_bytes = 0, total_elems = 0;
     auto rlen = [&](int r) { return rp[(size_t)r + 1] - rp[(size_t)r]; };
     for (int r = 0; r < nrows; ++r) {
         if (rlen(r) > kLongRow) {
@@ -1220,9 +1388,8 @@ static void upload_sell(Handle *h, CsrDev &M, int nrows, int ncols, const std::v
             long_rp.push_back((int)long_col.size());
         }
     }
-    const size_t budget = (size_t)kStageBytesMax - kTileRows * 4;
     for (int w0 = 0; w0 < nrows;) {
-        // largest tile (multiple of 32 rows, at most kTileRows) whose values + indices + window fit a stage
+        // largest tile (multiple of 32 rows, at most kTileRows) whose block + window fit a stage
         int R = std::min(kTileRows, nrows - w0);
         int cnt = 0, c0 = 0, elems = 0;
         for (;;) {
@@ -1246,67 +1413,98 @@ static void upload_sell(Handle *h, CsrDev &M, int nrows, int ncols, const std::v
                 cnt = cmax - c0 + 1;
                 if (cnt > kWinCapMax) cnt = 0;
             }
-            if ((size_t)elems * 12 + (size_t)cnt * 16 <= budget) break;
+            if ((size_t)elems * 12 + widths.size() * 128 + (size_t)cnt * 16 <= (size_t)kStageBytesMax) break;
             if (R > 32) { R = std::max(32, ((R / 2) + 31) & ~31); continue; }
             cnt = 0;     // a single slice (at most kLongRow wide, 36 KB): drop the window
             break;
         }
         TileMeta T{};
-        T.rmap = (int)rowloc.size();
+        T.boff = (long long)total_bytes;
         T.row0 = w0; T.nrows = R;
         T.cmin = cnt > 0 ? c0 : 0; T.ccnt = cnt;
-        T.eoff = sl_off.back(); T.elems = elems;
-        win_cap = std::max(win_cap, cnt);
-        val_cap = std::max(val_cap, elems);
+        T.elems = elems;
         T.ns = (int)widths.size();
         for (int i = 0; i < kTileSlices; ++i) T.width[i] = i < T.ns ? widths[(size_t)i] : 0;
-        for (size_t i = 0; i < order.size(); i += 32) {
-            for (size_t l = 0; l < 32; ++l) {
-                const int r = (i + l < order.size()) ? order[i + l] : -1;
-                slice_rows.push_back(r);
-                rowloc.push_back(r >= 0 ? r - w0 : -1);
-            }
-            sl_off.push_back(sl_off.back() + widths[i / 32] * 32);
-        }
+        const size_t bytes = (size_t)elems * 12 + (size_t)T.ns * 128;
+        win_cap = std::max(win_cap, cnt);
+        blk_cap = std::max(blk_cap, bytes);
+        tperm0.push_back((int)total_elems);
+        total_bytes += bytes;
+        total_elems += (size_t)elems;
+        std::vector<int> lanes;
+        for (size_t i = 0; i < order.size(); i += 32)
+            for (size_t l = 0; l < 32; ++l) lanes.push_back((i + l < order.size()) ? order[i + l] : -1);
+        tile_rows.push_back(std::move(lanes));
         tiles.push_back(T);
         w0 += R;
     }
-    const int nslice = (int)sl_off.size() - 1;
-    const size_t padded = (size_t)sl_off.back();
-    std::vector<int> scol(padded, 0), sperm(padded, -1);
-    for (const TileMeta &T : tiles) {
+    // Order of the entries inside every row: the gather of step j reads, for the 8 lanes of a
+    // quarter warp, 8 window entries of 16 bytes — conflict-free iff their columns differ mod 8.
+    // Greedy: at every step each lane takes, among its remaining entries, the one whose bank group
+    // is least used by the lanes of its quarter so far (ties: smallest column).  `eorder` holds, per
+    // lane, the permutation of the row's CSR entries.
+    // fill the blocks: [values (refreshed on the device) | indices | lane -> row map]
+    std::vector<unsigned char> tbuf(total_bytes + 128, 0);
+    std::vector<int> sperm(total_elems + 8, -1);
+    for (size_t ti = 0; ti < tiles.size(); ++ti) {
+        const TileMeta &T = tiles[ti];
         const int cbase = T.ccnt > 0 ? T.cmin : 0;
-        const int s0 = T.rmap / 32;
-        for (int sidx = s0; sidx < s0 + T.ns; ++sidx) {
-            const int off = sl_off[(size_t)sidx], width = (sl_off[(size_t)sidx + 1] - off) / 32;
-            const int npair = width / 2;
+        int *cols = reinterpret_cast<int *>(tbuf.data() + T.boff + (size_t)T.elems * 8);
+        int *rmap = reinterpret_cast<int *>(tbuf.data() + T.boff + (size_t)T.elems * 12);
+        int *tp = sperm.data() + tperm0[ti];
+        int off = 0;
+        std::vector<int> eorder, used;
+        for (int sl = 0; sl < T.ns; ++sl) {
+            const int width = T.width[sl], npair = width / 2;
+            eorder.assign((size_t)32 * std::max(width, 1), -1);
+            used.assign((size_t)32 * std::max(width, 1), 0);
+            for (int q0 = 0; q0 < 32; q0 += 8) {
+                for (int j = 0; j < width; ++j) {
+                    int cnt8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    for (int l = q0; l < q0 + 8; ++l) {
+                        const int r = tile_rows[ti][(size_t)sl * 32 + l];
+                        if (r < 0) continue;
+                        const int base = rp[(size_t)r], len = rp[(size_t)r + 1] - base;
+                        if (j >= len) continue;
+                        int best = -1, bestc = 1 << 30;
+                        for (int e = 0; e < len; ++e) {
+                            if (used[(size_t)l * width + e]) continue;
+                            const int bg = T.ccnt > 0 ? ((ci[(size_t)(base + e)] - cbase) & 7) : 0;
+                            if (cnt8[bg] < bestc) { bestc = cnt8[bg]; best = e; }
+                        }
+                        used[(size_t)l * width + best] = 1;
+                        eorder[(size_t)l * width + j] = best;
+                        if (T.ccnt > 0) cnt8[(ci[(size_t)(base + best)] - cbase) & 7]++;
+                    }
+                }
+            }
             for (int l = 0; l < 32; ++l) {
-                const int r = slice_rows[(size_t)sidx * 32 + l];
+                const int r = tile_rows[ti][(size_t)sl * 32 + l];
+                rmap[sl * 32 + l] = r >= 0 ? r - T.row0 : -1;
                 int len = 0, base = 0;
                 if (r >= 0) { base = rp[(size_t)r]; len = rp[(size_t)r + 1] - base; }
                 for (int j = 0; j < width; ++j) {
                     // pair rows: entries 2p, 2p+1 of a lane are adjacent; an odd last entry is a plain row
-                    const size_t q = (j < 2 * npair) ? (size_t)off + ((size_t)(j >> 1) * 32 + l) * 2 + (j & 1)
-                                                     : (size_t)off + (size_t)npair * 64 + l;
-                    if (j < len) { scol[q] = ci[(size_t)(base + j)] - cbase; sperm[q] = perm[(size_t)(base + j)]; }
-                    else { scol[q] = 0; sperm[q] = -1; }     // padding: value 0, valid column
+                    const int q = (j < 2 * npair) ? off + ((j >> 1) * 32 + l) * 2 + (j & 1) : off + npair * 64 + l;
+                    if (j < len) {
+                        const int e = eorder[(size_t)l * width + j];
+                        cols[q] = ci[(size_t)(base + e)] - cbase; tp[q] = perm[(size_t)(base + e)];
+                    } else { cols[q] = 0; tp[q] = -1; }     // padding: value 0, valid column
                 }
             }
+            off += width * 32;
         }
     }
-    M.nslice = nslice;
-    M.padded = (int64_t)padded;
+    M.padded = (int64_t)total_elems;
     M.nlong = (int)long_row.size();
     M.ntiles = (int)tiles.size();
     M.win_cap = (win_cap + 7) & ~7;
-    M.val_cap = (val_cap + 31) & ~31;
-    M.stage_bytes = (int)((((size_t)M.val_cap * 12 + kTileRows * 4 + (size_t)M.win_cap * 16) + 127) & ~(size_t)127);
+    M.blk_cap = (int)((blk_cap + 127) & ~(size_t)127);
+    M.stage_bytes = (int)((((size_t)M.blk_cap + (size_t)M.win_cap * 16) + 127) & ~(size_t)127);
     M.nstage = std::max(2, std::min(kMaxStages, kRingBudget / M.stage_bytes));
-    M.rowloc.from(rowloc, h->stream);
-    M.scol.from(scol, h->stream);
+    M.tbuf.from(tbuf, h->stream);
     M.sperm.from(sperm, h->stream);
-    M.sval.alloc(padded + 8);
-    M.sval.zero(h->stream);
+    M.tperm0.from(tperm0, h->stream);
     M.tiles.alloc((tiles.size() + 1) * sizeof(TileMeta));
     if (!tiles.empty()) FPSB_CUDA(cudaMemcpyAsync(M.tiles.p, tiles.data(), tiles.size() * sizeof(TileMeta), cudaMemcpyHostToDevice, h->stream));
     M.rowflag.from(rowflag, h->stream);
@@ -1335,6 +1533,16 @@ static void launch_step(Handle *h, const CsrDev &M, const StepParams &P, bool pa
     h->launches += 1;
 }
 
+void phase_timers(unsigned long long *out, int reset) {
+#ifdef FPSB_PHASE_TIMERS
+    if (out) cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)); }
+#else
+    if (out) for (int i = 0; i < 16; ++i) out[i] = 0;
+    (void)reset;
+#endif
+}
+
 void csr_build(Handle *h) {
     const int m = (int)h->ncon, n = (int)h->nvar;
     {
@@ -1356,9 +1564,9 @@ void csr_build(Handle *h) {
 
 void csr_refresh_values(Handle *h) {
     for (CsrDev *M : {&h->A, &h->At}) {
-        if (M->padded > 0) {
-            int grid = (int)((M->padded + 255) / 256);
-            gather_vals_kernel<<<grid, 256, 0, h->stream>>>((int)M->padded, M->sperm.p, h->coo_vals.p, M->sval.p);
+        if (M->ntiles > 0) {
+            refresh_tiles_kernel<<<M->ntiles, 256, 0, h->stream>>>(reinterpret_cast<const TileMeta *>(M->tiles.p), M->tperm0.p,
+                                                                   M->sperm.p, h->coo_vals.p, M->tbuf.p);
             h->launches += 1;
         }
         const int nl = (int)(M->long_col.n > 8 ? M->long_col.n - 8 : 0);
@@ -1371,9 +1579,14 @@ void csr_refresh_values(Handle *h) {
 }
 
 static void fill_csr(StepParams &P, const CsrDev &M) {
-    P.tiles = reinterpret_cast<const TileMeta *>(M.tiles.p); P.ntiles = M.ntiles; P.win_cap = M.win_cap; P.val_cap = M.val_cap;
-    P.rowloc = M.rowloc.p; P.scol = M.scol.p; P.sval = M.sval.p;
+    P.tiles = reinterpret_cast<const TileMeta *>(M.tiles.p); P.ntiles = M.ntiles; P.win_cap = M.win_cap; P.blk_cap = M.blk_cap;
+    P.tbuf = M.tbuf.p;
     P.stage_bytes = M.stage_bytes; P.nstage = M.nstage; P.nlong = M.nlong;
+    {
+        static const int env_inflight = [] { const char *e = getenv("FPSB_INFLIGHT"); return e ? atoi(e) : 0; }();
+        P.inflight = env_inflight > 0 ? env_inflight : 2;
+        if (P.inflight > M.nstage) P.inflight = M.nstage;
+    }
     P.rowflag = M.nlong > 0 ? M.rowflag.p : nullptr;
     P.long_row = M.long_row.p; P.long_rp = M.long_rp.p; P.long_col = M.long_col.p; P.long_val = M.long_val.p;
     P.nrows = M.nrows;
@@ -1573,6 +1786,9 @@ struct Engine {
     void loop(F body, int chunk) {
         int k = 0, pending = 0, slot = 0;
         int64_t hard_cap = (int64_t)4000000000LL;
+#if FPSB_EXP > 0
+        if (const char *e = getenv("FPSB_MAXLOOP")) hard_cap = atoll(e);     // timing experiments only
+#endif
         bool done = false;
         while (!done && k < hard_cap) {
             for (int c = 0; c < chunk; ++c) body(++k);

@@ -6,7 +6,7 @@ raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-i
 rows = list(csv.reader(raw.splitlines()))
 hdr = rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
-body = [r for r in rows[2:] if len(r) == len(hdr)]
+body = [r for r in rows[2:] if len(r) == len(hdr) and r[ix["# Samples"]].isdigit()]
 tot = sum(int(r[ix["# Samples"]] or 0) for r in body)
 toti = sum(int(r[ix["Instructions Executed"]] or 0) for r in body)
 print("kernel", rows[0][1], "samples", tot, "warp-instructions", toti, "SASS lines", len(body))
