@@ -803,15 +803,20 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, 
 #if FPSB_EXP >= 9 && FPSB_EXP <= 11
     P.ntiles = 0;        // experiment: launch overhead only (prologue + reduction + scalar recurrences)
 #endif
+    // Programmatic dependent launch: this grid may be scheduled while the previous kernel of the
+    // stream drains (its CTAs free their SMs one by one).  Everything above the wait touches only
+    // this CTA's own shared memory; everything below may read what the previous kernel wrote.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (tid == 0) {
+        for (int s = 0; s < nstage; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], kGroupWarps); }
+        mbar_fence_init();
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     // ---- prologue: one round trip brings both slot states into shared memory ----
     if (use_state) {
         const double *g = reinterpret_cast<const double *>(P.st);
         double *d = reinterpret_cast<double *>(sS);
         for (int i = tid; i < (int)(2 * sizeof(SlotState) / sizeof(double)); i += kStepThreads) d[i] = __ldcg(g + i);
-    }
-    if (tid == 0) {
-        for (int s = 0; s < nstage; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], kGroupWarps); }
-        mbar_fence_init();
     }
     __syncthreads();
     const bool act0 = P.io[0].mode != MD_NONE && (!use_state || sS[0].active);
@@ -892,7 +897,6 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, 
         const CoefR C0 = to_regs(sC[0]), C1 = to_regs(sC[1]);
         double *const self0 = PAIR ? reinterpret_cast<double *>(P.self2) : P.io[0].self;
         double *const self1 = PAIR ? reinterpret_cast<double *>(P.self2) + 1 : P.io[1].self;
-        const int self_stride = PAIR ? 2 : 1;
         int k = g;
         int tile = cta + k * gsz;
         PT_DECL;
@@ -1528,8 +1532,16 @@ static void launch_step(Handle *h, const CsrDev &M, const StepParams &P, bool pa
         h->launches += 1;
     }
     const size_t smem = (size_t)M.nstage * (size_t)M.stage_bytes;
-    if (pair) gk_step_kernel<true><<<M.grid, kStepThreads, smem, h->stream>>>(P, use_state);
-    else gk_step_kernel<false><<<M.grid, kStepThreads, smem, h->stream>>>(P, use_state);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)M.grid); cfg.blockDim = dim3(kStepThreads);
+    cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool no_pdl = getenv("FPSB_NO_PDL") != nullptr;
+    cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
+    if (pair) FPSB_CUDA(cudaLaunchKernelEx(&cfg, gk_step_kernel<true>, P, use_state));
+    else FPSB_CUDA(cudaLaunchKernelEx(&cfg, gk_step_kernel<false>, P, use_state));
     h->launches += 1;
 }
 
