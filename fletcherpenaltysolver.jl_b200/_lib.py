@@ -54,6 +54,8 @@ EXPORTS = [
     "fpsb_ldlt_solve_two_mixed", "fpsb_ldlt_solve_two_least_squares", "fpsb_ldlt_solve_two_extras",
     "fpsb_symbolic_create", "fpsb_symbolic_destroy", "fpsb_symbolic_sizes", "fpsb_symbolic_get",
     "fpsb_symbolic_plan_info", "fpsb_order_dissection", "fpsb_batch_solve_two",
+    "fpsb_dist_unique_id", "fpsb_dist_attach", "fpsb_dist_jprod", "fpsb_dist_jtprod",
+    "fpsb_dist_solve_two_mixed", "fpsb_dist_solve_two_least_squares",
 ]
 
 _lib = None

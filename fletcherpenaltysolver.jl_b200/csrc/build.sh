@@ -21,5 +21,5 @@ for f in "$HERE"/fpsb_symbolic.cpp "$HERE"/fpsb_batch.cu; do
     EXTRA="$EXTRA $o"
   fi
 done
-"$NVCC" $ARCH -shared -o "$OUT" "$HERE/build/fpsb_krylov.o" "$HERE/build/fpsb_ldlt.o" "$HERE/build/fpsb_api.o" $EXTRA -lcudart
+"$NVCC" $ARCH -shared -o "$OUT" -ldl "$HERE/build/fpsb_krylov.o" "$HERE/build/fpsb_ldlt.o" "$HERE/build/fpsb_api.o" $EXTRA -lcudart
 echo "built $OUT"

@@ -155,6 +155,7 @@ int fpsb_destroy(fpsb_handle hh) {
     if (!h) return FPSB_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    dist_free(h);
     iter_free(h);
     ldlt_free(h);
     if (h->pin) cudaFreeHost(h->pin);
@@ -354,6 +355,83 @@ int fpsb_iter_solve_two_extras(fpsb_handle h, double delta, const double *rhs1, 
 int fpsb_ldlt_solve_two_extras(fpsb_handle h, double delta, const double *rhs1, const double *rhs2,
                                double *u1, double *u2, int loc, fpsb_krylov_stats stats[2]) {
     return extras(h, true, delta, rhs1, rhs2, u1, u2, loc, stats);
+}
+
+/* ---- row-partitioned Krylov over NCCL ------------------------------------------------ */
+int fpsb_dist_unique_id(void *out128) {
+    REQUIRE(out128, FPSB_EINVAL, "fpsb_dist_unique_id: NULL");
+    FPSB_TRY
+    dist_unique_id(out128);
+    return FPSB_OK;
+    FPSB_CATCH
+}
+int fpsb_dist_attach(fpsb_handle hh, int nranks, int rank, const void *nccl_id128, int64_t own_off, int64_t n_own,
+                     const int64_t *recv_start, const int64_t *recv_cnt, const int64_t *send_ptr, const int64_t *send_idx) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQUIRE(h && nccl_id128 && recv_start && recv_cnt && send_ptr, FPSB_EINVAL, "fpsb_dist_attach: NULL argument");
+    REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, FPSB_EINVAL, "fpsb_dist_attach: bad rank / nranks");
+    REQUIRE(own_off >= 0 && n_own >= 0 && own_off + n_own <= h->nvar, FPSB_EINVAL, "fpsb_dist_attach: owned block outside the extended space");
+    REQUIRE(send_ptr[0] == 0 && (send_ptr[nranks] == 0 || send_idx), FPSB_EINVAL, "fpsb_dist_attach: bad send lists");
+    for (int p = 0; p < nranks; ++p) {
+        REQUIRE(send_ptr[p + 1] >= send_ptr[p], FPSB_EINVAL, "fpsb_dist_attach: send_ptr must be non-decreasing");
+        REQUIRE(recv_cnt[p] >= 0 && recv_start[p] >= 0 && recv_start[p] + recv_cnt[p] <= h->nvar, FPSB_EINVAL, "fpsb_dist_attach: halo block outside the extended space");
+    }
+    for (int64_t i = 0; i < send_ptr[nranks]; ++i)
+        REQUIRE(send_idx[i] >= own_off && send_idx[i] < own_off + n_own, FPSB_EINVAL, "fpsb_dist_attach: send index is not an owned column");
+    FPSB_TRY
+    FPSB_CUDA(cudaSetDevice(h->device));
+    dist_attach(h, nranks, rank, nccl_id128, own_off, n_own, recv_start, recv_cnt, send_ptr, send_idx);
+    return FPSB_OK;
+    FPSB_CATCH
+}
+static int dist_spmv(fpsb_handle hh, bool transpose, const double *x, double *y, int loc) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQUIRE(h && x && y, FPSB_EINVAL, "NULL argument");
+    REQUIRE(h->dist, FPSB_ESTATE, "not a row-partitioned handle (call fpsb_dist_attach first)");
+    REQUIRE(h->have_vals, FPSB_ESTATE, "Jacobian values not set (call fpsb_set_jac_values first)");
+    FPSB_TRY
+    FPSB_CUDA(cudaSetDevice(h->device));
+    const int64_t nown = dist_n_own(h);
+    const size_t nin = transpose ? (size_t)h->ncon : (size_t)nown, nout = transpose ? (size_t)nown : (size_t)h->ncon;
+    Staged S(h, loc, nin, nout);
+    const double *dx = S.in(x, nin);
+    double *dy = S.out(y, nout);
+    if (transpose) dist_jtprod(h, dx, dy); else dist_jprod(h, dx, dy);
+    S.finish();
+    return FPSB_OK;
+    FPSB_CATCH
+}
+int fpsb_dist_jprod(fpsb_handle h, const double *x_own, double *y_loc, int loc) { return dist_spmv(h, false, x_own, y_loc, loc); }
+int fpsb_dist_jtprod(fpsb_handle h, const double *u_loc, double *y_own, int loc) { return dist_spmv(h, true, u_loc, y_own, loc); }
+
+static int dist_solve(fpsb_handle hh, int kind, double delta, int64_t nvar_global, int64_t ncon_global, const double *rhs1,
+                      const double *rhs2, double *p1, double *q1, double *p2, double *q2, int loc, fpsb_krylov_stats *stats) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQUIRE(h && rhs1 && rhs2 && p1 && q1 && p2 && q2 && stats, FPSB_EINVAL, "NULL argument");
+    REQUIRE(h->dist, FPSB_ESTATE, "not a row-partitioned handle (call fpsb_dist_attach first)");
+    REQUIRE(h->have_vals, FPSB_ESTATE, "Jacobian values not set (call fpsb_set_jac_values first)");
+    FPSB_TRY
+    FPSB_CUDA(cudaSetDevice(h->device));
+    const size_t n = (size_t)dist_n_own(h), m = (size_t)h->ncon;
+    const size_t n2 = kind == 0 ? m : n;
+    Staged S(h, loc, n + n2, 2 * n + 2 * m);
+    const double *d1 = S.in(rhs1, n), *d2 = S.in(rhs2, n2);
+    double *dp1 = S.out(p1, n), *dq1 = S.out(q1, m), *dp2 = S.out(p2, n), *dq2 = S.out(q2, m);
+    if (kind == 0) dist_solve_two_mixed(h, delta, d1, d2, dp1, dq1, dp2, dq2, stats, nvar_global, ncon_global);
+    else dist_solve_two_least_squares(h, delta, d1, d2, dp1, dq1, dp2, dq2, stats, nvar_global, ncon_global);
+    S.finish();
+    return FPSB_OK;
+    FPSB_CATCH
+}
+int fpsb_dist_solve_two_mixed(fpsb_handle h, double delta, int64_t nvar_global, int64_t ncon_global, const double *rhs1,
+                              const double *rhs2, double *p1, double *q1, double *p2, double *q2, int loc,
+                              fpsb_krylov_stats stats[2]) {
+    return dist_solve(h, 0, delta, nvar_global, ncon_global, rhs1, rhs2, p1, q1, p2, q2, loc, stats);
+}
+int fpsb_dist_solve_two_least_squares(fpsb_handle h, double delta, int64_t nvar_global, int64_t ncon_global,
+                                      const double *rhs1, const double *rhs2, double *p1, double *q1, double *p2,
+                                      double *q2, int loc, fpsb_krylov_stats stats[2]) {
+    return dist_solve(h, 1, delta, nvar_global, ncon_global, rhs1, rhs2, p1, q1, p2, q2, loc, stats);
 }
 
 }  // extern "C"

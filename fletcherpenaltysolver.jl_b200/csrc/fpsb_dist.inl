@@ -1,0 +1,447 @@
+// fpsb_dist.inl — row-partitioned Krylov path over several GPUs (BASELINE config C3).
+// Included at the end of fpsb_krylov.cu (same translation unit: it drives the same kernels).
+//
+// One process per GPU.  Rank r owns a block of constraint rows of A (m-space) and a contiguous block
+// of variables (n-space).  Its local operator is A_loc (m_loc x n_ext) where the n_ext "extended"
+// columns are the owned block plus the halo columns its rows touch, kept in global column order so
+// the tile windows stay narrow:   [ halo of lower ranks | owned | halo of higher ranks ].
+//
+//   jprod  (m-space step)  needs the halo entries of the gathered n-space pair:  owners pack the
+//                          requested entries, ncclSend/ncclRecv lands them in the halo slots, then
+//                          the ordinary fused step kernel runs on A_loc.
+//   jtprod (n-space step)  A_loc' u produces partial sums for every extended row: the halo partials
+//                          travel to their owners (ncclSend/ncclRecv), are added there in rank
+//                          order, and the Krylov row epilogue runs on the owned rows only.
+//   norms                  the kernels leave their local sums in a 4-double buffer (tot_out);
+//                          ncclAllReduce(sum) + finish_kernel replace the fused last-CTA recurrences.
+//
+// Every rank runs the same scalar recurrences on the same all-reduced sums, so the slot states stay
+// bitwise identical across ranks and all ranks take the same number of iterations.
+// NCCL is bound at run time (dlopen) so that libfpsb200.so loads on machines without it.
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi *nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        // an NCCL already in the process (e.g. PyTorch's) wins; FPSB_NCCL_LIB overrides the search
+        const char *names[] = {getenv("FPSB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char *nm : names) {
+            if (!nm || !*nm) continue;
+            api.lib = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+            if (api.lib) break;
+        }
+        if (api.lib) {
+#define FPSB_SYM(field, name) *(void **)(&api.field) = dlsym(api.lib, name)
+            FPSB_SYM(GetUniqueId, "ncclGetUniqueId");
+            FPSB_SYM(CommInitRank, "ncclCommInitRank");
+            FPSB_SYM(CommDestroy, "ncclCommDestroy");
+            FPSB_SYM(AllReduce, "ncclAllReduce");
+            FPSB_SYM(Send, "ncclSend");
+            FPSB_SYM(Recv, "ncclRecv");
+            FPSB_SYM(GroupStart, "ncclGroupStart");
+            FPSB_SYM(GroupEnd, "ncclGroupEnd");
+            FPSB_SYM(GetErrorString, "ncclGetErrorString");
+#undef FPSB_SYM
+            if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.Send || !api.Recv || !api.GroupStart || !api.GroupEnd)
+                api.lib = nullptr;
+        }
+    }
+    return api.lib ? &api : nullptr;
+}
+
+#define FPSB_NCCL(call)                                                                   \
+    do {                                                                                  \
+        ncclResult_t r__ = (call);                                                        \
+        if (r__ != ncclSuccess) {                                                         \
+            NcclApi *a__ = nccl_api();                                                    \
+            set_error("%s:%d: %s -> NCCL error %d (%s)", __FILE__, __LINE__, #call, (int)r__, \
+                      (a__ && a__->GetErrorString) ? a__->GetErrorString(r__) : "?");     \
+            throw CudaFail{FPSB_ECUDA};                                                   \
+        }                                                                                 \
+    } while (0)
+
+struct DistCtx {
+    int nranks = 1, rank = 0;
+    ncclComm_t comm = nullptr;
+    int64_t own_off = 0, n_own = 0;
+    std::vector<int64_t> recv_start, recv_cnt;      // per peer: my halo slots [start, start + cnt) of the extended space
+    std::vector<int64_t> send_ptr;                  // per peer: range of send_idx
+    DevBuf<int> send_idx;                           // owned extended indices other ranks keep as halo
+    DevBuf<double2> sendbuf, recvbuf;               // packed entries (sum of send counts)
+    DevBuf<double2> S;                              // raw A_loc' partial sums of both columns (n_ext)
+    DevBuf<double> tot;                             // 4 doubles: local sums -> all-reduced sums
+    int64_t nsend = 0;
+};
+
+void dist_free(Handle *h) {
+    if (!h->dist) return;
+    NcclApi *api = nccl_api();
+    if (h->dist->comm && api && api->CommDestroy) api->CommDestroy(h->dist->comm);
+    delete h->dist;
+    h->dist = nullptr;
+}
+
+int64_t dist_n_own(Handle *h) { return h->dist ? h->dist->n_own : 0; }
+
+void dist_unique_id(void *out128) {
+    NcclApi *api = nccl_api();
+    if (!api) { set_error("NCCL (libnccl.so.2) is not available on this machine"); throw CudaFail{FPSB_ECUDA}; }
+    ncclUniqueId id;
+    FPSB_NCCL(api->GetUniqueId(&id));
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(out128, &id, 128);
+}
+
+void dist_attach(Handle *h, int nranks, int rank, const void *id128, int64_t own_off, int64_t n_own,
+                 const int64_t *recv_start, const int64_t *recv_cnt, const int64_t *send_ptr, const int64_t *send_idx) {
+    NcclApi *api = nccl_api();
+    if (!api) { set_error("NCCL (libnccl.so.2) is not available on this machine"); throw CudaFail{FPSB_ECUDA}; }
+    dist_free(h);
+    iter_setup(h);
+    DistCtx *D = new DistCtx();
+    h->dist = D;
+    D->nranks = nranks; D->rank = rank; D->own_off = own_off; D->n_own = n_own;
+    D->recv_start.assign(recv_start, recv_start + nranks);
+    D->recv_cnt.assign(recv_cnt, recv_cnt + nranks);
+    D->send_ptr.assign(send_ptr, send_ptr + nranks + 1);
+    D->nsend = send_ptr[nranks];
+    std::vector<int> idx((size_t)D->nsend);
+    for (int64_t i = 0; i < D->nsend; ++i) idx[(size_t)i] = (int)send_idx[i];
+    D->send_idx.from(idx, h->stream);
+    D->sendbuf.alloc((size_t)D->nsend + 8);
+    D->recvbuf.alloc((size_t)D->nsend + 8);
+    D->S.alloc((size_t)h->nvar + 8);
+    D->tot.alloc(8);
+    D->tot.zero(h->stream);
+    FPSB_CUDA(cudaStreamSynchronize(h->stream));
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    FPSB_NCCL(api->CommInitRank(&D->comm, nranks, id, rank));
+}
+
+// ---- kernels of the exchange ------------------------------------------------------------------------
+__global__ void pack_pairs_kernel(int n, const int *idx, const double2 *src, double2 *dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
+}
+__global__ void unpack_cols_kernel(int n, const double2 *src, double *dst0, double *dst1) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { if (dst0) dst0[i] = src[i].x; if (dst1) dst1[i] = src[i].y; }
+}
+// owner side of the scatter-add: one launch per peer, peers in rank order (deterministic sums)
+__global__ void add_pairs_kernel(int n, const int *idx, const double2 *src, double2 *dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const double2 a = src[i]; double2 d = dst[idx[i]]; d.x += a.x; d.y += a.y; dst[idx[i]] = d; }
+}
+
+// Krylov row epilogue over the OWNED rows of the n-space after the scatter-add (the step kernel's
+// phase 2, un-fused): S holds the complete row sums, self2 the interleaved pair of this row space
+struct DistEpiParams {
+    int n_own, own_off;
+    const double2 *S;
+    double2 *self2;
+    SlotIO io[2];
+    SlotState *st;
+    double *partials;
+    unsigned *counter;
+    double *tot_out;
+};
+__global__ void __launch_bounds__(kBlock) dist_epilogue_kernel(DistEpiParams P) {
+    __shared__ double s_red[4 * 32];
+    __shared__ Coef sC[2];
+    __shared__ int s_last;
+    const int tid = threadIdx.x;
+    const bool act0 = P.io[0].mode != MD_NONE && P.st[0].active;
+    const bool act1 = P.io[1].mode != MD_NONE && P.st[1].active;
+    if (!act0 && !act1) return;
+    if (tid == 0) {
+        load_coef(sC[0], P.io[0], &P.st[0], true);
+        load_coef(sC[1], P.io[1], &P.st[1], true);
+        if (!act0) { sC[0].mode = MD_NONE; sC[0].rd0 = sC[0].rd1 = sC[0].wr0 = sC[0].wr1 = sC[0].rdself = 0; }
+        if (!act1) { sC[1].mode = MD_NONE; sC[1].rd0 = sC[1].rd1 = sC[1].wr0 = sC[1].wr1 = sC[1].rdself = 0; }
+    }
+    __syncthreads();
+    const CoefR C0 = to_regs(sC[0]), C1 = to_regs(sC[1]);
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = blockIdx.x * blockDim.x + tid; i < P.n_own; i += gridDim.x * blockDim.x) {
+        const int row = P.own_off + i;
+        const double2 sm = P.S[row];
+        const double2 old2 = P.self2[row];
+        double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+        if (C0.rd0()) a00 = P.io[0].a0[row];
+        if (C0.rd1()) a01 = P.io[0].a1[row];
+        if (C1.rd0()) a10 = P.io[1].a0[row];
+        if (C1.rd1()) a11 = P.io[1].a1[row];
+        double n0 = old2.x, n1 = old2.y;
+        if (act0) n0 = row_epilogue(C0, sm.x, old2.x, a00, a01, acc[0], acc[1]);
+        if (act1) n1 = row_epilogue(C1, sm.y, old2.y, a10, a11, acc[2], acc[3]);
+        P.self2[row] = make_double2(n0, n1);
+        if (C0.wr0()) P.io[0].a0[row] = a00;
+        if (C0.wr1()) P.io[0].a1[row] = a01;
+        if (C1.wr0()) P.io[1].a0[row] = a10;
+        if (C1.wr1()) P.io[1].a1[row] = a11;
+    }
+    block_sum<4>(acc, s_red);
+    if (tid == 0) {
+        double *pp = P.partials + (size_t)blockIdx.x * 4;
+        pp[0] = acc[0]; pp[1] = acc[1]; pp[2] = acc[2]; pp[3] = acc[3];
+        __threadfence();
+        const unsigned t = atomicAdd(P.counter, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double tot[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = tid; i < (int)gridDim.x; i += kBlock) {
+        const double *pp = P.partials + (size_t)i * 4;
+        tot[0] += __ldcg(pp + 0); tot[1] += __ldcg(pp + 1); tot[2] += __ldcg(pp + 2); tot[3] += __ldcg(pp + 3);
+    }
+    block_sum<4>(tot, s_red);
+    if (tid == 0) {
+        P.tot_out[0] = tot[0]; P.tot_out[1] = tot[1]; P.tot_out[2] = tot[2]; P.tot_out[3] = tot[3];
+        *P.counter = 0;
+    }
+}
+
+// the scalar recurrences on the all-reduced sums (what the last CTA does on a single GPU)
+__global__ void finish_kernel(SlotState *st, int kind, int m0, int m1, const double *tot, int *done_flag) {
+    __shared__ SlotState sS[2];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < (int)(2 * sizeof(SlotState) / sizeof(double)); i += blockDim.x)
+        reinterpret_cast<double *>(sS)[i] = reinterpret_cast<const double *>(st)[i];
+    __syncthreads();
+    if (tid == 0) {
+        if (kind == 0) {                      // step: m0 / m1 are the modes of the two slots
+            if (m0 != MD_NONE && sS[0].active) finish_step(sS[0], m0, tot[0], tot[1]);
+            if (m1 != MD_NONE && sS[1].active) finish_step(sS[1], m1, tot[2], tot[3]);
+        } else {                              // element-wise: m0 = op, m1 = slot
+            const bool is_init = (m0 == EW_INIT_LSQR || m0 == EW_INIT_CRAIG || m0 == EW_MINRES_INIT || m0 == EW_CGLS_INIT);
+            if (is_init || sS[m1].active) finish_ew(sS[m1], m0, tot[0]);
+        }
+        if (!sS[0].active && !sS[1].active) *done_flag = 1;
+    }
+    __syncthreads();
+    for (int i = tid; i < (int)(2 * sizeof(SlotState) / sizeof(double)); i += blockDim.x)
+        reinterpret_cast<double *>(st)[i] = reinterpret_cast<const double *>(sS)[i];
+}
+
+// ---- host side --------------------------------------------------------------------------------------
+struct DistEngine {
+    Handle *h;
+    DistCtx *D;
+    NcclApi *api;
+    Engine E;
+    DistEngine(Handle *hh) : h(hh), D(hh->dist), api(nccl_api()), E(hh) { E.tot_out = D->tot.p; }
+
+    void allreduce_finish(int kind, int m0, int m1) {
+        FPSB_NCCL(api->AllReduce(D->tot.p, D->tot.p, 4, ncclDouble, ncclSum, D->comm, h->stream));
+        finish_kernel<<<1, 64, 0, h->stream>>>(E.W->st.p, kind, m0, m1, D->tot.p, E.W->done.p);
+        h->launches += 1;
+    }
+    // owners -> halo slots of an interleaved pair living in the extended n-space
+    void gather_halo(double2 *pair) {
+        if (D->nranks == 1) return;
+        if (D->nsend > 0) {
+            pack_pairs_kernel<<<(unsigned)((D->nsend + 255) / 256), 256, 0, h->stream>>>((int)D->nsend, D->send_idx.p, pair, D->sendbuf.p);
+            h->launches += 1;
+        }
+        FPSB_NCCL(api->GroupStart());
+        for (int p = 0; p < D->nranks; ++p) {
+            if (p == D->rank) continue;
+            const int64_t ns = D->send_ptr[p + 1] - D->send_ptr[p];
+            if (ns > 0) FPSB_NCCL(api->Send(D->sendbuf.p + D->send_ptr[p], (size_t)ns * 2, ncclDouble, p, D->comm, h->stream));
+            if (D->recv_cnt[p] > 0) FPSB_NCCL(api->Recv(pair + D->recv_start[p], (size_t)D->recv_cnt[p] * 2, ncclDouble, p, D->comm, h->stream));
+        }
+        FPSB_NCCL(api->GroupEnd());
+    }
+    // halo partial sums -> owners, added in rank order
+    void scatter_add(double2 *S) {
+        if (D->nranks == 1) return;
+        FPSB_NCCL(api->GroupStart());
+        for (int p = 0; p < D->nranks; ++p) {
+            if (p == D->rank) continue;
+            const int64_t nr = D->send_ptr[p + 1] - D->send_ptr[p];
+            if (D->recv_cnt[p] > 0) FPSB_NCCL(api->Send(S + D->recv_start[p], (size_t)D->recv_cnt[p] * 2, ncclDouble, p, D->comm, h->stream));
+            if (nr > 0) FPSB_NCCL(api->Recv(D->recvbuf.p + D->send_ptr[p], (size_t)nr * 2, ncclDouble, p, D->comm, h->stream));
+        }
+        FPSB_NCCL(api->GroupEnd());
+        for (int p = 0; p < D->nranks; ++p) {
+            const int64_t nr = D->send_ptr[p + 1] - D->send_ptr[p];
+            if (p == D->rank || nr == 0) continue;
+            add_pairs_kernel<<<(unsigned)((nr + 255) / 256), 256, 0, h->stream>>>((int)nr, D->send_idx.p + D->send_ptr[p],
+                                                                                 D->recvbuf.p + D->send_ptr[p], S);
+            h->launches += 1;
+        }
+    }
+    // S = A_loc' [Gm.x Gm.y]  (raw sums of both columns, every extended row) followed by the exchange
+    void jt_partials(const double2 *gm_pair) {
+        StepParams P = E.base_n;
+        P.io[0] = io_mode(MD_PLAIN); P.io[1] = io_mode(MD_PLAIN);
+        P.gin2 = gm_pair; P.self2 = D->S.p;
+        P.tot_out = nullptr;
+        if (h->At.grid == 0) { D->S.zero(h->stream); return; }
+        launch_step(h, h->At, P, true, 0);
+        scatter_add(D->S.p);
+    }
+    // n-space half step: partial sums, exchange, epilogue on the owned rows, all-reduce, recurrences
+    void step_n(const SlotIO &io0, const SlotIO &io1) {
+        jt_partials(E.W->Gm.p);
+        DistEpiParams Q{};
+        Q.n_own = (int)D->n_own; Q.own_off = (int)D->own_off;
+        Q.S = D->S.p; Q.self2 = E.W->Gn.p;
+        Q.io[0] = io0; Q.io[1] = io1;
+        Q.st = E.W->st.p; Q.partials = E.W->partials.p; Q.counter = E.W->counter.p; Q.tot_out = D->tot.p;
+        const int grid = std::max(1, std::min(E.W->ew_grid, (int)((D->n_own + kBlock - 1) / kBlock)));
+        dist_epilogue_kernel<<<grid, kBlock, 0, h->stream>>>(Q);
+        h->launches += 1;
+        allreduce_finish(0, io0.mode, io1.mode);
+    }
+    // m-space half step: halo gather, fused step kernel on A_loc (rows are local), all-reduce, recurrences
+    void step_m(const SlotIO &io0, const SlotIO &io1) {
+        gather_halo(E.W->Gn.p);
+        E.step(true, true, io0, io1);
+        allreduce_finish(0, io0.mode, io1.mode);
+    }
+    void ew(int op, int slot, int n, const double *in0, double *v0, double *v1, double *v2, double2 *pair, int pair_slot, double c0) {
+        E.ew(op, slot, n, in0, v0, v1, v2, nullptr, nullptr, pair, pair_slot, c0, 1);
+        allreduce_finish(1, op, slot);
+    }
+};
+
+// plain distributed products (owned slices in / out); used by the parity tests of the exchange
+void dist_jprod(Handle *h, const double *x_own, double *y_loc) {
+    DistEngine X(h);
+    IterWs *W = h->iter;
+    DistCtx *D = h->dist;
+    // stage x in column 0 of the gathered pair of the extended space
+    W->Gn.zero(h->stream);
+    X.E.tot_out = nullptr;
+    X.E.ew(EW_INIT_LSQR, 0, (int)D->n_own, x_own, nullptr, nullptr, nullptr, nullptr, nullptr, W->Gn.p + D->own_off, 0, 1.0, 0);
+    X.gather_halo(W->Gn.p);
+    if (h->A.grid == 0) return;
+    StepParams P = X.E.base_m;
+    P.io[0] = io_mode(MD_PLAIN); P.io[1] = io_mode(MD_PLAIN);
+    P.gin2 = W->Gn.p; P.self2 = W->Gm.p; P.tot_out = nullptr;
+    launch_step(h, h->A, P, true, 0);
+    unpack_cols_kernel<<<(unsigned)((h->ncon + 255) / 256), 256, 0, h->stream>>>((int)h->ncon, W->Gm.p, y_loc, nullptr);
+    h->launches += 1;
+}
+void dist_jtprod(Handle *h, const double *u_loc, double *y_own) {
+    DistEngine X(h);
+    IterWs *W = h->iter;
+    DistCtx *D = h->dist;
+    W->Gm.zero(h->stream);
+    X.E.tot_out = nullptr;
+    X.E.ew(EW_INIT_LSQR, 0, (int)h->ncon, u_loc, nullptr, nullptr, nullptr, nullptr, nullptr, W->Gm.p, 0, 1.0, 0);
+    X.jt_partials(W->Gm.p);
+    unpack_cols_kernel<<<(unsigned)((D->n_own + 255) / 256), 256, 0, h->stream>>>((int)D->n_own, D->S.p + D->own_off, y_own, nullptr);
+    h->launches += 1;
+}
+
+// p_i = rhs_i - (A' q_i) on the owned rows, for one or two columns
+__global__ void residual_own_kernel(int n, const double2 *S, const double *rhs0, const double *rhs1, double *p0, double *p1) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const double2 s = S[i]; if (p0) p0[i] = rhs0[i] - s.x; if (p1) p1[i] = rhs1[i] - s.y; }
+}
+
+// Row-partitioned solve_two_mixed (src/solve_linear_system.jl:107-140): rhs1 / p1 / p2 are the OWNED
+// n-space slices, rhs2 / q1 / q2 the local m-space slices
+void dist_solve_two_mixed(Handle *h, double delta, const double *rhs1, const double *rhs2, double *p1, double *q1,
+                          double *p2, double *q2, fpsb_krylov_stats *st, int64_t nvar_global, int64_t ncon_global) {
+    DistEngine X(h);
+    Engine &E = X.E;
+    IterWs *W = h->iter;
+    DistCtx *D = h->dist;
+    const fpsb_iter_opts &o = h->iopts;
+    const int64_t n = nvar_global, m = ncon_global;
+    const int n_own = (int)D->n_own, m_loc = (int)h->ncon;
+    E.begin(make_lsqr(sqrt(delta), o.ls_atol, o.ls_rtol, o.ls_itmax, n, m),
+            make_craig(delta, o.ln_atol, o.ln_rtol, o.ln_btol, o.ln_conlim, o.ln_itmax, m, n));
+    W->Gn.zero(h->stream); W->Gm.zero(h->stream);
+    W->an[1][0].zero(h->stream); W->an[1][1].zero(h->stream);
+    W->am[0][1].zero(h->stream);
+    X.ew(EW_INIT_LSQR, 0, n_own, rhs1, nullptr, nullptr, nullptr, W->Gn.p + D->own_off, 0, 1.0);
+    X.ew(EW_INIT_CRAIG, 1, m_loc, rhs2, W->am[1][0].p, W->am[1][1].p, nullptr, W->Gm.p, 1, -1.0);
+    SlotIO l_init = io_mode(MD_LSQR_INIT_M), l_u = io_mode(MD_LSQR_U);
+    SlotIO l_v = io_mode(MD_LSQR_V, W->am[0][0].p, W->am[0][1].p);
+    SlotIO c_v = io_mode(MD_CRAIG_V, W->an[1][0].p, W->an[1][1].p);
+    SlotIO c_u = io_mode(MD_CRAIG_U, W->am[1][0].p, W->am[1][1].p);
+    E.mark_begin();
+    X.step_m(l_init, io_none());
+    E.loop([&](int) {
+        X.step_n(l_u, c_v);
+        X.step_m(l_v, c_u);
+    }, kChunk);
+    E.mark_end();
+    E.tot_out = nullptr;
+    // outputs: q1 = x_lsqr ; p1 = rhs1 - A' q1 ; p2 = -(x_craig + pending) ; q2 = y_craig
+    E.ew(EW_COPY, 0, m_loc, W->am[0][1].p, q1, nullptr, nullptr, nullptr, nullptr, nullptr, -1, 1.0, 0);
+    E.ew(EW_COPY, 1, m_loc, W->am[1][1].p, q2, nullptr, nullptr, nullptr, nullptr, nullptr, -1, 1.0, 0);
+    // the CRAIG flush reads the pending coefficients of the (replicated) state: owned rows only
+    E.ew(EW_CRAIG_FLUSH, 1, n_own, nullptr, W->an[1][0].p + D->own_off, W->an[1][1].p + D->own_off, p2, nullptr, nullptr,
+         W->Gn.p + D->own_off, 1, 1.0, 1);
+    // A' q1 through the exchange (Gm column 0 <- q1 ; column 1 zero)
+    W->Gm.zero(h->stream);
+    E.ew(EW_INIT_LSQR, 0, m_loc, q1, nullptr, nullptr, nullptr, nullptr, nullptr, W->Gm.p, 0, 1.0, 0);
+    X.jt_partials(W->Gm.p);
+    residual_own_kernel<<<(unsigned)((n_own + 255) / 256), 256, 0, h->stream>>>(n_own, D->S.p + D->own_off, rhs1, nullptr, p1, nullptr);
+    h->launches += 1;
+    E.fetch(st);
+}
+
+// Row-partitioned solve_two_least_squares (src/solve_linear_system.jl:79-105): two LSQR solves in lock step
+void dist_solve_two_least_squares(Handle *h, double delta, const double *rhs1, const double *rhs2, double *p1, double *q1,
+                                  double *p2, double *q2, fpsb_krylov_stats *st, int64_t nvar_global, int64_t ncon_global) {
+    DistEngine X(h);
+    Engine &E = X.E;
+    IterWs *W = h->iter;
+    DistCtx *D = h->dist;
+    const fpsb_iter_opts &o = h->iopts;
+    const int64_t n = nvar_global, m = ncon_global;
+    const int n_own = (int)D->n_own, m_loc = (int)h->ncon;
+    SlotState s = make_lsqr(sqrt(delta), o.ls_atol, o.ls_rtol, o.ls_itmax, n, m);
+    E.begin(s, s);
+    W->Gn.zero(h->stream); W->Gm.zero(h->stream);
+    W->am[0][1].zero(h->stream); W->am[1][1].zero(h->stream);
+    X.ew(EW_INIT_LSQR, 0, n_own, rhs1, nullptr, nullptr, nullptr, W->Gn.p + D->own_off, 0, 1.0);
+    X.ew(EW_INIT_LSQR, 1, n_own, rhs2, nullptr, nullptr, nullptr, W->Gn.p + D->own_off, 1, 1.0);
+    SlotIO init0 = io_mode(MD_LSQR_INIT_M), init1 = io_mode(MD_LSQR_INIT_M);
+    SlotIO u0 = io_mode(MD_LSQR_U), u1 = io_mode(MD_LSQR_U);
+    SlotIO v0 = io_mode(MD_LSQR_V, W->am[0][0].p, W->am[0][1].p);
+    SlotIO v1 = io_mode(MD_LSQR_V, W->am[1][0].p, W->am[1][1].p);
+    E.mark_begin();
+    X.step_m(init0, init1);
+    E.loop([&](int) {
+        X.step_n(u0, u1);
+        X.step_m(v0, v1);
+    }, kChunk);
+    E.mark_end();
+    E.tot_out = nullptr;
+    E.ew(EW_COPY, 0, m_loc, W->am[0][1].p, q1, nullptr, nullptr, nullptr, nullptr, nullptr, -1, 1.0, 0);
+    E.ew(EW_COPY, 1, m_loc, W->am[1][1].p, q2, nullptr, nullptr, nullptr, nullptr, nullptr, -1, 1.0, 0);
+    // p_i = rhs_i - A' q_i : one two-column product through the exchange
+    {
+        // interleave q1, q2 into Gm
+        W->Gm.zero(h->stream);
+        E.ew(EW_INIT_LSQR, 0, m_loc, q1, nullptr, nullptr, nullptr, nullptr, nullptr, W->Gm.p, 0, 1.0, 0);
+        E.ew(EW_INIT_LSQR, 1, m_loc, q2, nullptr, nullptr, nullptr, nullptr, nullptr, W->Gm.p, 1, 1.0, 0);
+    }
+    X.jt_partials(W->Gm.p);
+    residual_own_kernel<<<(unsigned)((n_own + 255) / 256), 256, 0, h->stream>>>(n_own, D->S.p + D->own_off, rhs1, rhs2, p1, p2);
+    h->launches += 1;
+    E.fetch(st);
+}

@@ -94,6 +94,7 @@ struct SlotState {
 
 struct IterWs;     // defined in fpsb_krylov.cu
 struct LdltPlan;   // defined in fpsb_ldlt.cu
+struct DistCtx;    // defined in fpsb_dist.inl (row-partitioned multi-GPU runs)
 
 struct Handle {
     int device = 0;
@@ -112,6 +113,7 @@ struct Handle {
     DevBuf<double> stage_in, stage_out;
     IterWs *iter = nullptr;
     LdltPlan *ldlt = nullptr;
+    DistCtx *dist = nullptr;
     fpsb_iter_opts iopts{};
     bool iopts_set = false;
     double prof_loop_ms = 0.0;          // CUDA-event time of the last Krylov loop region
@@ -132,6 +134,19 @@ void iter_solve_two_least_squares(Handle *h, double delta, const double *rhs1, c
                                   fpsb_krylov_stats *st);
 void iter_solve_two_extras(Handle *h, double delta, const double *rhs1, const double *rhs2, double *u1,
                            double *u2, fpsb_krylov_stats *st, bool ldlt_variant);
+
+// fpsb_dist.inl (row-partitioned Krylov over NCCL)
+void dist_unique_id(void *out128);
+void dist_attach(Handle *h, int nranks, int rank, const void *id128, int64_t own_off, int64_t n_own,
+                 const int64_t *recv_start, const int64_t *recv_cnt, const int64_t *send_ptr, const int64_t *send_idx);
+void dist_free(Handle *h);
+int64_t dist_n_own(Handle *h);
+void dist_jprod(Handle *h, const double *x_own, double *y_loc);
+void dist_jtprod(Handle *h, const double *u_loc, double *y_own);
+void dist_solve_two_mixed(Handle *h, double delta, const double *rhs1, const double *rhs2, double *p1, double *q1,
+                          double *p2, double *q2, fpsb_krylov_stats *st, int64_t nvar_global, int64_t ncon_global);
+void dist_solve_two_least_squares(Handle *h, double delta, const double *rhs1, const double *rhs2, double *p1, double *q1,
+                                  double *p2, double *q2, fpsb_krylov_stats *st, int64_t nvar_global, int64_t ncon_global);
 
 // symbolic.cpp / ldlt.cu
 void ldlt_analyze(Handle *h, const int64_t *P, const fpsb_ldlt_opts *opts);

@@ -23,6 +23,22 @@
 #include <cstring>
 #include <cstdlib>
 
+// NCCL types for fpsb_dist.inl (bound at run time with dlopen; the header is optional)
+#include <dlfcn.h>
+#if __has_include(<nccl.h>)
+#include <nccl.h>
+#else
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+typedef int ncclDataType_t;
+typedef int ncclRedOp_t;
+#define ncclSuccess 0
+#define ncclDouble 8
+#define ncclSum 0
+#endif
+
+
 #ifndef FPSB_EXP
 #define FPSB_EXP 0     /* > 0: timing experiments that deliberately break the numerics (never shipped) */
 #endif
@@ -93,6 +109,8 @@ struct StepParams {
     double *partials;      // [grid][4]
     unsigned *counter;
     int *done_flag;        // set to 1 when no slot remains active
+    double *tot_out;       // row-partitioned runs: the last CTA leaves the four local sums here instead of
+                           // running the scalar recurrences (an all-reduce and finish_kernel follow)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1081,6 +1099,13 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, 
         tot[2] += __ldcg(pp + 2); tot[3] += __ldcg(pp + 3);
     }
     block_sum<4>(tot, s_red);
+    if (P.tot_out != nullptr) {
+        if (tid == 0) {
+            P.tot_out[0] = tot[0]; P.tot_out[1] = tot[1]; P.tot_out[2] = tot[2]; P.tot_out[3] = tot[3];
+            *P.counter = 0;
+        }
+        return;
+    }
     // scalar recurrences on the shared-memory copy of the slot states (global memory would cost one
     // L2 round trip per field), then one coalesced write-back
     if (tid == 0) {
@@ -1182,6 +1207,7 @@ struct EwParams {
     unsigned *counter;
     int *done_flag;
     int use_state;
+    double *tot_out;       // row-partitioned runs: local sum left here, finish_kernel follows the all-reduce
 };
 
 __global__ void __launch_bounds__(kBlock) ew_kernel(EwParams P) {
@@ -1298,6 +1324,11 @@ __global__ void __launch_bounds__(kBlock) ew_kernel(EwParams P) {
     double tot[1] = {0.0};
     for (int i = threadIdx.x; i < (int)gridDim.x; i += kBlock) tot[0] += __ldcg(P.partials + i);
     block_sum<1>(tot, s_red);
+    if (threadIdx.x == 0 && P.tot_out != nullptr) {
+        P.tot_out[0] = tot[0]; P.tot_out[1] = 0.0; P.tot_out[2] = 0.0; P.tot_out[3] = 0.0;
+        *P.counter = 0;
+        return;
+    }
     if (threadIdx.x == 0) {
         finish_ew(*S, P.op, tot[0]);
         if (!P.st[0].active && !P.st[1].active) *P.done_flag = 1;
@@ -1757,6 +1788,7 @@ struct Engine {
     Handle *h;
     IterWs *W;
     StepParams base_m, base_n;   // M: rows of A (m-space rows), N: rows of A' (n-space rows)
+    double *tot_out = nullptr;   // non-null: row-partitioned run (see fpsb_dist.inl)
     Engine(Handle *hh) : h(hh), W(hh->iter) {
         memset(&base_m, 0, sizeof(base_m));
         memset(&base_n, 0, sizeof(base_n));
@@ -1778,6 +1810,7 @@ struct Engine {
     void step(bool mspace, bool pair, const SlotIO &io0, const SlotIO &io1) {
         StepParams P = mspace ? base_m : base_n;
         P.io[0] = io0; P.io[1] = io1;
+        P.tot_out = tot_out;
         const CsrDev &M = mspace ? h->A : h->At;
         launch_step(h, M, P, pair, 1);
     }
@@ -1789,6 +1822,7 @@ struct Engine {
         P.v0 = v0; P.v1 = v1; P.v2 = v2; P.v3 = v3; P.v4 = v4; P.pair = pair; P.c0 = c0;
         P.st = W->st.p; P.partials = W->partials.p; P.counter = W->counter.p; P.done_flag = W->done.p;
         P.use_state = use_state;
+        P.tot_out = tot_out;
         int grid = std::max(1, std::min(W->ew_grid, (n + kBlock - 1) / kBlock));
         ew_kernel<<<grid, kBlock, 0, h->stream>>>(P);
         h->launches += 1;
@@ -2041,5 +2075,8 @@ void iter_solve_two_extras(Handle *h, double delta, const double *rhs1, const do
         st[1] = tmp[1];
     }
 }
+
+
+#include "fpsb_dist.inl"
 
 }  // namespace fpsb

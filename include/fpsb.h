@@ -224,6 +224,35 @@ int fpsb_batch_solve_two(int64_t ninst, int nvar, int ncon, int kind, const doub
                          const double *rhs1, const double *rhs2, double *p1, double *q1, double *p2,
                          double *q2, int *factorized, const fpsb_ldlt_opts *opts, int loc, int device);
 
+/* ---------------------------------------------------------------------------------------------
+ * Row-partitioned Krylov path over several GPUs (one process per GPU, NCCL over NVLink) — what the
+ * reference would reach by giving every Julia process a row block of the Jacobian (the
+ * reference itself is single-process, src/solve_linear_system.jl:79-140).
+ *
+ * Rank r creates its handle with fpsb_create on its LOCAL operator A_loc (ncon = owned constraint
+ * rows, nvar = n_ext "extended" columns = owned variables + the halo columns its rows touch, in
+ * global column order) and then attaches the exchange pattern:
+ *   own_off, n_own        the owned variables are the extended columns [own_off, own_off + n_own)
+ *   recv_start/recv_cnt   [nranks] my halo slots owned by peer p: extended columns [start, start+cnt)
+ *   send_ptr/send_idx     [nranks+1] / [send_ptr[nranks]] owned extended columns peer p keeps as halo
+ * jprod needs a gather of halo values (ncclSend/ncclRecv), jtprod a scatter-add of halo partial sums,
+ * the Krylov inner products one ncclAllReduce of 4 doubles per half iteration.
+ * Vectors: n-space arguments are the OWNED slices (n_own), m-space arguments the local rows (ncon).
+ * fpsb_dist_unique_id: rank 0 makes the 128-byte ncclUniqueId the host program broadcasts. */
+int fpsb_dist_unique_id(void *out128);
+int fpsb_dist_attach(fpsb_handle h, int nranks, int rank, const void *nccl_id128, int64_t own_off,
+                     int64_t n_own, const int64_t *recv_start, const int64_t *recv_cnt,
+                     const int64_t *send_ptr, const int64_t *send_idx);
+int fpsb_dist_jprod(fpsb_handle h, const double *x_own, double *y_loc, int loc);
+int fpsb_dist_jtprod(fpsb_handle h, const double *u_loc, double *y_own, int loc);
+int fpsb_dist_solve_two_mixed(fpsb_handle h, double delta, int64_t nvar_global, int64_t ncon_global,
+                              const double *rhs1, const double *rhs2, double *p1, double *q1, double *p2,
+                              double *q2, int loc, fpsb_krylov_stats stats[2]);
+int fpsb_dist_solve_two_least_squares(fpsb_handle h, double delta, int64_t nvar_global,
+                                      int64_t ncon_global, const double *rhs1, const double *rhs2,
+                                      double *p1, double *q1, double *p2, double *q2, int loc,
+                                      fpsb_krylov_stats stats[2]);
+
 #ifdef __cplusplus
 }
 #endif
