@@ -111,6 +111,12 @@ struct StepParams {
     int *done_flag;        // set to 1 when no slot remains active
     double *tot_out;       // row-partitioned runs: the last CTA leaves the four local sums here instead of
                            // running the scalar recurrences (an all-reduce and finish_kernel follow)
+    // deferred recurrences (LSQR / CRAIG loops): this launch leaves only its per-CTA partials; the NEXT
+    // launch reduces them in its prologue (every CTA, same fixed order), runs the recurrences on its
+    // shared-memory state copy, and CTA 0 publishes the state to st_out (the other state buffer)
+    SlotState *st_out;             // non-null: deferred mode
+    const double *pend_partials;   // partials of the previous launch (null: nothing pending)
+    int pend_nparts, pend_m0, pend_m1;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -830,13 +836,35 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, 
         mbar_fence_init();
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    // ---- prologue: one round trip brings both slot states into shared memory ----
+    // ---- prologue: one round trip brings both slot states (and the previous launch's partials) in ----
+    __shared__ double s_tot[4];
     if (use_state) {
         const double *g = reinterpret_cast<const double *>(P.st);
         double *d = reinterpret_cast<double *>(sS);
         for (int i = tid; i < (int)(2 * sizeof(SlotState) / sizeof(double)); i += kStepThreads) d[i] = __ldcg(g + i);
     }
+    if (P.pend_partials != nullptr) {
+        // deferred recurrences of the previous step: fixed-order sum of its per-CTA partials ...
+        double tot[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int i = tid; i < P.pend_nparts; i += kStepThreads) {
+            const double *pp = P.pend_partials + (size_t)i * 4;
+            tot[0] += __ldcg(pp + 0); tot[1] += __ldcg(pp + 1);
+            tot[2] += __ldcg(pp + 2); tot[3] += __ldcg(pp + 3);
+        }
+        block_sum<4>(tot, s_red);
+        if (tid == 0) { s_tot[0] = tot[0]; s_tot[1] = tot[1]; s_tot[2] = tot[2]; s_tot[3] = tot[3]; }
+        __syncthreads();
+        // ... then the two slots' scalar recurrences side by side (thread 0 and thread 32)
+        if (tid == 0 && P.pend_m0 != MD_NONE && sS[0].active) finish_step(sS[0], P.pend_m0, s_tot[0], s_tot[1]);
+        if (tid == 32 && P.pend_m1 != MD_NONE && sS[1].active) finish_step(sS[1], P.pend_m1, s_tot[2], s_tot[3]);
+    }
     __syncthreads();
+    if (P.st_out != nullptr && cta == 0) {
+        if (tid == 0 && !sS[0].active && !sS[1].active) *P.done_flag = 1;
+        const double *src = reinterpret_cast<const double *>(sS);
+        double *dst = reinterpret_cast<double *>(P.st_out);
+        for (int i = tid; i < (int)(2 * sizeof(SlotState) / sizeof(double)); i += kStepThreads) dst[i] = src[i];
+    }
     const bool act0 = P.io[0].mode != MD_NONE && (!use_state || sS[0].active);
     const bool act1 = P.io[1].mode != MD_NONE && (!use_state || sS[1].active);
     if (!act0 && !act1) return;
@@ -1079,8 +1107,16 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, 
     return;
 #endif
 
-    // deterministic norms: one partial per CTA, the last CTA reduces them in a fixed order
+    // deterministic norms: one partial per CTA, reduced in a fixed order — by the next launch's
+    // prologue (deferred mode) or by this grid's last CTA
     block_sum<4>(acc, s_red);
+    if (P.st_out != nullptr) {
+        if (tid == 0) {
+            double *pp = P.partials + (size_t)cta * 4;
+            pp[0] = acc[0]; pp[1] = acc[1]; pp[2] = acc[2]; pp[3] = acc[3];
+        }
+        return;
+    }
     if (tid == 0) {
         double *pp = P.partials + (size_t)cta * 4;
         pp[0] = acc[0]; pp[1] = acc[1]; pp[2] = acc[2]; pp[3] = acc[3];
@@ -1122,6 +1158,31 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, 
         double *dst = reinterpret_cast<double *>(P.st);
         for (int i = tid; i < (int)(2 * sizeof(SlotState) / sizeof(double)); i += kStepThreads) dst[i] = src[i];
     }
+}
+
+// recurrences of a deferred step whose successor is not a step launch (end of a chunk / of the loop)
+__global__ void __launch_bounds__(256) flush_finish_kernel(SlotState *st, const double *partials, int nparts, int m0, int m1,
+                                                           int *done_flag) {
+    __shared__ double s_red[4 * 32];
+    __shared__ SlotState sS[2];
+    __shared__ double s_tot[4];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < (int)(2 * sizeof(SlotState) / sizeof(double)); i += 256)
+        reinterpret_cast<double *>(sS)[i] = reinterpret_cast<const double *>(st)[i];
+    double tot[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = tid; i < nparts; i += 256) {
+        const double *pp = partials + (size_t)i * 4;
+        tot[0] += pp[0]; tot[1] += pp[1]; tot[2] += pp[2]; tot[3] += pp[3];
+    }
+    block_sum<4>(tot, s_red);
+    if (tid == 0) { s_tot[0] = tot[0]; s_tot[1] = tot[1]; s_tot[2] = tot[2]; s_tot[3] = tot[3]; }
+    __syncthreads();
+    if (tid == 0 && m0 != MD_NONE && sS[0].active) finish_step(sS[0], m0, s_tot[0], s_tot[1]);
+    if (tid == 32 && m1 != MD_NONE && sS[1].active) finish_step(sS[1], m1, s_tot[2], s_tot[3]);
+    __syncthreads();
+    if (tid == 0 && !sS[0].active && !sS[1].active) *done_flag = 1;
+    for (int i = tid; i < (int)(2 * sizeof(SlotState) / sizeof(double)); i += 256)
+        reinterpret_cast<double *>(st)[i] = reinterpret_cast<const double *>(sS)[i];
 }
 
 // rows longer than kLongRow: one CTA per row, strided over the row, fixed-tree block reduction.
@@ -1376,6 +1437,7 @@ struct IterWs {
     int64_t prof_launch0 = 0, prof_launch1 = 0;
     bool prof_armed = false;
     int ew_grid = 0;
+    size_t partials_stride = 0;          // two partials buffers (deferred recurrences)
 };
 
 static void build_csr_host(int nrows, int ncols, int64_t nnz, const int64_t *ri, const int64_t *cj,
@@ -1687,10 +1749,11 @@ void iter_setup(Handle *h) {
         for (int k = 0; k < 5; ++k) W->am[s][k].alloc(m + 4);
     }
     W->ym.alloc(m + 4);
-    W->st.alloc(2);
+    W->st.alloc(4);          // two state buffers (deferred recurrences ping-pong between them)
     int maxblk = std::max(h->A.grid + h->A.nlong, h->At.grid + h->At.nlong);
     W->ew_grid = 148 * 4;
-    W->partials.alloc((size_t)std::max(maxblk, W->ew_grid) * 4 + 16);
+    W->partials_stride = (size_t)std::max(maxblk, W->ew_grid) * 4 + 16;
+    W->partials.alloc(2 * W->partials_stride);
     W->counter.alloc(4);
     W->done.alloc(4);
     W->counter.zero(h->stream);
@@ -1800,9 +1863,23 @@ struct Engine {
         base_m.gin2 = W->Gn.p; base_m.self2 = W->Gm.p;
         base_n.gin2 = W->Gm.p; base_n.self2 = W->Gn.p;
     }
+    // deferred recurrences (see StepParams): host-side bookkeeping
+    bool defer = false;          // set by the LSQR / CRAIG drivers around their loops
+    int cur = 0;                 // state buffer holding the current slot states
+    int pbuf = 0;                // partials buffer the next deferred launch writes
+    struct Pending { bool valid = false; int m0 = 0, m1 = 0, nparts = 0, buf = 0; } pend;
+    SlotState *st_cur() const { return W->st.p + 2 * cur; }
+    double *partials_buf(int b) const { return W->partials.p + (size_t)b * W->partials_stride; }
+    void flush_pending() {
+        if (!pend.valid) return;
+        flush_finish_kernel<<<1, 256, 0, h->stream>>>(st_cur(), partials_buf(pend.buf), pend.nparts, pend.m0, pend.m1, W->done.p);
+        h->launches += 1;
+        pend.valid = false;
+    }
     void begin(const SlotState &s0, const SlotState &s1) {
         SlotState hs[2] = {s0, s1};
         memcpy(W->h_st, hs, sizeof(hs));
+        cur = 0; pbuf = 0; pend.valid = false; defer = false;
         FPSB_CUDA(cudaMemcpyAsync(W->st.p, W->h_st, sizeof(hs), cudaMemcpyHostToDevice, h->stream));
         FPSB_CUDA(cudaMemsetAsync(W->done.p, 0, sizeof(int), h->stream));
         W->counter.zero(h->stream);
@@ -1812,15 +1889,31 @@ struct Engine {
         P.io[0] = io0; P.io[1] = io1;
         P.tot_out = tot_out;
         const CsrDev &M = mspace ? h->A : h->At;
+        if (M.grid == 0) return;
+        if (defer && tot_out == nullptr && M.nlong == 0) {
+            P.st = st_cur();
+            P.st_out = W->st.p + 2 * (cur ^ 1);
+            P.partials = partials_buf(pbuf);
+            if (pend.valid) { P.pend_partials = partials_buf(pend.buf); P.pend_nparts = pend.nparts; P.pend_m0 = pend.m0; P.pend_m1 = pend.m1; }
+            launch_step(h, M, P, pair, 1);
+            cur ^= 1;
+            pend.valid = true; pend.m0 = io0.mode; pend.m1 = io1.mode; pend.nparts = M.grid; pend.buf = pbuf;
+            pbuf ^= 1;
+            return;
+        }
+        flush_pending();
+        P.st = st_cur();
+        P.partials = partials_buf(0);
         launch_step(h, M, P, pair, 1);
     }
     void ew(int op, int slot, int n, const double *in0, double *v0, double *v1, double *v2, double *v3,
             double *v4, double2 *pair, int pair_slot, double c0, int use_state = 1) {
         if (n == 0 && !(use_state)) return;
+        if (use_state) flush_pending();
         EwParams P{};
         P.op = op; P.slot = slot; P.n = n; P.pair_slot = pair_slot; P.in0 = in0;
         P.v0 = v0; P.v1 = v1; P.v2 = v2; P.v3 = v3; P.v4 = v4; P.pair = pair; P.c0 = c0;
-        P.st = W->st.p; P.partials = W->partials.p; P.counter = W->counter.p; P.done_flag = W->done.p;
+        P.st = st_cur(); P.partials = partials_buf(0); P.counter = W->counter.p; P.done_flag = W->done.p;
         P.use_state = use_state;
         P.tot_out = tot_out;
         int grid = std::max(1, std::min(W->ew_grid, (n + kBlock - 1) / kBlock));
@@ -1863,11 +1956,15 @@ struct Engine {
         W->prof_armed = true;
     }
     void mark_end() {
+        flush_pending();
+        defer = false;
         FPSB_CUDA(cudaEventRecord(W->pev[1], h->stream));
         W->prof_launch1 = h->launches;
     }
     void fetch(fpsb_krylov_stats *st) {
-        FPSB_CUDA(cudaMemcpyAsync(W->h_st, W->st.p, 2 * sizeof(SlotState), cudaMemcpyDeviceToHost, h->stream));
+        flush_pending();
+        defer = false;
+        FPSB_CUDA(cudaMemcpyAsync(W->h_st, st_cur(), 2 * sizeof(SlotState), cudaMemcpyDeviceToHost, h->stream));
         FPSB_CUDA(cudaStreamSynchronize(h->stream));
         stats_from(W->h_st[0], st[0]);
         stats_from(W->h_st[1], st[1]);
@@ -1926,6 +2023,7 @@ void iter_solve_two_mixed(Handle *h, double delta, const double *rhs1, const dou
     SlotIO c_v = io_mode(MD_CRAIG_V, W->an[1][0].p, W->an[1][1].p);
     SlotIO c_u = io_mode(MD_CRAIG_U, W->am[1][0].p, W->am[1][1].p);
     E.mark_begin();
+    E.defer = true;
     E.step(true, true, l_init, io_none());
     E.loop([&](int) {
         E.step(false, true, l_u, c_v);
@@ -1959,6 +2057,7 @@ void iter_solve_two_least_squares(Handle *h, double delta, const double *rhs1, c
     SlotIO v0 = io_mode(MD_LSQR_V, W->am[0][0].p, W->am[0][1].p);
     SlotIO v1 = io_mode(MD_LSQR_V, W->am[1][0].p, W->am[1][1].p);
     E.mark_begin();
+    E.defer = true;
     E.step(true, true, init0, init1);
     E.loop([&](int) {
         E.step(false, true, u0, u1);
@@ -2050,6 +2149,7 @@ void iter_solve_two_extras(Handle *h, double delta, const double *rhs1, const do
         lsqr_init(E, 0, rhs1);
         SlotIO l_init = io_mode(MD_LSQR_INIT_M), l_u = io_mode(MD_LSQR_U);
         SlotIO l_v = io_mode(MD_LSQR_V, W->am[0][0].p, W->am[0][1].p);
+        E.defer = true;
         E.step(true, true, l_init, io_none());
         E.loop([&](int) {
             E.step(false, true, l_u, io_none());
