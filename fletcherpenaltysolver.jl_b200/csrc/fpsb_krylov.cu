@@ -753,7 +753,7 @@ constexpr int kWinCapMax = 1536;          // window capacity (entries of 16 byte
 constexpr int kLongThreads = 256;
 
 struct __align__(16) TileMeta {
-    long long boff;      // byte offset of the tile's block [values elems*8 | indices elems*4 | row map ns*128]
+    long long boff;      // byte offset of the tile's block [values elems*8 | indices elems*2 (window-relative u16) or elems*4 (global) | row map ns*32 (u8)]
     int elems;           // stored entries (multiple of 32)
     int ns;              // slices in the tile, ns <= kTileSlices
     int cmin, ccnt;      // gather window (ccnt == 0: gather from global memory, indices are global columns)
@@ -762,6 +762,11 @@ struct __align__(16) TileMeta {
 };
 static_assert(sizeof(TileMeta) == 48 && kTileSlices == 4, "TileMeta is loaded as three int4");
 static_assert(kGroupWarps == kTileSlices, "phase 1 maps one warp to one slice");
+static_assert(kTileRows < 255, "the lane -> row map is stored as bytes (255 = padding lane)");
+
+__host__ __device__ __forceinline__ unsigned tile_block_bytes(int elems, int ns, int ccnt) {
+    return (unsigned)elems * (ccnt > 0 ? 10u : 12u) + (unsigned)ns * 32u;
+}
 
 __device__ __forceinline__ TileMeta load_tile(const TileMeta *tiles, int t) {
     const int4 *tp = reinterpret_cast<const int4 *>(tiles + t);
@@ -908,7 +913,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, 
                 PT_MARK(1);
                 unsigned char *st = s_dyn + (size_t)s * stage_bytes;
                 if (blocks) {
-                    const uint32_t bytes = (uint32_t)T.elems * 12u + (uint32_t)T.ns * 128u;
+                    const uint32_t bytes = tile_block_bytes(T.elems, T.ns, T.ccnt);
                     mbar_expect_tx(&full_bar[s], bytes);
                     if (bytes) tma_bulk_g2s(st, P.tbuf + T.boff, bytes, &full_bar[s]);
                 } else {
@@ -990,13 +995,14 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, 
 
             const unsigned char *st = s_dyn + (size_t)s * stage_bytes;
             const double *s_val = reinterpret_cast<const double *>(st);
-            const int *s_col = reinterpret_cast<const int *>(st + (size_t)T.elems * 8);
-            const int *s_map = reinterpret_cast<const int *>(st + (size_t)T.elems * 12);
+            const bool windowed = T.ccnt > 0;
+            const int *s_col = reinterpret_cast<const int *>(st + (size_t)T.elems * 8);                        // global columns
+            const unsigned short *s_c16 = reinterpret_cast<const unsigned short *>(st + (size_t)T.elems * 8);   // window-relative
+            const unsigned char *s_map = st + (size_t)T.elems * (windowed ? 10 : 12);
             unsigned char *s_win = const_cast<unsigned char *>(st) + (size_t)P.blk_cap;
             const double2 *win2 = reinterpret_cast<const double2 *>(s_win);
             double *win0 = reinterpret_cast<double *>(s_win);
             double *win1 = win0 + P.win_cap;
-            const bool windowed = T.ccnt > 0;
 
             PT_MARK(1);
             ok = mbar_wait(&full_bar[s], (uint32_t)((k / nstage) & 1)) && ok;
@@ -1020,22 +1026,24 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, 
                 int lrow = -1;
                 if (wid < T.ns() && FPSB_EXP != 3 && FPSB_EXP != 7 && FPSB_EXP != 12) {
                     lrow = s_map[wid * 32 + lane];
+                    if (lrow == 255) lrow = -1;
                     const double2 *sv = reinterpret_cast<const double2 *>(s_val + off) + lane;
                     const int2 *sc = reinterpret_cast<const int2 *>(s_col + off) + lane;
+                    const ushort2 *sc16 = reinterpret_cast<const ushort2 *>(s_c16 + off) + lane;
                     const bool tail = (width & 1) != 0;
                     if (PAIR) {
                         if (windowed) {
 #pragma unroll 5
                             for (int p = 0; p < npair; ++p) {
                                 const double2 v = sv[p * 32];
-                                const int2 c = sc[p * 32];
+                                const ushort2 c = sc16[p * 32];
                                 const double2 x0 = win2[c.x], x1 = win2[c.y];
                                 s0 = fma(v.x, x0.x, s0); s1 = fma(v.x, x0.y, s1);
                                 u0 = fma(v.y, x1.x, u0); u1 = fma(v.y, x1.y, u1);
                             }
                             if (tail) {
                                 const double v = s_val[off + npair * 64 + lane];
-                                const double2 x = win2[s_col[off + npair * 64 + lane]];
+                                const double2 x = win2[s_c16[off + npair * 64 + lane]];
                                 s0 = fma(v, x.x, s0); s1 = fma(v, x.y, s1);
                             }
                         } else {
@@ -1061,11 +1069,14 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, 
 #pragma unroll 5
                         for (int p = 0; p < npair; ++p) {
                             const double2 v = sv[p * 32];
-                            const int2 c = sc[p * 32];
-                            gather_fma(v.x, c.x, s0, s1);
-                            gather_fma(v.y, c.y, u0, u1);
+                            int cx, cy;
+                            if (windowed) { const ushort2 c = sc16[p * 32]; cx = c.x; cy = c.y; }
+                            else { const int2 c = sc[p * 32]; cx = c.x; cy = c.y; }
+                            gather_fma(v.x, cx, s0, s1);
+                            gather_fma(v.y, cy, u0, u1);
                         }
-                        if (tail) gather_fma(s_val[off + npair * 64 + lane], s_col[off + npair * 64 + lane], s0, s1);
+                        if (tail) gather_fma(s_val[off + npair * 64 + lane],
+                                             windowed ? (int)s_c16[off + npair * 64 + lane] : s_col[off + npair * 64 + lane], s0, s1);
                     }
                 }
                 if (lrow >= 0) sum[lrow] = make_double2(s0 + u0, s1 + u1);
@@ -1510,7 +1521,7 @@ static void upload_sell(Handle *h, CsrDev &M, int nrows, int ncols, const std::v
                 cnt = cmax - c0 + 1;
                 if (cnt > kWinCapMax) cnt = 0;
             }
-            if ((size_t)elems * 12 + widths.size() * 128 + (size_t)cnt * 16 <= (size_t)kStageBytesMax) break;
+            if ((size_t)tile_block_bytes(elems, (int)widths.size(), cnt) + (size_t)cnt * 16 <= (size_t)kStageBytesMax) break;
             if (R > 32) { R = std::max(32, ((R / 2) + 31) & ~31); continue; }
             cnt = 0;     // a single slice (at most kLongRow wide, 36 KB): drop the window
             break;
@@ -1522,7 +1533,7 @@ static void upload_sell(Handle *h, CsrDev &M, int nrows, int ncols, const std::v
         T.elems = elems;
         T.ns = (int)widths.size();
         for (int i = 0; i < kTileSlices; ++i) T.width[i] = i < T.ns ? widths[(size_t)i] : 0;
-        const size_t bytes = (size_t)elems * 12 + (size_t)T.ns * 128;
+        const size_t bytes = (((size_t)tile_block_bytes(elems, T.ns, cnt)) + 127) & ~(size_t)127;    // blocks start 128-byte aligned
         win_cap = std::max(win_cap, cnt);
         blk_cap = std::max(blk_cap, bytes);
         tperm0.push_back((int)total_elems);
@@ -1546,8 +1557,10 @@ static void upload_sell(Handle *h, CsrDev &M, int nrows, int ncols, const std::v
     for (size_t ti = 0; ti < tiles.size(); ++ti) {
         const TileMeta &T = tiles[ti];
         const int cbase = T.ccnt > 0 ? T.cmin : 0;
+        const bool win = T.ccnt > 0;
         int *cols = reinterpret_cast<int *>(tbuf.data() + T.boff + (size_t)T.elems * 8);
-        int *rmap = reinterpret_cast<int *>(tbuf.data() + T.boff + (size_t)T.elems * 12);
+        unsigned short *cols16 = reinterpret_cast<unsigned short *>(tbuf.data() + T.boff + (size_t)T.elems * 8);
+        unsigned char *rmap = tbuf.data() + T.boff + (size_t)T.elems * (win ? 10 : 12);
         int *tp = sperm.data() + tperm0[ti];
         int off = 0;
         std::vector<int> eorder, used;
@@ -1577,16 +1590,18 @@ static void upload_sell(Handle *h, CsrDev &M, int nrows, int ncols, const std::v
             }
             for (int l = 0; l < 32; ++l) {
                 const int r = tile_rows[ti][(size_t)sl * 32 + l];
-                rmap[sl * 32 + l] = r >= 0 ? r - T.row0 : -1;
+                rmap[sl * 32 + l] = (unsigned char)(r >= 0 ? r - T.row0 : 255);
                 int len = 0, base = 0;
                 if (r >= 0) { base = rp[(size_t)r]; len = rp[(size_t)r + 1] - base; }
                 for (int j = 0; j < width; ++j) {
                     // pair rows: entries 2p, 2p+1 of a lane are adjacent; an odd last entry is a plain row
                     const int q = (j < 2 * npair) ? off + ((j >> 1) * 32 + l) * 2 + (j & 1) : off + npair * 64 + l;
+                    int cval = 0;
                     if (j < len) {
                         const int e = eorder[(size_t)l * width + j];
-                        cols[q] = ci[(size_t)(base + e)] - cbase; tp[q] = perm[(size_t)(base + e)];
-                    } else { cols[q] = 0; tp[q] = -1; }     // padding: value 0, valid column
+                        cval = ci[(size_t)(base + e)] - cbase; tp[q] = perm[(size_t)(base + e)];
+                    } else tp[q] = -1;                       // padding: value 0, valid column
+                    if (win) cols16[q] = (unsigned short)cval; else cols[q] = cval;
                 }
             }
             off += width * 32;
