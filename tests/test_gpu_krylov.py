@@ -208,3 +208,30 @@ def test_tight_tolerance_reaches_direct_accuracy():
     # the least-norm (CRAIG) half honours the tightened tolerances; the LSQR half keeps Krylov.jl's
     # axtol = btol = sqrt(eps), which the reference's call site (solve_least_square) cannot override
     assert res2 < 1e-10 and res1 < 1e-5, (res1, res2, st)
+
+
+@pytest.mark.parametrize("delta", [0.0, 1e-2])
+def test_solves_on_unstructured_matrix_with_long_rows(oracle, delta):
+    """Tiles whose column span exceeds the shared-memory window gather from global memory, rows
+    longer than the SELL limit go through the long-row kernel (whose norm partials join the step
+    kernel's reduction): both paths inside full LSQR / CRAIG solves against the oracle."""
+    rng = np.random.default_rng(17)
+    m, n = 300, 5000
+    A = sp.random(m, n, density=0.004, random_state=3, format="lil")
+    A[7, :400] = rng.standard_normal(400)              # two long rows (> 96 entries)
+    A[200, 1000:1300] = rng.standard_normal(300)
+    A = A.tocsr()
+    A.data[:] = rng.standard_normal(A.nnz)
+    H = _handle(A)
+    v = rng.standard_normal(n); u = rng.standard_normal(m); v3 = rng.standard_normal(n)
+    assert _rel(H.jprod(v), A @ v) < 1e-13 and _rel(H.jtprod(u), A.T @ u) < 1e-13
+    got = H.iter_solve_two_mixed(delta, v, u)
+    ref = oracle.IterativeOracle(A).solve_two_mixed(delta, v, u)
+    for a, b in zip(got[:4], ref[:4]):
+        assert _rel(a, b) < 1e-6
+    for s, o in zip(got[4], ref[4]):
+        assert s["solved"] == o["solved"] and abs(s["niter"] - o["niter"]) <= 1
+    got = H.iter_solve_two_least_squares(delta, v, v3)
+    ref = oracle.IterativeOracle(A).solve_two_least_squares(delta, v, v3)
+    for a, b in zip(got[:4], ref[:4]):
+        assert _rel(a, b) < 1e-6
