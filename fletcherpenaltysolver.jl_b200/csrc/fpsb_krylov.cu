@@ -744,7 +744,7 @@ constexpr int kTileSlices = kTileRows / 32;
 constexpr int kGroups = 3;
 constexpr int kGroupThreads = kTileRows;                      // phase 1: a warp per slice ; phase 2: a thread per row
 constexpr int kGroupWarps = kGroupThreads / 32;
-constexpr int kProducerThreads = 64;                           // warp 0: tile blocks, warp 1: gather windows
+constexpr int kProducerThreads = 128;                          // warps 0,1: tile blocks (even / odd tiles), warps 2,3: gather windows
 constexpr int kStepThreads = kProducerThreads + kGroups * kGroupThreads;
 constexpr int kStageBytesMax = 40 * 1024;                      // tile block + window
 constexpr int kMaxStages = 8;
@@ -890,15 +890,19 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, 
     if (tid < kProducerThreads) {
         // ------------------------------- producers -------------------------------
         if ((tid & 31) == 0) {
-            const bool blocks = tid == 0;      // warp 0: tile blocks ; warp 1: gather windows
-            // tile descriptors are fetched two tiles ahead of their use
-            int k = 0, tile = cta, t1 = cta + gsz;
+            // a bulk copy costs its issuing thread a few hundred ns whatever its size: two warps share
+            // the tile blocks (even / odd tiles of this CTA), two more the gather windows
+            const int role = tid >> 5;
+            const bool blocks = role < 2;
+            const int par = role & 1;
+            // tile descriptors are fetched two of this producer's tiles ahead of their use
+            int k = par, tile = cta + par * gsz, t1 = tile + 2 * gsz;
             PT_DECL;
             TileMeta T{}, T1{};
             if (tile < P.ntiles) T = load_tile(P.tiles, tile);
             if (t1 < P.ntiles) T1 = load_tile(P.tiles, t1);
-            for (; tile < P.ntiles; ++k) {
-                const int t2 = t1 + gsz;
+            for (; tile < P.ntiles; k += 2) {
+                const int t2 = t1 + 2 * gsz;
                 TileMeta T2{};
                 if (t2 < P.ntiles) T2 = load_tile(P.tiles, t2);
                 const int s = k % nstage;

@@ -4,7 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import fpsb200, bench
 from fpsb200 import _lib
-n, m, k, w = 1_000_000, 500_000, 20, 64
+scale = float(os.environ.get("FPSB_SCALE", "1"))
+n, m, k, w = int(1_000_000 * scale), int(500_000 * scale), 20, 64
 A, jrow, jcol, vals, r1, r2 = bench.make_workload(n, m, k, w, 1234)
 H = fpsb200.B200Handle(n, m, jrow, jcol)
 o = fpsb200.IterOpts()
