@@ -182,7 +182,7 @@ def main():
                        "step = solve_two_mixed (Jacobian refresh + LSQR/CRAIG 2-RHS solve), Krylov path, "
                        f"reference tolerances sqrt(eps), delta={args.delta}",
            "n": n, "m": m, "nnz": m * k, "nnz_per_row": k, "window": w, "delta": args.delta,
-           "l2_policy": "inputs larger than L2 (CSR of A and A' = 240 MB streamed every iteration vs 126 MB L2)",
+           "l2_policy": "inputs larger than L2 (tile blocks of A and A' = 200 MB + 100 MB of Krylov vectors streamed every iteration vs 126 MB L2)",
            "parallelism": f"{args.gpus} independent instance(s), one per GPU, no collective"}
     if args.impl == "reference":
         run_reference(args, cfg)
