@@ -12,11 +12,11 @@ mkdir -p "$HERE/build"
 "$NVCC" $COMMON ${PTXAS_V:+-Xptxas -v} -c "$HERE/fpsb_ldlt.cu" -o "$HERE/build/fpsb_ldlt.o"
 "$NVCC" $COMMON -c "$HERE/fpsb_api.cu" -o "$HERE/build/fpsb_api.o"
 EXTRA=""
-for f in "$HERE"/fpsb_symbolic.cpp "$HERE"/fpsb_batch.cu; do
+for f in "$HERE"/fpsb_symbolic.cpp "$HERE"/fpsb_batch.cu "$HERE"/fpsb_fpnlp.cu; do
   if [ -f "$f" ]; then
     o="$HERE/build/$(basename "${f%.*}").o"
     # the batch kernel mirrors the reference's scalar LDL' operation by operation: no FMA contraction
-    FM=""; case "$f" in *fpsb_batch.cu) FM="-fmad=false";; esac
+    FM=""; case "$f" in *fpsb_batch.cu|*fpsb_fpnlp.cu) FM="-fmad=false";; esac
     "$NVCC" $COMMON $FM -c "$f" -o "$o"
     EXTRA="$EXTRA $o"
   fi

@@ -156,6 +156,7 @@ int fpsb_destroy(fpsb_handle hh) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     dist_free(h);
+    fp_free(h);
     iter_free(h);
     ldlt_free(h);
     if (h->pin) cudaFreeHost(h->pin);
@@ -432,6 +433,69 @@ int fpsb_dist_solve_two_least_squares(fpsb_handle h, double delta, int64_t nvar_
                                       const double *rhs1, const double *rhs2, double *p1, double *q1, double *p2,
                                       double *q2, int loc, fpsb_krylov_stats stats[2]) {
     return dist_solve(h, 1, delta, nvar_global, ncon_global, rhs1, rhs2, p1, q1, p2, q2, loc, stats);
+}
+
+/* ---- device-resident FletcherPenaltyNLP glue; all vector arguments are DEVICE pointers ---- */
+int fpsb_fp_ys_gs(fpsb_handle hh, double sigma, const double *p1, const double *q1, const double *p2, const double *q2,
+                  double *gs, double *ys, double *v, double *w) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQUIRE(h && p1 && q1 && p2 && q2 && gs && ys && v && w, FPSB_EINVAL, "fpsb_fp_ys_gs: NULL argument");
+    FPSB_TRY
+    FPSB_CUDA(cudaSetDevice(h->device));
+    fp_ys_gs(h, h->nvar, h->ncon, sigma, p1, q1, p2, q2, gs, ys, v, w);
+    return FPSB_OK;
+    FPSB_CATCH
+}
+int fpsb_fp_obj(fpsb_handle hh, double fx, double rho, double eta, const double *c, const double *ys, const double *x,
+                const double *xk, double *phi) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQUIRE(h && c && ys && phi, FPSB_EINVAL, "fpsb_fp_obj: NULL argument");
+    FPSB_TRY
+    FPSB_CUDA(cudaSetDevice(h->device));
+    *phi = fp_obj(h, h->nvar, h->ncon, fx, rho, eta, c, ys, x, xk);
+    return FPSB_OK;
+    FPSB_CATCH
+}
+int fpsb_fp_grad(fpsb_handle hh, double sigma, double rho, double eta, const double *gs, const double *Hsv, const double *v,
+                 const double *Sstw, const double *Jtc, const double *x, const double *xk, double *g) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQUIRE(h && gs && Hsv && v && Sstw && g, FPSB_EINVAL, "fpsb_fp_grad: NULL argument");
+    REQUIRE(!(rho > 0.0) || Jtc, FPSB_EINVAL, "fpsb_fp_grad: rho > 0 needs J'c");
+    REQUIRE(!(eta > 0.0) || (x && xk), FPSB_EINVAL, "fpsb_fp_grad: eta > 0 needs x and xk");
+    FPSB_TRY
+    FPSB_CUDA(cudaSetDevice(h->device));
+    fp_grad(h, h->nvar, sigma, rho, eta, gs, Hsv, v, Sstw, Jtc, x, xk, g);
+    return FPSB_OK;
+    FPSB_CATCH
+}
+int fpsb_fp_ptv(fpsb_handle hh, const double *v, const double *p1, double *Ptv) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQUIRE(h && v && p1 && Ptv, FPSB_EINVAL, "fpsb_fp_ptv: NULL argument");
+    FPSB_TRY
+    FPSB_CUDA(cudaSetDevice(h->device));
+    fp_ptv(h, h->nvar, v, p1, Ptv);
+    return FPSB_OK;
+    FPSB_CATCH
+}
+int fpsb_fp_hprod2(fpsb_handle hh, double sigma, double rho, double eta, double obj_weight, const double *p2,
+                   const double *HsPtv, const double *Ptv, const double *Hcv, const double *JtJv, const double *v, double *Hv) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQUIRE(h && p2 && HsPtv && Ptv && v && Hv, FPSB_EINVAL, "fpsb_fp_hprod2: NULL argument");
+    REQUIRE(!(rho > 0.0) || (Hcv && JtJv), FPSB_EINVAL, "fpsb_fp_hprod2: rho > 0 needs Hcv and J'Jv");
+    FPSB_TRY
+    FPSB_CUDA(cudaSetDevice(h->device));
+    fp_hprod2(h, h->nvar, sigma, rho, eta, obj_weight, p2, HsPtv, Ptv, Hcv, JtJv, v, Hv);
+    return FPSB_OK;
+    FPSB_CATCH
+}
+int fpsb_fp_hash(fpsb_handle hh, const double *x, uint64_t *key) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQUIRE(h && key && (x || h->nvar == 0), FPSB_EINVAL, "fpsb_fp_hash: NULL argument");
+    FPSB_TRY
+    FPSB_CUDA(cudaSetDevice(h->device));
+    *key = fp_hash(h, h->nvar, x);
+    return FPSB_OK;
+    FPSB_CATCH
 }
 
 }  // extern "C"

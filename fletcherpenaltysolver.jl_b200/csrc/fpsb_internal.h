@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 #include "../../include/fpsb.h"
@@ -95,6 +96,7 @@ struct SlotState {
 struct IterWs;     // defined in fpsb_krylov.cu
 struct LdltPlan;   // defined in fpsb_ldlt.cu
 struct DistCtx;    // defined in fpsb_dist.inl (row-partitioned multi-GPU runs)
+struct FpWs;       // defined in fpsb_fpnlp.cu
 
 struct Handle {
     int device = 0;
@@ -114,6 +116,7 @@ struct Handle {
     IterWs *iter = nullptr;
     LdltPlan *ldlt = nullptr;
     DistCtx *dist = nullptr;
+    FpWs *fp = nullptr;
     fpsb_iter_opts iopts{};
     bool iopts_set = false;
     double prof_loop_ms = 0.0;          // CUDA-event time of the last Krylov loop region
@@ -147,6 +150,19 @@ void dist_solve_two_mixed(Handle *h, double delta, const double *rhs1, const dou
                           double *p2, double *q2, fpsb_krylov_stats *st, int64_t nvar_global, int64_t ncon_global);
 void dist_solve_two_least_squares(Handle *h, double delta, const double *rhs1, const double *rhs2, double *p1, double *q1,
                                   double *p2, double *q2, fpsb_krylov_stats *st, int64_t nvar_global, int64_t ncon_global);
+
+// fpsb_fpnlp.cu (device-resident FletcherPenaltyNLP glue)
+void fp_free(Handle *h);
+void fp_ys_gs(Handle *h, int64_t n, int64_t m, double sigma, const double *p1, const double *q1, const double *p2,
+              const double *q2, double *gs, double *ys, double *v, double *w);
+double fp_obj(Handle *h, int64_t n, int64_t m, double fx, double rho, double eta, const double *c, const double *ys,
+              const double *x, const double *xk);
+void fp_grad(Handle *h, int64_t n, double sigma, double rho, double eta, const double *gs, const double *Hsv, const double *v,
+             const double *Sstw, const double *Jtc, const double *x, const double *xk, double *g);
+void fp_ptv(Handle *h, int64_t n, const double *v, const double *p1, double *Ptv);
+void fp_hprod2(Handle *h, int64_t n, double sigma, double rho, double eta, double obj_weight, const double *p2, const double *HsPtv,
+               const double *Ptv, const double *Hcv, const double *JtJv, const double *v, double *Hv);
+uint64_t fp_hash(Handle *h, int64_t n, const double *x);
 
 // symbolic.cpp / ldlt.cu
 void ldlt_analyze(Handle *h, const int64_t *P, const fpsb_ldlt_opts *opts);

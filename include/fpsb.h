@@ -253,6 +253,30 @@ int fpsb_dist_solve_two_least_squares(fpsb_handle h, double delta, int64_t nvar_
                                       double *p1, double *q1, double *p2, double *q2, int loc,
                                       fpsb_krylov_stats stats[2]);
 
+/* ---------------------------------------------------------------------------------------------
+ * Device-resident FletcherPenaltyNLP glue: the vector combinations either side of the
+ * 2-RHS solves, fused, on the handle's stream.  ALL vector arguments are DEVICE pointers (n = nvar,
+ * m = ncon of the handle); together with loc = FPSB_DEVICE solves this keeps x, g, c, y(x) and the
+ * penalty gradient in HBM across the outer loop of src/algo.jl.
+ *   fpsb_fp_ys_gs   gs = p1 + sigma p2, ys = q1 + sigma q2, v = p2, w = q2   src/model-Fletcherpenaltynlp.jl:244-248
+ *   fpsb_fp_hash    memo key of x computed on the device (replaces hash(x), :235)
+ *   fpsb_fp_obj     phi = fx - c'ys + rho/2 |c|^2 (+ eta/2 |x - xk|^2)       :364-367   (x, xk may be NULL when eta = 0)
+ *   fpsb_fp_grad    g = gs - Hsv + sigma v + Sstw (+ rho Jtc) (+ eta (x - xk))   :382-398
+ *   fpsb_fp_ptv     Ptv = v - p1                                              :544
+ *   fpsb_fp_hprod2  Hv = obj_weight (p2 - HsPtv + 2 sigma Ptv (+ Hcv + rho JtJv) (+ eta v))   :546-568 (Val(2)) */
+int fpsb_fp_ys_gs(fpsb_handle h, double sigma, const double *p1, const double *q1, const double *p2,
+                  const double *q2, double *gs, double *ys, double *v, double *w);
+int fpsb_fp_hash(fpsb_handle h, const double *x, uint64_t *key);
+int fpsb_fp_obj(fpsb_handle h, double fx, double rho, double eta, const double *c, const double *ys,
+                const double *x, const double *xk, double *phi);
+int fpsb_fp_grad(fpsb_handle h, double sigma, double rho, double eta, const double *gs, const double *Hsv,
+                 const double *v, const double *Sstw, const double *Jtc, const double *x, const double *xk,
+                 double *g);
+int fpsb_fp_ptv(fpsb_handle h, const double *v, const double *p1, double *Ptv);
+int fpsb_fp_hprod2(fpsb_handle h, double sigma, double rho, double eta, double obj_weight, const double *p2,
+                   const double *HsPtv, const double *Ptv, const double *Hcv, const double *JtJv,
+                   const double *v, double *Hv);
+
 #ifdef __cplusplus
 }
 #endif
