@@ -7,15 +7,17 @@
 //   solve_least_norm    (CRAIG, M=I/delta)   src/solve_two_systems_struct.jl:210-244
 //   solve_two_mixed / least_squares / extras src/solve_linear_system.jl:45-140 (Iterative), :142-159 (LDLt extras)
 //
-// Design (B200): the Jacobian lives in HBM as CSR(A) and CSR(A') (no atomics, deterministic).
-// One CTA per row block: the block's values+indices are staged into shared memory with two TMA
-// 1-D bulk copies (cp.async.bulk + mbarrier), a sub-warp reduces every row against BOTH
-// right-hand-side columns with a single 16-byte gather per nonzero (the two Golub-Kahan
-// vectors are interleaved), and the row epilogue applies the axpby / norm / delayed x,w updates
-// of the Krylov method so that every vector is read and written once per iteration.
-// Norms use fixed-order reductions (per-CTA partials, last CTA finishes) and the scalar
-// recurrences (Givens rotations, stopping tests) run on the device in the last CTA; the host only
-// polls a done flag every few iterations.
+// Design (B200): the Jacobian lives in HBM twice, as A and as A' (both products are gather-type row
+// products: no atomics, deterministic), each as a tiled SELL-32 operator whose tiles are single
+// contiguous blocks [values | 16-bit window-relative indices | row map].  Persistent CTAs (one per
+// SM) stream the tiles through a shared-memory ring with TMA bulk copies (cp.async.bulk + mbarrier,
+// four producer warps), three consumer groups reduce every row against BOTH right-hand-side columns
+// with one 16-byte shared-memory gather per nonzero (the two Golub-Kahan vectors are interleaved),
+// and the row epilogue applies the axpby / norm / delayed x,w updates of the Krylov method so that
+// every vector is read and written once per iteration.  Norms use fixed-order reductions; the
+// scalar recurrences (Givens rotations, stopping tests) run on the device — inside the LSQR / CRAIG
+// loops deferred into the prologue of the next launch — and the host only polls a done flag every
+// few iterations.  See the comment above gk_step_kernel and DESIGN.md §4.
 #include "fpsb_internal.h"
 #include "fpsb_device.cuh"
 #include <algorithm>
