@@ -1885,6 +1885,7 @@ struct Engine {
         base_n.gin2 = W->Gm.p; base_n.self2 = W->Gn.p;
     }
     // deferred recurrences (see StepParams): host-side bookkeeping
+    int64_t max_it = 0;          // largest itmax of the two slots (bounds the host loop)
     bool defer = false;          // set by the LSQR / CRAIG drivers around their loops
     int cur = 0;                 // state buffer holding the current slot states
     int pbuf = 0;                // partials buffer the next deferred launch writes
@@ -1901,6 +1902,7 @@ struct Engine {
         SlotState hs[2] = {s0, s1};
         memcpy(W->h_st, hs, sizeof(hs));
         cur = 0; pbuf = 0; pend.valid = false; defer = false;
+        max_it = std::max<int64_t>(s0.algo != ALGO_NONE ? s0.itmax : 0, s1.algo != ALGO_NONE ? s1.itmax : 0);
         FPSB_CUDA(cudaMemcpyAsync(W->st.p, W->h_st, sizeof(hs), cudaMemcpyHostToDevice, h->stream));
         FPSB_CUDA(cudaMemsetAsync(W->done.p, 0, sizeof(int), h->stream));
         W->counter.zero(h->stream);
@@ -1945,7 +1947,9 @@ struct Engine {
     template <class F>
     void loop(F body, int chunk) {
         int k = 0, pending = 0, slot = 0;
-        int64_t hard_cap = (int64_t)4000000000LL;
+        // every method stops at its itmax at the latest; the cap only guards against a step that cannot
+        // run its recurrences at all (degenerate operator) — it must never be what ends a healthy solve
+        int64_t hard_cap = max_it + 4 * (int64_t)chunk + 8;
 #if FPSB_EXP > 0
         if (const char *e = getenv("FPSB_MAXLOOP")) hard_cap = atoll(e);     // timing experiments only
 #endif
@@ -2024,9 +2028,37 @@ static void lsqr_init(Engine &E, int slot, const double *rhs) {
     E.ew(EW_INIT_LSQR, slot, (int)E.h->nvar, rhs, nullptr, nullptr, nullptr, nullptr, nullptr, E.W->Gn.p, slot, 1.0);
 }
 
+// K = [I A'; A -delta I] with no constraints or no variables: closed forms (nothing to iterate on).
+// Returns true when it handled the call.
+__global__ void fill_kernel(int n, double *dst, const double *src, double c) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src ? c * src[i] : 0.0;
+}
+static bool degenerate_two(Handle *h, int kind, double delta, const double *rhs1, const double *rhs2, double *p1, double *q1,
+                           double *p2, double *q2, fpsb_krylov_stats *st) {
+    const int64_t n = h->nvar, m = h->ncon;
+    if (n > 0 && m > 0) return false;
+    auto fill = [&](int64_t cnt, double *dst, const double *src, double c) {
+        if (cnt > 0) { fill_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>((int)cnt, dst, src, c); h->launches += 1; }
+    };
+    // no constraints: K = I            -> p = rhs (n-space right-hand sides), nothing else
+    // no variables:   K = -delta I     -> q2 = -rhs2 / delta for the mixed system (0 when delta = 0)
+    fill(n, p1, rhs1, 1.0);
+    fill(n, p2, kind == 1 ? rhs2 : nullptr, 1.0);
+    fill(m, q1, nullptr, 0.0);
+    fill(m, q2, (kind == 0 && delta != 0.0) ? rhs2 : nullptr, delta != 0.0 ? -1.0 / delta : 0.0);
+    FPSB_CUDA(cudaStreamSynchronize(h->stream));
+    for (int s = 0; s < 2; ++s) {
+        memset(&st[s], 0, sizeof(st[s]));
+        st[s].solved = 1; st[s].status = FPSB_ST_SOLVED;
+    }
+    return true;
+}
+
 void iter_solve_two_mixed(Handle *h, double delta, const double *rhs1, const double *rhs2, double *p1,
                           double *q1, double *p2, double *q2, fpsb_krylov_stats *st) {
     iter_setup(h);
+    if (degenerate_two(h, 0, delta, rhs1, rhs2, p1, q1, p2, q2, st)) return;
     Engine E(h);
     IterWs *W = h->iter;
     const fpsb_iter_opts &o = h->iopts;
@@ -2063,6 +2095,7 @@ void iter_solve_two_least_squares(Handle *h, double delta, const double *rhs1, c
                                   double *p1, double *q1, double *p2, double *q2,
                                   fpsb_krylov_stats *st) {
     iter_setup(h);
+    if (degenerate_two(h, 1, delta, rhs1, rhs2, p1, q1, p2, q2, st)) return;
     Engine E(h);
     IterWs *W = h->iter;
     const fpsb_iter_opts &o = h->iopts;
@@ -2156,6 +2189,18 @@ static void run_cgls(Engine &E, int slot, const double *rhs, double *out) {
 void iter_solve_two_extras(Handle *h, double delta, const double *rhs1, const double *rhs2, double *u1,
                            double *u2, fpsb_krylov_stats *st, bool ldlt_variant) {
     iter_setup(h);
+    if (h->nvar == 0 || h->ncon == 0) {
+        // (A A' + tau I) u = rhs with no variables: u1 = 0 (A rhs1 is empty), u2 = rhs2 / tau ; no constraints: nothing
+        const double tau = std::max(delta, 1e-14);
+        if (h->ncon > 0) {
+            fill_kernel<<<(unsigned)((h->ncon + 255) / 256), 256, 0, h->stream>>>((int)h->ncon, u1, nullptr, 0.0);
+            fill_kernel<<<(unsigned)((h->ncon + 255) / 256), 256, 0, h->stream>>>((int)h->ncon, u2, rhs2, 1.0 / tau);
+            h->launches += 2;
+        }
+        FPSB_CUDA(cudaStreamSynchronize(h->stream));
+        for (int s = 0; s < 2; ++s) { memset(&st[s], 0, sizeof(st[s])); st[s].solved = 1; st[s].status = FPSB_ST_SOLVED; }
+        return;
+    }
     Engine E(h);
     IterWs *W = h->iter;
     const fpsb_iter_opts &o = h->iopts;

@@ -235,3 +235,32 @@ def test_solves_on_unstructured_matrix_with_long_rows(oracle, delta):
     ref = oracle.IterativeOracle(A).solve_two_least_squares(delta, v, v3)
     for a, b in zip(got[:4], ref[:4]):
         assert _rel(a, b) < 1e-6
+
+
+def test_degenerate_shapes_terminate_and_match(oracle):
+    """Empty and ragged inputs: no constraints, no variables (closed forms, nothing to iterate on), a
+    structurally empty Jacobian, 1 x 1, and more constraints than variables — every call returns,
+    and wherever the oracle defines the answer the results agree."""
+    rng = np.random.default_rng(0)
+    # no constraints: K = I ; no variables: K = -delta I
+    H = _handle(sp.csr_matrix((0, 5)))
+    r1 = rng.standard_normal(5)
+    p1, q1, p2, q2, st = H.iter_solve_two_mixed(1e-2, r1, np.zeros(0))
+    assert np.array_equal(p1, r1) and not p2.any() and q1.size == 0 and q2.size == 0 and st[0]["solved"] and st[1]["solved"]
+    P1, _, P2, _, _ = H.iter_solve_two_least_squares(0.0, r1, 2 * r1)
+    assert np.array_equal(P1, r1) and np.array_equal(P2, 2 * r1)
+    H = _handle(sp.csr_matrix((4, 0)))
+    r2 = rng.standard_normal(4)
+    p1, q1, p2, q2, st = H.iter_solve_two_mixed(0.25, np.zeros(0), r2)
+    assert not q1.any() and np.allclose(q2, -r2 / 0.25) and p1.size == 0
+    # shapes the iterations do run on
+    for A in (sp.csr_matrix((3, 5)), sp.csr_matrix(np.array([[2.0]])), sp.csr_matrix(np.arange(15.0).reshape(5, 3) + 1)):
+        m, n = A.shape
+        H = _handle(A)
+        r1, r2 = rng.standard_normal(n), rng.standard_normal(m)
+        got = H.iter_solve_two_mixed(1e-2, r1, r2)
+        ref = oracle.IterativeOracle(A).solve_two_mixed(1e-2, r1, r2)
+        for s, o in zip(got[4], ref[4]):
+            assert s["solved"] == o["solved"] and s["inconsistent"] == o["inconsistent"] and abs(s["niter"] - o["niter"]) <= 1
+        for a, b in zip(got[:4], ref[:4]):
+            assert np.allclose(a, b, rtol=1e-6, atol=1e-9)
