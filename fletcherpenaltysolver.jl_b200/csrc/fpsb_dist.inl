@@ -83,6 +83,9 @@ struct DistCtx {
     DevBuf<double2> sendbuf, recvbuf;               // packed entries (sum of send counts)
     DevBuf<double2> S;                              // raw A_loc' partial sums of both columns (n_ext)
     DevBuf<double> tot;                             // 4 doubles: local sums -> all-reduced sums
+    DevBuf<int> bidx;                               // owned rows that receive halo contributions (sorted, unique)
+    int64_t nbound = 0;
+    bool fused_n = false;                           // n-space step fused for the interior rows
     int64_t nsend = 0;
 };
 
@@ -126,6 +129,24 @@ void dist_attach(Handle *h, int nranks, int rank, const void *id128, int64_t own
     D->S.alloc((size_t)h->nvar + 8);
     D->tot.alloc(8);
     D->tot.zero(h->stream);
+    // Fused n-space step: interior owned rows get the ordinary fused epilogue; halo rows and the owned
+    // rows other ranks contribute to ("boundary") only leave their raw sums (row flag 2) and are finished
+    // by boundary_epilogue_kernel after the exchange.  Needs the lane-per-row tiles (no long rows in A').
+    {
+        std::vector<unsigned char> flag((size_t)h->nvar + 8, 0);
+        for (int64_t i = 0; i < h->nvar; ++i) if (i < own_off || i >= own_off + n_own) flag[(size_t)i] = 2;
+        std::vector<int> b(idx.begin(), idx.end());
+        std::sort(b.begin(), b.end());
+        b.erase(std::unique(b.begin(), b.end()), b.end());
+        for (int v : b) flag[(size_t)v] = 2;
+        D->nbound = (int64_t)b.size();
+        D->fused_n = h->At.nlong == 0 && D->nbound <= 65536;
+        if (D->fused_n) {
+            D->bidx.from(b, h->stream);
+            FPSB_CUDA(cudaMemcpyAsync(h->At.rowflag.p, flag.data(), (size_t)h->nvar, cudaMemcpyHostToDevice, h->stream));
+            h->At.has_raw_rows = true;
+        }
+    }
     FPSB_CUDA(cudaStreamSynchronize(h->stream));
     ncclUniqueId id;
     memcpy(&id, id128, 128);
@@ -217,6 +238,46 @@ __global__ void __launch_bounds__(kBlock) dist_epilogue_kernel(DistEpiParams P) 
     }
 }
 
+// epilogue of the boundary rows after the exchange (one CTA: the list is short), its norm sums are
+// added to the ones the fused step kernel left in tot
+__global__ void __launch_bounds__(kBlock) boundary_epilogue_kernel(int nb, const int *bidx, DistEpiParams P) {
+    __shared__ double s_red[4 * 32];
+    __shared__ Coef sC[2];
+    const int tid = threadIdx.x;
+    const bool act0 = P.io[0].mode != MD_NONE && P.st[0].active;
+    const bool act1 = P.io[1].mode != MD_NONE && P.st[1].active;
+    if (!act0 && !act1) return;
+    if (tid == 0) {
+        load_coef(sC[0], P.io[0], &P.st[0], true);
+        load_coef(sC[1], P.io[1], &P.st[1], true);
+        if (!act0) { sC[0].mode = MD_NONE; sC[0].rd0 = sC[0].rd1 = sC[0].wr0 = sC[0].wr1 = sC[0].rdself = 0; }
+        if (!act1) { sC[1].mode = MD_NONE; sC[1].rd0 = sC[1].rd1 = sC[1].wr0 = sC[1].wr1 = sC[1].rdself = 0; }
+    }
+    __syncthreads();
+    const CoefR C0 = to_regs(sC[0]), C1 = to_regs(sC[1]);
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = tid; i < nb; i += kBlock) {
+        const int row = bidx[i];
+        const double2 sm = P.S[row];
+        const double2 old2 = P.self2[row];
+        double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+        if (C0.rd0()) a00 = P.io[0].a0[row];
+        if (C0.rd1()) a01 = P.io[0].a1[row];
+        if (C1.rd0()) a10 = P.io[1].a0[row];
+        if (C1.rd1()) a11 = P.io[1].a1[row];
+        double n0 = old2.x, n1 = old2.y;
+        if (act0) n0 = row_epilogue(C0, sm.x, old2.x, a00, a01, acc[0], acc[1]);
+        if (act1) n1 = row_epilogue(C1, sm.y, old2.y, a10, a11, acc[2], acc[3]);
+        P.self2[row] = make_double2(n0, n1);
+        if (C0.wr0()) P.io[0].a0[row] = a00;
+        if (C0.wr1()) P.io[0].a1[row] = a01;
+        if (C1.wr0()) P.io[1].a0[row] = a10;
+        if (C1.wr1()) P.io[1].a1[row] = a11;
+    }
+    block_sum<4>(acc, s_red);
+    if (tid == 0) { P.tot_out[0] += acc[0]; P.tot_out[1] += acc[1]; P.tot_out[2] += acc[2]; P.tot_out[3] += acc[3]; }
+}
+
 // the scalar recurrences on the all-reduced sums (what the last CTA does on a single GPU)
 __global__ void finish_kernel(SlotState *st, int kind, int m0, int m1, const double *tot, int *done_flag) {
     __shared__ SlotState sS[2];
@@ -292,22 +353,39 @@ struct DistEngine {
         StepParams P = E.base_n;
         P.io[0] = io_mode(MD_PLAIN); P.io[1] = io_mode(MD_PLAIN);
         P.gin2 = gm_pair; P.self2 = D->S.p;
-        P.tot_out = nullptr;
+        P.tot_out = nullptr; P.raw_out = nullptr;          // plain product: every row's sum goes to S through self2
         if (h->At.grid == 0) { D->S.zero(h->stream); return; }
         launch_step(h, h->At, P, true, 0);
         scatter_add(D->S.p);
     }
-    // n-space half step: partial sums, exchange, epilogue on the owned rows, all-reduce, recurrences
+    // n-space half step.  Fused variant: the step kernel runs the epilogue of the interior owned rows
+    // itself and leaves the raw sums of the halo / boundary rows; those are exchanged, added, and
+    // finished by one small kernel.  Fallback (long rows in A', huge boundary): partial sums for every
+    // row, exchange, separate epilogue over all owned rows.
     void step_n(const SlotIO &io0, const SlotIO &io1) {
-        jt_partials(E.W->Gm.p);
         DistEpiParams Q{};
         Q.n_own = (int)D->n_own; Q.own_off = (int)D->own_off;
         Q.S = D->S.p; Q.self2 = E.W->Gn.p;
         Q.io[0] = io0; Q.io[1] = io1;
         Q.st = E.W->st.p; Q.partials = E.W->partials.p; Q.counter = E.W->counter.p; Q.tot_out = D->tot.p;
-        const int grid = std::max(1, std::min(E.W->ew_grid, (int)((D->n_own + kBlock - 1) / kBlock)));
-        dist_epilogue_kernel<<<grid, kBlock, 0, h->stream>>>(Q);
-        h->launches += 1;
+        if (D->fused_n) {
+            StepParams P = E.base_n;
+            P.io[0] = io0; P.io[1] = io1;
+            P.tot_out = D->tot.p; P.raw_out = D->S.p;
+            P.st = E.W->st.p;
+            if (h->At.grid == 0) return;
+            launch_step(h, h->At, P, true, 1);
+            scatter_add(D->S.p);
+            if (D->nbound > 0) {
+                boundary_epilogue_kernel<<<1, kBlock, 0, h->stream>>>((int)D->nbound, D->bidx.p, Q);
+                h->launches += 1;
+            }
+        } else {
+            jt_partials(E.W->Gm.p);
+            const int grid = std::max(1, std::min(E.W->ew_grid, (int)((D->n_own + kBlock - 1) / kBlock)));
+            dist_epilogue_kernel<<<grid, kBlock, 0, h->stream>>>(Q);
+            h->launches += 1;
+        }
         allreduce_finish(0, io0.mode, io1.mode);
     }
     // m-space half step: halo gather, fused step kernel on A_loc (rows are local), all-reduce, recurrences

@@ -60,7 +60,8 @@ struct CsrDev {
     DevBuf<int> sperm, tperm0;                 // sperm: stored entry -> COO index (-1 = padding); first entry per tile
     DevBuf<unsigned char> tbuf;                // tile blocks [values | indices | lane -> row map], back to back
     DevBuf<unsigned char> tiles;               // TileMeta[ntiles] (fpsb_krylov.cu)
-    DevBuf<unsigned char> rowflag;             // 1 = long row
+    DevBuf<unsigned char> rowflag;             // 1 = long row, 2 = raw row (row-partitioned runs)
+    bool has_raw_rows = false;
     int ntiles = 0, win_cap = 0, blk_cap = 0, stage_bytes = 0, nstage = 0;
     DevBuf<int> long_row, long_rp, long_col, long_perm;
     DevBuf<double> long_val;

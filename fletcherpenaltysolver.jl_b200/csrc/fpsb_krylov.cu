@@ -97,7 +97,8 @@ struct StepParams {
     int nlong;
     const unsigned char *tbuf;   // the tiles' blocks, back to back
     int blk_cap;           // capacity of the block part of a ring stage (bytes)
-    const unsigned char *rowflag;   // nrows : 1 for long rows (nullptr when there are none)
+    const unsigned char *rowflag;   // nrows : 1 long row (own kernel), 2 raw row (row sums go to raw_out, no epilogue); nullptr: all 0
+    double2 *raw_out;               // row-partitioned runs: raw sums of the halo / boundary rows (see fpsb_dist.inl)
     // long rows (CSR)
     const int *long_row;
     const int *long_rp;
@@ -969,8 +970,9 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, 
             if (nntile < P.ntiles) Tnn = load_ctile(P.tiles, nntile);
             // row-epilogue operands of this thread's row: in flight during the wait and phase 1
             const int row = T.row0 + t;
-            const bool has_row = FPSB_EXP != 4 && FPSB_EXP != 7 && FPSB_EXP != 12 && t < T.nrows() &&
-                                 !(P.rowflag != nullptr && P.rowflag[row]);
+            int rflag = (P.rowflag != nullptr && t < T.nrows()) ? (int)P.rowflag[row] : 0;
+            if (rflag == 2 && P.raw_out == nullptr) rflag = 0;     // raw rows only matter to launches that ask for them
+            const bool has_row = FPSB_EXP != 4 && FPSB_EXP != 7 && FPSB_EXP != 12 && t < T.nrows() && rflag == 0;
             double2 old2 = make_double2(0.0, 0.0);
             double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
             if (has_row && FPSB_EXP != 5) {
@@ -1095,6 +1097,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, 
             group_bar(g);
             PT_MARK(4);
             // ---------------- phase 2: row epilogue in natural row order, a thread per row ----------------
+            if (rflag == 2) P.raw_out[row] = sum[t];          // halo / boundary row of a row-partitioned run
             if (has_row) {
                 const double2 sm = sum[t];
                 double n0 = old2.x, n1 = old2.y;
@@ -1713,7 +1716,7 @@ static void fill_csr(StepParams &P, const CsrDev &M) {
         P.inflight = env_inflight > 0 ? env_inflight : 2;
         if (P.inflight > M.nstage) P.inflight = M.nstage;
     }
-    P.rowflag = M.nlong > 0 ? M.rowflag.p : nullptr;
+    P.rowflag = (M.nlong > 0 || M.has_raw_rows) ? M.rowflag.p : nullptr;
     P.long_row = M.long_row.p; P.long_rp = M.long_rp.p; P.long_col = M.long_col.p; P.long_val = M.long_val.p;
     P.nrows = M.nrows;
 }
