@@ -64,8 +64,11 @@ class DeviceSparseQP(AbstractNLPModel):
 class DeviceFletcherPenaltyNLP:
     """FletcherPenaltyNLP(nlp, sigma, rho, delta, Val(2); qds = ...) with device-resident state."""
 
-    def __init__(self, nlp, sigma=1.0, rho=0.0, delta=0.0, *, qds=None, device="cuda"):
+    def __init__(self, nlp, sigma=1.0, rho=0.0, delta=0.0, hessian_approx=2, *, qds=None, device="cuda",
+                 consistent_gradient=False):
         import torch
+        assert hessian_approx == 2, "Val(1) needs ghjvprod and stays on the host mirror"
+        self.consistent_gradient = consistent_gradient      # see FletcherPenaltyNLP
         self.torch = torch
         self.nlp = nlp
         self.explicit_linear_constraints = False
@@ -84,6 +87,14 @@ class DeviceFletcherPenaltyNLP:
         self.ys, self.w = (torch.empty(m, **f64) for _ in range(2))
         self.neval = dict(obj=0, grad=0, hprod=0)
         self._lib = _lib.lib()
+
+    @property
+    def shahx(self):
+        return self.key
+
+    @shahx.setter
+    def shahx(self, value):          # `shahx = 0` drops the memo (what reinit! does to the sub-state)
+        self.key = None if not value else value
 
     def _hash(self, x):
         k = C.c_uint64()
@@ -113,7 +124,7 @@ class DeviceFletcherPenaltyNLP:
     def grad(self, x):
         self.neval["grad"] += 1
         gs, ys, v, w = self._compute_ys_gs(x)
-        Hsv = self.nlp.hprod(x, ys, v, obj_weight=1.0)
+        Hsv = self.nlp.hprod(x, -ys if self.consistent_gradient else ys, v, obj_weight=1.0)
         Sstw = self.nlp.hprod(x, w, gs, obj_weight=0.0)
         Jtc = self.handle.jtprod(self.cx) if self.rho > 0.0 else None
         g = self.torch.empty_like(x)

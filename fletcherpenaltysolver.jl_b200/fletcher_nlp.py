@@ -14,8 +14,13 @@ class FletcherPenaltyNLP:
     """FletcherPenaltyNLP(nlp, sigma, rho, delta, hessian_approx; qds = LDLtSolver(nlp, 0.0))."""
 
     def __init__(self, nlp, sigma=1.0, rho=0.0, delta=0.0, hessian_approx=2, x0=None, *, qds=None,
-                 explicit_linear_constraints=False):
+                 explicit_linear_constraints=False, consistent_gradient=False):
         assert hessian_approx in (1, 2)
+        # Reference quirk (DESIGN §2): grad! hands +ys to hprod! (src/model-Fletcherpenaltynlp.jl:382, 415)
+        # where the derivative of obj needs H(x, -ys), the matrix hprod! itself uses (:534).  The two only
+        # differ when the constraints have curvature and c(x) != 0.  False = the reference's formula
+        # (drop-in parity), True = the exact gradient of obj.
+        self.consistent_gradient = consistent_gradient
         self.nlp = nlp
         self.explicit_linear_constraints = explicit_linear_constraints
         nvar = nlp.meta.nvar
@@ -83,7 +88,7 @@ class FletcherPenaltyNLP:
         self.neval["grad"] += 1
         gs, ys, v, w = self._compute_ys_gs(x)
         c = self.cx
-        Hsv = self._hprod_nln(x, ys, v, obj_weight=1.0)
+        Hsv = self._hprod_nln(x, -ys if self.consistent_gradient else ys, v, obj_weight=1.0)
         Sstw = self._hprod_nln(x, w, gs, obj_weight=0.0)
         gx = gs - Hsv + self.sigma * v + Sstw
         if self.rho > 0.0:

@@ -237,3 +237,155 @@ def poisson_control(N, alpha=1e-2):
     Q = np.concatenate([np.ones(m), alpha * np.ones(m)])
     q = np.concatenate([-yd, np.zeros(m)])
     return SparseQPModel(Q, q, A, hvec, name=f"poisson-control-{N}")
+
+
+# --------------------------------------------------------------------------------------------------
+# the reference's own small test problems (BASELINE configs C1 / C5), derivatives written by hand
+# (the reference gets them from ADNLPModels' automatic differentiation)
+# --------------------------------------------------------------------------------------------------
+def _cm(f, g, c, J, Hf, Hc, x0, ncon, lcon=None, ucon=None, name=""):
+    return CallableModel(f, g, c, J, Hf, Hc, np.asarray(x0, dtype=np.float64), ncon, lcon=lcon, ucon=ucon, name=name)
+
+
+def reference_test_problem(name):
+    """One of the problems `fps_solve` is tested on in the reference:
+    test/test-2.jl (rosenbrock_sum, simple, hs6, hs7, hs8, hs9, hs26, hs27, unbounded_quad_penalty, spurious, flt),
+    test/rank-deficient.jl:23-29 (hs61), docs/src/tutorial.md (hs28), docs/src/fine-tuneFPS.md:25-33
+    (readme_eq: Rosenbrock with x1 x2 = 1) and README.md:59-65 (readme_ineq: 0 <= x1 x2 - 1 <= 1)."""
+    A = np.array
+    Z = lambda n: (lambda x, j: np.zeros((n, n)))
+    rosen_f = lambda x: (x[0] - 1.0) ** 2 + 100 * (x[1] - x[0] ** 2) ** 2
+    rosen_g = lambda x: A([2 * (x[0] - 1) - 400 * x[0] * (x[1] - x[0] ** 2), 200 * (x[1] - x[0] ** 2)])
+    rosen_H = lambda x: A([[2 - 400 * x[1] + 1200 * x[0] ** 2, -400 * x[0]], [-400 * x[0], 200.0]])
+    if name == "rosenbrock_sum":
+        return _cm(rosen_f, rosen_g, lambda x: A([x[0] + x[1]]), lambda x: A([[1.0, 1.0]]), rosen_H, Z(2),
+                   [-1.2, 1.0], 1, lcon=[1.0], name=name)
+    if name == "simple":
+        return unit_test_model_sum(10)
+    if name == "hs6":
+        return _cm(lambda x: (1 - x[0]) ** 2, lambda x: A([-2 * (1 - x[0]), 0.0]),
+                   lambda x: A([10 * (x[1] - x[0] ** 2)]), lambda x: A([[-20 * x[0], 10.0]]),
+                   lambda x: A([[2.0, 0.0], [0.0, 0.0]]), lambda x, j: A([[-20.0, 0.0], [0.0, 0.0]]),
+                   [-1.2, 1.0], 1, name=name)
+    if name == "hs7":
+        return _cm(lambda x: np.log(1 + x[0] ** 2) - x[1], lambda x: A([2 * x[0] / (1 + x[0] ** 2), -1.0]),
+                   lambda x: A([(1 + x[0] ** 2) ** 2 + x[1] ** 2 - 4]),
+                   lambda x: A([[4 * x[0] * (1 + x[0] ** 2), 2 * x[1]]]),
+                   lambda x: A([[2 * (1 - x[0] ** 2) / (1 + x[0] ** 2) ** 2, 0.0], [0.0, 0.0]]),
+                   lambda x, j: A([[4 + 12 * x[0] ** 2, 0.0], [0.0, 2.0]]), [2.0, 2.0], 1, name=name)
+    if name == "hs8":
+        return _cm(lambda x: -1.0, lambda x: np.zeros(2), lambda x: A([x[0] ** 2 + x[1] ** 2 - 25, x[0] * x[1] - 9]),
+                   lambda x: A([[2 * x[0], 2 * x[1]], [x[1], x[0]]]), lambda x: np.zeros((2, 2)),
+                   lambda x, j: 2 * np.eye(2) if j == 0 else A([[0.0, 1.0], [1.0, 0.0]]), [2.0, 1.0], 2, name=name)
+    if name == "hs9":
+        a, b = np.pi / 12, np.pi / 16
+        return _cm(lambda x: np.sin(a * x[0]) * np.cos(b * x[1]),
+                   lambda x: A([a * np.cos(a * x[0]) * np.cos(b * x[1]), -b * np.sin(a * x[0]) * np.sin(b * x[1])]),
+                   lambda x: A([4 * x[0] - 3 * x[1]]), lambda x: A([[4.0, -3.0]]),
+                   lambda x: A([[-a * a * np.sin(a * x[0]) * np.cos(b * x[1]), -a * b * np.cos(a * x[0]) * np.sin(b * x[1])],
+                                [-a * b * np.cos(a * x[0]) * np.sin(b * x[1]), -b * b * np.sin(a * x[0]) * np.cos(b * x[1])]]),
+                   Z(2), [0.0, 0.0], 1, name=name)
+    if name == "hs26":
+        def Hf(x):
+            t = 12 * (x[1] - x[2]) ** 2
+            return A([[2.0, -2.0, 0.0], [-2.0, 2 + t, -t], [0.0, -t, t]])
+        return _cm(lambda x: (x[0] - x[1]) ** 2 + (x[1] - x[2]) ** 4,
+                   lambda x: A([2 * (x[0] - x[1]), -2 * (x[0] - x[1]) + 4 * (x[1] - x[2]) ** 3, -4 * (x[1] - x[2]) ** 3]),
+                   lambda x: A([(1 + x[1] ** 2) * x[0] + x[2] ** 4 - 3]),
+                   lambda x: A([[1 + x[1] ** 2, 2 * x[0] * x[1], 4 * x[2] ** 3]]), Hf,
+                   lambda x, j: A([[0.0, 2 * x[1], 0.0], [2 * x[1], 2 * x[0], 0.0], [0.0, 0.0, 12 * x[2] ** 2]]),
+                   [-2.6, 2.0, 2.0], 1, name=name)
+    if name == "hs27":
+        return _cm(lambda x: 0.01 * (x[0] - 1) ** 2 + (x[1] - x[0] ** 2) ** 2,
+                   lambda x: A([0.02 * (x[0] - 1) - 4 * x[0] * (x[1] - x[0] ** 2), 2 * (x[1] - x[0] ** 2), 0.0]),
+                   lambda x: A([x[0] + x[2] ** 2 + 1.0]), lambda x: A([[1.0, 0.0, 2 * x[2]]]),
+                   lambda x: A([[0.02 - 4 * x[1] + 12 * x[0] ** 2, -4 * x[0], 0.0], [-4 * x[0], 2.0, 0.0], [0.0, 0.0, 0.0]]),
+                   lambda x, j: np.diag([0.0, 0.0, 2.0]), [2.0, 2.0, 2.0], 1, name=name)
+    if name == "unbounded_quad_penalty":
+        return _cm(lambda x: x[0] ** 3 * x[1] ** 3, lambda x: A([3 * x[0] ** 2 * x[1] ** 3, 3 * x[0] ** 3 * x[1] ** 2]),
+                   lambda x: A([x[0] ** 2 + x[1] ** 2 - 1]), lambda x: A([[2 * x[0], 2 * x[1]]]),
+                   lambda x: A([[6 * x[0] * x[1] ** 3, 9 * x[0] ** 2 * x[1] ** 2], [9 * x[0] ** 2 * x[1] ** 2, 6 * x[0] ** 3 * x[1]]]),
+                   lambda x, j: 2 * np.eye(2), [0.0, 0.0], 1, name=name)
+    if name == "spurious":
+        return _cm(lambda x: 0.0, lambda x: np.zeros(1), lambda x: A([x[0] ** 3 + x[0] - 2.0]),
+                   lambda x: A([[3 * x[0] ** 2 + 1]]), lambda x: np.zeros((1, 1)), lambda x, j: A([[6 * x[0]]]),
+                   [0.0], 1, name=name)
+    if name == "flt":
+        return _cm(lambda x: (x[1] - 1) ** 2, lambda x: A([0.0, 2 * (x[1] - 1)]), lambda x: A([x[0] ** 2, x[0] ** 3]),
+                   lambda x: A([[2 * x[0], 0.0], [3 * x[0] ** 2, 0.0]]), lambda x: np.diag([0.0, 2.0]),
+                   lambda x, j: np.diag([2.0, 0.0]) if j == 0 else np.diag([6 * x[0], 0.0]), [1.0, 0.0], 2, name="FLT")
+    if name == "hs61":
+        return _cm(lambda x: 4 * x[0] ** 2 + 2 * x[1] ** 2 + 2 * x[2] ** 2 - 33 * x[0] + 16 * x[1] - 24 * x[2],
+                   lambda x: A([8 * x[0] - 33, 4 * x[1] + 16, 4 * x[2] - 24]),
+                   lambda x: A([3 * x[0] - 2 * x[1] ** 2 - 7, 4 * x[0] - x[2] ** 2 - 11]),
+                   lambda x: A([[3.0, -4 * x[1], 0.0], [4.0, 0.0, -2 * x[2]]]), lambda x: np.diag([8.0, 4.0, 4.0]),
+                   lambda x, j: np.diag([0.0, -4.0, 0.0]) if j == 0 else np.diag([0.0, 0.0, -2.0]),
+                   [0.0, 0.0, 0.0], 2, name=name)
+    if name == "hs28":
+        return _cm(lambda x: (x[0] + x[1]) ** 2 + (x[1] + x[2]) ** 2,
+                   lambda x: A([2 * (x[0] + x[1]), 2 * (x[0] + x[1]) + 2 * (x[1] + x[2]), 2 * (x[1] + x[2])]),
+                   lambda x: A([x[0] + 2 * x[1] + 3 * x[2] - 1]), lambda x: A([[1.0, 2.0, 3.0]]),
+                   lambda x: A([[2.0, 2.0, 0.0], [2.0, 4.0, 2.0], [0.0, 2.0, 2.0]]), Z(3), [-4.0, 1.0, 1.0], 1, name=name)
+    if name in ("readme_eq", "readme_ineq"):
+        f = lambda x: 100 * (x[1] - x[0] ** 2) ** 2 + (x[0] - 1) ** 2
+        return _cm(f, rosen_g, lambda x: A([x[0] * x[1] - 1]), lambda x: A([[x[1], x[0]]]), rosen_H,
+                   lambda x, j: A([[0.0, 1.0], [1.0, 0.0]]), [-1.2, 1.0], 1, lcon=[0.0],
+                   ucon=[0.0] if name == "readme_eq" else [1.0], name=name)
+    raise KeyError(name)
+
+
+REFERENCE_TEST_PROBLEMS = ("rosenbrock_sum", "simple", "hs6", "hs7", "hs8", "hs9", "hs26", "hs27",
+                           "unbounded_quad_penalty", "spurious", "flt", "hs61", "hs28", "readme_eq")
+
+
+class SlackModel(AbstractNLPModel):
+    """Equalities + bounded slacks for a model with inequalities: c_j(x) - s_j = 0, lcon_j <= s_j <= ucon_j
+    (the role of NLPModelsModifiers.SlackModel at src/FletcherPenaltySolver.jl:140-143).  Variables [x; s],
+    one slack per inequality row in row order."""
+
+    def __init__(self, model):
+        super().__init__()
+        self.model = model
+        me = model.meta
+        self.ineq = np.flatnonzero(np.asarray(me.lcon) < np.asarray(me.ucon))
+        ns, n = len(self.ineq), me.nvar
+        lcon, ucon = np.array(me.lcon, dtype=np.float64), np.array(me.ucon, dtype=np.float64)
+        lvar = np.concatenate([me.lvar, lcon[self.ineq]])
+        uvar = np.concatenate([me.uvar, ucon[self.ineq]])
+        lcon[self.ineq] = 0.0
+        ucon[self.ineq] = 0.0
+        r, c = model.jac_structure()
+        self._rows = np.concatenate([np.asarray(r, dtype=np.int64), self.ineq.astype(np.int64)])
+        self._cols = np.concatenate([np.asarray(c, dtype=np.int64), n + np.arange(ns, dtype=np.int64)])
+        self.meta = NLPModelMeta(n + ns, me.ncon, x0=np.concatenate([me.x0, np.zeros(ns)]), lcon=lcon, ucon=ucon,
+                                 nnzj=len(self._rows), name=me.name + "-slack", lvar=lvar, uvar=uvar)
+        self.n = n
+
+    def obj(self, x):
+        self.counters.neval_obj += 1
+        return self.model.obj(x[:self.n])
+
+    def grad(self, x):
+        self.counters.neval_grad += 1
+        return np.concatenate([self.model.grad(x[:self.n]), np.zeros(len(self.ineq))])
+
+    def cons(self, x):
+        self.counters.neval_cons += 1
+        c = np.array(self.model.cons(x[:self.n]), dtype=np.float64)
+        c[self.ineq] -= x[self.n:]
+        return c
+
+    def jac_structure(self):
+        return self._rows, self._cols
+
+    def jac_coord(self, x):
+        self.counters.neval_jac += 1
+        return np.concatenate([self.model.jac_coord(x[:self.n]), -np.ones(len(self.ineq))])
+
+    def hprod(self, x, y, v, obj_weight=1.0):
+        self.counters.neval_hprod += 1
+        return np.concatenate([self.model.hprod(x[:self.n], y, v[:self.n], obj_weight=obj_weight),
+                               np.zeros(len(self.ineq))])
+
+    def ghjvprod(self, x, g, v):
+        return self.model.ghjvprod(x[:self.n], g[:self.n], v[:self.n])

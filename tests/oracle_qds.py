@@ -9,6 +9,7 @@ class OracleLDLt(QDSolver):
     def __init__(self, nlp, _zero=0.0, P=None, **kw):
         self.rows, self.cols = nlp.jac_structure()
         n, m = nlp.meta.nvar, nlp.meta.ncon
+        kw = {k: v for k, v in kw.items() if k in ("ldlt_tol", "ldlt_r1", "ldlt_r2")}   # like the reference's kwargs...
         self.o = O.LDLtOracle(n, m, self.rows, self.cols, np.arange(n + m) if P is None else P, **kw)
         self.handle = None
 
@@ -26,7 +27,7 @@ class OracleLDLt(QDSolver):
 class OracleIterative(QDSolver):
     def __init__(self, nlp, _zero=0.0, **kw):
         self.nlp = nlp
-        self.kw = kw
+        self.kw = {k: v for k, v in kw.items() if k.split("_")[0] in ("ls", "ln", "ne")}
         self.o = None
         self.handle = None
 

@@ -1,0 +1,84 @@
+"""GPU: `fps_solve` end to end with the 2-RHS solves in libfpsb200.so (`qds_solver = :ldlt | :iterative`,
+src/parameters.jl:197, 290-299) against the same outer loop driven by the CPU oracle: same status,
+iteration counts within +-1, solution / multipliers to 1e-6 (BASELINE north_star), on the reference's
+solver tests (test/test-2.jl, test/rank-deficient.jl:22-36, docs/src/fine-tuneFPS.md:25-33 = BASELINE
+config C1), plus the device-resident loop (SURVEY §8 f1 + f3) on a sparse QP."""
+import importlib
+import warnings
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(nlp, qds, **kw):
+    F = importlib.import_module("fpsb200.fps_solve")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return F.fps_solve(nlp, nlp.meta.x0, qds_solver=qds, **kw)
+
+
+# problems whose iterates pass through a singular Jacobian take a random restoration step in both runs
+# (same seed) but amplify rounding differently: status must agree, iterates are compared loosely
+DEGENERATE = ("unbounded_quad_penalty", "flt")
+
+
+@pytest.mark.parametrize("solver", ["ldlt", "iterative"])
+@pytest.mark.parametrize("ha", [2, 1])
+@pytest.mark.parametrize("name", ["readme_eq", "rosenbrock_sum", "simple", "hs6", "hs7", "hs8", "hs9", "hs26",
+                                  "hs27", "spurious", "hs61", "hs28", "unbounded_quad_penalty", "flt"])
+def test_fps_solve_matches_oracle_driven_run(oracle, name, solver, ha):
+    import fpsb200
+    import oracle_qds
+    from fpsb200 import models
+    nlp = models.reference_test_problem(name)
+    got = _run(nlp, solver, hessian_approx=ha)                                    # "ldlt" / "iterative" keys
+    assert isinstance(got.solver_specific["solver"].qdsolver,
+                      fpsb200.LDLtSolver if solver == "ldlt" else fpsb200.IterativeSolver)
+    nlp2 = models.reference_test_problem(name)
+    if solver == "ldlt":
+        P = got.solver_specific["solver"].qdsolver.handle.ldlt_symbolic()["P"]   # same elimination order
+        ref = _run(nlp2, lambda m, z, **kw: oracle_qds.OracleLDLt(m, z, P=P, **kw), hessian_approx=ha)
+    else:
+        ref = _run(nlp2, oracle_qds.OracleIterative, hessian_approx=ha)
+    assert got.status == ref.status == "first_order"
+    if name in DEGENERATE:
+        assert abs(got.iter - ref.iter) <= 3
+        return
+    assert abs(got.iter - ref.iter) <= 1
+    tol = 1e-6
+    assert np.linalg.norm(got.solution - ref.solution) <= tol * max(1.0, np.linalg.norm(ref.solution))
+    assert np.linalg.norm(got.multipliers - ref.multipliers) <= tol * max(1.0, np.linalg.norm(ref.multipliers))
+    assert abs(got.objective - ref.objective) <= tol * max(1.0, abs(ref.objective))
+
+
+@pytest.mark.parametrize("solver", ["ldlt", "iterative"])
+def test_fps_solve_sparse_qp_host_and_device_resident(solver):
+    """Equality QP (BASELINE config C2 shape, small): host-buffer loop vs the loop with every vector in HBM
+    (DeviceFletcherPenaltyNLP + FPSB_DEVICE solves + trunk on device tensors); both against the KKT solution."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    import torch
+    import fpsb200
+    from fpsb200 import models
+    n, m = 600, 250
+    qp = models.sparse_qp(n, m, nnz_per_row=6, w=24, seed=11)
+    K = sp.bmat([[sp.diags(qp.Q), qp.A.T], [qp.A, None]], format="csc")
+    sol = spla.spsolve(K, np.concatenate([-qp.q, qp.b]))
+    xstar, lam = sol[:n], sol[n:]
+    host = _run(qp, solver)
+    assert host.status == "first_order"
+    assert np.linalg.norm(host.solution - xstar) <= 1e-5 * np.linalg.norm(xstar)
+    assert np.linalg.norm(host.multipliers - lam) <= 1e-4 * max(1.0, np.linalg.norm(lam))
+    dqp = fpsb200.DeviceSparseQP(qp)
+    F = importlib.import_module("fpsb200.fps_solve")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        dev = F.fps_solve(dqp, torch.zeros(n, dtype=torch.float64, device="cuda"), qds_solver=solver,
+                          model_factory=fpsb200.DeviceFletcherPenaltyNLP)
+    model = dev.solver_specific["solver"].model
+    assert isinstance(model, fpsb200.DeviceFletcherPenaltyNLP) and model.gs.is_cuda and model.ys.is_cuda
+    assert dev.status == host.status and abs(dev.iter - host.iter) <= 1
+    assert np.linalg.norm(dev.solution - host.solution) <= 1e-6 * np.linalg.norm(host.solution)
+    assert np.linalg.norm(dev.multipliers - host.multipliers) <= 1e-6 * max(1.0, np.linalg.norm(host.multipliers))
