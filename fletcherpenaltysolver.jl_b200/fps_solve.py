@@ -622,7 +622,7 @@ class FPSSSolver:
                                       "solver (ipopt / knitro in the reference); not provided here")
         if isinstance(qds_solver, QDSolver):
             self.qdsolver = qds_solver
-        elif isinstance(qds_solver, type):
+        elif isinstance(qds_solver, type) or callable(qds_solver):
             self.qdsolver = qds_solver(nlp, 0.0, **kwargs)
         else:
             self.qdsolver = qdsolver_correspondence[str(qds_solver).lstrip(":")](nlp, 0.0, **kwargs)
