@@ -385,6 +385,31 @@ int fpsb_dist_attach(fpsb_handle hh, int nranks, int rank, const void *nccl_id12
     return FPSB_OK;
     FPSB_CATCH
 }
+int64_t fpsb_dist_peer_blob_bytes(void) { return dist_peer_blob_bytes(); }
+int fpsb_dist_peer_export(fpsb_handle hh, void *blob_out) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQUIRE(h && blob_out, FPSB_EINVAL, "fpsb_dist_peer_export: NULL argument");
+    REQUIRE(h->dist, FPSB_ESTATE, "not a row-partitioned handle (call fpsb_dist_attach first)");
+    FPSB_TRY
+    FPSB_CUDA(cudaSetDevice(h->device));
+    dist_peer_export(h, blob_out);
+    return FPSB_OK;
+    FPSB_CATCH
+}
+int fpsb_dist_peer_attach(fpsb_handle hh, const void *blobs) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQUIRE(h && blobs, FPSB_EINVAL, "fpsb_dist_peer_attach: NULL argument");
+    REQUIRE(h->dist, FPSB_ESTATE, "not a row-partitioned handle (call fpsb_dist_attach first)");
+    FPSB_TRY
+    FPSB_CUDA(cudaSetDevice(h->device));
+    dist_peer_attach(h, blobs);
+    return FPSB_OK;
+    FPSB_CATCH
+}
+int fpsb_dist_peer_active(fpsb_handle hh) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    return (h && dist_peer_active(h)) ? 1 : 0;
+}
 static int dist_spmv(fpsb_handle hh, bool transpose, const double *x, double *y, int loc) {
     Handle *h = reinterpret_cast<Handle *>(hh);
     REQUIRE(h && x && y, FPSB_EINVAL, "NULL argument");

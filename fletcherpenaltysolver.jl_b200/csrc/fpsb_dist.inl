@@ -17,6 +17,16 @@
 //
 // Every rank runs the same scalar recurrences on the same all-reduced sums, so the slot states stay
 // bitwise identical across ranks and all ranks take the same number of iterations.
+//
+// Two transports for the three exchanges:
+//   * peer memory (default once fpsb_dist_peer_attach has run): every rank owns a "mailbox" in HBM that
+//     its peers map through CUDA IPC and write over NVLink.  ONE small kernel per half iteration
+//     (xchg_kernel) does, in order: put the halo partial sums into the owners' mailboxes -> signal ->
+//     wait -> add them in rank order -> epilogue of the boundary rows -> put the fresh halo values of
+//     the gathered pair and the 4 local norm sums into the peers' mailboxes -> signal -> wait -> sum the
+//     norm partials in rank order -> scalar recurrences.  No NCCL call, no host involvement; an
+//     iteration is 4 launches (step, xchg, step, xchg) instead of 8 kernels + 4 NCCL operations.
+//   * NCCL (FPSB_DIST_NCCL=1, or when peer attach was not called): ncclSend/ncclRecv + ncclAllReduce.
 // NCCL is bound at run time (dlopen) so that libfpsb200.so loads on machines without it.
 struct NcclApi {
     void *lib = nullptr;
@@ -87,12 +97,48 @@ struct DistCtx {
     int64_t nbound = 0;
     bool fused_n = false;                           // n-space step fused for the interior rows
     int64_t nsend = 0;
+    // ---- peer-memory transport ----
+    static constexpr int kMaxRanks = 8;
+    bool peer = false;                              // mailboxes mapped, xchg_kernel replaces NCCL
+    unsigned char *mbox = nullptr;                  // my mailbox (cudaMalloc, exported through CUDA IPC)
+    size_t mbox_bytes = 0;
+    int64_t nrecv = 0;                              // sum of recv_cnt
+    std::vector<int64_t> ga_off;                    // per source peer: start (in double2) of its slice of my gather inbox
+    unsigned char *peer_mbox[kMaxRanks] = {};       // peers' mailboxes mapped into this process (self = mbox)
+    int64_t sc_at_peer[kMaxRanks] = {}, ga_at_peer[kMaxRanks] = {};   // where my slices start in the peers' inboxes
+    int64_t peer_nsend[kMaxRanks] = {}, peer_nrecv[kMaxRanks] = {};   // the peers' inbox sizes (mailbox layout)
+    DevBuf<int64_t> d_meta;                         // device copy of recv_start | recv_cnt | send_ptr | ga_off
+    DevBuf<int> d_err;
+    DevBuf<unsigned long long> d_bar;               // grid-barrier arrivals of xchg_kernel (monotonic)
+    unsigned long long bar_base = 0;
+    static constexpr int kXchgMaxGrid = 64;
+    DevBuf<double> xparts;                          // per-CTA norm partials of the boundary rows
+    DevBuf<int> bptr, bsrc;                         // per boundary row: the scatter-inbox entries added to it
+    uint64_t sig = 0, n_sc = 0, n_ga = 0, n_tot = 0;   // signals / exchanges issued so far (same on every rank)
+    bool halo_fresh = false;                        // the halo slots of Gn hold the current values
+};
+
+// mailbox layout (bytes):  flags u64[8] | tot double[2][8][4] | scatter inbox double2[2][nsend] | gather inbox double2[2][nrecv]
+__host__ __device__ static inline size_t mbox_off_tot() { return 8 * sizeof(uint64_t); }
+__host__ __device__ static inline size_t mbox_off_sc() { return mbox_off_tot() + 2 * 8 * 4 * sizeof(double); }
+__host__ __device__ static inline size_t mbox_off_ga(int64_t nsend) { return mbox_off_sc() + 2 * (size_t)nsend * sizeof(double2); }
+static inline size_t mbox_size(int64_t nsend, int64_t nrecv) { return mbox_off_ga(nsend) + 2 * (size_t)nrecv * sizeof(double2) + 64; }
+
+// what a rank publishes so that its peers can map and address its mailbox
+struct PeerBlob {
+    cudaIpcMemHandle_t handle;
+    int64_t nsend, nrecv;
+    int64_t sc_off[DistCtx::kMaxRanks];             // per source peer p: where p's partial sums land (double2 units) = send_ptr[p]
+    int64_t ga_off[DistCtx::kMaxRanks];             // per source peer p: where p's halo values land
 };
 
 void dist_free(Handle *h) {
     if (!h->dist) return;
     NcclApi *api = nccl_api();
     if (h->dist->comm && api && api->CommDestroy) api->CommDestroy(h->dist->comm);
+    for (int p = 0; p < h->dist->nranks && p < DistCtx::kMaxRanks; ++p)
+        if (p != h->dist->rank && h->dist->peer_mbox[p]) cudaIpcCloseMemHandle(h->dist->peer_mbox[p]);
+    if (h->dist->mbox) cudaFree(h->dist->mbox);
     delete h->dist;
     h->dist = nullptr;
 }
@@ -141,8 +187,18 @@ void dist_attach(Handle *h, int nranks, int rank, const void *id128, int64_t own
         for (int v : b) flag[(size_t)v] = 2;
         D->nbound = (int64_t)b.size();
         D->fused_n = h->At.nlong == 0 && D->nbound <= 65536;
-        if (D->fused_n) {
+        {
+            // per boundary row the positions of its contributions in the scatter inbox, peers in rank order
+            std::vector<int> bp(b.size() + 1, 0), bs(idx.size());
+            for (size_t i = 0; i < idx.size(); ++i) bp[(size_t)(std::lower_bound(b.begin(), b.end(), idx[i]) - b.begin()) + 1]++;
+            for (size_t r = 0; r < b.size(); ++r) bp[r + 1] += bp[r];
+            std::vector<int> fill(bp.begin(), bp.end() - 1);
+            for (size_t i = 0; i < idx.size(); ++i) bs[(size_t)fill[(size_t)(std::lower_bound(b.begin(), b.end(), idx[i]) - b.begin())]++] = (int)i;
+            D->bptr.from(bp, h->stream);
+            D->bsrc.from(bs, h->stream);
             D->bidx.from(b, h->stream);
+        }
+        if (D->fused_n) {
             FPSB_CUDA(cudaMemcpyAsync(h->At.rowflag.p, flag.data(), (size_t)h->nvar, cudaMemcpyHostToDevice, h->stream));
             h->At.has_raw_rows = true;
         }
@@ -152,6 +208,66 @@ void dist_attach(Handle *h, int nranks, int rank, const void *id128, int64_t own
     memcpy(&id, id128, 128);
     FPSB_NCCL(api->CommInitRank(&D->comm, nranks, id, rank));
 }
+
+// ---- peer-memory transport: mailbox export / mapping ---------------------------------------------
+int64_t dist_peer_blob_bytes() { return (int64_t)sizeof(PeerBlob); }
+
+// allocates this rank's mailbox and fills the blob its peers need (the host program all-gathers the blobs)
+void dist_peer_export(Handle *h, void *blob_out) {
+    DistCtx *D = h->dist;
+    if (D->nranks > DistCtx::kMaxRanks) { set_error("peer-memory transport supports up to %d ranks", DistCtx::kMaxRanks); throw CudaFail{FPSB_EINVAL}; }
+    if (!D->mbox) {
+        D->nrecv = 0;
+        D->ga_off.assign((size_t)D->nranks, 0);
+        for (int p = 0; p < D->nranks; ++p) { D->ga_off[(size_t)p] = D->nrecv; D->nrecv += D->recv_cnt[(size_t)p]; }
+        D->mbox_bytes = mbox_size(D->nsend, D->nrecv);
+        FPSB_CUDA(cudaMalloc((void **)&D->mbox, D->mbox_bytes));
+        FPSB_CUDA(cudaMemset(D->mbox, 0, D->mbox_bytes));
+        std::vector<int64_t> meta;
+        meta.insert(meta.end(), D->recv_start.begin(), D->recv_start.end());
+        meta.insert(meta.end(), D->recv_cnt.begin(), D->recv_cnt.end());
+        meta.insert(meta.end(), D->send_ptr.begin(), D->send_ptr.end());
+        meta.insert(meta.end(), D->ga_off.begin(), D->ga_off.end());
+        D->d_meta.from(meta, h->stream);
+        D->d_err.alloc(8);
+        D->d_err.zero(h->stream);
+        D->d_bar.alloc(8);
+        D->d_bar.zero(h->stream);
+        D->xparts.alloc((size_t)DistCtx::kXchgMaxGrid * 4 + 8);
+        D->xparts.zero(h->stream);
+        FPSB_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    PeerBlob B;
+    memset(&B, 0, sizeof(B));
+    FPSB_CUDA(cudaIpcGetMemHandle(&B.handle, D->mbox));
+    B.nsend = D->nsend; B.nrecv = D->nrecv;
+    for (int p = 0; p < D->nranks; ++p) { B.sc_off[p] = D->send_ptr[(size_t)p]; B.ga_off[p] = D->ga_off[(size_t)p]; }
+    memcpy(blob_out, &B, sizeof(B));
+}
+
+// blobs: nranks PeerBlobs in rank order (every rank passes the same array)
+void dist_peer_attach(Handle *h, const void *blobs) {
+    DistCtx *D = h->dist;
+    if (!D->mbox) { set_error("fpsb_dist_peer_attach: call fpsb_dist_peer_export first"); throw CudaFail{FPSB_ESTATE}; }
+    const PeerBlob *B = reinterpret_cast<const PeerBlob *>(blobs);
+    for (int p = 0; p < D->nranks; ++p) {
+        D->peer_nsend[p] = B[p].nsend; D->peer_nrecv[p] = B[p].nrecv;
+        D->sc_at_peer[p] = B[p].sc_off[D->rank];
+        D->ga_at_peer[p] = B[p].ga_off[D->rank];
+        if (p == D->rank) { D->peer_mbox[p] = D->mbox; continue; }
+        // what I send to p in the scatter is what p counts as "sent to me" in the gather, and vice versa
+        if (B[p].sc_off[D->rank] + D->recv_cnt[(size_t)p] > B[p].nsend || B[p].ga_off[D->rank] + (D->send_ptr[(size_t)p + 1] - D->send_ptr[(size_t)p]) > B[p].nrecv) {
+            set_error("fpsb_dist_peer_attach: the halo lists of ranks %d and %d do not match", D->rank, p);
+            throw CudaFail{FPSB_EINVAL};
+        }
+        void *ptr = nullptr;
+        FPSB_CUDA(cudaIpcOpenMemHandle(&ptr, B[p].handle, cudaIpcMemLazyEnablePeerAccess));
+        D->peer_mbox[p] = reinterpret_cast<unsigned char *>(ptr);
+    }
+    const char *force = getenv("FPSB_DIST_NCCL");
+    D->peer = !(force && *force && *force != '0');
+}
+bool dist_peer_active(Handle *h) { return h->dist && h->dist->peer; }
 
 // ---- kernels of the exchange ------------------------------------------------------------------------
 __global__ void pack_pairs_kernel(int n, const int *idx, const double2 *src, double2 *dst) {
@@ -240,13 +356,11 @@ __global__ void __launch_bounds__(kBlock) dist_epilogue_kernel(DistEpiParams P) 
 
 // epilogue of the boundary rows after the exchange (one CTA: the list is short), its norm sums are
 // added to the ones the fused step kernel left in tot
-__global__ void __launch_bounds__(kBlock) boundary_epilogue_kernel(int nb, const int *bidx, DistEpiParams P) {
-    __shared__ double s_red[4 * 32];
-    __shared__ Coef sC[2];
+__device__ __forceinline__ void boundary_epilogue(int nb, const int *bidx, const DistEpiParams &P, double *s_red /* 4*32 */, Coef *sC /* 2 */) {
     const int tid = threadIdx.x;
     const bool act0 = P.io[0].mode != MD_NONE && P.st[0].active;
     const bool act1 = P.io[1].mode != MD_NONE && P.st[1].active;
-    if (!act0 && !act1) return;
+    if (!act0 && !act1) return;                              // uniform over the CTA
     if (tid == 0) {
         load_coef(sC[0], P.io[0], &P.st[0], true);
         load_coef(sC[1], P.io[1], &P.st[1], true);
@@ -256,7 +370,7 @@ __global__ void __launch_bounds__(kBlock) boundary_epilogue_kernel(int nb, const
     __syncthreads();
     const CoefR C0 = to_regs(sC[0]), C1 = to_regs(sC[1]);
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int i = tid; i < nb; i += kBlock) {
+    for (int i = tid; i < nb; i += (int)blockDim.x) {
         const int row = bidx[i];
         const double2 sm = P.S[row];
         const double2 old2 = P.self2[row];
@@ -276,6 +390,11 @@ __global__ void __launch_bounds__(kBlock) boundary_epilogue_kernel(int nb, const
     }
     block_sum<4>(acc, s_red);
     if (tid == 0) { P.tot_out[0] += acc[0]; P.tot_out[1] += acc[1]; P.tot_out[2] += acc[2]; P.tot_out[3] += acc[3]; }
+}
+__global__ void __launch_bounds__(kBlock) boundary_epilogue_kernel(int nb, const int *bidx, DistEpiParams P) {
+    __shared__ double s_red[4 * 32];
+    __shared__ Coef sC[2];
+    boundary_epilogue(nb, bidx, P, s_red, sC);
 }
 
 // the scalar recurrences on the all-reduced sums (what the last CTA does on a single GPU)
@@ -300,15 +419,275 @@ __global__ void finish_kernel(SlotState *st, int kind, int m0, int m1, const dou
         reinterpret_cast<double *>(st)[i] = reinterpret_cast<const double *>(sS)[i];
 }
 
+// ---- peer-memory exchange -------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+struct XchgParams {
+    int nranks, rank;
+    int do_scatter, do_epi, do_gather, kind, m0, m1;   // kind: -1 no recurrence, 0 step (m0/m1 = modes), 1 element-wise (m0 = op, m1 = slot)
+    unsigned long long sig;                            // signals issued before this exchange
+    unsigned long long bar_base;                       // arrivals at the grid barrier before this launch
+    int sc_par, ga_par, tot_par;                       // inbox halves this exchange uses
+    long long nsend, nrecv;                            // my inbox sizes (entries)
+    const long long *meta;                             // recv_start[R] | recv_cnt[R] | send_ptr[R+1] | ga_off[R]
+    const int *send_idx;
+    double2 *S;                                        // raw / partial row sums of the extended n-space
+    double2 *pair;                                     // gathered pair of the extended n-space
+    int nbound;
+    const int *bidx, *bptr, *bsrc;                     // boundary rows; per row the inbox entries added to it (rank order)
+    DistEpiParams Q;
+    double *tot;
+    double *xparts;                                    // per-CTA norm partials of the boundary rows
+    SlotState *st;
+    int *done_flag;
+    int *err;
+    unsigned long long *bar;
+    unsigned char *mine;
+    unsigned char *peer[DistCtx::kMaxRanks];
+    long long sc_at_peer[DistCtx::kMaxRanks], ga_at_peer[DistCtx::kMaxRanks];
+    long long peer_nsend[DistCtx::kMaxRanks], peer_nrecv[DistCtx::kMaxRanks];
+};
+
+// Software grid barrier.  The exchange kernel is stream-ordered behind a step kernel and has at most 64
+// CTAs, so all of them are resident.  Writes issued before it (remote puts included) are visible to
+// the whole system afterwards.
+__device__ __forceinline__ void xchg_grid_barrier(const XchgParams &P, unsigned long long target) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && gridDim.x > 1) {
+        atomicAdd(P.bar, 1ull);
+        const unsigned long long t0 = global_ns();
+        while (*reinterpret_cast<volatile unsigned long long *>(P.bar) < target) {
+            if (global_ns() - t0 > 4000000000ull) { atomicExch(P.err, 2); break; }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+// CTA 0 tells every peer (flag = seq); every CTA waits until every peer has told this rank the same
+__device__ __forceinline__ void xchg_signal_wait(const XchgParams &P, unsigned long long seq) {
+    const int t = threadIdx.x;
+    if (t < P.nranks && t != P.rank) {
+        if (blockIdx.x == 0) st_release_sys(reinterpret_cast<unsigned long long *>(P.peer[t]) + P.rank, seq);
+        const unsigned long long *f = reinterpret_cast<const unsigned long long *>(P.mine) + t;
+        const unsigned long long t0 = global_ns();
+        while (ld_acquire_sys(f) < seq) {
+            if (global_ns() - t0 > 4000000000ull) { atomicExch(P.err, 1); break; }     // 4 s: a peer died
+        }
+    }
+    __syncthreads();
+}
+
+// <= 64 CTAs.  See the header of this file for the sequence; three grid barriers per launch.
+__global__ void __launch_bounds__(kBlock) xchg_kernel(XchgParams P) {
+    __shared__ double s_red[4 * 32];
+    __shared__ Coef sC[2];
+    __shared__ SlotState sS[2];
+    const int tid = threadIdx.x, nt = (int)blockDim.x, R = P.nranks;
+    const long long gtid = (long long)blockIdx.x * nt + tid, gsz = (long long)gridDim.x * nt;
+    if (*reinterpret_cast<volatile int *>(P.err) != 0) return;
+    const long long *recv_start = P.meta, *recv_cnt = P.meta + R, *send_ptr = P.meta + 2 * R, *ga_off = P.meta + 3 * R + 1;
+    unsigned long long seq = P.sig, bar = P.bar_base;
+    const unsigned long long G = gridDim.x;
+
+    // ---- 1. halo partial sums -> the owners' scatter inboxes
+    if (P.do_scatter) {
+        for (int p = 0; p < R; ++p) {
+            if (p == P.rank) continue;
+            const long long cnt = recv_cnt[p];
+            if (cnt == 0) continue;
+            double2 *dst = reinterpret_cast<double2 *>(P.peer[p] + mbox_off_sc()) + (size_t)P.sc_par * P.peer_nsend[p] + P.sc_at_peer[p];
+            const double2 *src = P.S + recv_start[p];
+            for (long long i = gtid; i < cnt; i += gsz) dst[i] = src[i];
+        }
+    }
+    xchg_grid_barrier(P, bar += G);
+    if (P.do_scatter) xchg_signal_wait(P, ++seq);
+
+    // ---- 2. boundary rows: add what the peers sent (rank order), then the Krylov row epilogue
+    const bool act0 = P.do_epi && P.Q.io[0].mode != MD_NONE && P.Q.st[0].active;
+    const bool act1 = P.do_epi && P.Q.io[1].mode != MD_NONE && P.Q.st[1].active;
+    const bool epi = act0 || act1;
+    if (epi) {
+        if (tid == 0) {
+            load_coef(sC[0], P.Q.io[0], &P.Q.st[0], true);
+            load_coef(sC[1], P.Q.io[1], &P.Q.st[1], true);
+            if (!act0) { sC[0].mode = MD_NONE; sC[0].rd0 = sC[0].rd1 = sC[0].wr0 = sC[0].wr1 = sC[0].rdself = 0; }
+            if (!act1) { sC[1].mode = MD_NONE; sC[1].rd0 = sC[1].rd1 = sC[1].wr0 = sC[1].wr1 = sC[1].rdself = 0; }
+        }
+        __syncthreads();
+    }
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    if (P.do_scatter || epi) {
+        CoefR C0{}, C1{};
+        if (epi) { C0 = to_regs(sC[0]); C1 = to_regs(sC[1]); }
+        const double2 *inbox = reinterpret_cast<const double2 *>(P.mine + mbox_off_sc()) + (size_t)P.sc_par * P.nsend;
+        for (long long b = gtid; b < P.nbound; b += gsz) {
+            const int row = P.bidx[b];
+            double2 sm = P.S[row];
+            if (P.do_scatter) {
+                for (int k = P.bptr[b]; k < P.bptr[b + 1]; ++k) {
+                    const double2 a = __ldcg(inbox + P.bsrc[k]);
+                    sm.x += a.x; sm.y += a.y;
+                }
+                P.S[row] = sm;
+            }
+            if (epi) {
+                const double2 old2 = P.Q.self2[row];
+                double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+                if (C0.rd0()) a00 = P.Q.io[0].a0[row];
+                if (C0.rd1()) a01 = P.Q.io[0].a1[row];
+                if (C1.rd0()) a10 = P.Q.io[1].a0[row];
+                if (C1.rd1()) a11 = P.Q.io[1].a1[row];
+                double n0 = old2.x, n1 = old2.y;
+                if (act0) n0 = row_epilogue(C0, sm.x, old2.x, a00, a01, acc[0], acc[1]);
+                if (act1) n1 = row_epilogue(C1, sm.y, old2.y, a10, a11, acc[2], acc[3]);
+                P.Q.self2[row] = make_double2(n0, n1);
+                if (C0.wr0()) P.Q.io[0].a0[row] = a00;
+                if (C0.wr1()) P.Q.io[0].a1[row] = a01;
+                if (C1.wr0()) P.Q.io[1].a0[row] = a10;
+                if (C1.wr1()) P.Q.io[1].a1[row] = a11;
+            }
+        }
+    }
+    if (epi) {
+        block_sum<4>(acc, s_red);
+        if (tid == 0) { double *pp = P.xparts + (size_t)blockIdx.x * 4; pp[0] = acc[0]; pp[1] = acc[1]; pp[2] = acc[2]; pp[3] = acc[3]; }
+    }
+    xchg_grid_barrier(P, bar += G);
+
+    // ---- 3. fresh halo values of the gathered pair and the local norm sums -> the peers
+    if (P.do_gather) {
+        for (int p = 0; p < R; ++p) {
+            if (p == P.rank) continue;
+            const long long b = send_ptr[p], e = send_ptr[p + 1];
+            if (b == e) continue;
+            double2 *dst = reinterpret_cast<double2 *>(P.peer[p] + mbox_off_ga(P.peer_nsend[p])) + (size_t)P.ga_par * P.peer_nrecv[p] + P.ga_at_peer[p];
+            for (long long i = b + gtid; i < e; i += gsz) dst[i - b] = P.pair[P.send_idx[i]];
+        }
+    }
+    if (blockIdx.x == 0 && (epi || P.kind >= 0)) {
+        if (epi && tid < 4) {
+            double v = P.tot[tid];
+            for (unsigned c = 0; c < gridDim.x; ++c) v += __ldcg(P.xparts + (size_t)c * 4 + tid);
+            P.tot[tid] = v;
+        }
+        __syncthreads();
+        if (P.kind >= 0 && tid < 4) {
+            const double v = P.tot[tid];
+            for (int p = 0; p < R; ++p) {
+                if (p == P.rank) continue;
+                reinterpret_cast<double *>(P.peer[p] + mbox_off_tot())[((size_t)P.tot_par * DistCtx::kMaxRanks + P.rank) * 4 + tid] = v;
+            }
+        }
+    }
+    xchg_grid_barrier(P, bar += G);
+    if (P.do_gather || P.kind >= 0) {
+        if (R > 1) xchg_signal_wait(P, ++seq);
+        if (P.do_gather) {
+            const double2 *inbox = reinterpret_cast<const double2 *>(P.mine + mbox_off_ga(P.nsend)) + (size_t)P.ga_par * P.nrecv;
+            for (int p = 0; p < R; ++p) {
+                if (p == P.rank) continue;
+                const long long cnt = recv_cnt[p];
+                double2 *dst = P.pair + recv_start[p];
+                const double2 *src = inbox + ga_off[p];
+                for (long long i = gtid; i < cnt; i += gsz) dst[i] = __ldcg(src + i);
+            }
+        }
+        if (P.kind >= 0 && blockIdx.x == 0) {
+            // norm partials of all ranks in rank order (identical on every rank), then the scalar recurrences
+            for (int i = tid; i < (int)(2 * sizeof(SlotState) / sizeof(double)); i += nt)
+                reinterpret_cast<double *>(sS)[i] = reinterpret_cast<const double *>(P.st)[i];
+            __syncthreads();
+            if (tid == 0) {
+                double tot[4] = {0.0, 0.0, 0.0, 0.0};
+                const double *in = reinterpret_cast<const double *>(P.mine + mbox_off_tot()) + (size_t)P.tot_par * DistCtx::kMaxRanks * 4;
+                for (int r = 0; r < R; ++r)
+                    for (int k = 0; k < 4; ++k) tot[k] += (r == P.rank) ? P.tot[k] : __ldcg(in + r * 4 + k);
+                for (int k = 0; k < 4; ++k) P.tot[k] = tot[k];
+                if (P.kind == 0) {
+                    if (P.m0 != MD_NONE && sS[0].active) finish_step(sS[0], P.m0, tot[0], tot[1]);
+                    if (P.m1 != MD_NONE && sS[1].active) finish_step(sS[1], P.m1, tot[2], tot[3]);
+                } else {
+                    const bool is_init = (P.m0 == EW_INIT_LSQR || P.m0 == EW_INIT_CRAIG || P.m0 == EW_MINRES_INIT || P.m0 == EW_CGLS_INIT);
+                    if (is_init || sS[P.m1].active) finish_ew(sS[P.m1], P.m0, tot[0]);
+                }
+                if (!sS[0].active && !sS[1].active) *P.done_flag = 1;
+            }
+            __syncthreads();
+            for (int i = tid; i < (int)(2 * sizeof(SlotState) / sizeof(double)); i += nt)
+                reinterpret_cast<double *>(P.st)[i] = reinterpret_cast<const double *>(sS)[i];
+        }
+    }
+}
+
 // ---- host side --------------------------------------------------------------------------------------
 struct DistEngine {
     Handle *h;
     DistCtx *D;
     NcclApi *api;
     Engine E;
-    DistEngine(Handle *hh) : h(hh), D(hh->dist), api(nccl_api()), E(hh) { E.tot_out = D->tot.p; }
+    DistEngine(Handle *hh) : h(hh), D(hh->dist), api(nccl_api()), E(hh) { E.tot_out = D->tot.p; D->halo_fresh = false; }
+
+    // one launch of the peer-memory exchange (see xchg_kernel)
+    void xchg(bool do_scatter, bool do_epi, bool do_gather, int kind, int m0, int m1, const DistEpiParams *Q = nullptr) {
+        XchgParams P{};
+        P.nranks = D->nranks; P.rank = D->rank;
+        P.do_scatter = do_scatter; P.do_epi = do_epi; P.do_gather = do_gather; P.kind = kind; P.m0 = m0; P.m1 = m1;
+        P.sig = D->sig;
+        P.sc_par = (int)(D->n_sc & 1); P.ga_par = (int)(D->n_ga & 1); P.tot_par = (int)(D->n_tot & 1);
+        P.nsend = D->nsend; P.nrecv = D->nrecv;
+        P.meta = reinterpret_cast<const long long *>(D->d_meta.p);
+        P.send_idx = D->send_idx.p;
+        P.S = D->S.p; P.pair = E.W->Gn.p;
+        P.nbound = (int)D->nbound; P.bidx = D->bidx.p; P.bptr = D->bptr.p; P.bsrc = D->bsrc.p;
+        P.xparts = D->xparts.p; P.bar = D->d_bar.p; P.bar_base = D->bar_base;
+        if (Q) P.Q = *Q;
+        P.tot = D->tot.p; P.st = E.W->st.p; P.done_flag = E.W->done.p; P.err = D->d_err.p;
+        P.mine = D->mbox;
+        for (int p = 0; p < D->nranks; ++p) {
+            P.peer[p] = D->peer_mbox[p];
+            P.sc_at_peer[p] = D->sc_at_peer[p]; P.ga_at_peer[p] = D->ga_at_peer[p];
+            P.peer_nsend[p] = D->peer_nsend[p]; P.peer_nrecv[p] = D->peer_nrecv[p];
+        }
+        // the lists are short (two grid lines per neighbour for a strip partition): one entry per thread
+        int64_t work = 0;
+        if (do_scatter) work = std::max<int64_t>(work, std::max(D->nrecv, D->nbound));
+        if (do_epi) work = std::max<int64_t>(work, D->nbound);
+        if (do_gather) work = std::max<int64_t>(work, std::max(D->nsend, D->nrecv));
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(DistCtx::kXchgMaxGrid, (work + kBlock - 1) / kBlock));
+        xchg_kernel<<<grid, kBlock, 0, h->stream>>>(P);
+        h->launches += 1;
+        if (grid > 1) D->bar_base += 3ull * (unsigned long long)grid;
+        if (D->nranks > 1) {
+            if (do_scatter) { D->sig += 1; D->n_sc += 1; }
+            if (do_gather || kind >= 0) D->sig += 1;
+        }
+        if (do_gather) { D->n_ga += 1; D->halo_fresh = true; }
+        if (kind >= 0) D->n_tot += 1;
+    }
+    void check_peer_error() {
+        if (!D->peer) return;
+        int e = 0;
+        FPSB_CUDA(cudaMemcpyAsync(&e, D->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        FPSB_CUDA(cudaStreamSynchronize(h->stream));
+        if (e) { set_error("row-partitioned run: a peer did not answer within 4 s (peer-memory exchange)"); throw CudaFail{FPSB_ECUDA}; }
+    }
 
     void allreduce_finish(int kind, int m0, int m1) {
+        if (D->peer) { xchg(false, false, false, kind, m0, m1); return; }
         FPSB_NCCL(api->AllReduce(D->tot.p, D->tot.p, 4, ncclDouble, ncclSum, D->comm, h->stream));
         finish_kernel<<<1, 64, 0, h->stream>>>(E.W->st.p, kind, m0, m1, D->tot.p, E.W->done.p);
         h->launches += 1;
@@ -316,6 +695,7 @@ struct DistEngine {
     // owners -> halo slots of an interleaved pair living in the extended n-space
     void gather_halo(double2 *pair) {
         if (D->nranks == 1) return;
+        if (D->peer && pair == E.W->Gn.p) { xchg(false, false, true, -1, 0, 0); return; }
         if (D->nsend > 0) {
             pack_pairs_kernel<<<(unsigned)((D->nsend + 255) / 256), 256, 0, h->stream>>>((int)D->nsend, D->send_idx.p, pair, D->sendbuf.p);
             h->launches += 1;
@@ -332,6 +712,7 @@ struct DistEngine {
     // halo partial sums -> owners, added in rank order
     void scatter_add(double2 *S) {
         if (D->nranks == 1) return;
+        if (D->peer && S == D->S.p) { xchg(true, false, false, -1, 0, 0); return; }
         FPSB_NCCL(api->GroupStart());
         for (int p = 0; p < D->nranks; ++p) {
             if (p == D->rank) continue;
@@ -375,6 +756,11 @@ struct DistEngine {
             P.st = E.W->st.p;
             if (h->At.grid == 0) return;
             launch_step(h, h->At, P, true, 1);
+            if (D->peer) {
+                // scatter-add + boundary epilogue + halo gather for the next m-space step + norms + recurrences
+                xchg(D->nranks > 1, true, D->nranks > 1, 0, io0.mode, io1.mode, &Q);
+                return;
+            }
             scatter_add(D->S.p);
             if (D->nbound > 0) {
                 boundary_epilogue_kernel<<<1, kBlock, 0, h->stream>>>((int)D->nbound, D->bidx.p, Q);
@@ -385,17 +771,20 @@ struct DistEngine {
             const int grid = std::max(1, std::min(E.W->ew_grid, (int)((D->n_own + kBlock - 1) / kBlock)));
             dist_epilogue_kernel<<<grid, kBlock, 0, h->stream>>>(Q);
             h->launches += 1;
+            D->halo_fresh = false;
         }
         allreduce_finish(0, io0.mode, io1.mode);
     }
     // m-space half step: halo gather, fused step kernel on A_loc (rows are local), all-reduce, recurrences
     void step_m(const SlotIO &io0, const SlotIO &io1) {
-        gather_halo(E.W->Gn.p);
+        if (!(D->peer && D->halo_fresh)) gather_halo(E.W->Gn.p);
         E.step(true, true, io0, io1);
         allreduce_finish(0, io0.mode, io1.mode);
     }
     void ew(int op, int slot, int n, const double *in0, double *v0, double *v1, double *v2, double2 *pair, int pair_slot, double c0) {
         E.ew(op, slot, n, in0, v0, v1, v2, nullptr, nullptr, pair, pair_slot, c0, 1);
+        const bool npair = pair >= E.W->Gn.p && pair < E.W->Gn.p + h->nvar;      // the n-space pair changed
+        if (npair) D->halo_fresh = false;
         allreduce_finish(1, op, slot);
     }
 };
@@ -417,6 +806,7 @@ void dist_jprod(Handle *h, const double *x_own, double *y_loc) {
     launch_step(h, h->A, P, true, 0);
     unpack_cols_kernel<<<(unsigned)((h->ncon + 255) / 256), 256, 0, h->stream>>>((int)h->ncon, W->Gm.p, y_loc, nullptr);
     h->launches += 1;
+    X.check_peer_error();
 }
 void dist_jtprod(Handle *h, const double *u_loc, double *y_own) {
     DistEngine X(h);
@@ -428,6 +818,7 @@ void dist_jtprod(Handle *h, const double *u_loc, double *y_own) {
     X.jt_partials(W->Gm.p);
     unpack_cols_kernel<<<(unsigned)((D->n_own + 255) / 256), 256, 0, h->stream>>>((int)D->n_own, D->S.p + D->own_off, y_own, nullptr);
     h->launches += 1;
+    X.check_peer_error();
 }
 
 // p_i = rhs_i - (A' q_i) on the owned rows, for one or two columns
@@ -479,6 +870,7 @@ void dist_solve_two_mixed(Handle *h, double delta, const double *rhs1, const dou
     residual_own_kernel<<<(unsigned)((n_own + 255) / 256), 256, 0, h->stream>>>(n_own, D->S.p + D->own_off, rhs1, nullptr, p1, nullptr);
     h->launches += 1;
     E.fetch(st);
+    X.check_peer_error();
 }
 
 // Row-partitioned solve_two_least_squares (src/solve_linear_system.jl:79-105): two LSQR solves in lock step
@@ -522,4 +914,5 @@ void dist_solve_two_least_squares(Handle *h, double delta, const double *rhs1, c
     residual_own_kernel<<<(unsigned)((n_own + 255) / 256), 256, 0, h->stream>>>(n_own, D->S.p + D->own_off, rhs1, rhs2, p1, p2);
     h->launches += 1;
     E.fetch(st);
+    X.check_peer_error();
 }

@@ -144,6 +144,10 @@ void dist_unique_id(void *out128);
 void dist_attach(Handle *h, int nranks, int rank, const void *id128, int64_t own_off, int64_t n_own,
                  const int64_t *recv_start, const int64_t *recv_cnt, const int64_t *send_ptr, const int64_t *send_idx);
 void dist_free(Handle *h);
+int64_t dist_peer_blob_bytes();
+void dist_peer_export(Handle *h, void *blob_out);
+void dist_peer_attach(Handle *h, const void *blobs);
+bool dist_peer_active(Handle *h);
 int64_t dist_n_own(Handle *h);
 void dist_jprod(Handle *h, const double *x_own, double *y_loc);
 void dist_jtprod(Handle *h, const double *u_loc, double *y_own);

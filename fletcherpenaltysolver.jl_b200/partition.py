@@ -112,7 +112,7 @@ class RowPartition:
 class DistHandle:
     """One rank of the row-partitioned Krylov solver (needs a GPU; NCCL is bound by libfpsb200)."""
 
-    def __init__(self, part, rank, device=0, dist=None, opts=None):
+    def __init__(self, part, rank, device=0, dist=None, opts=None, peer=True):
         from . import _lib
         from .qdsolver import B200Handle
         try:
@@ -142,6 +142,20 @@ class DistHandle:
         _lib.check(lib.fpsb_dist_attach(self.H.h, C.c_int(self.world), C.c_int(rank), ident, C.c_int64(L.own_off),
                                         C.c_int64(L.n_own), p64(self._keep[0]), p64(self._keep[1]), p64(self._keep[2]),
                                         p64(self._keep[3]) if len(L.send_idx) else None), "fpsb_dist_attach")
+        # peer-memory transport: all-gather the mailbox descriptors, map the peers (NCCL stays the fallback)
+        self.peer = False
+        if peer and self.world <= 8:
+            lib.fpsb_dist_peer_blob_bytes.restype = C.c_int64
+            nb = int(lib.fpsb_dist_peer_blob_bytes())
+            blob = (C.c_ubyte * nb)()
+            _lib.check(lib.fpsb_dist_peer_export(self.H.h, blob), "fpsb_dist_peer_export")
+            blobs = [bytes(blob)]
+            if self.world > 1:
+                blobs = [None] * self.world
+                dist.all_gather_object(blobs, bytes(blob))
+            allb = (C.c_ubyte * (nb * self.world)).from_buffer_copy(b"".join(blobs))
+            _lib.check(lib.fpsb_dist_peer_attach(self.H.h, allb), "fpsb_dist_peer_attach")
+            self.peer = bool(lib.fpsb_dist_peer_active(self.H.h))
 
     def set_jac_values(self, vals_global):
         """vals_global: jac_coord values in the GLOBAL COO order (numpy); this rank keeps its rows."""

@@ -243,6 +243,19 @@ int fpsb_dist_unique_id(void *out128);
 int fpsb_dist_attach(fpsb_handle h, int nranks, int rank, const void *nccl_id128, int64_t own_off,
                      int64_t n_own, const int64_t *recv_start, const int64_t *recv_cnt,
                      const int64_t *send_ptr, const int64_t *send_idx);
+/* Peer-memory transport (NVLink / NVSwitch, up to 8 ranks of one node): every rank owns a mailbox in
+ * HBM that its peers map through CUDA IPC; one small kernel per half iteration then does the halo
+ * scatter-add, the boundary rows' epilogue, the halo gather and the all-reduction of the Krylov inner
+ * products by writing into the peers' mailboxes and spinning on sequence flags — no NCCL call on the
+ * iteration path (4 launches per Krylov iteration instead of 8 kernels + 4 NCCL operations).
+ *   1. every rank: fpsb_dist_peer_export(h, blob)      blob = fpsb_dist_peer_blob_bytes() bytes
+ *   2. the host program all-gathers the blobs (rank order)
+ *   3. every rank: fpsb_dist_peer_attach(h, blobs)
+ * Without these calls (or with FPSB_DIST_NCCL=1) the exchanges go through NCCL. */
+int64_t fpsb_dist_peer_blob_bytes(void);
+int fpsb_dist_peer_export(fpsb_handle h, void *blob_out);
+int fpsb_dist_peer_attach(fpsb_handle h, const void *blobs);
+int fpsb_dist_peer_active(fpsb_handle h);
 int fpsb_dist_jprod(fpsb_handle h, const double *x_own, double *y_loc, int loc);
 int fpsb_dist_jtprod(fpsb_handle h, const double *u_loc, double *y_own, int loc);
 int fpsb_dist_solve_two_mixed(fpsb_handle h, double delta, int64_t nvar_global, int64_t ncon_global,
