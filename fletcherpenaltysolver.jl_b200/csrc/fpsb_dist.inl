@@ -464,9 +464,10 @@ struct XchgParams {
 // CTAs, so all of them are resident.  Writes issued before it (remote puts included) are visible to
 // the whole system afterwards.
 __device__ __forceinline__ void xchg_grid_barrier(const XchgParams &P, unsigned long long target) {
+    if (gridDim.x == 1) { __syncthreads(); return; }        // a single CTA fences right before it signals
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0 && gridDim.x > 1) {
+    if (threadIdx.x == 0) {
         atomicAdd(P.bar, 1ull);
         const unsigned long long t0 = global_ns();
         while (*reinterpret_cast<volatile unsigned long long *>(P.bar) < target) {
@@ -479,6 +480,7 @@ __device__ __forceinline__ void xchg_grid_barrier(const XchgParams &P, unsigned 
 // CTA 0 tells every peer (flag = seq); every CTA waits until every peer has told this rank the same
 __device__ __forceinline__ void xchg_signal_wait(const XchgParams &P, unsigned long long seq) {
     const int t = threadIdx.x;
+    if (gridDim.x == 1) { __threadfence_system(); __syncthreads(); }
     if (t < P.nranks && t != P.rank) {
         if (blockIdx.x == 0) st_release_sys(reinterpret_cast<unsigned long long *>(P.peer[t]) + P.rank, seq);
         const unsigned long long *f = reinterpret_cast<const unsigned long long *>(P.mine) + t;

@@ -970,12 +970,13 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, 
             if (nntile < P.ntiles) Tnn = load_ctile(P.tiles, nntile);
             // row-epilogue operands of this thread's row: in flight during the wait and phase 1
             const int row = T.row0 + t;
+            // the row flag is only consumed in phase 2: the operand loads below do not wait for it (they are
+            // in bounds for flagged rows too), so the flag costs no extra round trip per tile
             int rflag = (P.rowflag != nullptr && t < T.nrows()) ? (int)P.rowflag[row] : 0;
-            if (rflag == 2 && P.raw_out == nullptr) rflag = 0;     // raw rows only matter to launches that ask for them
-            const bool has_row = FPSB_EXP != 4 && FPSB_EXP != 7 && FPSB_EXP != 12 && t < T.nrows() && rflag == 0;
+            const bool in_row = FPSB_EXP != 4 && FPSB_EXP != 7 && FPSB_EXP != 12 && t < T.nrows();
             double2 old2 = make_double2(0.0, 0.0);
             double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
-            if (has_row && FPSB_EXP != 5) {
+            if (in_row && FPSB_EXP != 5) {
                 if (PAIR) old2 = P.self2[row];
                 else {
                     if (C0.rdself()) old2.x = self0[row];
@@ -1097,6 +1098,8 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, 
             group_bar(g);
             PT_MARK(4);
             // ---------------- phase 2: row epilogue in natural row order, a thread per row ----------------
+            if (rflag == 2 && P.raw_out == nullptr) rflag = 0;     // raw rows only matter to launches that ask for them
+            const bool has_row = in_row && rflag == 0;
             if (rflag == 2) P.raw_out[row] = sum[t];          // halo / boundary row of a row-partitioned run
             if (has_row) {
                 const double2 sm = sum[t];
