@@ -113,9 +113,11 @@ struct DistCtx {
     unsigned long long bar_base = 0;
     static constexpr int kXchgMaxGrid = 64;
     DevBuf<double> xparts;                          // per-CTA norm partials of the boundary rows
-    DevBuf<int> bptr, bsrc;                         // per boundary row: the scatter-inbox entries added to it
+    DevBuf<int> bptr, bsrc, bpeer;                  // per boundary row: its entries of the send list (= scatter-inbox positions) and their peers
+    DevBuf<PeerTail> d_ptail;                       // for the m-space step kernel's own exchange (see gk_step_kernel)
     uint64_t sig = 0, n_sc = 0, n_ga = 0, n_tot = 0;   // signals / exchanges issued so far (same on every rank)
     bool halo_fresh = false;                        // the halo slots of Gn hold the current values
+    bool tail = false;                              // m-space steps all-reduce inside the step kernel's last CTA (experiment)
 };
 
 // mailbox layout (bytes):  flags u64[8] | tot double[2][8][4] | scatter inbox double2[2][nsend] | gather inbox double2[2][nrecv]
@@ -194,8 +196,15 @@ void dist_attach(Handle *h, int nranks, int rank, const void *id128, int64_t own
             for (size_t r = 0; r < b.size(); ++r) bp[r + 1] += bp[r];
             std::vector<int> fill(bp.begin(), bp.end() - 1);
             for (size_t i = 0; i < idx.size(); ++i) bs[(size_t)fill[(size_t)(std::lower_bound(b.begin(), b.end(), idx[i]) - b.begin())]++] = (int)i;
+            std::vector<int> bpr(bs.size());
+            for (size_t k = 0; k < bs.size(); ++k) {
+                int pp = 0;
+                while (pp + 1 < nranks && (int64_t)bs[k] >= send_ptr[pp + 1]) ++pp;
+                bpr[k] = pp;
+            }
             D->bptr.from(bp, h->stream);
             D->bsrc.from(bs, h->stream);
+            D->bpeer.from(bpr, h->stream);
             D->bidx.from(b, h->stream);
         }
         if (D->fused_n) {
@@ -264,8 +273,20 @@ void dist_peer_attach(Handle *h, const void *blobs) {
         FPSB_CUDA(cudaIpcOpenMemHandle(&ptr, B[p].handle, cudaIpcMemLazyEnablePeerAccess));
         D->peer_mbox[p] = reinterpret_cast<unsigned char *>(ptr);
     }
+    {
+        PeerTail T{};
+        T.nranks = D->nranks; T.rank = D->rank; T.mine = D->mbox; T.err = D->d_err.p;
+        for (int p = 0; p < D->nranks; ++p) T.peer[p] = D->peer_mbox[p];
+        std::vector<PeerTail> v(1, T);
+        D->d_ptail.from(v, h->stream);
+        FPSB_CUDA(cudaStreamSynchronize(h->stream));
+    }
     const char *force = getenv("FPSB_DIST_NCCL");
     D->peer = !(force && *force && *force != '0');
+    // experiment (off by default: measured 130.6 vs 128.5 us per iteration on 2 GPUs, no gain over the
+    // separate single-CTA exchange launch): FPSB_DIST_TAIL=1 lets the m-space step kernel's last CTA all-reduce
+    const char *tl = getenv("FPSB_DIST_TAIL");
+    D->tail = (tl && *tl && *tl != '0');
 }
 bool dist_peer_active(Handle *h) { return h->dist && h->dist->peer; }
 
@@ -420,20 +441,6 @@ __global__ void finish_kernel(SlotState *st, int kind, int m0, int m1, const dou
 }
 
 // ---- peer-memory exchange -------------------------------------------------------------------------
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long global_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-
 struct XchgParams {
     int nranks, rank;
     int do_scatter, do_epi, do_gather, kind, m0, m1;   // kind: -1 no recurrence, 0 step (m0/m1 = modes), 1 element-wise (m0 = op, m1 = slot)
@@ -446,7 +453,7 @@ struct XchgParams {
     double2 *S;                                        // raw / partial row sums of the extended n-space
     double2 *pair;                                     // gathered pair of the extended n-space
     int nbound;
-    const int *bidx, *bptr, *bsrc;                     // boundary rows; per row the inbox entries added to it (rank order)
+    const int *bidx, *bptr, *bsrc, *bpeer;             // boundary rows; per row its send-list entries (rank order) and their peers
     DistEpiParams Q;
     double *tot;
     double *xparts;                                    // per-CTA norm partials of the boundary rows
@@ -460,29 +467,26 @@ struct XchgParams {
     long long peer_nsend[DistCtx::kMaxRanks], peer_nrecv[DistCtx::kMaxRanks];
 };
 
-// Software grid barrier.  The exchange kernel is stream-ordered behind a step kernel and has at most 64
-// CTAs, so all of them are resident.  Writes issued before it (remote puts included) are visible to
-// the whole system afterwards.
-__device__ __forceinline__ void xchg_grid_barrier(const XchgParams &P, unsigned long long target) {
-    if (gridDim.x == 1) { __syncthreads(); return; }        // a single CTA fences right before it signals
+// "Last CTA" ticket on a monotonic counter: every CTA arrives after its own writes (remote puts included)
+// are visible system-wide; the one that completes the round learns that everybody's are.
+__device__ __forceinline__ bool xchg_ticket(const XchgParams &P, unsigned long long last_value, int *s_flag) {
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-        atomicAdd(P.bar, 1ull);
-        const unsigned long long t0 = global_ns();
-        while (*reinterpret_cast<volatile unsigned long long *>(P.bar) < target) {
-            if (global_ns() - t0 > 4000000000ull) { atomicExch(P.err, 2); break; }
-        }
+        const unsigned long long old = atomicAdd(P.bar, 1ull);
+        *s_flag = (old == last_value);
         __threadfence();
     }
     __syncthreads();
+    return *s_flag != 0;
 }
-// CTA 0 tells every peer (flag = seq); every CTA waits until every peer has told this rank the same
-__device__ __forceinline__ void xchg_signal_wait(const XchgParams &P, unsigned long long seq) {
+__device__ __forceinline__ void xchg_signal(const XchgParams &P, unsigned long long seq) {
     const int t = threadIdx.x;
-    if (gridDim.x == 1) { __threadfence_system(); __syncthreads(); }
+    if (t < P.nranks && t != P.rank) st_release_sys(reinterpret_cast<unsigned long long *>(P.peer[t]) + P.rank, seq);
+}
+__device__ __forceinline__ void xchg_wait(const XchgParams &P, unsigned long long seq) {
+    const int t = threadIdx.x;
     if (t < P.nranks && t != P.rank) {
-        if (blockIdx.x == 0) st_release_sys(reinterpret_cast<unsigned long long *>(P.peer[t]) + P.rank, seq);
         const unsigned long long *f = reinterpret_cast<const unsigned long long *>(P.mine) + t;
         const unsigned long long t0 = global_ns();
         while (ld_acquire_sys(f) < seq) {
@@ -492,19 +496,29 @@ __device__ __forceinline__ void xchg_signal_wait(const XchgParams &P, unsigned l
     __syncthreads();
 }
 
-// <= 64 CTAs.  See the header of this file for the sequence; three grid barriers per launch.
+// <= 64 CTAs, all resident (the kernel is stream-ordered behind a step kernel).  Sequence:
+//   1. halo partial sums -> owners' scatter inboxes ; ticket ; the last CTA signals ; everybody waits for the peers
+//   2. a thread per boundary row: add the peers' partials (rank order), Krylov row epilogue, put the row's
+//      fresh pair value into the gather inboxes of the peers that keep it as halo ; per-CTA norm partials
+//   3. ticket ; the last CTA sums the partials, puts the four local sums to every peer and signals ;
+//      everybody waits for the peers, unpacks its share of the gather inbox ; the last CTA sums the ranks'
+//      norm sums in rank order and runs the scalar recurrences
 __global__ void __launch_bounds__(kBlock) xchg_kernel(XchgParams P) {
     __shared__ double s_red[4 * 32];
     __shared__ Coef sC[2];
     __shared__ SlotState sS[2];
+    __shared__ int s_flag;
     const int tid = threadIdx.x, nt = (int)blockDim.x, R = P.nranks;
     const long long gtid = (long long)blockIdx.x * nt + tid, gsz = (long long)gridDim.x * nt;
-    if (*reinterpret_cast<volatile int *>(P.err) != 0) return;
     const long long *recv_start = P.meta, *recv_cnt = P.meta + R, *send_ptr = P.meta + 2 * R, *ga_off = P.meta + 3 * R + 1;
+    // static index data of this thread's first boundary row: requested before anything else
+    int row0 = -1, k0 = 0, k1 = 0;
+    if (gtid < P.nbound) { row0 = P.bidx[gtid]; k0 = P.bptr[gtid]; k1 = P.bptr[gtid + 1]; }
+    if (*reinterpret_cast<volatile int *>(P.err) != 0) return;
     unsigned long long seq = P.sig, bar = P.bar_base;
     const unsigned long long G = gridDim.x;
 
-    // ---- 1. halo partial sums -> the owners' scatter inboxes
+    // ---- 1
     if (P.do_scatter) {
         for (int p = 0; p < R; ++p) {
             if (p == P.rank) continue;
@@ -514,11 +528,12 @@ __global__ void __launch_bounds__(kBlock) xchg_kernel(XchgParams P) {
             const double2 *src = P.S + recv_start[p];
             for (long long i = gtid; i < cnt; i += gsz) dst[i] = src[i];
         }
+        bar += G;
+        if (xchg_ticket(P, bar - 1, &s_flag)) xchg_signal(P, seq + 1);
+        xchg_wait(P, ++seq);
     }
-    xchg_grid_barrier(P, bar += G);
-    if (P.do_scatter) xchg_signal_wait(P, ++seq);
 
-    // ---- 2. boundary rows: add what the peers sent (rank order), then the Krylov row epilogue
+    // ---- 2
     const bool act0 = P.do_epi && P.Q.io[0].mode != MD_NONE && P.Q.st[0].active;
     const bool act1 = P.do_epi && P.Q.io[1].mode != MD_NONE && P.Q.st[1].active;
     const bool epi = act0 || act1;
@@ -532,35 +547,48 @@ __global__ void __launch_bounds__(kBlock) xchg_kernel(XchgParams P) {
         __syncthreads();
     }
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    if (P.do_scatter || epi) {
+    if (P.do_scatter || epi || P.do_gather) {
         CoefR C0{}, C1{};
         if (epi) { C0 = to_regs(sC[0]); C1 = to_regs(sC[1]); }
         const double2 *inbox = reinterpret_cast<const double2 *>(P.mine + mbox_off_sc()) + (size_t)P.sc_par * P.nsend;
         for (long long b = gtid; b < P.nbound; b += gsz) {
-            const int row = P.bidx[b];
-            double2 sm = P.S[row];
-            if (P.do_scatter) {
-                for (int k = P.bptr[b]; k < P.bptr[b + 1]; ++k) {
-                    const double2 a = __ldcg(inbox + P.bsrc[k]);
-                    sm.x += a.x; sm.y += a.y;
+            int row = row0, kb = k0, ke = k1;
+            if (b != gtid) { row = P.bidx[b]; kb = P.bptr[b]; ke = P.bptr[b + 1]; }
+            double2 val = P.pair[row];                      // the row's entry of the gathered pair (== Q.self2 when epi)
+            if (P.do_scatter || epi) {
+                double2 sm = P.S[row];
+                if (P.do_scatter) {
+                    for (int k = kb; k < ke; ++k) {
+                        const double2 a = __ldcg(inbox + P.bsrc[k]);
+                        sm.x += a.x; sm.y += a.y;
+                    }
+                    P.S[row] = sm;
                 }
-                P.S[row] = sm;
+                if (epi) {
+                    const double2 old2 = val;
+                    double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+                    if (C0.rd0()) a00 = P.Q.io[0].a0[row];
+                    if (C0.rd1()) a01 = P.Q.io[0].a1[row];
+                    if (C1.rd0()) a10 = P.Q.io[1].a0[row];
+                    if (C1.rd1()) a11 = P.Q.io[1].a1[row];
+                    double n0 = old2.x, n1 = old2.y;
+                    if (act0) n0 = row_epilogue(C0, sm.x, old2.x, a00, a01, acc[0], acc[1]);
+                    if (act1) n1 = row_epilogue(C1, sm.y, old2.y, a10, a11, acc[2], acc[3]);
+                    val = make_double2(n0, n1);
+                    P.pair[row] = val;
+                    if (C0.wr0()) P.Q.io[0].a0[row] = a00;
+                    if (C0.wr1()) P.Q.io[0].a1[row] = a01;
+                    if (C1.wr0()) P.Q.io[1].a0[row] = a10;
+                    if (C1.wr1()) P.Q.io[1].a1[row] = a11;
+                }
             }
-            if (epi) {
-                const double2 old2 = P.Q.self2[row];
-                double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
-                if (C0.rd0()) a00 = P.Q.io[0].a0[row];
-                if (C0.rd1()) a01 = P.Q.io[0].a1[row];
-                if (C1.rd0()) a10 = P.Q.io[1].a0[row];
-                if (C1.rd1()) a11 = P.Q.io[1].a1[row];
-                double n0 = old2.x, n1 = old2.y;
-                if (act0) n0 = row_epilogue(C0, sm.x, old2.x, a00, a01, acc[0], acc[1]);
-                if (act1) n1 = row_epilogue(C1, sm.y, old2.y, a10, a11, acc[2], acc[3]);
-                P.Q.self2[row] = make_double2(n0, n1);
-                if (C0.wr0()) P.Q.io[0].a0[row] = a00;
-                if (C0.wr1()) P.Q.io[0].a1[row] = a01;
-                if (C1.wr0()) P.Q.io[1].a0[row] = a10;
-                if (C1.wr1()) P.Q.io[1].a1[row] = a11;
+            if (P.do_gather) {
+                // the peers that keep this row as halo: entry i of my send list belongs to peer bpeer[k]
+                for (int k = kb; k < ke; ++k) {
+                    const int i = P.bsrc[k], p = P.bpeer[k];
+                    double2 *dst = reinterpret_cast<double2 *>(P.peer[p] + mbox_off_ga(P.peer_nsend[p])) + (size_t)P.ga_par * P.peer_nrecv[p] + P.ga_at_peer[p];
+                    dst[i - send_ptr[p]] = val;
+                }
             }
         }
     }
@@ -568,70 +596,63 @@ __global__ void __launch_bounds__(kBlock) xchg_kernel(XchgParams P) {
         block_sum<4>(acc, s_red);
         if (tid == 0) { double *pp = P.xparts + (size_t)blockIdx.x * 4; pp[0] = acc[0]; pp[1] = acc[1]; pp[2] = acc[2]; pp[3] = acc[3]; }
     }
-    xchg_grid_barrier(P, bar += G);
 
-    // ---- 3. fresh halo values of the gathered pair and the local norm sums -> the peers
-    if (P.do_gather) {
-        for (int p = 0; p < R; ++p) {
-            if (p == P.rank) continue;
-            const long long b = send_ptr[p], e = send_ptr[p + 1];
-            if (b == e) continue;
-            double2 *dst = reinterpret_cast<double2 *>(P.peer[p] + mbox_off_ga(P.peer_nsend[p])) + (size_t)P.ga_par * P.peer_nrecv[p] + P.ga_at_peer[p];
-            for (long long i = b + gtid; i < e; i += gsz) dst[i - b] = P.pair[P.send_idx[i]];
-        }
-    }
-    if (blockIdx.x == 0 && (epi || P.kind >= 0)) {
+    // ---- 3
+    bar += G;
+    const bool last = xchg_ticket(P, bar - 1, &s_flag);
+    const bool talk = P.do_gather || P.kind >= 0;
+    if (last) {
         if (epi && tid < 4) {
             double v = P.tot[tid];
             for (unsigned c = 0; c < gridDim.x; ++c) v += __ldcg(P.xparts + (size_t)c * 4 + tid);
             P.tot[tid] = v;
         }
         __syncthreads();
-        if (P.kind >= 0 && tid < 4) {
+        if (P.kind >= 0 && tid < 4 && R > 1) {
             const double v = P.tot[tid];
             for (int p = 0; p < R; ++p) {
                 if (p == P.rank) continue;
                 reinterpret_cast<double *>(P.peer[p] + mbox_off_tot())[((size_t)P.tot_par * DistCtx::kMaxRanks + P.rank) * 4 + tid] = v;
             }
+            __threadfence_system();
+        }
+        __syncthreads();
+        if (talk && R > 1) xchg_signal(P, seq + 1);
+    }
+    if (talk && R > 1) xchg_wait(P, ++seq);
+    if (P.do_gather) {
+        const double2 *inbox = reinterpret_cast<const double2 *>(P.mine + mbox_off_ga(P.nsend)) + (size_t)P.ga_par * P.nrecv;
+        for (int p = 0; p < R; ++p) {
+            if (p == P.rank) continue;
+            const long long cnt = recv_cnt[p];
+            double2 *dst = P.pair + recv_start[p];
+            const double2 *src = inbox + ga_off[p];
+            for (long long i = gtid; i < cnt; i += gsz) dst[i] = __ldcg(src + i);
         }
     }
-    xchg_grid_barrier(P, bar += G);
-    if (P.do_gather || P.kind >= 0) {
-        if (R > 1) xchg_signal_wait(P, ++seq);
-        if (P.do_gather) {
-            const double2 *inbox = reinterpret_cast<const double2 *>(P.mine + mbox_off_ga(P.nsend)) + (size_t)P.ga_par * P.nrecv;
-            for (int p = 0; p < R; ++p) {
-                if (p == P.rank) continue;
-                const long long cnt = recv_cnt[p];
-                double2 *dst = P.pair + recv_start[p];
-                const double2 *src = inbox + ga_off[p];
-                for (long long i = gtid; i < cnt; i += gsz) dst[i] = __ldcg(src + i);
+    if (P.kind >= 0 && last) {
+        // norm sums of all ranks in rank order (identical on every rank), then the scalar recurrences
+        for (int i = tid; i < (int)(2 * sizeof(SlotState) / sizeof(double)); i += nt)
+            reinterpret_cast<double *>(sS)[i] = reinterpret_cast<const double *>(P.st)[i];
+        __syncthreads();
+        if (tid == 0) {
+            double tot[4] = {0.0, 0.0, 0.0, 0.0};
+            const double *in = reinterpret_cast<const double *>(P.mine + mbox_off_tot()) + (size_t)P.tot_par * DistCtx::kMaxRanks * 4;
+            for (int r = 0; r < R; ++r)
+                for (int k = 0; k < 4; ++k) tot[k] += (r == P.rank) ? P.tot[k] : __ldcg(in + r * 4 + k);
+            for (int k = 0; k < 4; ++k) P.tot[k] = tot[k];
+            if (P.kind == 0) {
+                if (P.m0 != MD_NONE && sS[0].active) finish_step(sS[0], P.m0, tot[0], tot[1]);
+                if (P.m1 != MD_NONE && sS[1].active) finish_step(sS[1], P.m1, tot[2], tot[3]);
+            } else {
+                const bool is_init = (P.m0 == EW_INIT_LSQR || P.m0 == EW_INIT_CRAIG || P.m0 == EW_MINRES_INIT || P.m0 == EW_CGLS_INIT);
+                if (is_init || sS[P.m1].active) finish_ew(sS[P.m1], P.m0, tot[0]);
             }
+            if (!sS[0].active && !sS[1].active) *P.done_flag = 1;
         }
-        if (P.kind >= 0 && blockIdx.x == 0) {
-            // norm partials of all ranks in rank order (identical on every rank), then the scalar recurrences
-            for (int i = tid; i < (int)(2 * sizeof(SlotState) / sizeof(double)); i += nt)
-                reinterpret_cast<double *>(sS)[i] = reinterpret_cast<const double *>(P.st)[i];
-            __syncthreads();
-            if (tid == 0) {
-                double tot[4] = {0.0, 0.0, 0.0, 0.0};
-                const double *in = reinterpret_cast<const double *>(P.mine + mbox_off_tot()) + (size_t)P.tot_par * DistCtx::kMaxRanks * 4;
-                for (int r = 0; r < R; ++r)
-                    for (int k = 0; k < 4; ++k) tot[k] += (r == P.rank) ? P.tot[k] : __ldcg(in + r * 4 + k);
-                for (int k = 0; k < 4; ++k) P.tot[k] = tot[k];
-                if (P.kind == 0) {
-                    if (P.m0 != MD_NONE && sS[0].active) finish_step(sS[0], P.m0, tot[0], tot[1]);
-                    if (P.m1 != MD_NONE && sS[1].active) finish_step(sS[1], P.m1, tot[2], tot[3]);
-                } else {
-                    const bool is_init = (P.m0 == EW_INIT_LSQR || P.m0 == EW_INIT_CRAIG || P.m0 == EW_MINRES_INIT || P.m0 == EW_CGLS_INIT);
-                    if (is_init || sS[P.m1].active) finish_ew(sS[P.m1], P.m0, tot[0]);
-                }
-                if (!sS[0].active && !sS[1].active) *P.done_flag = 1;
-            }
-            __syncthreads();
-            for (int i = tid; i < (int)(2 * sizeof(SlotState) / sizeof(double)); i += nt)
-                reinterpret_cast<double *>(P.st)[i] = reinterpret_cast<const double *>(sS)[i];
-        }
+        __syncthreads();
+        for (int i = tid; i < (int)(2 * sizeof(SlotState) / sizeof(double)); i += nt)
+            reinterpret_cast<double *>(P.st)[i] = reinterpret_cast<const double *>(sS)[i];
     }
 }
 
@@ -654,7 +675,7 @@ struct DistEngine {
         P.meta = reinterpret_cast<const long long *>(D->d_meta.p);
         P.send_idx = D->send_idx.p;
         P.S = D->S.p; P.pair = E.W->Gn.p;
-        P.nbound = (int)D->nbound; P.bidx = D->bidx.p; P.bptr = D->bptr.p; P.bsrc = D->bsrc.p;
+        P.nbound = (int)D->nbound; P.bidx = D->bidx.p; P.bptr = D->bptr.p; P.bsrc = D->bsrc.p; P.bpeer = D->bpeer.p;
         P.xparts = D->xparts.p; P.bar = D->d_bar.p; P.bar_base = D->bar_base;
         if (Q) P.Q = *Q;
         P.tot = D->tot.p; P.st = E.W->st.p; P.done_flag = E.W->done.p; P.err = D->d_err.p;
@@ -672,7 +693,7 @@ struct DistEngine {
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(DistCtx::kXchgMaxGrid, (work + kBlock - 1) / kBlock));
         xchg_kernel<<<grid, kBlock, 0, h->stream>>>(P);
         h->launches += 1;
-        if (grid > 1) D->bar_base += 3ull * (unsigned long long)grid;
+        D->bar_base += (do_scatter ? 2ull : 1ull) * (unsigned long long)grid;
         if (D->nranks > 1) {
             if (do_scatter) { D->sig += 1; D->n_sc += 1; }
             if (do_gather || kind >= 0) D->sig += 1;
@@ -780,6 +801,15 @@ struct DistEngine {
     // m-space half step: halo gather, fused step kernel on A_loc (rows are local), all-reduce, recurrences
     void step_m(const SlotIO &io0, const SlotIO &io1) {
         if (!(D->peer && D->halo_fresh)) gather_halo(E.W->Gn.p);
+        if (D->peer && D->tail && h->A.grid > 0 && h->A.nlong == 0) {
+            // the step kernel's last CTA exchanges the four sums with the peers and runs the recurrences
+            E.ptail = D->d_ptail.p; E.pt_sig = D->sig; E.pt_par = (int)(D->n_tot & 1);
+            E.step(true, true, io0, io1);
+            E.ptail = nullptr;
+            if (D->nranks > 1) D->sig += 1;
+            D->n_tot += 1;
+            return;
+        }
         E.step(true, true, io0, io1);
         allreduce_finish(0, io0.mode, io1.mode);
     }

@@ -87,6 +87,30 @@ struct SlotIO {
 
 struct TileMeta;
 
+// Row-partitioned runs with the peer-memory transport (fpsb_dist.inl): what the last CTA of an m-space
+// step needs to all-reduce its four norm sums through the peers' mailboxes and run the recurrences itself
+constexpr int kMboxMaxRanks = 8;
+constexpr size_t kMboxOffTot = 8 * sizeof(uint64_t);        // mailbox: flags u64[8] | tot double[2][8][4] | ...
+struct PeerTail {
+    int nranks, rank;
+    unsigned char *mine;
+    unsigned char *peer[kMboxMaxRanks];
+    int *err;
+};
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 struct StepParams {
     // tiled SELL-32 operator (see the kernel comment)
     const TileMeta *tiles;
@@ -120,6 +144,10 @@ struct StepParams {
     SlotState *st_out;             // non-null: deferred mode
     const double *pend_partials;   // partials of the previous launch (null: nothing pending)
     int pend_nparts, pend_m0, pend_m1;
+    // peer-memory tail (with tot_out): the last CTA exchanges the sums and finishes the step itself
+    const PeerTail *ptail;
+    unsigned long long pt_sig;     // signals issued before this launch
+    int pt_par;                    // half of the peers' tot inbox this exchange uses
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1158,12 +1186,44 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, 
         tot[2] += __ldcg(pp + 2); tot[3] += __ldcg(pp + 3);
     }
     block_sum<4>(tot, s_red);
-    if (P.tot_out != nullptr) {
+    if (P.tot_out != nullptr && P.ptail == nullptr) {
         if (tid == 0) {
             P.tot_out[0] = tot[0]; P.tot_out[1] = tot[1]; P.tot_out[2] = tot[2]; P.tot_out[3] = tot[3];
             *P.counter = 0;
         }
         return;
+    }
+    if (P.ptail != nullptr) {
+        // all-reduce over the ranks through the mailboxes: put, signal, wait, sum in rank order
+        const PeerTail &X = *P.ptail;
+        const int R = X.nranks;
+        const unsigned long long seq = P.pt_sig + 1;
+        if (tid == 0) {
+            for (int p = 0; p < R; ++p) {
+                if (p == X.rank) continue;
+                double *dst = reinterpret_cast<double *>(X.peer[p] + kMboxOffTot) + ((size_t)P.pt_par * kMboxMaxRanks + X.rank) * 4;
+                dst[0] = tot[0]; dst[1] = tot[1]; dst[2] = tot[2]; dst[3] = tot[3];
+            }
+            __threadfence_system();
+        }
+        __syncthreads();
+        if (tid < R && tid != X.rank) {
+            st_release_sys(reinterpret_cast<unsigned long long *>(X.peer[tid]) + X.rank, seq);
+            const unsigned long long *f = reinterpret_cast<const unsigned long long *>(X.mine) + tid;
+            const unsigned long long t0 = global_ns();
+            while (ld_acquire_sys(f) < seq) {
+                if (global_ns() - t0 > 4000000000ull) { atomicExch(X.err, 1); break; }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const double *in = reinterpret_cast<const double *>(X.mine + kMboxOffTot) + (size_t)P.pt_par * kMboxMaxRanks * 4;
+            double all[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int r = 0; r < R; ++r)
+                for (int q = 0; q < 4; ++q) all[q] += (r == X.rank) ? tot[q] : __ldcg(in + r * 4 + q);
+            tot[0] = all[0]; tot[1] = all[1]; tot[2] = all[2]; tot[3] = all[3];
+            P.tot_out[0] = tot[0]; P.tot_out[1] = tot[1]; P.tot_out[2] = tot[2]; P.tot_out[3] = tot[3];
+        }
     }
     // scalar recurrences on the shared-memory copy of the slot states (global memory would cost one
     // L2 round trip per field), then one coalesced write-back
@@ -1879,6 +1939,9 @@ struct Engine {
     IterWs *W;
     StepParams base_m, base_n;   // M: rows of A (m-space rows), N: rows of A' (n-space rows)
     double *tot_out = nullptr;   // non-null: row-partitioned run (see fpsb_dist.inl)
+    const PeerTail *ptail = nullptr;          // set around a step whose last CTA does the peer exchange itself
+    unsigned long long pt_sig = 0;
+    int pt_par = 0;
     Engine(Handle *hh) : h(hh), W(hh->iter) {
         memset(&base_m, 0, sizeof(base_m));
         memset(&base_n, 0, sizeof(base_n));
@@ -1917,6 +1980,7 @@ struct Engine {
         StepParams P = mspace ? base_m : base_n;
         P.io[0] = io0; P.io[1] = io1;
         P.tot_out = tot_out;
+        P.ptail = ptail; P.pt_sig = pt_sig; P.pt_par = pt_par;
         const CsrDev &M = mspace ? h->A : h->At;
         if (M.grid == 0) return;
         if (defer && tot_out == nullptr && M.nlong == 0) {
