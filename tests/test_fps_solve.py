@@ -167,3 +167,18 @@ def test_consistent_gradient_is_the_derivative_of_obj(qds):
         gfd = np.array([(fp.obj(x + h * e) - fp.obj(x - h * e)) / (2 * h) for e in np.eye(3)])
         err = np.abs(fp.grad(x) - gfd).max() / np.abs(gfd).max()
         assert (err < 1e-7) == expect_exact
+
+
+def test_inequalities_go_through_the_slack_model(qds):
+    """README.md:59-65 (0 <= x1 x2 - 1 <= 1): SlackModel + bounded subproblem; the statistics come back in the
+    original variables (src/FletcherPenaltySolver.jl:138-184).  With a slack at its bound the penalty function is
+    not exact, so feasibility only improves as sigma grows — the run ends on sigma_max (:186-187), feasible to 1e-5."""
+    nlp = models.reference_test_problem("readme_ineq")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        stats = F.fps_solve(nlp, qds_solver=qds["ldlt"], consistent_gradient=True)
+    assert stats.solution.shape == (2,)
+    c = nlp.cons(stats.solution)[0]
+    assert -1e-5 <= c <= 1.0 + 1e-5
+    assert stats.status in ("first_order", "unknown") and stats.solver_specific["sigma"] > 1e3
+    assert abs(stats.objective - 360.3798) < 1e-2
