@@ -2,7 +2,7 @@
 import csv, subprocess, sys
 rep, kid = sys.argv[1], (sys.argv[2] if len(sys.argv) > 2 else "0")
 blk = int(sys.argv[3]) if len(sys.argv) > 3 else 100
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-id", kid], capture_output=True, text=True).stdout
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + (["--kernel-id", kid] if kid not in ("0", "") else []), capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr = rows[1]; ix = {h: i for i, h in enumerate(hdr)}
 body = [r for r in rows[2:] if len(r) == len(hdr) and r[ix["# Samples"]].isdigit()]
