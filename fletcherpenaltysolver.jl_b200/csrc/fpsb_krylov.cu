@@ -153,6 +153,13 @@ struct StepParams {
 // ------------------------------------------------------------------------------------------------
 // scalar recurrences (one thread, last CTA) — line-by-line the reference algorithms
 // ------------------------------------------------------------------------------------------------
+// experiment: the scalar recurrences as one out-of-line function (4 inlined copies make the step kernel
+// 16.5 K instructions; see profiles/README.md on instruction-fetch cost)
+#ifdef FPSB_FINISH_NOINLINE
+#define FPSB_FINISH_INLINE __noinline__
+#else
+#define FPSB_FINISH_INLINE
+#endif
 __device__ void slot_stop(SlotState &S) { S.active = 0; }
 
 __device__ void lsqr_status(SlotState &S) {
@@ -520,7 +527,7 @@ __device__ void fin_cgls_em(SlotState &S, double pp) {
     if (S.solved || S.tired) { S.status = S.solved ? FPSB_ST_SOLVED : FPSB_ST_TIRED; S.active = 0; }
 }
 
-__device__ void finish_step(SlotState &S, int mode, double a0, double a1) {
+__device__ FPSB_FINISH_INLINE void finish_step(SlotState &S, int mode, double a0, double a1) {
     switch (mode) {
         case MD_LSQR_INIT_M: fin_lsqr_init_m(S, a0); break;
         case MD_LSQR_U: fin_lsqr_u(S, a0); break;

@@ -73,6 +73,13 @@ class _V:
         return bool((a == b).all())
 
     @staticmethod
+    def maximum(a, b):
+        if hasattr(a, "detach"):
+            import torch
+            return torch.maximum(a, b)
+        return np.maximum(a, b)
+
+    @staticmethod
     def clip(a, lo, hi):
         if hasattr(a, "detach"):
             import torch
@@ -218,10 +225,8 @@ class _Stopping:
         nxk = max(_V.norm(st.x), 1.0)
         nlk = 1.0 if st.lam is None else max(_V.norm(st.lam), 1.0)
         c = st.cx
-        viol = (c - self._ucon)
-        low = (self._lcon - c)
-        cpart = _V.clip(viol, low, abs(viol) + abs(low)) if len(c) else c   # max(viol, low)
-        cpart = _V.clip(cpart, cpart * 0.0, abs(cpart)) / nxk if len(c) else c  # max(., 0)
+        # max.(cx .- ucon, lcon .- cx, 0) ./ max(‖x‖, 1)
+        cpart = _V.maximum(_V.maximum(c - self._ucon, self._lcon - c), c * 0.0) / nxk if len(c) else c
         if self.has_bounds:
             rpart = st.x - _V.clip(st.x - st.res, self._lvar, self._uvar)
         else:
