@@ -406,9 +406,12 @@ def trunk(model, x0, *, atol=1e-7, rtol=1e-7, max_iter=20000, max_time=300.0, un
         snorm = _V.norm(s)
         tiny_step = snorm <= 1e-6 * max(1.0, _V.norm(x))
         # a model decrease below the rounding error of φσ itself cannot be verified: three in a row = stalled
-        noise_steps = noise_steps + 1 if pred <= 10 * EPS * max(1.0, abs(f)) else 0
+        in_noise = pred <= 10 * EPS * max(1.0, abs(f))
+        if not in_noise:
+            noise_steps = 0
         ft = model.obj(xt)
         ared = f - ft
+        gt = None
         # rounding guard of trust-region codes: tiny reductions are measured against the model
         if abs(ared) <= 10 * EPS * max(1.0, abs(f)) and abs(pred) <= 10 * EPS * max(1.0, abs(f)):
             rho = 1.0
@@ -416,18 +419,29 @@ def trunk(model, x0, *, atol=1e-7, rtol=1e-7, max_iter=20000, max_time=300.0, un
             rho = -1.0
         else:
             rho = ared / pred
+        if rho < 1e-4 and pred > 0.0 and pred <= 1e3 * EPS * max(1.0, abs(f)) and not math.isnan(ft):
+            # the function values are noise at this scale: measure the reduction with the slopes at both
+            # ends, -(g + g⁺)'s / 2 (Conn, Gould & Toint §17.4.2); φσ(xt) is memoised, the gradient costs no solve
+            gt = model.grad(xt)
+            ared_g = -0.5 * _V.dot(g + gt, s)
+            if not math.isnan(ared_g) and ared_g / pred >= 1e-4:
+                rho = ared_g / pred
         if verbose:
             print(f"  trunk {it:4d} f={f: .6e} |g|={score:.2e} Δ={radius:.2e} |s|={snorm:.2e} ρ={rho: .2e} cg={nprod}")
         if rho >= 1e-4:
             x, f = xt, ft
-            g = model.grad(x)
-            score = _V.ninf(pgrad(x, g))
+            g = gt if gt is not None else model.grad(x)
+            new_score = _V.ninf(pgrad(x, g))
+            if in_noise:                                      # unverifiable step: a stall unless the gradient still drops
+                noise_steps = 0 if new_score <= 0.9 * score else noise_steps + 1
+            score = new_score
             if rho >= 0.99 and snorm >= 0.99 * radius:
                 radius = min(3.0 * radius, 1e20)
             small_steps = small_steps + 1 if snorm <= EPS * max(1.0, _V.norm(x)) else 0
         else:
             radius = min(radius, snorm) / 3.0
             small_steps += 1 if radius <= EPS * max(1.0, _V.norm(x)) else 0
+            noise_steps += 1 if in_noise else 0
         it += 1
         if small_steps >= 3 or noise_steps >= 3 or radius < 1e-300:
             out.stalled = True
