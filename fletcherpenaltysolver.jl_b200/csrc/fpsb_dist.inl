@@ -657,6 +657,37 @@ __global__ void __launch_bounds__(kBlock) xchg_kernel(XchgParams P) {
 }
 
 // ---- host side --------------------------------------------------------------------------------------
+// FPSB_DIST_PROF=1: an event after every launch of the distributed loop; the mean time between consecutive
+// events is printed per kind and rank at the end of the solve (tools/dist_bench.py; profiling only)
+struct DistProf {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> tag;
+    size_t used = 0;
+    DistProf() { const char *e = getenv("FPSB_DIST_PROF"); on = e && *e && *e != '0'; }
+    void mark(int t, cudaStream_t s) {
+        if (!on || used >= 8192) return;
+        if (used == ev.size()) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); tag.push_back(0); }
+        tag[used] = t;
+        cudaEventRecord(ev[used++], s);
+    }
+    void report(int rank) {
+        if (!on || used < 2) { used = 0; return; }
+        const char *names[] = {"start", "step_n", "xchg_after_n", "step_m", "xchg_after_m", "other"};
+        double sum[6] = {0, 0, 0, 0, 0, 0}; int cnt[6] = {0, 0, 0, 0, 0, 0};
+        for (size_t i = 1; i < used; ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+            sum[tag[i]] += ms; cnt[tag[i]]++;
+        }
+        fprintf(stderr, "[fpsb dist prof] rank %d:", rank);
+        for (int t = 1; t < 6; ++t) if (cnt[t]) fprintf(stderr, "  %s %.1f us x %d", names[t], 1e3 * sum[t] / cnt[t], cnt[t]);
+        fprintf(stderr, "\n");
+        used = 0;
+    }
+};
+static DistProf g_dist_prof;
+
 struct DistEngine {
     Handle *h;
     DistCtx *D;
@@ -691,6 +722,7 @@ struct DistEngine {
         if (do_epi) work = std::max<int64_t>(work, D->nbound);
         if (do_gather) work = std::max<int64_t>(work, std::max(D->nsend, D->nrecv));
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(DistCtx::kXchgMaxGrid, (work + kBlock - 1) / kBlock));
+        // (launching this kernel with programmatic dependent launch on both sides was measured: no gain)
         xchg_kernel<<<grid, kBlock, 0, h->stream>>>(P);
         h->launches += 1;
         D->bar_base += (do_scatter ? 2ull : 1ull) * (unsigned long long)grid;
@@ -767,6 +799,10 @@ struct DistEngine {
     // finished by one small kernel.  Fallback (long rows in A', huge boundary): partial sums for every
     // row, exchange, separate epilogue over all owned rows.
     void step_n(const SlotIO &io0, const SlotIO &io1) {
+        step_n_impl(io0, io1);
+        g_dist_prof.mark(2, h->stream);
+    }
+    void step_n_impl(const SlotIO &io0, const SlotIO &io1) {
         DistEpiParams Q{};
         Q.n_own = (int)D->n_own; Q.own_off = (int)D->own_off;
         Q.S = D->S.p; Q.self2 = E.W->Gn.p;
@@ -779,6 +815,7 @@ struct DistEngine {
             P.st = E.W->st.p;
             if (h->At.grid == 0) return;
             launch_step(h, h->At, P, true, 1);
+            g_dist_prof.mark(1, h->stream);
             if (D->peer) {
                 // scatter-add + boundary epilogue + halo gather for the next m-space step + norms + recurrences
                 xchg(D->nranks > 1, true, D->nranks > 1, 0, io0.mode, io1.mode, &Q);
@@ -811,7 +848,9 @@ struct DistEngine {
             return;
         }
         E.step(true, true, io0, io1);
+        g_dist_prof.mark(3, h->stream);
         allreduce_finish(0, io0.mode, io1.mode);
+        g_dist_prof.mark(4, h->stream);
     }
     void ew(int op, int slot, int n, const double *in0, double *v0, double *v1, double *v2, double2 *pair, int pair_slot, double c0) {
         E.ew(op, slot, n, in0, v0, v1, v2, nullptr, nullptr, pair, pair_slot, c0, 1);
@@ -883,11 +922,13 @@ void dist_solve_two_mixed(Handle *h, double delta, const double *rhs1, const dou
     SlotIO c_u = io_mode(MD_CRAIG_U, W->am[1][0].p, W->am[1][1].p);
     E.mark_begin();
     X.step_m(l_init, io_none());
+    g_dist_prof.mark(0, h->stream);
     E.loop([&](int) {
         X.step_n(l_u, c_v);
         X.step_m(l_v, c_u);
     }, kChunk);
     E.mark_end();
+    g_dist_prof.report(D->rank);
     E.tot_out = nullptr;
     // outputs: q1 = x_lsqr ; p1 = rhs1 - A' q1 ; p2 = -(x_craig + pending) ; q2 = y_craig
     E.ew(EW_COPY, 0, m_loc, W->am[0][1].p, q1, nullptr, nullptr, nullptr, nullptr, nullptr, -1, 1.0, 0);

@@ -62,7 +62,7 @@ def test_dist_world1_matches_oracle(oracle):
         assert _rel(a, b) < 1e-11
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, peer=True):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -73,7 +73,8 @@ def _worker(rank, world, port, q):
     A, jr, jc, vals, r1, r2, r3 = _problem()
     m, n = A.shape
     part = RowPartition(n, m, jr, jc, world)
-    D = DistHandle(part, rank, device=rank, dist=dist)
+    D = DistHandle(part, rank, device=rank, dist=dist, peer=peer)
+    assert D.peer == peer                      # the requested transport is the one that runs (no silent fallback)
     D.set_jac_values(vals)
     L = D.loc
     own = slice(L.col0, L.col0 + L.n_own)
@@ -87,7 +88,8 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_dist_world2_matches_single_gpu(oracle):
+@pytest.mark.parametrize("transport", ["peer-memory", "nccl"])
+def test_dist_world2_matches_single_gpu(oracle, transport):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
@@ -95,8 +97,8 @@ def test_dist_world2_matches_single_gpu(oracle):
     import fpsb200
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 32500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 32500 + (os.getpid() % 2000) + (0 if transport == "nccl" else 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, transport == "peer-memory")) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted((q.get(timeout=600) for _ in range(2)), key=lambda t: t[0])
