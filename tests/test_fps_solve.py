@@ -182,3 +182,17 @@ def test_inequalities_go_through_the_slack_model(qds):
     assert -1e-5 <= c <= 1.0 + 1e-5
     assert stats.status in ("first_order", "unknown") and stats.solver_specific["sigma"] > 1e3
     assert abs(stats.objective - 360.3798) < 1e-2
+
+
+def test_unconstrained_problem(qds):
+    """test/solvertest.jl:1-8 (`unconstrained_nlp`): ncon = 0, the penalty function is f itself."""
+    A = np.array
+    f = lambda x: (x[0] - 1.0) ** 2 + 100 * (x[1] - x[0] ** 2) ** 2
+    g = lambda x: A([2 * (x[0] - 1) - 400 * x[0] * (x[1] - x[0] ** 2), 200 * (x[1] - x[0] ** 2)])
+    H = lambda x: A([[2 - 400 * x[1] + 1200 * x[0] ** 2, -400 * x[0]], [-400 * x[0], 200.0]])
+    for key in ("ldlt", "iterative"):
+        nlp = models.CallableModel(f, g, lambda x: np.zeros(0), lambda x: np.zeros((0, 2)), H, lambda x, j: np.zeros((2, 2)),
+                                   A([-1.2, 1.0]), 0, name="rosenbrock")
+        stats = F.fps_solve(nlp, qds_solver=qds[key])
+        assert stats.status == "first_order" and np.linalg.norm(stats.solution - 1.0) < 1e-3
+        assert stats.multipliers.shape == (0,) and stats.primal_feas == 0.0
