@@ -17,7 +17,7 @@ class FletcherPenaltyNLP:
                  explicit_linear_constraints=False, consistent_gradient=False):
         assert hessian_approx in (1, 2)
         # Reference quirk: grad! hands +ys to hprod! (src/model-Fletcherpenaltynlp.jl:382, 415)
-        # where the derivative of obj needs H(x, -ys), the matrix hprod! itself uses (:534).  The two only
+        # where the derivative of obj needs H(x, -ys), the matrix hprod! itself uses (:538-539).  The two only
         # differ when the constraints have curvature and c(x) != 0.  False = the reference's formula
         # (drop-in parity), True = the exact gradient of obj.
         self.consistent_gradient = consistent_gradient
