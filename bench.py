@@ -132,9 +132,15 @@ def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # all the host threads the path can use: the OpenMP build of the port (row loops of the two SpMVs and the
+    # element-wise / reduction loops of LSQR and CRAIG); the sequential build stays the checker of the tests
+    os.environ.setdefault("FPS_ORACLE_OMP", "1")
     n, m, k, w = cfg["n"], cfg["m"], cfg["nnz_per_row"], cfg["window"]
     A, jrow, jcol, vals, rhs1, rhs2 = make_workload(n, m, k, w, args.seed)
     run = oracle_solve_timer(A, rhs1, rhs2, args.delta)
+    from oracle import oracle as _O
+    _O.lib()
+    threads = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1)) if _O.THREADED else 1
     for _ in range(min(args.warmup, 1)):
         run()
     times, st = [], None
@@ -149,10 +155,12 @@ def run_reference(args, cfg):
         "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": cfg,
-        "cpu_baseline": {"value": val, "unit": "solves/s", "cores": 1, "kind": "port",
+        "cpu_baseline": {"value": val, "unit": "solves/s", "cores": threads, "kind": "port",
                          "sample": f"{args.steps} full-size solve_two_mixed calls (LSQR {st[0]['niter']} it + "
-                                   f"CRAIG {st[1]['niter']} it), oracle/fps_oracle.c, 1 thread of "
-                                   f"{os.cpu_count()} available; the Julia reference is not runnable here"},
+                                   f"CRAIG {st[1]['niter']} it), oracle/fps_oracle.c"
+                                   + (f" built with OpenMP, {threads} threads" if threads > 1 else ", 1 thread")
+                                   + f" of {os.cpu_count()} host cores; the Julia reference is not runnable here "
+                                     "(its own path is single-threaded apart from BLAS-1)"},
         "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -388,15 +396,32 @@ def main():
     # ---- CPU baseline (oracle port, bounded sample) -------------------------------------------------
     cpu = None
     if not args.no_cpu_baseline:
+        # the OpenMP build of the port with every host thread (what --impl reference times), plus one solve on a
+        # single thread: the reference's own path is single-threaded apart from BLAS-1
+        os.environ.setdefault("FPS_ORACLE_OMP", "1")
         run = oracle_solve_timer(A, rhs1, rhs2, args.delta)
+        from oracle import oracle as _O
+        _O.lib()
+        threads, t1 = 1, None
+        if _O.THREADED:
+            import ctypes
+            gomp = ctypes.CDLL("libgomp.so.1")
+            threads = int(gomp.omp_get_max_threads())
+            gomp.omp_set_num_threads(1)
+            t1, _ = run()
+            gomp.omp_set_num_threads(threads)
+            run()                                    # warm the thread pool
         ts, ost = [], None
         for _ in range(args.cpu_baseline_solves):
             tt, ost = run()
             ts.append(tt)
-        cpu = {"value": len(ts) / sum(ts), "unit": "solves/s", "cores": 1, "kind": "port",
+        cpu = {"value": len(ts) / sum(ts), "unit": "solves/s", "cores": threads, "kind": "port",
                "sample": f"{len(ts)} full-size solve_two_mixed calls ({sum(ts):.1f} s; LSQR {ost[0]['niter']} it + "
-                         f"CRAIG {ost[1]['niter']} it) with oracle/fps_oracle.c, gcc -O3, 1 thread of "
-                         f"{os.cpu_count()} host cores (the reference path is single-threaded; Julia absent)"}
+                         f"CRAIG {ost[1]['niter']} it) with oracle/fps_oracle.c, gcc -O3"
+                         + (f" -fopenmp, {threads} threads" if threads > 1 else ", 1 thread")
+                         + f" of {os.cpu_count()} host cores (Julia absent)"}
+        if t1 is not None:
+            cpu["single_thread_value"] = 1.0 / t1
 
     value = args.gpus * args.steps / (max_ms * 1e-3)
     e2e_value = args.gpus * args.steps / (e2e_ms * 1e-3)

@@ -302,9 +302,19 @@ typedef struct {
     const i64 *trp, *tci; const double *tvx;   /* CSR of A' */
 } fo_mat;
 
+/* -DFO_OMP (oracle/Makefile: libfps_oracle_omp.so) threads the row loops and the element-wise loops of the
+ * Krylov methods for bench.py's reference arm ("all the host threads it can use").  The checker used by the
+ * tests is always the sequential build: its sums have one fixed order. */
+#ifdef FO_OMP
+#define FO_PAR _Pragma("omp parallel for schedule(static)")
+#define FO_PAR_SUM _Pragma("omp parallel for schedule(static) reduction(+:s)")
+#else
+#define FO_PAR
+#define FO_PAR_SUM
+#endif
 static void csr_mv(i64 nr, const i64 *rp, const i64 *ci, const double *vx, const double *x, double *y)
 {
-    for (i64 i = 0; i < nr; i++) {
+    FO_PAR for (i64 i = 0; i < nr; i++) {
         double s = 0.0;
         for (i64 p = rp[i]; p < rp[i + 1]; p++) s += vx[p] * x[ci[p]];
         y[i] = s;
@@ -330,7 +340,7 @@ static void op_tmul(const fo_op *o, const double *x, double *y)
 }
 
 static double dotr(i64 n, const double *a, const double *b)
-{ double s = 0.0; for (i64 i = 0; i < n; i++) s += a[i] * b[i]; return s; }
+{ double s = 0.0; FO_PAR_SUM for (i64 i = 0; i < n; i++) s += a[i] * b[i]; return s; }
 static double nrm2(i64 n, const double *a) { return sqrt(dotr(n, a, a)); }
 
 /* Krylov.jl sym_givens */
@@ -380,7 +390,7 @@ void fo_lsqr(const fo_op *Op, const double *b, double lambda, double atol, doubl
     memset(st, 0, sizeof(*st));
     double lambda2 = lambda * lambda;
     double ctol = conlim > 0 ? 1.0 / conlim : 0.0;
-    for (i64 i = 0; i < n; i++) x[i] = 0.0;
+    FO_PAR for (i64 i = 0; i < n; i++) x[i] = 0.0;
     memcpy(u, b, (size_t)m * sizeof(double));
     double beta1 = nrm2(m, u);
     if (beta1 == 0.0) {
@@ -389,7 +399,7 @@ void fo_lsqr(const fo_op *Op, const double *b, double lambda, double atol, doubl
     }
     {
     double beta = beta1;
-    for (i64 i = 0; i < m; i++) u[i] /= beta1;
+    FO_PAR for (i64 i = 0; i < m; i++) u[i] /= beta1;
     op_tmul(Op, u, Atu);
     memcpy(v, Atu, (size_t)n * sizeof(double));
     double Anorm2 = dotr(n, v, v);
@@ -407,7 +417,7 @@ void fo_lsqr(const fo_op *Op, const double *b, double lambda, double atol, doubl
         st->niter = 0; st->solved = 1; st->inconsistent = 0; st->status = FO_ST_ZERO_ATB;
         st->rnorm = rNorm; goto done;
     }
-    for (i64 i = 0; i < n; i++) v[i] /= alpha;
+    FO_PAR for (i64 i = 0; i < n; i++) v[i] /= alpha;
     memcpy(w, v, (size_t)n * sizeof(double));
     double phibar = beta1, rhobar = alpha;
     int solved_lim = ArNorm / (Anorm * rNorm) <= axtol;
@@ -423,17 +433,17 @@ void fo_lsqr(const fo_op *Op, const double *b, double lambda, double atol, doubl
         iter++;
         /* beta_{k+1} u_{k+1} = A v_k - alpha_k u_k */
         op_mul(Op, v, Av);
-        for (i64 i = 0; i < m; i++) u[i] = Av[i] - alpha * u[i];
+        FO_PAR for (i64 i = 0; i < m; i++) u[i] = Av[i] - alpha * u[i];
         beta = nrm2(m, u);
         if (beta != 0.0) {
-            for (i64 i = 0; i < m; i++) u[i] /= beta;
+            FO_PAR for (i64 i = 0; i < m; i++) u[i] /= beta;
             Anorm2 = Anorm2 + alpha * alpha + beta * beta;
             if (lambda > 0) Anorm2 += lambda2;
             /* alpha_{k+1} v_{k+1} = A' u_{k+1} - beta_{k+1} v_k */
             op_tmul(Op, u, Atu);
-            for (i64 i = 0; i < n; i++) v[i] = Atu[i] - beta * v[i];
+            FO_PAR for (i64 i = 0; i < n; i++) v[i] = Atu[i] - beta * v[i];
             alpha = nrm2(n, v);
-            if (alpha != 0.0) for (i64 i = 0; i < n; i++) v[i] /= alpha;
+            if (alpha != 0.0) FO_PAR for (i64 i = 0; i < n; i++) v[i] /= alpha;
         }
         double c1, s1, rhobar1;
         sym_givens(rhobar, lambda, &c1, &s1, &rhobar1);
@@ -451,9 +461,9 @@ void fo_lsqr(const fo_op *Op, const double *b, double lambda, double atol, doubl
         rhobar = -c * alpha;
         dNorm2 += dotr(n, w, w) / (rho * rho);
         double sigma = phi / rho;
-        for (i64 i = 0; i < n; i++) x[i] += sigma * w[i];
+        FO_PAR for (i64 i = 0; i < n; i++) x[i] += sigma * w[i];
         double tr = theta / rho;
-        for (i64 i = 0; i < n; i++) w[i] = v[i] - tr * w[i];
+        FO_PAR for (i64 i = 0; i < n; i++) w[i] = v[i] - tr * w[i];
         double delta = s2 * rho;
         double gammabar = -c2 * rho;
         double rhs = phi - delta * z;
@@ -518,10 +528,10 @@ void fo_craig(const fo_op *Op, const double *b, int sqd, double mscale, double l
     double *Atu = (double *)malloc((size_t)n * sizeof(double));
     memset(st, 0, sizeof(*st));
     if (sqd) lambda = 1.0;
-    for (i64 i = 0; i < n; i++) x[i] = 0.0;
-    for (i64 i = 0; i < m; i++) y[i] = 0.0;
+    FO_PAR for (i64 i = 0; i < n; i++) x[i] = 0.0;
+    FO_PAR for (i64 i = 0; i < m; i++) y[i] = 0.0;
     memcpy(Mu, b, (size_t)m * sizeof(double));
-    for (i64 i = 0; i < m; i++) u[i] = mscale * Mu[i];
+    FO_PAR for (i64 i = 0; i < m; i++) u[i] = mscale * Mu[i];
     double beta1 = sqrt(dotr(m, u, Mu));
     double rNorm = beta1;
     if (beta1 == 0.0) {
@@ -531,7 +541,7 @@ void fo_craig(const fo_op *Op, const double *b, int sqd, double mscale, double l
     {
     double beta1sq = beta1 * beta1;
     double beta = beta1, theta = beta1, xi = -1.0, delta = lambda, rho_prev = 1.0;
-    for (i64 i = 0; i < m; i++) { u[i] /= beta1; Mu[i] /= beta1; }
+    FO_PAR for (i64 i = 0; i < m; i++) { u[i] /= beta1; Mu[i] /= beta1; }
     double Anorm2 = 0.0, Anorm = 0.0, Dnorm2 = 0.0, Acond = 0.0, xNorm2 = 0.0;
     i64 iter = 0;
     if (itmax == 0) itmax = m + n;
@@ -549,39 +559,39 @@ void fo_craig(const fo_op *Op, const double *b, int sqd, double mscale, double l
     while (!(solved || inconsistent || ill_cond || tired)) {
         /* alpha_{k+1} v_{k+1} = A' u_{k+1} - beta_{k+1} v_k */
         op_tmul(Op, u, Atu);
-        for (i64 i = 0; i < n; i++) v[i] = Atu[i] - beta * v[i];
+        FO_PAR for (i64 i = 0; i < n; i++) v[i] = Atu[i] - beta * v[i];
         double alpha = nrm2(n, v);
         if (alpha == 0.0) { inconsistent = 1; continue; }
-        for (i64 i = 0; i < n; i++) v[i] /= alpha;
+        FO_PAR for (i64 i = 0; i < n; i++) v[i] /= alpha;
         Anorm2 += alpha * alpha;
         if (lambda > 0) sym_givens(alpha, delta, &c1, &s1, &rho);
         else rho = alpha;
         xi = -theta / rho * xi;
         if (lambda > 0) {
-            for (i64 i = 0; i < n; i++) x[i] += xi * c1 * v[i];
-            for (i64 i = 0; i < n; i++) x[i] += xi * s1 * w2[i];
-            for (i64 i = 0; i < n; i++) w2[i] = s1 * v[i] - c1 * w2[i];
+            FO_PAR for (i64 i = 0; i < n; i++) x[i] += xi * c1 * v[i];
+            FO_PAR for (i64 i = 0; i < n; i++) x[i] += xi * s1 * w2[i];
+            FO_PAR for (i64 i = 0; i < n; i++) w2[i] = s1 * v[i] - c1 * w2[i];
         } else {
-            for (i64 i = 0; i < n; i++) x[i] += xi * v[i];
+            FO_PAR for (i64 i = 0; i < n; i++) x[i] += xi * v[i];
         }
         double tr = theta / rho_prev, xr = xi / rho;
-        for (i64 i = 0; i < m; i++) w[i] = u[i] - tr * w[i];
-        for (i64 i = 0; i < m; i++) y[i] += xr * w[i];
+        FO_PAR for (i64 i = 0; i < m; i++) w[i] = u[i] - tr * w[i];
+        FO_PAR for (i64 i = 0; i < m; i++) y[i] += xr * w[i];
         /* Krylov.jl craig.jl accumulates the 2-norm (not its square) here; kept as upstream. */
         Dnorm2 += nrm2(m, w);
         /* beta_{k+1} M u_{k+1} = A v_k - alpha_k M u_k */
         op_mul(Op, v, Av);
-        for (i64 i = 0; i < m; i++) Mu[i] = Av[i] - alpha * Mu[i];
-        for (i64 i = 0; i < m; i++) u[i] = mscale * Mu[i];
+        FO_PAR for (i64 i = 0; i < m; i++) Mu[i] = Av[i] - alpha * Mu[i];
+        FO_PAR for (i64 i = 0; i < m; i++) u[i] = mscale * Mu[i];
         beta = sqrt(dotr(m, u, Mu));
-        if (beta != 0.0) for (i64 i = 0; i < m; i++) { u[i] /= beta; Mu[i] /= beta; }
+        if (beta != 0.0) FO_PAR for (i64 i = 0; i < m; i++) { u[i] /= beta; Mu[i] /= beta; }
         double gamma = 0.0;
         if (lambda > 0) { theta = c1 * beta; gamma = s1 * beta; }
         else theta = beta;
         if (lambda > 0) {
             double c2, s2;
             sym_givens(lambda, gamma, &c2, &s2, &delta);
-            for (i64 i = 0; i < n; i++) w2[i] *= s2;
+            FO_PAR for (i64 i = 0; i < n; i++) w2[i] *= s2;
         }
         Anorm2 += beta * beta;
         Anorm = sqrt(Anorm2);
@@ -629,7 +639,7 @@ void fo_minres(const fo_op *Op, const double *b, double lambda, double atol, dou
     memset(st, 0, sizeof(*st));
     const double epsM = DBL_EPSILON;
     double ctol = conlim > 0 ? 1.0 / conlim : 0.0;
-    for (i64 i = 0; i < n; i++) x[i] = 0.0;
+    FO_PAR for (i64 i = 0; i < n; i++) x[i] = 0.0;
     memcpy(r1, b, (size_t)n * sizeof(double));
     memcpy(r2, r1, (size_t)n * sizeof(double));
     double *v = r2;
@@ -659,20 +669,20 @@ void fo_minres(const fo_op *Op, const double *b, double lambda, double atol, dou
     while (!(solved || tired || ill_cond)) {
         iter++;
         op_mul(Op, v, y);
-        if (lambda != 0.0) for (i64 i = 0; i < n; i++) y[i] += lambda * v[i];
-        for (i64 i = 0; i < n; i++) y[i] /= beta;
-        if (iter >= 2) { double c = beta / oldbeta; for (i64 i = 0; i < n; i++) y[i] -= c * r1[i]; }
+        if (lambda != 0.0) FO_PAR for (i64 i = 0; i < n; i++) y[i] += lambda * v[i];
+        FO_PAR for (i64 i = 0; i < n; i++) y[i] /= beta;
+        if (iter >= 2) { double c = beta / oldbeta; FO_PAR for (i64 i = 0; i < n; i++) y[i] -= c * r1[i]; }
         double alpha = dotr(n, v, y) / beta;
-        { double c = alpha / beta; for (i64 i = 0; i < n; i++) y[i] -= c * r2[i]; }
+        { double c = alpha / beta; FO_PAR for (i64 i = 0; i < n; i++) y[i] -= c * r2[i]; }
         double delta = cs * deltabar + sn * alpha;
         double *w;
         if (iter == 1) w = w2;
         else {
-            if (iter >= 3) for (i64 i = 0; i < n; i++) w1[i] *= -eps_;
+            if (iter >= 3) FO_PAR for (i64 i = 0; i < n; i++) w1[i] *= -eps_;
             w = w1;
-            for (i64 i = 0; i < n; i++) w[i] -= delta * w2[i];
+            FO_PAR for (i64 i = 0; i < n; i++) w[i] -= delta * w2[i];
         }
-        { double c = 1.0 / beta; for (i64 i = 0; i < n; i++) w[i] += c * v[i]; }
+        { double c = 1.0 / beta; FO_PAR for (i64 i = 0; i < n; i++) w[i] += c * v[i]; }
         memcpy(r1, r2, (size_t)n * sizeof(double));
         memcpy(r2, y, (size_t)n * sizeof(double));
         oldbeta = beta;
@@ -690,8 +700,8 @@ void fo_minres(const fo_op *Op, const double *b, double lambda, double atol, dou
         sn = beta / gamma;
         double phi = cs * phibar;
         phibar = sn * phibar;
-        { double c = 1.0 / gamma; for (i64 i = 0; i < n; i++) w[i] *= c; }
-        for (i64 i = 0; i < n; i++) x[i] += phi * w[i];
+        { double c = 1.0 / gamma; FO_PAR for (i64 i = 0; i < n; i++) w[i] *= c; }
+        FO_PAR for (i64 i = 0; i < n; i++) x[i] += phi * w[i];
         xENorm2 += phi * phi;
         if (iter >= 2) { double *t = w1; w1 = w2; w2 = t; }
         err_vec[iter % WINDOW] = phi;
@@ -752,7 +762,7 @@ void fo_cgls(const fo_op *Op, const double *b, double lambda, double atol, doubl
     double *s = (double *)malloc((size_t)n * sizeof(double));
     double *p = (double *)malloc((size_t)n * sizeof(double));
     memset(st, 0, sizeof(*st));
-    for (i64 i = 0; i < n; i++) x[i] = 0.0;
+    FO_PAR for (i64 i = 0; i < n; i++) x[i] = 0.0;
     memcpy(r, b, (size_t)m * sizeof(double));
     double bNorm = nrm2(m, r);
     if (bNorm == 0.0) { st->niter = 0; st->solved = 1; st->status = FO_ST_ZERO_RHS; goto done; }
@@ -771,13 +781,13 @@ void fo_cgls(const fo_op *Op, const double *b, double lambda, double atol, doubl
         double delta = dotr(m, q, q);
         if (lambda > 0) delta += lambda * dotr(n, p, p);
         double alpha = gamma / delta;
-        for (i64 i = 0; i < n; i++) x[i] += alpha * p[i];
-        for (i64 i = 0; i < m; i++) r[i] -= alpha * q[i];
+        FO_PAR for (i64 i = 0; i < n; i++) x[i] += alpha * p[i];
+        FO_PAR for (i64 i = 0; i < m; i++) r[i] -= alpha * q[i];
         op_tmul(Op, r, s);
-        if (lambda > 0) for (i64 i = 0; i < n; i++) s[i] -= lambda * x[i];
+        if (lambda > 0) FO_PAR for (i64 i = 0; i < n; i++) s[i] -= lambda * x[i];
         double gamma_next = dotr(n, s, s);
         double beta = gamma_next / gamma;
-        for (i64 i = 0; i < n; i++) p[i] = s[i] + beta * p[i];
+        FO_PAR for (i64 i = 0; i < n; i++) p[i] = s[i] + beta * p[i];
         gamma = gamma_next;
         rNorm = nrm2(m, r);
         ArNorm = sqrt(gamma);

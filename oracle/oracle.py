@@ -61,11 +61,34 @@ class IterTol(C.Structure):
 _lib = None
 
 
+def _threaded_so():
+    """libfps_oracle_omp.so (-fopenmp -DFO_OMP): only bench.py's reference arm asks for it (FPS_ORACLE_OMP=1);
+    falls back to the sequential build when OpenMP is not available."""
+    so = os.path.join(_HERE, "libfps_oracle_omp.so")
+    src = os.path.join(_HERE, "fps_oracle.c")
+    try:
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-C", _HERE, "-B", "libfps_oracle_omp.so"], stdout=subprocess.DEVNULL,
+                                  stderr=subprocess.DEVNULL)
+        C.CDLL(so)
+        return so
+    except (OSError, subprocess.CalledProcessError):
+        return None
+
+
+THREADED = False
+
+
 def lib():
-    global _lib
+    global _lib, THREADED
     if _lib is None:
         build()
-        _lib = C.CDLL(_SO)
+        so = _SO
+        if os.environ.get("FPS_ORACLE_OMP", "0") not in ("", "0"):
+            t = _threaded_so()
+            if t is not None:
+                so, THREADED = t, True
+        _lib = C.CDLL(so)
         _lib.fo_ldl_analyze.restype = C.c_void_p
         _lib.fo_ldlt_create.restype = C.c_void_p
         _lib.fo_ldlt_str.restype = C.c_void_p
