@@ -196,3 +196,30 @@ def test_unconstrained_problem(qds):
         stats = F.fps_solve(nlp, qds_solver=qds[key])
         assert stats.status == "first_order" and np.linalg.norm(stats.solution - 1.0) < 1e-3
         assert stats.multipliers.shape == (0,) and stats.primal_feas == 0.0
+
+
+def test_stopping_statuses(qds):
+    """`status_stopping_to_stats` outcomes other than :first_order (src/algo.jl:269): iteration limit of the outer
+    loop, time limit, sigma_max exceeded -> fail_sub_pb -> :unknown (:186-187)."""
+    nlp = models.reference_test_problem("hs61")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        s = F.fps_solve(nlp, qds_solver=qds["ldlt"], atol=1e-14, rtol=1e-14, max_iter=0)
+        assert s.status == "max_iter" and s.iter == 1
+        s = F.fps_solve(models.reference_test_problem("hs61"), qds_solver=qds["ldlt"], atol=1e-14, rtol=1e-14, max_time=0.0)
+        assert s.status == "max_time"
+        # a penalty parameter that may not grow: the first failed feasibility check ends the run as :unknown
+        s = F.fps_solve(models.reference_test_problem("readme_ineq"), qds_solver=qds["ldlt"], consistent_gradient=True,
+                        **{"σ_max": 1.5e3})
+        assert s.status == "unknown" and s.solver_specific["sigma"] > 1.5e3
+
+
+def test_stats_fields_and_multipliers_sign(qds):
+    """stats.multipliers = -ys (src/algo.jl:137): with L = f + λ'c the KKT residual g + J'λ vanishes at the solution."""
+    nlp = models.reference_test_problem("hs7")
+    s = F.fps_solve(nlp, qds_solver=qds["iterative"])
+    x, lam = s.solution, s.multipliers
+    J = nlp.jac_coord(x).reshape(1, 2)
+    assert np.linalg.norm(nlp.grad(x) + J.T @ lam) < 1e-5
+    assert s.elapsed_time >= 0 and s.objective == pytest.approx(-np.sqrt(3), abs=1e-6)
+    assert set(s.solver_specific) >= {"sigma", "rho", "delta", "restoration", "feasibility", "solver"}
