@@ -710,7 +710,10 @@ def _update_parameters(meta, model, feas):
     model.sigma *= meta.sigma_update
     if not feas:
         model.rho *= meta.rho_update
-    model.shahx = 0                      # the penalty changed: drop the memo (reinit! of the sub-state)
+    # The penalty changed.  The reference keeps its memo here (it is keyed on hash(x) only), so its
+    # first evaluation at the unchanged x still sees ys / gs of the OLD sigma; this loop drops the memo instead —
+    # a deliberate deviation in the driver, the memo rule itself (fletcher_nlp.py) is the reference's.
+    model.shahx = 0
 
 
 def _update_parameters_unbdd(meta, model, feas):
