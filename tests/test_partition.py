@@ -163,3 +163,22 @@ def test_row_partition_exchange_gloo_world2():
     for r in res:
         assert r[1] and r[2]
         assert np.allclose(r[3], r[4], rtol=1e-12)
+
+
+def test_multisegment_window_prototype():
+    """tools/proto/multiseg_tiles.py (round-2 design prototype, CPU only): tiles of the Poisson-control operator with up to
+    three window segments and 16-bit concatenation-relative indices reproduce A x and A' x."""
+    import importlib.util
+    import scipy.sparse as sp
+    from fpsb200 import models
+    spec = importlib.util.spec_from_file_location("multiseg_tiles", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "proto", "multiseg_tiles.py"))
+    ms = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ms)
+    A = models.poisson_control(48).A.tocsr()
+    rng = np.random.default_rng(1)
+    for M in (A, sp.csr_matrix(A.T)):
+        tiles = ms.build(M)
+        assert all(len(T["segs"]) <= 3 and sum(l for _, l in T["segs"]) <= ms.CAP for T in tiles)
+        assert sum(T["nrows"] for T in tiles) == M.shape[0]
+        x = rng.standard_normal(M.shape[1])
+        assert np.abs(ms.emulate(tiles, x, M.shape[0]) - M @ x).max() < 1e-9 * np.abs(M.data).max()
