@@ -105,10 +105,12 @@ function B200IterativeSolver(nlp::AbstractNLPModel{T, S}, ::T; explicit_linear_c
 end
 
 """
-    B200LDLtSolver(nlp, ::T; ldlt_tol, ldlt_r1, ldlt_r2, P = nothing, kwargs...) <: QDSolver
+    B200LDLtSolver(nlp, ::T; ldlt_tol, ldlt_r1, ldlt_r2, P = nothing, ordering = :auto, kwargs...) <: QDSolver
 
 `ldl_analyze` happens here (host ordering + symbolic analysis, uploaded to the GPU); `P` (1-based)
-plays the role of `ldl_analyze(A, P)`.
+plays the role of `ldl_analyze(A, P)`.  Without `P`, `ordering` picks the built-in one: `:amd` (minimum
+degree, what the reference does), `:dissection` (shallow elimination tree for the GPU) or `:auto`
+(minimum degree below 20 000 unknowns, dissection from there on — same rule as the Python mirror).
 """
 struct B200LDLtSolver{T} <: QDSolver
   h::FpsbHandle
@@ -119,11 +121,18 @@ struct B200LDLtSolver{T} <: QDSolver
 end
 
 function B200LDLtSolver(nlp::AbstractNLPModel{T, S}, ::T; explicit_linear_constraints = false,
-    ldlt_tol = √eps(T), ldlt_r1 = √eps(T), ldlt_r2 = -√eps(T), P = nothing, kwargs...) where {T, S}
+    ldlt_tol = √eps(T), ldlt_r1 = √eps(T), ldlt_r2 = -√eps(T), P = nothing, ordering = :auto,
+    kwargs...) where {T, S}
   T == Float64 || error("libfpsb200 computes in Float64")
   rows, cols, nnzj, ncon = _structure(nlp, explicit_linear_constraints)
   nvar = nlp.meta.nvar
   h = FpsbHandle(nvar, ncon, rows, cols)
+  if P === nothing && (ordering == :dissection || (ordering == :auto && nvar + ncon >= 20_000))
+    P = Vector{Int64}(undef, nvar + ncon)
+    _fpsb_check(ccall((:fpsb_order_dissection, libfpsb), Cint,
+      (Int64, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Cint, Cint, Ptr{Int64}),
+      nvar, ncon, nnzj, rows, cols, 1, 0, P), "fpsb_order_dissection")
+  end
   opts = Ref(FpsbLdltOpts(ldlt_tol, ldlt_r1, ldlt_r2))
   Pp = P === nothing ? Ptr{Int64}(C_NULL) : pointer(Vector{Int64}(P))
   GC.@preserve P _fpsb_check(ccall((:fpsb_ldlt_analyze, libfpsb), Cint,
