@@ -18,6 +18,15 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+void caller_order_in(Handle *h) {
+    FPSB_CUDA(cudaEventRecord(h->ev_in, h->caller_stream));
+    FPSB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_in, 0));
+}
+void caller_order_out(Handle *h) {
+    FPSB_CUDA(cudaEventRecord(h->ev_out, h->stream));
+    FPSB_CUDA(cudaStreamWaitEvent(h->caller_stream, h->ev_out, 0));
+}
+
 // pinned staging area large enough for `count` doubles
 static double *pin(Handle *h, size_t count) {
     if (count > h->pin_count) {
@@ -44,6 +53,7 @@ struct Staged {
     size_t in_off = 0, out_off = 0;
     std::vector<std::pair<double *, std::pair<size_t, size_t>>> outs;   // (host dst, (offset, count))
     Staged(Handle *hh, int l, size_t in_total, size_t out_total) : h(hh), loc(l) {
+        if (loc == FPSB_DEVICE) caller_order_in(h);      // the caller's kernels wrote the inputs on its own stream
         if (loc == FPSB_HOST) {
             if (h->stage_in.n < in_total + 8) h->stage_in.alloc(in_total + 8);
             if (h->stage_out.n < out_total + 8) h->stage_out.alloc(out_total + 8);
@@ -71,7 +81,7 @@ struct Staged {
         return d;
     }
     void finish() {
-        if (loc == FPSB_DEVICE) { FPSB_CUDA(cudaStreamSynchronize(h->stream)); return; }
+        if (loc == FPSB_DEVICE) { caller_order_out(h); FPSB_CUDA(cudaStreamSynchronize(h->stream)); return; }
         double *hp = h->pin + in_off;   // staged results go after the inputs in the pinned area
         std::vector<char> direct(outs.size(), 0);
         for (size_t i = 0; i < outs.size(); ++i) {
@@ -140,6 +150,8 @@ int fpsb_create(int64_t nvar, int64_t ncon, int64_t nnzj, const int64_t *jrow, c
     FPSB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     FPSB_CUDA(cudaEventCreate(&h->ev0));
     FPSB_CUDA(cudaEventCreate(&h->ev1));
+    FPSB_CUDA(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+    FPSB_CUDA(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
     csr_build(h);
     fpsb_iter_default_opts(nvar, ncon, &h->iopts);
     *out = reinterpret_cast<fpsb_handle>(h);
@@ -162,6 +174,8 @@ int fpsb_destroy(fpsb_handle hh) {
     if (h->pin) cudaFreeHost(h->pin);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_in) cudaEventDestroy(h->ev_in);
+    if (h->ev_out) cudaEventDestroy(h->ev_out);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return FPSB_OK;
@@ -191,6 +205,12 @@ int fpsb_dims(fpsb_handle hh, int64_t *nvar, int64_t *ncon, int64_t *nnzj) {
     return FPSB_OK;
 }
 void *fpsb_stream(fpsb_handle hh) { return hh ? (void *)reinterpret_cast<Handle *>(hh)->stream : nullptr; }
+int fpsb_set_caller_stream(fpsb_handle hh, void *stream) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQUIRE(h, FPSB_EINVAL, "NULL handle");
+    h->caller_stream = reinterpret_cast<cudaStream_t>(stream);
+    return FPSB_OK;
+}
 int fpsb_synchronize(fpsb_handle hh) {
     Handle *h = reinterpret_cast<Handle *>(hh);
     REQUIRE(h, FPSB_EINVAL, "NULL handle");
@@ -239,6 +259,7 @@ int fpsb_set_jac_values(fpsb_handle hh, const double *vals, int loc) {
             memcpy(hp, vals, nz * sizeof(double));
             FPSB_CUDA(cudaMemcpyAsync(h->coo_vals.p, hp, nz * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         } else {
+            caller_order_in(h);
             FPSB_CUDA(cudaMemcpyAsync(h->coo_vals.p, vals, nz * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
         }
     }
@@ -467,7 +488,9 @@ int fpsb_fp_ys_gs(fpsb_handle hh, double sigma, const double *p1, const double *
     REQUIRE(h && p1 && q1 && p2 && q2 && gs && ys && v && w, FPSB_EINVAL, "fpsb_fp_ys_gs: NULL argument");
     FPSB_TRY
     FPSB_CUDA(cudaSetDevice(h->device));
+    caller_order_in(h);
     fp_ys_gs(h, h->nvar, h->ncon, sigma, p1, q1, p2, q2, gs, ys, v, w);
+    caller_order_out(h);
     return FPSB_OK;
     FPSB_CATCH
 }
@@ -477,6 +500,7 @@ int fpsb_fp_obj(fpsb_handle hh, double fx, double rho, double eta, const double 
     REQUIRE(h && c && ys && phi, FPSB_EINVAL, "fpsb_fp_obj: NULL argument");
     FPSB_TRY
     FPSB_CUDA(cudaSetDevice(h->device));
+    caller_order_in(h);
     *phi = fp_obj(h, h->nvar, h->ncon, fx, rho, eta, c, ys, x, xk);
     return FPSB_OK;
     FPSB_CATCH
@@ -489,7 +513,9 @@ int fpsb_fp_grad(fpsb_handle hh, double sigma, double rho, double eta, const dou
     REQUIRE(!(eta > 0.0) || (x && xk), FPSB_EINVAL, "fpsb_fp_grad: eta > 0 needs x and xk");
     FPSB_TRY
     FPSB_CUDA(cudaSetDevice(h->device));
+    caller_order_in(h);
     fp_grad(h, h->nvar, sigma, rho, eta, gs, Hsv, v, Sstw, Jtc, x, xk, g);
+    caller_order_out(h);
     return FPSB_OK;
     FPSB_CATCH
 }
@@ -498,7 +524,9 @@ int fpsb_fp_ptv(fpsb_handle hh, const double *v, const double *p1, double *Ptv) 
     REQUIRE(h && v && p1 && Ptv, FPSB_EINVAL, "fpsb_fp_ptv: NULL argument");
     FPSB_TRY
     FPSB_CUDA(cudaSetDevice(h->device));
+    caller_order_in(h);
     fp_ptv(h, h->nvar, v, p1, Ptv);
+    caller_order_out(h);
     return FPSB_OK;
     FPSB_CATCH
 }
@@ -509,7 +537,9 @@ int fpsb_fp_hprod2(fpsb_handle hh, double sigma, double rho, double eta, double 
     REQUIRE(!(rho > 0.0) || (Hcv && JtJv), FPSB_EINVAL, "fpsb_fp_hprod2: rho > 0 needs Hcv and J'Jv");
     FPSB_TRY
     FPSB_CUDA(cudaSetDevice(h->device));
+    caller_order_in(h);
     fp_hprod2(h, h->nvar, sigma, rho, eta, obj_weight, p2, HsPtv, Ptv, Hcv, JtJv, v, Hv);
+    caller_order_out(h);
     return FPSB_OK;
     FPSB_CATCH
 }
@@ -518,6 +548,7 @@ int fpsb_fp_hash(fpsb_handle hh, const double *x, uint64_t *key) {
     REQUIRE(h && key && (x || h->nvar == 0), FPSB_EINVAL, "fpsb_fp_hash: NULL argument");
     FPSB_TRY
     FPSB_CUDA(cudaSetDevice(h->device));
+    caller_order_in(h);
     *key = fp_hash(h, h->nvar, x);
     return FPSB_OK;
     FPSB_CATCH

@@ -31,8 +31,14 @@ struct DevBuf {
     size_t n = 0;
     void alloc(size_t count) {
         release();
+        const cudaError_t e = cudaMalloc((void **)&p, (count ? count : 1) * sizeof(T));
+        if (e != cudaSuccess) {
+            p = nullptr; n = 0;
+            cudaGetLastError();
+            fpsb::set_error("cudaMalloc of %zu bytes failed: %s", (count ? count : 1) * sizeof(T), cudaGetErrorString(e));
+            throw fpsb::CudaFail{e == cudaErrorMemoryAllocation ? FPSB_ENOMEM : FPSB_ECUDA};
+        }
         n = count;
-        FPSB_CUDA(cudaMalloc((void **)&p, (count ? count : 1) * sizeof(T)));
     }
     void zero(cudaStream_t s) { if (p) FPSB_CUDA(cudaMemsetAsync(p, 0, (n ? n : 1) * sizeof(T), s)); }
     void upload(const T *h, size_t count, cudaStream_t s) {
@@ -104,6 +110,11 @@ struct Handle {
     int num_sms = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // FPSB_DEVICE callers: the stream their own kernels run on (default: the legacy default stream, what
+    // PyTorch uses).  Every entry that takes device pointers orders h->stream after it on the way in and
+    // it after h->stream on the way out (the handle's stream is non-blocking: nothing is implicit).
+    cudaStream_t caller_stream = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
     int64_t nvar = 0, ncon = 0, nnzj = 0;
     std::vector<int64_t> jrow, jcol;          // 0-based COO structure (host copy)
     CsrDev A, At;                             // A (ncon x nvar) and A' (nvar x ncon)
@@ -123,6 +134,10 @@ struct Handle {
     double prof_loop_ms = 0.0;          // CUDA-event time of the last Krylov loop region
     int64_t prof_step_launches = 0;     // fused SpMM step kernels launched in that region
 };
+
+// api.cu: stream ordering against the caller of FPSB_DEVICE entries
+void caller_order_in(Handle *h);
+void caller_order_out(Handle *h);
 
 // krylov.cu
 void csr_build(Handle *h);

@@ -1275,6 +1275,8 @@ __global__ void __launch_bounds__(256) flush_finish_kernel(SlotState *st, const 
         reinterpret_cast<double *>(st)[i] = reinterpret_cast<const double *>(sS)[i];
 }
 
+#include "fpsb_loop.inl"
+
 // rows longer than kLongRow: one CTA per row, strided over the row, fixed-tree block reduction.
 // Launched before gk_step_kernel of the same step; leaves its norm partials at partials[pbase + row#].
 template <bool PAIR>
@@ -1528,6 +1530,11 @@ struct IterWs {
     bool prof_armed = false;
     int ew_grid = 0;
     size_t partials_stride = 0;          // two partials buffers (deferred recurrences)
+    // persistent loop kernel (fpsb_loop.inl)
+    DevBuf<double> loop_parts;           // [2][grid][4]
+    DevBuf<unsigned long long> gbar;     // grid-barrier arrivals (zeroed before every launch)
+    int *h_fin = nullptr;                // pinned [4]: done | phases run | error | -
+    int64_t prof_loop_launches = 0;      // chunk launches inside the profiled region
 };
 
 static void build_csr_host(int nrows, int ncols, int64_t nnz, const int64_t *ri, const int64_t *cj,
@@ -1751,6 +1758,7 @@ void csr_build(Handle *h) {
         h->num_sms = sms;
         FPSB_CUDA(cudaFuncSetAttribute(gk_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBudget + 8 * 1024));
         FPSB_CUDA(cudaFuncSetAttribute(gk_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBudget + 8 * 1024));
+        FPSB_CUDA(cudaFuncSetAttribute(gk_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBudget + 8 * 1024));
     }
     std::vector<int> rp, ci, perm;
     build_csr_host(m, n, h->nnzj, h->jrow.data(), h->jcol.data(), rp, ci, perm);
@@ -1852,6 +1860,10 @@ void iter_setup(Handle *h) {
     W->done.alloc(4);
     W->counter.zero(h->stream);
     W->done.zero(h->stream);
+    W->loop_parts.alloc((size_t)2 * 4 * (size_t)std::max(h->num_sms, 1) + 16);
+    W->gbar.alloc(2);
+    W->gbar.zero(h->stream);
+    FPSB_CUDA(cudaMallocHost((void **)&W->h_fin, 4 * sizeof(int)));
     FPSB_CUDA(cudaMallocHost((void **)&W->h_done, 2 * sizeof(int)));
     FPSB_CUDA(cudaMallocHost((void **)&W->h_st, 2 * sizeof(SlotState)));
     FPSB_CUDA(cudaEventCreateWithFlags(&W->ev[0], cudaEventDisableTiming));
@@ -1865,6 +1877,7 @@ void iter_free(Handle *h) {
     if (!h->iter) return;
     IterWs *W = h->iter;
     if (W->h_done) cudaFreeHost(W->h_done);
+    if (W->h_fin) cudaFreeHost(W->h_fin);
     if (W->h_st) cudaFreeHost(W->h_st);
     if (W->ev[0]) cudaEventDestroy(W->ev[0]);
     if (W->ev[1]) cudaEventDestroy(W->ev[1]);
@@ -1980,8 +1993,9 @@ struct Engine {
         cur = 0; pbuf = 0; pend.valid = false; defer = false;
         max_it = std::max<int64_t>(s0.algo != ALGO_NONE ? s0.itmax : 0, s1.algo != ALGO_NONE ? s1.itmax : 0);
         FPSB_CUDA(cudaMemcpyAsync(W->st.p, W->h_st, sizeof(hs), cudaMemcpyHostToDevice, h->stream));
-        FPSB_CUDA(cudaMemsetAsync(W->done.p, 0, sizeof(int), h->stream));
+        FPSB_CUDA(cudaMemsetAsync(W->done.p, 0, 4 * sizeof(int), h->stream));
         W->counter.zero(h->stream);
+        loop_phases_pending = false;
     }
     void step(bool mspace, bool pair, const SlotIO &io0, const SlotIO &io1) {
         StepParams P = mspace ? base_m : base_n;
@@ -2022,11 +2036,11 @@ struct Engine {
     }
     // run `body(k)` (k = 1, 2, ...) until the device reports every slot stopped
     template <class F>
-    void loop(F body, int chunk) {
+    void loop(F body, int chunk, int its_per_body = 1) {
         int k = 0, pending = 0, slot = 0;
         // every method stops at its itmax at the latest; the cap only guards against a step that cannot
         // run its recurrences at all (degenerate operator) — it must never be what ends a healthy solve
-        int64_t hard_cap = max_it + 4 * (int64_t)chunk + 8;
+        int64_t hard_cap = max_it / its_per_body + 4 * (int64_t)chunk + 8;
 #if FPSB_EXP > 0
         if (const char *e = getenv("FPSB_MAXLOOP")) hard_cap = atoll(e);     // timing experiments only
 #endif
@@ -2051,10 +2065,70 @@ struct Engine {
             throw CudaFail{FPSB_ECUDA};
         }
     }
+    // ---- persistent loop kernel (fpsb_loop.inl): a whole chunk of Krylov iterations per launch ----
+    bool loop_phases_pending = false;
+    static int env_int(const char *name, int dflt) { const char *e = getenv(name); return (e && *e) ? atoi(e) : dflt; }
+    // one ring geometry for both operators; false when the persistent kernel cannot run this handle
+    bool loop_geometry(int &blk_cap, int &win_cap, int &stage_bytes, int &nstage, int &grid) const {
+        static const int mode = env_int("FPSB_LOOP", 2);
+        if (mode == 0 || tot_out != nullptr) return false;
+        const CsrDev &A = h->A, &At = h->At;
+        if (A.nlong > 0 || At.nlong > 0 || A.ntiles == 0 || At.ntiles == 0) return false;
+        blk_cap = std::max(A.blk_cap, At.blk_cap);
+        win_cap = std::max(A.win_cap, At.win_cap);
+        stage_bytes = (int)((((size_t)blk_cap + (size_t)win_cap * 16) + 127) & ~(size_t)127);
+        nstage = std::min(kMaxStages, kRingBudget / stage_bytes);
+        if (nstage < 2) return false;
+        grid = std::max(1, std::min(h->num_sms, std::min(A.ntiles, At.ntiles)));
+        return true;
+    }
+    bool can_persist() const { int a, b, c, d, e; return loop_geometry(a, b, c, d, e); }
+    // LSQR / CRAIG loop: phases alternate n-space (rows of A') and m-space (rows of A), n-space first
+    void run_loop(const SlotIO &n0, const SlotIO &n1, const SlotIO &m0, const SlotIO &m1) {
+        flush_pending();
+        defer = false;
+        static const int mode = env_int("FPSB_LOOP", 2);
+        static const int chunk_it = std::max(1, env_int("FPSB_LOOP_CHUNK", 24));
+        LoopParams L;
+        memset(&L, 0, sizeof(L));
+        int blk_cap, win_cap, stage_bytes, nstage, grid;
+        if (!loop_geometry(blk_cap, win_cap, stage_bytes, nstage, grid)) { set_error("persistent loop: unsupported operator"); throw CudaFail{FPSB_ESTATE}; }
+        L.op[0] = base_n; L.op[0].io[0] = n0; L.op[0].io[1] = n1;
+        L.op[1] = base_m; L.op[1].io[0] = m0; L.op[1].io[1] = m1;
+        for (int i = 0; i < 2; ++i) {
+            L.op[i].blk_cap = blk_cap; L.op[i].win_cap = win_cap; L.op[i].stage_bytes = stage_bytes; L.op[i].nstage = nstage;
+            L.op[i].inflight = std::min(L.op[i].inflight, nstage);
+            L.op[i].st = st_cur();
+        }
+        L.first = 0;
+        L.nphase = 2 * chunk_it;
+        L.nspec = std::max(0, std::min(env_int("FPSB_LOOP_NSPEC", kGroups), nstage - 1));
+        L.early = mode >= 2 ? 1 : 0;
+        L.st = st_cur();
+        L.parts = W->loop_parts.p;
+        L.gbar = W->gbar.p;
+        L.done_flag = W->done.p;
+        const size_t smem = (size_t)nstage * (size_t)stage_bytes;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kStepThreads);
+        cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        loop([&](int) {
+            FPSB_CUDA(cudaMemsetAsync(W->gbar.p, 0, sizeof(unsigned long long), h->stream));
+            FPSB_CUDA(cudaLaunchKernelEx(&cfg, gk_loop_kernel, L));
+            h->launches += 1;
+            W->prof_loop_launches += 1;
+        }, 1, chunk_it);
+        loop_phases_pending = true;
+    }
     // CUDA-event bracket around the Krylov loop (first step kernel .. last chunk), for the roofline
     void mark_begin() {
         FPSB_CUDA(cudaEventRecord(W->pev[0], h->stream));
         W->prof_launch0 = h->launches;
+        W->prof_loop_launches = 0;
         W->prof_armed = true;
     }
     void mark_end() {
@@ -2067,14 +2141,21 @@ struct Engine {
         flush_pending();
         defer = false;
         FPSB_CUDA(cudaMemcpyAsync(W->h_st, st_cur(), 2 * sizeof(SlotState), cudaMemcpyDeviceToHost, h->stream));
+        FPSB_CUDA(cudaMemcpyAsync(W->h_fin, W->done.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         FPSB_CUDA(cudaStreamSynchronize(h->stream));
+        if (W->h_fin[2] != 0) {
+            set_error("persistent Krylov loop kernel failed (code %d: 1 = TMA/mbarrier wait, 2 = grid barrier timed out)", W->h_fin[2]);
+            throw CudaFail{FPSB_ECUDA};
+        }
         stats_from(W->h_st[0], st[0]);
         stats_from(W->h_st[1], st[1]);
         if (W->prof_armed) {
             float ms = 0.f;
             FPSB_CUDA(cudaEventElapsedTime(&ms, W->pev[0], W->pev[1]));
             h->prof_loop_ms = ms;
+            // half iterations executed: step launches + the phases the persistent kernel ran
             h->prof_step_launches = W->prof_launch1 - W->prof_launch0;
+            if (loop_phases_pending) h->prof_step_launches += (int64_t)W->h_fin[1] - W->prof_loop_launches;
             W->prof_armed = false;
         }
     }
@@ -2155,7 +2236,8 @@ void iter_solve_two_mixed(Handle *h, double delta, const double *rhs1, const dou
     E.mark_begin();
     E.defer = true;
     E.step(true, true, l_init, io_none());
-    E.loop([&](int) {
+    if (E.can_persist()) E.run_loop(l_u, c_v, l_v, c_u);
+    else E.loop([&](int) {
         E.step(false, true, l_u, c_v);
         E.step(true, true, l_v, c_u);
     }, kChunk);
@@ -2190,7 +2272,8 @@ void iter_solve_two_least_squares(Handle *h, double delta, const double *rhs1, c
     E.mark_begin();
     E.defer = true;
     E.step(true, true, init0, init1);
-    E.loop([&](int) {
+    if (E.can_persist()) E.run_loop(u0, u1, v0, v1);
+    else E.loop([&](int) {
         E.step(false, true, u0, u1);
         E.step(true, true, v0, v1);
     }, kChunk);
@@ -2294,7 +2377,8 @@ void iter_solve_two_extras(Handle *h, double delta, const double *rhs1, const do
         SlotIO l_v = io_mode(MD_LSQR_V, W->am[0][0].p, W->am[0][1].p);
         E.defer = true;
         E.step(true, true, l_init, io_none());
-        E.loop([&](int) {
+        if (E.can_persist()) E.run_loop(l_u, io_none(), l_v, io_none());
+        else E.loop([&](int) {
             E.step(false, true, l_u, io_none());
             E.step(true, true, l_v, io_none());
         }, kChunk);

@@ -98,12 +98,20 @@ __device__ __forceinline__ void gsync() {
 template <bool WARP>
 __device__ __forceinline__ void wait_done(const int *flag, int epoch, int tid, int *fail) {
     if (tid == 0) {
+        // A CTA that took an early ticket may legitimately wait for almost the whole factorisation: the
+        // bound is wall time (60 s: a scheduling bug, not a long factorisation), polled rarely
         int it = 0;
+        unsigned long long t0 = 0;
         while (ld_acquire(flag) != epoch) {
             __nanosleep(40);
             ++it;
-            if ((it & 1023) == 0 && ld_acquire(fail) == -2) break;     // someone already gave up
-            if (it > (1 << 24)) { atomicExch(fail, -2); break; }
+            if ((it & 1023) == 0) {
+                if (ld_acquire(fail) == -2) break;                      // someone already gave up
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 60000000000ull) { atomicExch(fail, -2); break; }
+            }
         }
         __threadfence();
     }
@@ -800,6 +808,7 @@ static int ldlt_solve_api(fpsb_handle hh, int kind, bool refactor, double delta,
     const size_t n = (size_t)h->nvar, m = (size_t)h->ncon;
     const size_t n2 = kind == 0 ? m : n;
     int ok = 0;
+    if (loc == FPSB_DEVICE) caller_order_in(h);      // the caller's kernels wrote the right-hand sides on its own stream
     if (refactor) ldlt_factorize(h, delta, &ok);
     // host staging (same scheme as the iterative path)
     double *d_in = nullptr, *d_out = nullptr, *pinned = nullptr;
@@ -833,6 +842,7 @@ static int ldlt_solve_api(fpsb_handle hh, int kind, bool refactor, double delta,
         memcpy(p2, res + n + m, n * sizeof(double));
         memcpy(q2, res + 2 * n + m, m * sizeof(double));
     } else {
+        caller_order_out(h);
         FPSB_CUDA(cudaStreamSynchronize(h->stream));
     }
     FPSB_CUDA(cudaGetLastError());

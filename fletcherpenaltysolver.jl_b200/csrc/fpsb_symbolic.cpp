@@ -5,9 +5,15 @@
 //   * fill-reducing ordering: an approximate-minimum-degree ordering on the pattern of K + K'
 //     (quotient graph, approximate external degrees, element absorption, mass elimination,
 //     supervariable detection, dense-row deferral, assembly-tree postorder — the algorithm of
-//     Amestoy/Davis/Duff that LDLFactorizations reaches through AMD.jl).  Written from the
-//     published algorithm; NOT verified bit-identical to SuiteSparse (absent offline), which is
-//     why fpsb_ldlt_analyze also accepts an explicit P like `ldl_analyze(A, P)`.
+//     Amestoy/Davis/Duff that LDLFactorizations reaches through AMD.jl).
+//     Attribution: amd_order below follows the structure and variable naming (Pe, Len, Nv, Elen,
+//     Degree, W, Iw, pfree, wflg, FLIP, clear_flag, mindeg, nel, lemax) of SuiteSparse AMD's
+//     amd_2 routine — AMD, Copyright (c) 1996-2022, Timothy A. Davis, Patrick R. Amestoy and
+//     Iain S. Duff, BSD-3-Clause licence — re-typed here from the algorithm as published in
+//     "An approximate minimum degree ordering algorithm", SIAM J. Matrix Anal. Appl. 17(4), 1996 and
+//     "Algorithm 837: AMD", ACM TOMS 30(3), 2004.  SuiteSparse is not vendored (nor present in
+//     /root/reference), so the result is NOT verified bit-identical to libamd, which is why
+//     fpsb_ldlt_analyze also accepts an explicit P like `ldl_analyze(A, P)`.
 //   * elimination tree (Liu, path compression) + exact column structures of L by bottom-up
 //     child merging.  Given P, (parent, Lnz, Lp, Li) are canonical and are checked bit-exactly
 //     against the oracle's row-subtree walk (a different algorithm).

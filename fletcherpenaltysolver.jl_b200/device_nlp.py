@@ -97,6 +97,7 @@ class DeviceFletcherPenaltyNLP:
         self.key = None if not value else value
 
     def _hash(self, x):
+        self.handle._follow_torch_stream(x)      # every fpsb_fp_* call is ordered against torch's current stream
         k = C.c_uint64()
         _lib.check(self._lib.fpsb_fp_hash(self.handle.h, _dp(x), C.byref(k)), "fpsb_fp_hash")
         return k.value

@@ -134,9 +134,12 @@ function B200LDLtSolver(nlp::AbstractNLPModel{T, S}, ::T; explicit_linear_constr
       nvar, ncon, nnzj, rows, cols, 1, 0, P), "fpsb_order_dissection")
   end
   opts = Ref(FpsbLdltOpts(ldlt_tol, ldlt_r1, ldlt_r2))
-  Pp = P === nothing ? Ptr{Int64}(C_NULL) : pointer(Vector{Int64}(P))
-  GC.@preserve P _fpsb_check(ccall((:fpsb_ldlt_analyze, libfpsb), Cint,
-    (Ptr{Cvoid}, Ptr{Int64}, Cint, Ref{FpsbLdltOpts}), h.ptr, Pp, 1, opts), "fpsb_ldlt_analyze")
+  Pv = P === nothing ? Int64[] : Vector{Int64}(P)     # the converted copy is what the ccall reads: root IT
+  GC.@preserve Pv begin
+    Pp = P === nothing ? Ptr{Int64}(C_NULL) : pointer(Pv)
+    _fpsb_check(ccall((:fpsb_ldlt_analyze, libfpsb), Cint,
+      (Ptr{Cvoid}, Ptr{Int64}, Cint, Ref{FpsbLdltOpts}), h.ptr, Pp, 1, opts), "fpsb_ldlt_analyze")
+  end
   return B200LDLtSolver{T}(h, zeros(T, nnzj), zeros(T, nvar), zeros(T, ncon), zeros(T, nvar),
     zeros(T, ncon), zeros(T, ncon), zeros(T, ncon), Vector{FpsbKrylovStats}(undef, 2))
 end

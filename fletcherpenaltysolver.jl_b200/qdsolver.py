@@ -59,14 +59,24 @@ class B200Handle:
             pass
 
     # -- helpers -------------------------------------------------------------------------------
-    @staticmethod
-    def _arg(a):
+    def _arg(self, a):
         """numpy array -> (pointer, FPSB_HOST); torch CUDA tensor / raw int -> (pointer, FPSB_DEVICE)."""
         if isinstance(a, np.ndarray):
             return _ptr(a), FPSB_HOST
         if hasattr(a, "data_ptr"):
+            if a.is_cuda:
+                self._follow_torch_stream(a)
             return C.c_void_p(a.data_ptr()), (FPSB_DEVICE if a.is_cuda else FPSB_HOST)
         raise TypeError("expected a numpy array or a torch tensor")
+
+    def _follow_torch_stream(self, t):
+        """Device tensors are produced / consumed on torch's current stream: tell the library, which orders
+        its own (non-blocking) stream against it on the way in and out of every FPSB_DEVICE call."""
+        import torch
+        s = int(torch.cuda.current_stream(t.device).cuda_stream)
+        if s != getattr(self, "_caller_stream", 0):
+            check(_lib.lib().fpsb_set_caller_stream(self.h, C.c_void_p(s)), "fpsb_set_caller_stream")
+            self._caller_stream = s
 
     @staticmethod
     def pin_host(a):
@@ -109,6 +119,7 @@ class B200Handle:
             return y
         import torch
         y = torch.empty(nout * ncols, dtype=torch.float64, device=x.device)
+        self._follow_torch_stream(x)
         check(fn(self.h, C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), C.c_int(FPSB_DEVICE)),
               fn.__name__)
         return y

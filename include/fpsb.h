@@ -100,6 +100,12 @@ int fpsb_pin_host(void *ptr, int64_t bytes);
 int fpsb_unpin_host(void *ptr);
 /* the handle's CUDA stream (cudaStream_t) so callers can order their own work / events on it */
 void *fpsb_stream(fpsb_handle h);
+/* FPSB_DEVICE callers: the stream (cudaStream_t) the caller's own kernels run on; default NULL = the
+ * legacy default stream (what PyTorch / CUDA.jl's default task stream use).  The handle's stream is
+ * non-blocking, so every entry that takes device pointers waits for this stream on the way in and
+ * makes it wait for the handle's stream on the way out: inputs written by caller kernels are seen,
+ * results are complete before the caller's next kernel reads them. */
+int fpsb_set_caller_stream(fpsb_handle h, void *stream);
 int fpsb_synchronize(fpsb_handle h);
 /* CUDA-event stopwatch on the handle's stream (used by bench.py for device-side timing) */
 int fpsb_timer_start(fpsb_handle h);
