@@ -133,15 +133,23 @@ def run_reference(args, cfg):
     if rank != 0:
         return
     # all the host threads the path can use: the OpenMP build of the port (row loops of the two SpMVs and the
-    # element-wise / reduction loops of LSQR and CRAIG); the sequential build stays the checker of the tests
+    # element-wise / reduction loops of LSQR and CRAIG); the sequential build stays the checker of the tests.
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: only rank 0 works here (the others returned above), so it
+    # takes the whole box — the same baseline at every N
     os.environ.setdefault("FPS_ORACLE_OMP", "1")
+    ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(ncores)
     n, m, k, w = cfg["n"], cfg["m"], cfg["nnz_per_row"], cfg["window"]
     A, jrow, jcol, vals, rhs1, rhs2 = make_workload(n, m, k, w, args.seed)
     run = oracle_solve_timer(A, rhs1, rhs2, args.delta)
     from oracle import oracle as _O
     _O.lib()
-    threads = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1)) if _O.THREADED else 1
-    for _ in range(min(args.warmup, 1)):
+    threads = 1
+    if _O.THREADED:
+        gomp = ctypes.CDLL("libgomp.so.1")
+        gomp.omp_set_num_threads(ncores)
+        threads = int(gomp.omp_get_max_threads())
+    for _ in range(args.warmup):
         run()
     times, st = [], None
     for _ in range(args.steps):
@@ -151,7 +159,7 @@ def run_reference(args, cfg):
     val = args.steps / tot
     line = {
         "impl": "reference", "metric": "2-RHS KKT solves/s", "value": val, "unit": "solves/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": cfg,
@@ -294,11 +302,12 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    traffic = None
-    try:        # DRAM bytes per launch of the same kernel from the committed ncu --set full capture (headline shape only)
+    traffic, traffic_src = None, None
+    try:        # DRAM bytes per half iteration of the same kernel from the committed ncu --set full capture (headline shape only)
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         if (n, m, k) == (1_000_000, 500_000, 20):
             traffic = float(tj["dram_bytes_per_launch"])
+            traffic_src = "static: " + tj.get("source", "profiles/traffic.json (ncu --set full capture of this kernel, not measured in this run)")
     except Exception:
         pass
     tot_bytes, eff_launches = algorithmic_bytes(n, m, nnz, st[0]["niter"], st[1]["niter"], args.delta)
@@ -308,7 +317,7 @@ def main():
         "bound": "hbm", "kernel": "gk_step_kernel<PAIR=true> (fused 2-column SpMM + Krylov row epilogue)",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "frac_of_nominal_8000": achieved / 8000.0, "peak_source": peak_src,
-        "traffic": traffic,
+        "traffic": traffic, "traffic_static": traffic is not None, "traffic_source": traffic_src,
         "bytes_per_launch": tot_bytes / eff_launches,
         "avg_launch_us": 1e3 * loop_ms_per_solve / eff_launches,
         "launches_per_solve": eff_launches,

@@ -594,6 +594,24 @@ __device__ __forceinline__ CoefR to_regs(const Coef &C) {
     return R;
 }
 
+// the read / write flags only (what the operand loads of a row need): k[] stays dead, i.e. costs no registers
+__device__ __forceinline__ CoefR coef_flags(const Coef &C) {
+    CoefR R;
+    R.mode = C.mode;
+    R.flags = (C.first ? 1 : 0) | (C.pend ? 2 : 0) | (C.lampos ? 4 : 0) | (C.rd0 ? 8 : 0) | (C.rd1 ? 16 : 0) |
+              (C.wr0 ? 32 : 0) | (C.wr1 ? 64 : 0) | (C.rdself ? 128 : 0);
+#pragma unroll
+    for (int i = 0; i < 7; ++i) R.k[i] = 0.0;
+    return R;
+}
+// the scalars of a mode, re-read from shared memory where they are used (16 registers per slot that need not
+// live through the row sums)
+__device__ __forceinline__ void coef_scalars(CoefR &R, const Coef &C) {
+    const volatile double *k = C.k;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) R.k[i] = k[i];
+}
+
 // k[] per mode:
 //   PLAIN        c0, c1h
 //   LSQR_INIT_M  gsc
@@ -744,32 +762,35 @@ __device__ __forceinline__ double row_epilogue(const CoefR &C, double sraw, doub
 // ------------------------------------------------------------------------------------------------
 // the fused SpMM step kernel — tiled SELL-32 streamed through a TMA ring by persistent CTAs.
 //
-// Layout: the rows of the operator are cut into tiles of up to kTileRows consecutive rows (as many
-// rows as fit a ring stage); inside a tile the rows are sorted by length and packed into slices of
-// 32 (lane == row).  A slice stores its entries as "pair rows": entries 2p and 2p+1 of the 32 lanes
-// are interleaved, so one 16-byte access brings two values and one 8-byte access two column indices
-// per lane (an odd last entry is stored as a plain 32-entry row).  Everything a tile needs from the
-// operator — [values | column indices | lane -> row map] — is ONE contiguous block in HBM.
+// Layout: the rows of the operator are cut into tiles of up to kTileRows (256) consecutive rows — as
+// many as fit a ring stage, so that a tile block is 25-30 KB whether rows are long or short; inside
+// a tile the rows are sorted by length and packed into up to 8 slices of 32 (lane == row).  A slice
+// stores its entries as "pair rows": entries 2p and 2p+1 of the 32 lanes are interleaved, so one
+// 16-byte access brings two values and one 8-byte access two column indices per lane (an odd last
+// entry is stored as a plain 32-entry row).  Everything a tile needs from the operator —
+// [values | column indices | lane -> row map] — is ONE contiguous block in HBM.
 //
 // One persistent CTA per SM walks the tiles b, b + grid, b + 2 grid, ... :
-//   producers (warps 0 and 1, one lane each) keep the ring full with cp.async.bulk (TMA) + mbarrier:
-//             warp 0 copies the tile's block, warp 1 the slice of the gathered vector(s) the tile
-//             can touch — columns [cmin, cmin + ccnt) — into the same ring stage.  Measured on
-//             B200 (tools/micro/tma_bw.cu): a bulk copy costs its issuing thread ~0.35 us whatever
-//             its size and an SM sustains one per ~0.17 us, so full HBM bandwidth needs >= 16 KB
-//             per copy: hence one big block per tile and two issuing warps.
-//             Every byte the SM needs from HBM is requested as large contiguous reads several
-//             tiles ahead of its use, none of it held in registers.
+//   producers (warps 0-3, one lane each) keep the ring full with cp.async.bulk (TMA) + mbarrier:
+//             warps 0/1 copy the blocks of the CTA's even / odd tiles, warps 2/3 the slice of the
+//             gathered vector(s) the tile can touch — columns [cmin, cmin + ccnt) — into the same
+//             ring stage.  Measured on B200 (tools/micro/tma_bw.cu): a bulk copy costs its issuing
+//             thread ~0.35 us whatever its size and an SM sustains one per ~0.17 us, so full HBM
+//             bandwidth needs >= 16 KB per copy: hence one big block per tile and two issuing warps.
 //   consumers kGroups groups of 4 warps; group g takes the CTA's tiles g, g + kGroups, ...
-//     phase 1  a warp per slice: values / indices are read conflict-free from the stage, the
-//              gathers cost shared-memory bank cycles instead of one L1 wavefront per distinct
-//              128-byte line; the two row sums of every row go to a small per-group buffer indexed
-//              by the row's position in the tile, and the stage is handed back to the producers.
-//     phase 2  the Krylov row epilogue runs over the tile's rows in natural order, so every
-//              vector it reads and writes is accessed fully coalesced even though SELL permuted
-//              the rows; its operands were requested before phase 1.
+//     phase 1  warp w reduces slices w and ns-1-w (the widest with the narrowest: balanced): values /
+//              indices are read conflict-free from the stage, the gathers cost shared-memory bank
+//              cycles instead of one L1 wavefront per distinct 128-byte line; the two row sums of
+//              every row go to a small per-group buffer indexed by the row's position in the tile,
+//              and the stage is handed back to the producers.
+//     phase 2  the Krylov row epilogue runs over the tile's rows in natural order (thread t: rows t
+//              and t + 128), so every vector it reads and writes is accessed fully coalesced even
+//              though SELL permuted the rows; the operands of the first row were requested before
+//              phase 1, those of the second while the first is finished.
 //   Groups are in different phases at any time, so the shared-memory pipe, the HBM stream and the
-//   epilogue traffic overlap inside one SM.
+//   epilogue traffic overlap inside one SM.  Measured (tools/loop_timers.py): a group needs ~1.8 us
+//   per tile almost independently of the tile's size (a latency chain, not a throughput limit),
+//   which is why short-row operators get 256-row tiles.
 // Tiles whose column span exceeds the window capacity gather from global memory instead.
 // Rows longer than kLongRow are handled by a small separate kernel (one CTA per row) launched
 // before this one; its per-row norm partials join the fixed-order reduction below.
@@ -777,10 +798,10 @@ __device__ __forceinline__ double row_epilogue(const CoefR &C, double sraw, doub
 // grid's last CTA adds the per-CTA partials in index order and runs the scalar recurrences.  The
 // result does not depend on the order in which CTAs finish.
 // ------------------------------------------------------------------------------------------------
-constexpr int kTileRows = 128;
+constexpr int kTileRows = 256;
 constexpr int kTileSlices = kTileRows / 32;
 constexpr int kGroups = 3;
-constexpr int kGroupThreads = kTileRows;                      // phase 1: a warp per slice ; phase 2: a thread per row
+constexpr int kGroupThreads = 128;                             // phase 1: a warp per slice pair ; phase 2: a thread per row pair
 constexpr int kGroupWarps = kGroupThreads / 32;
 constexpr int kProducerThreads = 128;                          // warps 0,1: tile blocks (even / odd tiles), warps 2,3: gather windows
 constexpr int kStepThreads = kProducerThreads + kGroups * kGroupThreads;
@@ -796,11 +817,13 @@ struct __align__(16) TileMeta {
     int ns;              // slices in the tile, ns <= kTileSlices
     int cmin, ccnt;      // gather window (ccnt == 0: gather from global memory, indices are global columns)
     int row0, nrows;     // rows [row0, row0 + nrows) of the operator
-    int width[kTileSlices];   // entries per row of each slice
+    unsigned char width[kTileSlices];   // entries per row of each slice (rows sorted by length: widths descend)
+    int nsell;           // rows stored in the slices (nrows minus the long rows): lane l of slice s is a row iff 32 s + l < nsell
+    int pad_;
 };
-static_assert(sizeof(TileMeta) == 48 && kTileSlices == 4, "TileMeta is loaded as three int4");
-static_assert(kGroupWarps == kTileSlices, "phase 1 maps one warp to one slice");
-static_assert(kTileRows < 255, "the lane -> row map is stored as bytes (255 = padding lane)");
+static_assert(sizeof(TileMeta) == 48 && kTileSlices == 8, "TileMeta is loaded as three int4");
+static_assert(kTileRows == 2 * kGroupThreads, "phase 2 maps a thread to rows t and t + 128");
+static_assert(kTileRows <= 256, "the lane -> row map is stored as bytes");
 
 __host__ __device__ __forceinline__ unsigned tile_block_bytes(int elems, int ns, int ccnt) {
     return (unsigned)elems * (ccnt > 0 ? 10u : 12u) + (unsigned)ns * 32u;
@@ -813,26 +836,41 @@ __device__ __forceinline__ TileMeta load_tile(const TileMeta *tiles, int t) {
     T.boff = (long long)(((unsigned long long)(unsigned)a.y << 32) | (unsigned)a.x);
     T.elems = a.z; T.ns = a.w;
     T.cmin = b.x; T.ccnt = b.y; T.row0 = b.z; T.nrows = b.w;
-    T.width[0] = c.x; T.width[1] = c.y; T.width[2] = c.z; T.width[3] = c.w;
+    *reinterpret_cast<int *>(&T.width[0]) = c.x; *reinterpret_cast<int *>(&T.width[4]) = c.y;
+    T.nsell = c.z; T.pad_ = 0;
+    return T;
+}
+// what a block producer needs of a descriptor
+struct PTile { long long boff; int elems, ns, cmin, ccnt; };
+__device__ __forceinline__ PTile load_ptile(const TileMeta *tiles, int t) {
+    const int4 *tp = reinterpret_cast<const int4 *>(tiles + t);
+    const int4 a = __ldg(tp);
+    const int2 b = __ldg(reinterpret_cast<const int2 *>(tp + 1));
+    PTile T;
+    T.boff = (long long)(((unsigned long long)(unsigned)a.y << 32) | (unsigned)a.x);
+    T.elems = a.z; T.ns = a.w; T.cmin = b.x; T.ccnt = b.y;
     return T;
 }
 
 // what a consumer keeps of a tile descriptor (registers): everything but the block offset
 struct CTile {
     int elems, cmin, ccnt, row0;
-    int pk;              // ns | nrows << 8
-    int wpk;             // the four slice widths, one byte each (widths <= kLongRow < 256)
-    __device__ __forceinline__ int ns() const { return pk & 0xff; }
-    __device__ __forceinline__ int nrows() const { return pk >> 8; }
-    __device__ __forceinline__ int width(int i) const { return (wpk >> (8 * i)) & 0xff; }
+    int pk;              // ns | nrows << 4 | nsell << 14
+    unsigned w0, w1;     // the eight slice widths, one byte each (widths <= kLongRow < 256)
+    __device__ __forceinline__ int ns() const { return pk & 0xf; }
+    __device__ __forceinline__ int nrows() const { return (pk >> 4) & 0x3ff; }
+    __device__ __forceinline__ int nsell() const { return pk >> 14; }
+    __device__ __forceinline__ int width(int i) const {
+        return (int)((((unsigned long long)w1 << 32 | (unsigned long long)w0) >> (8 * i)) & 0xffull);
+    }
 };
 __device__ __forceinline__ CTile load_ctile(const TileMeta *tiles, int t) {
     const int4 *tp = reinterpret_cast<const int4 *>(tiles + t);
     const int4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
     CTile T;
     T.elems = a.z; T.cmin = b.x; T.ccnt = b.y; T.row0 = b.z;
-    T.pk = a.w | (b.w << 8);
-    T.wpk = c.x | (c.y << 8) | (c.z << 16) | (c.w << 24);
+    T.pk = a.w | (b.w << 4) | (c.z << 14);
+    T.w0 = (unsigned)c.x; T.w1 = (unsigned)c.y;
     return T;
 }
 
@@ -842,20 +880,178 @@ __device__ __forceinline__ void group_bar(int g) {
 __device__ __forceinline__ void prefetch_l2(const void *p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
+// all consumer threads of the CTA (the producer warps never join: they run on 40 registers and leave early)
+__device__ __forceinline__ void consumers_bar() {
+    asm volatile("bar.sync %0, %1;" ::"n"(1 + kGroups), "n"(kGroups * kGroupThreads) : "memory");
+}
+// fixed-tree sum of 4 values per consumer thread; result valid in every lane of consumer warp 0
+__device__ __forceinline__ void consumers_sum4(double (&v)[4], double *scratch /* 4*32 */, int cw, int lane) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const double x = warp_sum(v[q]);
+        if (lane == 0) scratch[q * 32 + cw] = x;
+    }
+    consumers_bar();
+    if (cw == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = warp_sum(lane < kGroups * kGroupWarps ? scratch[q * 32 + lane] : 0.0);
+    }
+    consumers_bar();
+}
+// warp-group register reallocation (sm_90+): the four producer warps need ~40 registers, which frees
+// 24 more for every consumer thread (128 -> 152) out of the same 64 K register file
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+constexpr int kProducerRegs = 40, kConsumerRegs = 152;
+static_assert(kProducerThreads * kProducerRegs + kGroups * kGroupThreads * kConsumerRegs <= 65536, "register file");
+
+// ---- consumer building blocks shared by gk_step_kernel and gk_loop_kernel ----------------------------
+// operands of one row of the Krylov row epilogue
+struct RowOps { double2 old2; double a00, a01, a10, a11; };
+
+template <bool PAIR>
+__device__ __forceinline__ void load_row_ops(const StepParams &P, const CoefR &C0, const CoefR &C1, int row, RowOps &R) {
+    if (PAIR) R.old2 = P.self2[row];
+    else {
+        R.old2 = make_double2(0.0, 0.0);
+        if (C0.rdself()) R.old2.x = P.io[0].self[row];
+        if (C1.rdself()) R.old2.y = P.io[1].self[row];
+    }
+    R.a00 = R.a01 = R.a10 = R.a11 = 0.0;
+    if (C0.rd0()) R.a00 = __ldcs(P.io[0].a0 + row);
+    if (C0.rd1()) R.a01 = __ldcs(P.io[0].a1 + row);
+    if (C1.rd0()) R.a10 = __ldcs(P.io[1].a0 + row);
+    if (C1.rd1()) R.a11 = __ldcs(P.io[1].a1 + row);
+}
+// pull the epilogue operands of the group's next tile into L2 (no registers held)
+template <bool PAIR>
+__device__ __forceinline__ void prefetch_row_ops(const StepParams &P, const CoefR &C0, const CoefR &C1, int r2, int t) {
+    if (PAIR) { if ((t & 7) == 0) prefetch_l2(P.self2 + r2); }
+    else if ((t & 15) == 0) {
+        if (C0.rdself()) prefetch_l2(P.io[0].self + r2);
+        if (C1.rdself()) prefetch_l2(P.io[1].self + r2);
+    }
+    if ((t & 15) == 0) {
+        if (C0.rd0()) prefetch_l2(P.io[0].a0 + r2);
+        if (C0.rd1()) prefetch_l2(P.io[0].a1 + r2);
+        if (C1.rd0()) prefetch_l2(P.io[1].a0 + r2);
+        if (C1.rd1()) prefetch_l2(P.io[1].a1 + r2);
+    }
+}
+// the Krylov row epilogue of one row (phase 2) ; raw rows of a row-partitioned run only leave their sums
+template <bool PAIR>
+__device__ __forceinline__ void finish_row(const StepParams &P, const CoefR &C0, const CoefR &C1, bool act0, bool act1, int row,
+                                           int rflag, const double2 sm, RowOps &R, double (&acc)[4]) {
+    if (rflag == 2 && P.raw_out == nullptr) rflag = 0;     // raw rows only matter to launches that ask for them
+    if (rflag == 2) P.raw_out[row] = sm;                   // halo / boundary row of a row-partitioned run
+    if (rflag != 0) return;
+    double n0 = R.old2.x, n1 = R.old2.y;
+    if (act0) n0 = row_epilogue(C0, sm.x, R.old2.x, R.a00, R.a01, acc[0], acc[1]);
+    if (act1) n1 = row_epilogue(C1, sm.y, R.old2.y, R.a10, R.a11, acc[2], acc[3]);
+    if (PAIR) P.self2[row] = make_double2(n0, n1);
+    else {
+        if (act0) P.io[0].self[row] = n0;
+        if (act1) P.io[1].self[row] = n1;
+    }
+    if (C0.wr0()) __stcs(P.io[0].a0 + row, R.a00);
+    if (C0.wr1()) __stcs(P.io[0].a1 + row, R.a01);
+    if (C1.wr0()) __stcs(P.io[1].a0 + row, R.a10);
+    if (C1.wr1()) __stcs(P.io[1].a1 + row, R.a11);
+}
+// row sums of one slice against both columns (phase 1).  VOLATILE_GATHER: the gathered vector changes
+// during the kernel's life time (persistent loop), so global gathers must not use the read-only path
+template <bool PAIR, bool VOLATILE_GATHER>
+__device__ __forceinline__ double2 slice_sums(const StepParams &P, const unsigned char *st, int elems, bool windowed, int off, int width,
+                                              const unsigned char *s_win, bool act0, bool act1, int lane) {
+    const double *s_val = reinterpret_cast<const double *>(st);
+    const int *s_col = reinterpret_cast<const int *>(st + (size_t)elems * 8);                        // global columns
+    const unsigned short *s_c16 = reinterpret_cast<const unsigned short *>(st + (size_t)elems * 8);   // window-relative
+    const int npair = width >> 1;
+    const bool tail = (width & 1) != 0;
+    double s0 = 0.0, s1 = 0.0, u0 = 0.0, u1 = 0.0;     // two accumulator pairs: shorter DFMA chains
+    const double2 *sv = reinterpret_cast<const double2 *>(s_val + off) + lane;
+    const int2 *sc = reinterpret_cast<const int2 *>(s_col + off) + lane;
+    const ushort2 *sc16 = reinterpret_cast<const ushort2 *>(s_c16 + off) + lane;
+    if (PAIR) {
+        if (windowed) {
+            const double2 *win2 = reinterpret_cast<const double2 *>(s_win);
+#pragma unroll 5
+            for (int p = 0; p < npair; ++p) {
+                const double2 v = sv[p * 32];
+                const ushort2 c = sc16[p * 32];
+                const double2 x0 = win2[c.x], x1 = win2[c.y];
+                s0 = fma(v.x, x0.x, s0); s1 = fma(v.x, x0.y, s1);
+                u0 = fma(v.y, x1.x, u0); u1 = fma(v.y, x1.y, u1);
+            }
+            if (tail) {
+                const double v = s_val[off + npair * 64 + lane];
+                const double2 x = win2[s_c16[off + npair * 64 + lane]];
+                s0 = fma(v, x.x, s0); s1 = fma(v, x.y, s1);
+            }
+        } else {
+            const double2 *gin2 = P.gin2;
+            auto ld = [&](int c) { return VOLATILE_GATHER ? __ldcg(gin2 + c) : __ldg(gin2 + c); };
+#pragma unroll 5
+            for (int p = 0; p < npair; ++p) {
+                const double2 v = sv[p * 32];
+                const int2 c = sc[p * 32];
+                const double2 x0 = ld(c.x), x1 = ld(c.y);
+                s0 = fma(v.x, x0.x, s0); s1 = fma(v.x, x0.y, s1);
+                u0 = fma(v.y, x1.x, u0); u1 = fma(v.y, x1.y, u1);
+            }
+            if (tail) {
+                const double v = s_val[off + npair * 64 + lane];
+                const double2 x = ld(s_col[off + npair * 64 + lane]);
+                s0 = fma(v, x.x, s0); s1 = fma(v, x.y, s1);
+            }
+        }
+    } else {
+        const double *win0 = reinterpret_cast<const double *>(s_win);
+        const double *win1 = win0 + P.win_cap;
+        auto gather_fma = [&](double v, int c, double &r0, double &r1) {
+            if (act0) r0 = fma(v, windowed ? win0[c] : __ldg(P.io[0].gin + c), r0);
+            if (act1) r1 = fma(v, windowed ? win1[c] : __ldg(P.io[1].gin + c), r1);
+        };
+#pragma unroll 5
+        for (int p = 0; p < npair; ++p) {
+            const double2 v = sv[p * 32];
+            int cx, cy;
+            if (windowed) { const ushort2 c = sc16[p * 32]; cx = c.x; cy = c.y; }
+            else { const int2 c = sc[p * 32]; cx = c.x; cy = c.y; }
+            gather_fma(v.x, cx, s0, s1);
+            gather_fma(v.y, cy, u0, u1);
+        }
+        if (tail) gather_fma(s_val[off + npair * 64 + lane],
+                             windowed ? (int)s_c16[off + npair * 64 + lane] : s_col[off + npair * 64 + lane], s0, s1);
+    }
+    return make_double2(s0 + u0, s1 + u1);
+}
+// phase 1 of a tile: warp `wid` of the group reduces slices wid and ns - 1 - wid
+template <bool PAIR, bool VOLATILE_GATHER>
+__device__ __forceinline__ void tile_row_sums(const StepParams &P, const CTile &T, const unsigned char *st, const unsigned char *s_win,
+                                              bool act0, bool act1, int wid, int lane, double2 *sum) {
+    const int ns = T.ns();
+    const bool windowed = T.ccnt > 0;
+    const unsigned char *s_map = st + (size_t)T.elems * (windowed ? 10 : 12);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int sl = h == 0 ? wid : ns - 1 - wid;
+        if (h == 0 ? (sl >= ns) : (sl < kGroupWarps)) continue;
+        int off = 0;
+#pragma unroll
+        for (int i = 0; i < kTileSlices - 1; ++i) if (i < sl) off += T.width(i) * 32;
+        const double2 r = slice_sums<PAIR, VOLATILE_GATHER>(P, st, T.elems, windowed, off, T.width(sl), s_win, act0, act1, lane);
+        const int idx = sl * 32 + lane;
+        if (idx < T.nsell()) sum[s_map[idx]] = r;
+    }
+}
 
 #ifdef FPSB_PHASE_TIMERS
 __device__ unsigned long long g_phase_cycles[16];
-#define PT_DECL long long pt_t0 = clock64(), pt_acc[6] = {0, 0, 0, 0, 0, 0}
-#define PT_MARK(i) do { const long long pt_t1 = clock64(); pt_acc[i] += pt_t1 - pt_t0; pt_t0 = pt_t1; } while (0)
-#define PT_FLUSH(base, n) do { for (int pt_i = 0; pt_i < (n); ++pt_i) atomicAdd(&g_phase_cycles[(base) + pt_i], (unsigned long long)pt_acc[pt_i]); } while (0)
-#else
-#define PT_DECL
-#define PT_MARK(i)
-#define PT_FLUSH(base, n)
 #endif
 
 template <bool PAIR>
-__global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, int use_state) {
+__global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(const __grid_constant__ StepParams P, int use_state) {
     extern __shared__ __align__(128) unsigned char s_dyn[];
     __shared__ double2 s_sum[kGroups][2][kTileRows];        // [group][double buffer][row]
     __shared__ double s_red[4 * 32];
@@ -867,9 +1063,6 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, 
 
     const int tid = threadIdx.x;
     const int cta = blockIdx.x, nstage = P.nstage, gsz = (int)gridDim.x;
-#if FPSB_EXP >= 9 && FPSB_EXP <= 11
-    P.ntiles = 0;        // experiment: launch overhead only (prologue + reduction + scalar recurrences)
-#endif
     // Programmatic dependent launch: this grid may be scheduled while the previous kernel of the
     // stream drains (its CTAs free their SMs one by one).  Everything above the wait touches only
     // this CTA's own shared memory; everything below may read what the previous kernel wrote.
@@ -927,24 +1120,21 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, 
 
     if (tid < kProducerThreads) {
         // ------------------------------- producers -------------------------------
+        reg_dec<kProducerRegs>();
         if ((tid & 31) == 0) {
             // a bulk copy costs its issuing thread a few hundred ns whatever its size: two warps share
             // the tile blocks (even / odd tiles of this CTA), two more the gather windows
             const int role = tid >> 5;
             const bool blocks = role < 2;
             const int par = role & 1;
-            // tile descriptors are fetched two of this producer's tiles ahead of their use
-            int k = par, tile = cta + par * gsz, t1 = tile + 2 * gsz;
-            PT_DECL;
-            TileMeta T{}, T1{};
-            if (tile < P.ntiles) T = load_tile(P.tiles, tile);
-            if (t1 < P.ntiles) T1 = load_tile(P.tiles, t1);
+            // tile descriptors are fetched one of this producer's tiles ahead of their use
+            int k = par, tile = cta + par * gsz;
+            PTile T{}, T1{};
+            if (tile < P.ntiles) T = load_ptile(P.tiles, tile);
             for (; tile < P.ntiles; k += 2) {
-                const int t2 = t1 + 2 * gsz;
-                TileMeta T2{};
-                if (t2 < P.ntiles) T2 = load_tile(P.tiles, t2);
+                const int t1 = tile + 2 * gsz;
+                if (t1 < P.ntiles) T1 = load_ptile(P.tiles, t1);
                 const int s = k % nstage;
-                PT_MARK(0);
                 if (k >= nstage) ok = mbar_wait(&empty_bar[s], (uint32_t)((k / nstage - 1) & 1)) && ok;
                 // bounded run-ahead: tile k - inflight must have landed.  Everything an SM requests is
                 // served in order, so a deep TMA backlog is pure latency for the epilogue's own loads
@@ -952,7 +1142,6 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, 
                     const int kb = k - P.inflight;
                     ok = mbar_wait(&full_bar[kb % nstage], (uint32_t)((kb / nstage) & 1)) && ok;
                 }
-                PT_MARK(1);
                 unsigned char *st = s_dyn + (size_t)s * stage_bytes;
                 if (blocks) {
                     const uint32_t bytes = tile_block_bytes(T.elems, T.ns, T.ccnt);
@@ -961,7 +1150,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, 
                 } else {
                     unsigned char *s_win = st + (size_t)P.blk_cap;
                     uint32_t wbytes = 0, tot = 0;
-                    if (T.ccnt > 0 && FPSB_EXP != 12) {
+                    if (T.ccnt > 0) {
                         if (PAIR) { wbytes = (uint32_t)T.ccnt * 16u; tot = wbytes; }
                         else if (win_tma && !(T.ccnt & 1)) { wbytes = (uint32_t)T.ccnt * 8u; tot = wbytes * ((act0 ? 1u : 0u) + (act1 ? 1u : 0u)); }
                     }
@@ -975,24 +1164,24 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, 
                         }
                     }
                 }
-                T = T1; T1 = T2; tile = t1; t1 = t2;
-                PT_MARK(2);
+                T = T1; tile = t1;
             }
-            PT_FLUSH(blocks ? 0 : 3, 3);
+            if (!ok) atomicExch(P.done_flag, -1);
         }
-    } else {
-        // ------------------------------- consumers -------------------------------
+        return;          // the reductions and recurrences below belong to the consumer warps
+    }
+    // ------------------------------- consumers -------------------------------
+    const int ct = tid - kProducerThreads;
+    const int cw = ct >> 5, clane = ct & 31;
+    {
         // (1 CTA per SM with a 215 KB ring leaves almost no L1: a register spill costs an L2 round
-        //  trip, so this kernel must stay spill-free — hence 4-warp groups and <= 146 registers)
-        const int ct = tid - kProducerThreads;
+        //  trip, so this kernel must stay spill-free)
+        reg_inc<kConsumerRegs>();
         const int g = ct / kGroupThreads, t = ct % kGroupThreads;
         const int lane = t & 31, wid = t >> 5;
         const CoefR C0 = to_regs(sC[0]), C1 = to_regs(sC[1]);
-        double *const self0 = PAIR ? reinterpret_cast<double *>(P.self2) : P.io[0].self;
-        double *const self1 = PAIR ? reinterpret_cast<double *>(P.self2) + 1 : P.io[1].self;
         int k = g;
         int tile = cta + k * gsz;
-        PT_DECL;
         // tile descriptors are fetched two tiles ahead of their use; the row-epilogue operands of the
         // group's next tile are pulled into L2 one tile ahead (no registers held)
         CTile T{}, Tn{}, Tnn{};
@@ -1000,201 +1189,85 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, 
         if (tile + kGroups * gsz < P.ntiles) Tn = load_ctile(P.tiles, tile + kGroups * gsz);
         for (; tile < P.ntiles; k += kGroups) {
             const int s = k % nstage;
-            PT_MARK(0);
             const int ntile = cta + (k + kGroups) * gsz, nntile = cta + (k + 2 * kGroups) * gsz;
             if (nntile < P.ntiles) Tnn = load_ctile(P.tiles, nntile);
-            // row-epilogue operands of this thread's row: in flight during the wait and phase 1
-            const int row = T.row0 + t;
-            // the row flag is only consumed in phase 2: the operand loads below do not wait for it (they are
-            // in bounds for flagged rows too), so the flag costs no extra round trip per tile
-            int rflag = (P.rowflag != nullptr && t < T.nrows()) ? (int)P.rowflag[row] : 0;
-            const bool in_row = FPSB_EXP != 4 && FPSB_EXP != 7 && FPSB_EXP != 12 && t < T.nrows();
-            double2 old2 = make_double2(0.0, 0.0);
-            double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
-            if (in_row && FPSB_EXP != 5) {
-                if (PAIR) old2 = P.self2[row];
-                else {
-                    if (C0.rdself()) old2.x = self0[row];
-                    if (C1.rdself()) old2.y = self1[row];
-                }
-                if (C0.rd0()) a00 = __ldcs(P.io[0].a0 + row);
-                if (C0.rd1()) a01 = __ldcs(P.io[0].a1 + row);
-                if (C1.rd0()) a10 = __ldcs(P.io[1].a0 + row);
-                if (C1.rd1()) a11 = __ldcs(P.io[1].a1 + row);
+            // row-epilogue operands of this thread's first row: in flight during the wait and phase 1.
+            // The row flags are only consumed in phase 2: the operand loads do not wait for them (they are
+            // in bounds for flagged rows too), so the flags cost no extra round trip per tile
+            const int rowA = T.row0 + t, rowB = rowA + kGroupThreads;
+            const bool inA = t < T.nrows(), inB = t + kGroupThreads < T.nrows();
+            const int flagA = (P.rowflag != nullptr && inA) ? (int)P.rowflag[rowA] : 0;
+            const int flagB = (P.rowflag != nullptr && inB) ? (int)P.rowflag[rowB] : 0;
+            RowOps RA{};
+            if (inA) load_row_ops<PAIR>(P, C0, C1, rowA, RA);
+            if (ntile < P.ntiles) {
+                if (t < Tn.nrows()) prefetch_row_ops<PAIR>(P, C0, C1, Tn.row0 + t, t);
+                if (t + kGroupThreads < Tn.nrows()) prefetch_row_ops<PAIR>(P, C0, C1, Tn.row0 + kGroupThreads + t, t);
             }
-            if (ntile < P.ntiles && t < Tn.nrows()) {
-                const int r2 = Tn.row0 + t;
-                if (PAIR) { if ((t & 7) == 0) prefetch_l2(P.self2 + r2); }
-                else if ((t & 15) == 0) {
-                    if (C0.rdself()) prefetch_l2(self0 + r2);
-                    if (C1.rdself()) prefetch_l2(self1 + r2);
-                }
-                if ((t & 15) == 0) {
-                    if (C0.rd0()) prefetch_l2(P.io[0].a0 + r2);
-                    if (C0.rd1()) prefetch_l2(P.io[0].a1 + r2);
-                    if (C1.rd0()) prefetch_l2(P.io[1].a0 + r2);
-                    if (C1.rd1()) prefetch_l2(P.io[1].a1 + r2);
-                }
-            }
-
             const unsigned char *st = s_dyn + (size_t)s * stage_bytes;
-            const double *s_val = reinterpret_cast<const double *>(st);
-            const bool windowed = T.ccnt > 0;
-            const int *s_col = reinterpret_cast<const int *>(st + (size_t)T.elems * 8);                        // global columns
-            const unsigned short *s_c16 = reinterpret_cast<const unsigned short *>(st + (size_t)T.elems * 8);   // window-relative
-            const unsigned char *s_map = st + (size_t)T.elems * (windowed ? 10 : 12);
             unsigned char *s_win = const_cast<unsigned char *>(st) + (size_t)P.blk_cap;
-            const double2 *win2 = reinterpret_cast<const double2 *>(s_win);
-            double *win0 = reinterpret_cast<double *>(s_win);
-            double *win1 = win0 + P.win_cap;
-
-            PT_MARK(1);
             ok = mbar_wait(&full_bar[s], (uint32_t)((k / nstage) & 1)) && ok;
-            PT_MARK(2);
-            if (!PAIR && windowed && !(win_tma && !(T.ccnt & 1))) {
+            if (!PAIR && T.ccnt > 0 && !(win_tma && !(T.ccnt & 1))) {
                 // unaligned / odd-sized caller vectors: the group stages the window itself
+                double *win0 = reinterpret_cast<double *>(s_win);
+                double *win1 = win0 + P.win_cap;
                 for (int i = t; i < T.ccnt; i += kGroupThreads) {
                     if (act0) win0[i] = P.io[0].gin[T.cmin + i];
                     if (act1) win1[i] = P.io[1].gin[T.cmin + i];
                 }
                 group_bar(g);
             }
-            // ---------------- phase 1: row sums, a warp per slice ----------------
+            // ---------------- phase 1: row sums ----------------
             double2 *sum = s_sum[g][(k / kGroups) & 1];
-            {
-                int off = 0, width = T.width(0);
-#pragma unroll
-                for (int i = 1; i < kTileSlices; ++i) if (i <= wid) { off += T.width(i - 1) * 32; width = T.width(i); }
-                const int npair = width >> 1;
-                double s0 = 0.0, s1 = 0.0, u0 = 0.0, u1 = 0.0;     // two accumulator pairs: shorter DFMA chains
-                int lrow = -1;
-                if (wid < T.ns() && FPSB_EXP != 3 && FPSB_EXP != 7 && FPSB_EXP != 12) {
-                    lrow = s_map[wid * 32 + lane];
-                    if (lrow == 255) lrow = -1;
-                    const double2 *sv = reinterpret_cast<const double2 *>(s_val + off) + lane;
-                    const int2 *sc = reinterpret_cast<const int2 *>(s_col + off) + lane;
-                    const ushort2 *sc16 = reinterpret_cast<const ushort2 *>(s_c16 + off) + lane;
-                    const bool tail = (width & 1) != 0;
-                    if (PAIR) {
-                        if (windowed) {
-#pragma unroll 5
-                            for (int p = 0; p < npair; ++p) {
-                                const double2 v = sv[p * 32];
-                                const ushort2 c = sc16[p * 32];
-                                const double2 x0 = win2[c.x], x1 = win2[c.y];
-                                s0 = fma(v.x, x0.x, s0); s1 = fma(v.x, x0.y, s1);
-                                u0 = fma(v.y, x1.x, u0); u1 = fma(v.y, x1.y, u1);
-                            }
-                            if (tail) {
-                                const double v = s_val[off + npair * 64 + lane];
-                                const double2 x = win2[s_c16[off + npair * 64 + lane]];
-                                s0 = fma(v, x.x, s0); s1 = fma(v, x.y, s1);
-                            }
-                        } else {
-#pragma unroll 5
-                            for (int p = 0; p < npair; ++p) {
-                                const double2 v = sv[p * 32];
-                                const int2 c = sc[p * 32];
-                                const double2 x0 = __ldg(P.gin2 + c.x), x1 = __ldg(P.gin2 + c.y);
-                                s0 = fma(v.x, x0.x, s0); s1 = fma(v.x, x0.y, s1);
-                                u0 = fma(v.y, x1.x, u0); u1 = fma(v.y, x1.y, u1);
-                            }
-                            if (tail) {
-                                const double v = s_val[off + npair * 64 + lane];
-                                const double2 x = __ldg(P.gin2 + s_col[off + npair * 64 + lane]);
-                                s0 = fma(v, x.x, s0); s1 = fma(v, x.y, s1);
-                            }
-                        }
-                    } else {
-                        auto gather_fma = [&](double v, int c, double &r0, double &r1) {
-                            if (act0) r0 = fma(v, windowed ? win0[c] : __ldg(P.io[0].gin + c), r0);
-                            if (act1) r1 = fma(v, windowed ? win1[c] : __ldg(P.io[1].gin + c), r1);
-                        };
-#pragma unroll 5
-                        for (int p = 0; p < npair; ++p) {
-                            const double2 v = sv[p * 32];
-                            int cx, cy;
-                            if (windowed) { const ushort2 c = sc16[p * 32]; cx = c.x; cy = c.y; }
-                            else { const int2 c = sc[p * 32]; cx = c.x; cy = c.y; }
-                            gather_fma(v.x, cx, s0, s1);
-                            gather_fma(v.y, cy, u0, u1);
-                        }
-                        if (tail) gather_fma(s_val[off + npair * 64 + lane],
-                                             windowed ? (int)s_c16[off + npair * 64 + lane] : s_col[off + npair * 64 + lane], s0, s1);
-                    }
-                }
-                if (lrow >= 0) sum[lrow] = make_double2(s0 + u0, s1 + u1);
-            }
+            tile_row_sums<PAIR, false>(P, T, st, s_win, act0, act1, wid, lane, sum);
             // the stage is consumed: hand it back to the producers (one arrival per warp)
             if (!PAIR) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // group-staged windows
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
-            PT_MARK(3);
             group_bar(g);
-            PT_MARK(4);
-            // ---------------- phase 2: row epilogue in natural row order, a thread per row ----------------
-            if (rflag == 2 && P.raw_out == nullptr) rflag = 0;     // raw rows only matter to launches that ask for them
-            const bool has_row = in_row && rflag == 0;
-            if (rflag == 2) P.raw_out[row] = sum[t];          // halo / boundary row of a row-partitioned run
-            if (has_row) {
-                const double2 sm = sum[t];
-                double n0 = old2.x, n1 = old2.y;
-                if (act0) n0 = row_epilogue(C0, sm.x, old2.x, a00, a01, acc[0], acc[1]);
-                if (act1) n1 = row_epilogue(C1, sm.y, old2.y, a10, a11, acc[2], acc[3]);
-                if (FPSB_EXP != 6) {
-                    if (PAIR) P.self2[row] = make_double2(n0, n1);
-                    else {
-                        if (act0) self0[row] = n0;
-                        if (act1) self1[row] = n1;
-                    }
-                    if (C0.wr0()) __stcs(P.io[0].a0 + row, a00);
-                    if (C0.wr1()) __stcs(P.io[0].a1 + row, a01);
-                    if (C1.wr0()) __stcs(P.io[1].a0 + row, a10);
-                    if (C1.wr1()) __stcs(P.io[1].a1 + row, a11);
-                } else acc[1] += n0 + n1;
-            }
+            // ---------------- phase 2: row epilogue in natural row order ----------------
+            RowOps RB{};
+            if (inB) load_row_ops<PAIR>(P, C0, C1, rowB, RB);
+            if (inA) finish_row<PAIR>(P, C0, C1, act0, act1, rowA, flagA, sum[t], RA, acc);
+            if (inB) finish_row<PAIR>(P, C0, C1, act0, act1, rowB, flagB, sum[t + kGroupThreads], RB, acc);
             T = Tn; Tn = Tnn;
             tile = ntile;
-            PT_MARK(5);
         }
-        if (t == 0 && g == 0) PT_FLUSH(6, 6);
     }
     if (!ok) atomicExch(P.done_flag, -1);
     if (!use_state) return;
-#if FPSB_EXP == 10
-    return;
-#endif
 
     // deterministic norms: one partial per CTA, reduced in a fixed order — by the next launch's
     // prologue (deferred mode) or by this grid's last CTA
-    block_sum<4>(acc, s_red);
+    constexpr int kCons = kGroups * kGroupThreads;
+    consumers_sum4(acc, s_red, cw, clane);
     if (P.st_out != nullptr) {
-        if (tid == 0) {
+        if (ct == 0) {
             double *pp = P.partials + (size_t)cta * 4;
             pp[0] = acc[0]; pp[1] = acc[1]; pp[2] = acc[2]; pp[3] = acc[3];
         }
         return;
     }
-    if (tid == 0) {
+    if (ct == 0) {
         double *pp = P.partials + (size_t)cta * 4;
         pp[0] = acc[0]; pp[1] = acc[1]; pp[2] = acc[2]; pp[3] = acc[3];
         __threadfence();
         unsigned tk = atomicAdd(P.counter, 1u);
         s_last = (tk == gridDim.x - 1);
     }
-    __syncthreads();
+    consumers_bar();
     if (!s_last) return;
     __threadfence();
     double tot[4] = {0.0, 0.0, 0.0, 0.0};
     const int nparts = (int)gridDim.x + P.nlong;       // long-row partials follow the CTA partials
-    for (int i = tid; i < nparts; i += kStepThreads) {
+    for (int i = ct; i < nparts; i += kCons) {
         const double *pp = P.partials + (size_t)i * 4;
         tot[0] += __ldcg(pp + 0); tot[1] += __ldcg(pp + 1);
         tot[2] += __ldcg(pp + 2); tot[3] += __ldcg(pp + 3);
     }
-    block_sum<4>(tot, s_red);
+    consumers_sum4(tot, s_red, cw, clane);
     if (P.tot_out != nullptr && P.ptail == nullptr) {
-        if (tid == 0) {
+        if (ct == 0) {
             P.tot_out[0] = tot[0]; P.tot_out[1] = tot[1]; P.tot_out[2] = tot[2]; P.tot_out[3] = tot[3];
             *P.counter = 0;
         }
@@ -1205,7 +1278,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, 
         const PeerTail &X = *P.ptail;
         const int R = X.nranks;
         const unsigned long long seq = P.pt_sig + 1;
-        if (tid == 0) {
+        if (ct == 0) {
             for (int p = 0; p < R; ++p) {
                 if (p == X.rank) continue;
                 double *dst = reinterpret_cast<double *>(X.peer[p] + kMboxOffTot) + ((size_t)P.pt_par * kMboxMaxRanks + X.rank) * 4;
@@ -1213,17 +1286,17 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, 
             }
             __threadfence_system();
         }
-        __syncthreads();
-        if (tid < R && tid != X.rank) {
-            st_release_sys(reinterpret_cast<unsigned long long *>(X.peer[tid]) + X.rank, seq);
-            const unsigned long long *f = reinterpret_cast<const unsigned long long *>(X.mine) + tid;
+        consumers_bar();
+        if (ct < R && ct != X.rank) {
+            st_release_sys(reinterpret_cast<unsigned long long *>(X.peer[ct]) + X.rank, seq);
+            const unsigned long long *f = reinterpret_cast<const unsigned long long *>(X.mine) + ct;
             const unsigned long long t0 = global_ns();
             while (ld_acquire_sys(f) < seq) {
                 if (global_ns() - t0 > 4000000000ull) { atomicExch(X.err, 1); break; }
             }
         }
-        __syncthreads();
-        if (tid == 0) {
+        consumers_bar();
+        if (ct == 0) {
             const double *in = reinterpret_cast<const double *>(X.mine + kMboxOffTot) + (size_t)P.pt_par * kMboxMaxRanks * 4;
             double all[4] = {0.0, 0.0, 0.0, 0.0};
             for (int r = 0; r < R; ++r)
@@ -1233,20 +1306,21 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(StepParams P, 
         }
     }
     // scalar recurrences on the shared-memory copy of the slot states (global memory would cost one
-    // L2 round trip per field), then one coalesced write-back
-    if (tid == 0) {
-#if FPSB_EXP != 11
-        if (act0) finish_step(sS[0], P.io[0].mode, tot[0], tot[1]);
-        if (act1) finish_step(sS[1], P.io[1].mode, tot[2], tot[3]);
+    // L2 round trip per field): the two slots side by side on two warps, then one coalesced write-back
+    // (the totals live in consumer warp 0: slot 1's pair is handed over through shared memory)
+    if (ct == 0) { s_tot[2] = tot[2]; s_tot[3] = tot[3]; }
+    consumers_bar();
+    if (ct == 0 && act0) finish_step(sS[0], P.io[0].mode, tot[0], tot[1]);
+    if (ct == 32 && act1) finish_step(sS[1], P.io[1].mode, s_tot[2], s_tot[3]);
+    consumers_bar();
+    if (ct == 0) {
         if (!sS[0].active && !sS[1].active) *P.done_flag = 1;
-#endif
         *P.counter = 0;
     }
-    __syncthreads();
     {
         const double *src = reinterpret_cast<const double *>(sS);
         double *dst = reinterpret_cast<double *>(P.st);
-        for (int i = tid; i < (int)(2 * sizeof(SlotState) / sizeof(double)); i += kStepThreads) dst[i] = src[i];
+        for (int i = ct; i < (int)(2 * sizeof(SlotState) / sizeof(double)); i += kCons) dst[i] = src[i];
     }
 }
 
@@ -1582,10 +1656,10 @@ static void upload_sell(Handle *h, CsrDev &M, int nrows, int ncols, const std::v
             long_rp.push_back((int)long_col.size());
         }
     }
-    for (int w0 = 0; w0 < nrows;) {
-        // largest tile (multiple of 32 rows, at most kTileRows) whose block + window fit a stage
-        int R = std::min(kTileRows, nrows - w0);
-        int cnt = 0, c0 = 0, elems = 0;
+    // largest tile starting at row w0 with at most `want` rows whose block + window fit a stage (halving)
+    int cnt = 0, c0 = 0, elems = 0;
+    auto fit_tile = [&](int w0, int want) {
+        int R = std::min(want, nrows - w0);
         for (;;) {
             order.clear();
             int cmin = ncols, cmax = -1;
@@ -1612,13 +1686,39 @@ static void upload_sell(Handle *h, CsrDev &M, int nrows, int ncols, const std::v
             cnt = 0;     // a single slice (at most kLongRow wide, 36 KB): drop the window
             break;
         }
+        return R;
+    };
+    // Tile boundaries.  The persistent CTAs take tiles b, b + grid, ...: a tile count that is not a multiple
+    // of the grid leaves most SMs idle for one tile at the end of every pass (3.7 % at the headline size),
+    // so when there are enough tiles the rows are cut into a multiple of the grid of (slightly smaller) tiles
+    std::vector<int> cuts;                 // desired tile starts ; a tile that does not fit is split further
+    {
+        int ntl = 0;
+        for (int w0 = 0; w0 < nrows; ++ntl) w0 += fit_tile(w0, kTileRows);
+        const int G = std::max(1, h->num_sms);
+        static const bool no_cuts = getenv("FPSB_NO_CUTS") != nullptr;
+        if (ntl >= 4 * G && !no_cuts) {
+            const int64_t target = (int64_t)((ntl + G - 1) / G) * G;
+            for (int64_t i = 0; i < target; ++i) cuts.push_back((int)((i * (int64_t)nrows) / target));
+        }
+    }
+    size_t icut = 0;
+    for (int w0 = 0; w0 < nrows;) {
+        int want = kTileRows;
+        if (!cuts.empty()) {
+            while (icut < cuts.size() && cuts[icut] <= w0) ++icut;
+            const int next = icut < cuts.size() ? cuts[icut] : nrows;
+            want = std::min(kTileRows, next - w0);
+        }
+        const int R = fit_tile(w0, want);
         TileMeta T{};
         T.boff = (long long)total_bytes;
         T.row0 = w0; T.nrows = R;
         T.cmin = cnt > 0 ? c0 : 0; T.ccnt = cnt;
         T.elems = elems;
         T.ns = (int)widths.size();
-        for (int i = 0; i < kTileSlices; ++i) T.width[i] = i < T.ns ? widths[(size_t)i] : 0;
+        T.nsell = (int)order.size();
+        for (int i = 0; i < kTileSlices; ++i) T.width[i] = (unsigned char)(i < T.ns ? widths[(size_t)i] : 0);
         const size_t bytes = (((size_t)tile_block_bytes(elems, T.ns, cnt)) + 127) & ~(size_t)127;    // blocks start 128-byte aligned
         win_cap = std::max(win_cap, cnt);
         blk_cap = std::max(blk_cap, bytes);
@@ -1676,7 +1776,7 @@ static void upload_sell(Handle *h, CsrDev &M, int nrows, int ncols, const std::v
             }
             for (int l = 0; l < 32; ++l) {
                 const int r = tile_rows[ti][(size_t)sl * 32 + l];
-                rmap[sl * 32 + l] = (unsigned char)(r >= 0 ? r - T.row0 : 255);
+                rmap[sl * 32 + l] = (unsigned char)(r >= 0 ? r - T.row0 : 0);      // lanes >= nsell are padding (never stored)
                 int len = 0, base = 0;
                 if (r >= 0) { base = rp[(size_t)r]; len = rp[(size_t)r + 1] - base; }
                 for (int j = 0; j < width; ++j) {
@@ -1737,6 +1837,19 @@ static void launch_step(Handle *h, const CsrDev &M, const StepParams &P, bool pa
     if (pair) FPSB_CUDA(cudaLaunchKernelEx(&cfg, gk_step_kernel<true>, P, use_state));
     else FPSB_CUDA(cudaLaunchKernelEx(&cfg, gk_step_kernel<false>, P, use_state));
     h->launches += 1;
+}
+
+// debug builds (-DFPSB_LOOP_TIMERS): the stamps of the last persistent-loop launch, [64][160][8]
+void loop_timers(unsigned long long *out) {
+#ifdef FPSB_LOOP_TIMERS
+    cudaMemcpyFromSymbol(out, g_loop_t, sizeof(unsigned long long) * 64 * 160 * 16);
+    cudaMemcpyFromSymbol(out + 64 * 160 * 16, g_loop_seg, sizeof(unsigned long long) * 160 * 2 * kGroups * 8);
+    unsigned long long *z = new unsigned long long[160 * 2 * kGroups * 8]();
+    cudaMemcpyToSymbol(g_loop_seg, z, sizeof(unsigned long long) * 160 * 2 * kGroups * 8);
+    delete[] z;
+#else
+    (void)out;
+#endif
 }
 
 void phase_timers(unsigned long long *out, int reset) {
@@ -2079,7 +2192,9 @@ struct Engine {
         stage_bytes = (int)((((size_t)blk_cap + (size_t)win_cap * 16) + 127) & ~(size_t)127);
         nstage = std::min(kMaxStages, kRingBudget / stage_bytes);
         if (nstage < 2) return false;
-        grid = std::max(1, std::min(h->num_sms, std::min(A.ntiles, At.ntiles)));
+        { static const int cap = env_int("FPSB_LOOP_NSTAGE", 0); if (cap >= 2) nstage = std::min(nstage, cap); }
+        if (!getenv("FPSB_LOOP_ODD")) nstage &= ~1;              // even: every stage is always served by the same producer warp (fpsb_loop.inl)
+        grid = std::max(1, std::min(std::min(h->num_sms, kLoopMaxGrid), std::min(A.ntiles, At.ntiles)));
         return true;
     }
     bool can_persist() const { int a, b, c, d, e; return loop_geometry(a, b, c, d, e); }

@@ -35,6 +35,8 @@ struct LoopParams {
     int *done_flag;              // [0] done, [1] += phases run, [2] error
 };
 
+constexpr int kLoopMaxGrid = 192;      // CTAs of the persistent loop (records are polled 3 per lane of the two recurrence warps)
+
 struct LoopCtl {
     int pass;        // grid barriers passed: phase ph may read what phase ph - 1 wrote once pass >= ph
     int open1;       // recurrence warp 1: coefficients of phases < open1 are ready
@@ -60,29 +62,174 @@ __device__ __forceinline__ void red_release_gpu(unsigned long long *p, unsigned 
     asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
-__device__ __forceinline__ void consumers_bar() {
-    asm volatile("bar.sync %0, %1;" ::"n"(1 + kGroups), "n"(kGroups * kGroupThreads) : "memory");
+// Wait until *p >= want (shared-memory counter published with st_release_cta).  ONE thread polls, rarely:
+// a dozen warps spinning on shared memory flood the SM's memory-instruction queue, which is exactly what the
+// recurrence warps' own shared-memory accesses and shuffles have to get through (measured: 5 us per boundary)
+__device__ __forceinline__ void loop_wait_thread(const int *p, int want, const LoopCtl *ctl) {
+    unsigned it = 0;
+    while (*reinterpret_cast<const volatile int *>(p) < want) {
+        __nanosleep(100);
+        if ((++it & 1023) == 0 && *reinterpret_cast<const volatile int *>(&ctl->abort)) __trap();    // error path: end the launch, never hang
+    }
+    __threadfence_block();                                   // acquire side of st_release_cta
 }
-// spin until *p >= want (shared-memory counter published with st_release_cta); false: the CTA aborted
-__device__ __forceinline__ bool loop_wait(const int *p, int want, const LoopCtl *ctl) {
+__device__ __forceinline__ void loop_wait(const int *p, int want, const LoopCtl *ctl) {     // whole warp
+#ifdef FPSB_LOOP_TIGHTPOLL
     for (unsigned it = 0;; ++it) {
-        if (ld_acquire_cta(p) >= want) return true;
-        if ((it & 15) == 15) {
-            if (*reinterpret_cast<const volatile int *>(&ctl->abort)) __trap();    // error path: end the launch, never hang
-            __nanosleep(32);
+        if (ld_acquire_cta(p) >= want) return;
+        if ((it & 15) == 15) { if (*reinterpret_cast<const volatile int *>(&ctl->abort)) __trap(); __nanosleep(32); }
+    }
+#else
+    if ((threadIdx.x & 31) == 0) loop_wait_thread(p, want, ctl);
+    __syncwarp();
+#endif
+}
+
+#ifdef FPSB_LOOP_TIMERS
+// debug builds: per phase (first 64 of a launch) and CTA, globaltimer stamps of 8 points of the phase
+__device__ unsigned long long g_loop_t[64][160][16];
+#define LT_STAMP(ph, i) do { if ((ph) < 64 && cta < 160) g_loop_t[(ph)][cta][(i)] = global_ns(); } while (0)
+// per CTA, phase parity and consumer group: clock64 cycles thread 0 of the group spent in 6 segments of its tiles
+// (0 top / operand issue, 1 wait full, 2 row sums, 3 group barrier, 4 wait coefficients, 5 epilogue), [6] = tiles
+__device__ unsigned long long g_loop_seg[160][2][kGroups][8];
+// (accumulated in shared memory by thread 0 of each group, flushed once per phase: a global RMW per mark distorts)
+#define LS_DECL long long ls_t0 = clock64()
+#define LS_MARK(i) do { if (t == 0) { const long long ls_t1 = clock64(); s_seg[g][(i)] += (unsigned long long)(ls_t1 - ls_t0); ls_t0 = ls_t1; } } while (0)
+#define LS_RESET do { ls_t0 = clock64(); } while (0)
+#define LS_COUNT do { if (t == 0) s_seg[g][6] += 1; } while (0)
+#define LS_FLUSH do { if (t == 0 && cta < 160) { for (int q_ = 0; q_ < 8; ++q_) { g_loop_seg[cta][ph & 1][g][q_] += s_seg[g][q_]; s_seg[g][q_] = 0; } } } while (0)
+#else
+#define LT_STAMP(ph, i)
+#define LS_DECL
+#define LS_MARK(i)
+#define LS_RESET
+#define LS_COUNT
+#define LS_FLUSH
+#endif
+
+// (Tried and dropped: per-CTA records stamped in the sign bit so that arrival and partials are one L2 round trip:
+//  the 148 x 64 polling lanes slowed the CTAs that were still streaming by more than the round trip saved.)
+
+// Boundary work of recurrence warp r (consumer warp 0 or 1) before phase `ph` (1 <= ph <= nphase): wait for
+// every CTA's record of phase ph - 1, add them in a fixed order, run slot r's scalar recurrence, prepare the
+// coefficients of phase ph.  Warp 0 also publishes pass / open / stop_at and, in CTA 0, the final states.
+// (Inlined: a call inside the phase loop makes ptxas spill the tile loop. state around it.)
+__device__ __forceinline__ void loop_boundary(const LoopParams &L, int ph, int r, int lane, int cta, int gsz, SlotState *sS, Coef *sC,
+                                              LoopCtl &ctl, double *rsum /* 64 * 4 */) {
+    const double *base = L.parts + (size_t)((ph - 1) & 1) * gsz * 4;
+    if (lane == 0) LT_STAMP(ph - 1, r ? 15 : 14);
+#ifdef FPSB_LOOP_V1B
+    double tot[4] = {0.0, 0.0, 0.0, 0.0};
+    {
+        if (lane == 0) {
+            const unsigned long long want = (unsigned long long)ph * (unsigned long long)gsz;
+            while (ld_acquire_gpu(L.gbar) < want) { }
+        }
+        __syncwarp();
+        if (r == 0 && lane == 0) { st_release_cta(&ctl.pass, ph); LT_STAMP(ph - 1, 3); }
+        for (int i = lane; i < gsz; i += 32) {
+            const double2 a = __ldcg(reinterpret_cast<const double2 *>(base + (size_t)i * 4));
+            const double2 b = __ldcg(reinterpret_cast<const double2 *>(base + (size_t)i * 4 + 2));
+            tot[0] += a.x; tot[1] += a.y; tot[2] += b.x; tot[3] += b.y;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tot[q] = warp_sum(tot[q]);
+        if (r == 1) { tot[0] = tot[2]; tot[1] = tot[3]; }
+    }
+#else
+    double tot[4] = {0.0, 0.0, 0.0, 0.0};
+    {
+        // ONE thread per CTA polls the arrival counter (148 x 64 lanes polling the records themselves took a
+        // measurable share of the L2 request rate away from the CTAs that were still streaming)
+        if (r == 0 && lane == 0) {
+            const unsigned long long want = (unsigned long long)ph * (unsigned long long)gsz;
+            const unsigned long long t0 = global_ns();
+            unsigned spins = 0;
+            while (ld_acquire_gpu(L.gbar) < want) {
+                __nanosleep(40);
+                if ((++spins & 4095) == 0 && global_ns() - t0 > 2000000000ull) {     // 2 s: a CTA died
+                    ctl.abort = 1; atomicExch(L.done_flag + 2, 2); __threadfence_system(); __trap();
+                }
+            }
+        }
+        asm volatile("bar.sync %0, %1;" ::"n"(2 + kGroups), "n"(64) : "memory");      // the two recurrence warps
+        // the 64 lanes of the two recurrence warps share the records: lane gl adds those of CTAs gl, gl + 64, gl + 128
+        constexpr int kRecPerLane = kLoopMaxGrid / 64;
+        const int gl = r * 32 + lane;
+        double2 w[kRecPerLane][2];
+#pragma unroll
+        for (int j = 0; j < kRecPerLane; ++j) {
+            const int i = gl + 64 * j < gsz ? gl + 64 * j : gl;          // (out of range: a valid record, not added)
+            const double2 *rp = reinterpret_cast<const double2 *>(base + (size_t)i * 4);
+            w[j][0] = __ldcg(rp); w[j][1] = __ldcg(rp + 1);
+        }
+#pragma unroll
+        for (int j = 0; j < kRecPerLane; ++j) {
+            if (gl + 64 * j < gsz) { tot[0] += w[j][0].x; tot[1] += w[j][0].y; tot[2] += w[j][1].x; tot[3] += w[j][1].y; }
+        }
+        // lane partials -> shared memory -> one lane per warp adds them in lane order.  (A shuffle tree is 20
+        // DEPENDENT trips through the SM's memory-instruction queue, which the other consumers' row sums keep full
+        // at this point: measured 5.6 us; this is two trips.)
+        reinterpret_cast<double4 *>(rsum)[gl] = make_double4(tot[0], tot[1], tot[2], tot[3]);
+        asm volatile("bar.sync %0, %1;" ::"n"(2 + kGroups), "n"(64) : "memory");
+    }
+    if (r == 0 && lane == 0) { st_release_cta(&ctl.pass, ph); LT_STAMP(ph - 1, 3); }
+    if (lane == 0) {
+        // this warp's slot needs two of the four sums
+        const double2 *all = reinterpret_cast<const double2 *>(rsum) + r;
+        tot[0] = tot[1] = 0.0;
+#pragma unroll 8
+        for (int l = 0; l < 64; ++l) { const double2 v = all[2 * l]; tot[0] += v.x; tot[1] += v.y; }
+    }
+#endif
+    if (lane == 0) {
+        const StepParams &Pp = L.op[(L.first + ph - 1) & 1];
+        const int mode = Pp.io[r].mode;
+        const double t0 = tot[0], t1 = tot[1];
+        LT_STAMP(ph - 1, r ? 11 : 8);
+        if (mode != MD_NONE && sS[r].active) finish_step(sS[r], mode, t0, t1);
+        LT_STAMP(ph - 1, r ? 12 : 9);
+        const StepParams &Pn = L.op[(L.first + ph) & 1];
+        load_coef(sC[r], Pn.io[r], &sS[r], true);
+        if (!(Pn.io[r].mode != MD_NONE && sS[r].active)) {
+            sC[r].mode = MD_NONE; sC[r].rd0 = sC[r].rd1 = sC[r].wr0 = sC[r].wr1 = sC[r].rdself = 0;
+        }
+        LT_STAMP(ph - 1, r ? 13 : 10);
+        if (r == 1) st_release_cta(&ctl.open1, ph + 1);
+        else {
+            loop_wait_thread(&ctl.open1, ph + 1, &ctl);
+            if (!sS[0].active && !sS[1].active) ctl.stop_at = ph;
+            st_release_cta(&ctl.open, ph + 1);
+            LT_STAMP(ph - 1, 4);
+        }
+    }
+    if (r == 1) loop_wait(&ctl.open, ph + 1, &ctl);          // warp 1 learns the stop decision from warp 0
+    __syncwarp();
+    if (r == 0 && cta == 0 && (ph >= L.nphase || ctl.stop_at <= ph)) {
+        const double *src = reinterpret_cast<const double *>(sS);
+        double *dst = reinterpret_cast<double *>(L.st);
+        for (int i = lane; i < (int)(2 * sizeof(SlotState) / sizeof(double)); i += 32) dst[i] = src[i];
+        if (lane == 0) {
+            if (!sS[0].active && !sS[1].active) L.done_flag[0] = 1;
+            L.done_flag[1] += ph;
         }
     }
 }
 
 __global__ void __launch_bounds__(kStepThreads, 1) gk_loop_kernel(const __grid_constant__ LoopParams L) {
     extern __shared__ __align__(128) unsigned char s_dyn[];
-    __shared__ double2 s_sum[kGroups][2][kTileRows];
+    __shared__ double2 s_sum[kGroups][2][kTileRows];        // [group][double buffer][row]
     __shared__ double s_red[4 * 32];
     __shared__ alignas(8) uint64_t full_bar[kMaxStages];
     __shared__ alignas(8) uint64_t empty_bar[kMaxStages];
     __shared__ SlotState sS[2];
     __shared__ Coef sC[2];
     __shared__ LoopCtl ctl;
+    __shared__ __align__(32) double s_rsum[64 * 4];        // lane partials of the two recurrence warps
+#ifdef FPSB_LOOP_TIMERS
+    __shared__ unsigned long long s_seg[kGroups][8];
+    if (threadIdx.x < kGroups * 8) s_seg[threadIdx.x / 8][threadIdx.x % 8] = 0;
+#endif
 
     const int tid = threadIdx.x;
     const int cta = blockIdx.x, gsz = (int)gridDim.x;
@@ -107,9 +254,9 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_loop_kernel(const __grid_c
         return;
     }
     if (tid < 2) {
-        const StepParams *P0 = &L.op[L.first & 1];
-        load_coef(sC[tid], P0->io[tid], &sS[tid], true);
-        if (!(P0->io[tid].mode != MD_NONE && sS[tid].active)) {
+        const StepParams &P0 = L.op[L.first & 1];
+        load_coef(sC[tid], P0.io[tid], &sS[tid], true);
+        if (!(P0.io[tid].mode != MD_NONE && sS[tid].active)) {
             sC[tid].mode = MD_NONE; sC[tid].rd0 = sC[tid].rd1 = sC[tid].wr0 = sC[tid].wr1 = sC[tid].rdself = 0;
         }
     }
@@ -117,57 +264,111 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_loop_kernel(const __grid_c
     bool ok = true;
 
     if (tid < kProducerThreads) {
+        reg_dec<kProducerRegs>();
         if ((tid & 31) != 0) return;
         const int role = tid >> 5;
-        const bool blocks = role < 2;
         const int par = role & 1;
-        int kb = 0;                                          // tiles of this CTA in the phases before ph
+        if (role < 2) {
+            // ---- warps 0 / 1: tile blocks of the CTA's even / odd tiles.  The blocks do not depend on the previous
+            //      phase: the first nspec tiles of a phase are requested before the phase is decided ----
+            int kb = 0;                                      // tiles of this CTA in the phases before ph
+            for (int ph = 0; ph < L.nphase && ok; ++ph) {
+                const StepParams &P = L.op[(L.first + ph) & 1];
+                const TileMeta *tiles = P.tiles;
+                const int nt = P.ntiles;
+                const int cnt = cta < nt ? (nt - cta + gsz - 1) / gsz : 0;
+                bool decided = false, stop = false;
+                // this warp's tiles are those with an even (odd) GLOBAL ring index k = kb + kl: with an even number of
+                // stages every ring stage is then always filled by the same block / window producer (see the throttle)
+#ifdef FPSB_LOOP_KLPAR
+                const int kl0 = par;
+#else
+                const int kl0 = (par + kb) & 1;
+#endif
+                int tile = cta + kl0 * gsz;
+                PTile T{}, T1{};
+                if (kl0 < cnt) T = load_ptile(tiles, tile);
+#ifdef FPSB_LOOP_TWOAHEAD
+                PTile T2{};
+                if (kl0 + 2 < cnt) T1 = load_ptile(tiles, tile + 2 * gsz);
+#endif
+                for (int kl = kl0; kl < cnt; kl += 2) {
+                    if (!decided && kl >= L.nspec) {
+                        loop_wait_thread(&ctl.open, ph + 1, &ctl);
+                        decided = true;
+                        if (ctl.stop_at <= ph) { stop = true; break; }
+                    }
+                    const int t1 = tile + 2 * gsz;
+#ifdef FPSB_LOOP_TWOAHEAD
+                    if (kl + 4 < cnt) T2 = load_ptile(tiles, t1 + 2 * gsz);
+#else
+                    if (kl + 2 < cnt) T1 = load_ptile(tiles, t1);
+#endif
+                    const int k = kb + kl, s = k % nstage;
+                    if (k >= nstage) ok = mbar_wait(&empty_bar[s], (uint32_t)((k / nstage - 1) & 1)) && ok;
+                    // bounded run-ahead (see gk_step_kernel): this warp's previous tile must have landed.  The wait only
+                    // OBSERVES a full barrier, which is safe only while the observer cannot fall a whole barrier phase
+                    // behind (the parity test would then wait for the wrong phase and never return): tile k - 2 sits in
+                    // a stage that only this warp's own later tiles reuse (nstage is even), so it cannot.
+                    if (k >= 2) ok = mbar_wait(&full_bar[(k - 2) % nstage], (uint32_t)(((k - 2) / nstage) & 1)) && ok;
+                    const uint32_t bytes = tile_block_bytes(T.elems, T.ns, T.ccnt);
+                    mbar_expect_tx(&full_bar[s], bytes);
+                    if (bytes) tma_bulk_g2s(s_dyn + (size_t)s * stage_bytes, P.tbuf + T.boff, bytes, &full_bar[s]);
+#ifdef FPSB_LOOP_TWOAHEAD
+                    T = T1; T1 = T2; tile = t1;
+#else
+                    T = T1; tile = t1;
+#endif
+                }
+                if (!ok || stop) break;
+                if (!decided) {
+                    loop_wait_thread(&ctl.open, ph + 1, &ctl);
+                    if (ctl.stop_at <= ph) break;
+                }
+                kb += cnt;
+            }
+            if (!ok) { ctl.abort = 1; atomicExch(L.done_flag + 2, 1); __threadfence_system(); __trap(); }
+            return;
+        }
+        // ---- warps 2 / 3: gather windows of the even / odd tiles ----
+        int kb = 0;
         for (int ph = 0; ph < L.nphase && ok; ++ph) {
-            const StepParams *P = &L.op[(L.first + ph) & 1];
-            const TileMeta *tiles = P->tiles;
-            const int nt = P->ntiles;
+            const StepParams &P = L.op[(L.first + ph) & 1];
+            const TileMeta *tiles = P.tiles;
+            const int nt = P.ntiles;
             const int cnt = cta < nt ? (nt - cta + gsz - 1) / gsz : 0;
             bool opened = false;
-            if (!blocks) {
-                // the gather windows hold what the previous phase wrote: wait for the grid
-                if (!loop_wait(L.early ? &ctl.pass : &ctl.open, L.early ? ph : ph + 1, &ctl)) { ok = false; break; }
-                fence_proxy_async();                         // generic-proxy writes of the grid -> this thread's TMA reads
-            }
-            int kl = par, tile = cta + par * gsz, t1 = tile + 2 * gsz;
-            TileMeta T{}, T1{};
-            if (tile < nt) T = load_tile(tiles, tile);
-            if (t1 < nt) T1 = load_tile(tiles, t1);
+            // the gather windows hold what the previous phase wrote: wait for the grid
+            loop_wait_thread(L.early ? &ctl.pass : &ctl.open, L.early ? ph : ph + 1, &ctl);
+            fence_proxy_async();                             // generic-proxy writes of the grid -> this thread's TMA reads
+#ifdef FPSB_LOOP_KLPAR
+            const int kl0 = par;
+#else
+            const int kl0 = (par + kb) & 1;
+#endif
+            int kl = kl0, tile = cta + kl0 * gsz;
+            PTile T{}, T1{};
+            if (tile < nt) T = load_ptile(tiles, tile);
             bool stop = false;
             for (; kl < cnt; kl += 2) {
                 if (!opened && kl >= L.nspec) {
-                    if (!loop_wait(&ctl.open, ph + 1, &ctl)) { ok = false; break; }
+                    loop_wait_thread(&ctl.open, ph + 1, &ctl);
                     opened = true;
                     if (ctl.stop_at <= ph) { stop = true; break; }
                 }
-                const int t2 = t1 + 2 * gsz;
-                TileMeta T2{};
-                if (t2 < nt) T2 = load_tile(tiles, t2);
+                const int t1 = tile + 2 * gsz;
+                if (t1 < nt) T1 = load_ptile(tiles, t1);
                 const int k = kb + kl, s = k % nstage;
                 if (k >= nstage) ok = mbar_wait(&empty_bar[s], (uint32_t)((k / nstage - 1) & 1)) && ok;
-                if (k >= P->inflight) {
-                    const int kq = k - P->inflight;
-                    ok = mbar_wait(&full_bar[kq % nstage], (uint32_t)((kq / nstage) & 1)) && ok;
-                }
-                unsigned char *st = s_dyn + (size_t)s * stage_bytes;
-                if (blocks) {
-                    const uint32_t bytes = tile_block_bytes(T.elems, T.ns, T.ccnt);
-                    mbar_expect_tx(&full_bar[s], bytes);
-                    if (bytes) tma_bulk_g2s(st, P->tbuf + T.boff, bytes, &full_bar[s]);
-                } else {
-                    const uint32_t wbytes = T.ccnt > 0 ? (uint32_t)T.ccnt * 16u : 0u;
-                    mbar_expect_tx(&full_bar[s], wbytes);
-                    if (wbytes) tma_bulk_g2s(st + blk_cap, P->gin2 + T.cmin, wbytes, &full_bar[s]);
-                }
-                T = T1; T1 = T2; tile = t1; t1 = t2;
+                if (k >= 2) ok = mbar_wait(&full_bar[(k - 2) % nstage], (uint32_t)(((k - 2) / nstage) & 1)) && ok;
+                const uint32_t wbytes = T.ccnt > 0 ? (uint32_t)T.ccnt * 16u : 0u;
+                mbar_expect_tx(&full_bar[s], wbytes);
+                if (wbytes) tma_bulk_g2s(s_dyn + (size_t)s * stage_bytes + blk_cap, P.gin2 + T.cmin, wbytes, &full_bar[s]);
+                T = T1; tile = t1;
             }
             if (!ok || stop) break;
             if (!opened) {
-                if (!loop_wait(&ctl.open, ph + 1, &ctl)) { ok = false; break; }
+                loop_wait_thread(&ctl.open, ph + 1, &ctl);
                 if (ctl.stop_at <= ph) break;
             }
             kb += cnt;
@@ -177,22 +378,23 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_loop_kernel(const __grid_c
     }
 
     // ------------------------------- consumers -------------------------------
+    reg_inc<kConsumerRegs>();
     const int ct = tid - kProducerThreads;
     const int g = ct / kGroupThreads, t = ct % kGroupThreads;
     const int lane = t & 31, wid = t >> 5;
-    const int cw = ct >> 5;                                  // consumer warp 0..11 ; warps 0 and 1 run the recurrences
+    const int cw = ct >> 5;                                  // consumer warp 0..11
     int kb = 0;
     for (int ph = 0; ph < L.nphase; ++ph) {
-        const StepParams *P = &L.op[(L.first + ph) & 1];
-        const TileMeta *tiles = P->tiles;
-        const int nt = P->ntiles;
+        const StepParams &P = L.op[(L.first + ph) & 1];
+        const TileMeta *tiles = P.tiles;
+        const int nt = P.ntiles;
         const int cnt = cta < nt ? (nt - cta + gsz - 1) / gsz : 0;
         bool have_coef = false;
         CoefR C0{}, C1{};
         bool act0 = false, act1 = false;
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        // global gathers / the epilogue read what the previous phase wrote
-        if (!loop_wait(L.early ? &ctl.pass : &ctl.open, L.early ? ph : ph + 1, &ctl)) return;
+        // global gathers read what the previous phase wrote
+        loop_wait(L.early ? &ctl.pass : &ctl.open, L.early ? ph : ph + 1, &ctl);
         if (!L.early) {
             if (ctl.stop_at <= ph) {
                 // drain the tiles the block producers requested before the phase was decided
@@ -208,148 +410,81 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_loop_kernel(const __grid_c
             act0 = C0.mode != MD_NONE; act1 = C1.mode != MD_NONE;
             have_coef = true;
         }
+        if (ct == 0) LT_STAMP(ph, 7);
         int kl = g, tile = cta + kl * gsz;
         CTile T{}, Tn{}, Tnn{};
         if (tile < nt) T = load_ctile(tiles, tile);
         if (tile + kGroups * gsz < nt) Tn = load_ctile(tiles, tile + kGroups * gsz);
+        LS_DECL;
         for (; kl < cnt; kl += kGroups) {
+            LS_RESET; LS_COUNT;
             const int k = kb + kl, s = k % nstage;
             const int ntile = tile + kGroups * gsz, nntile = tile + 2 * kGroups * gsz;
             if (nntile < nt) Tnn = load_ctile(tiles, nntile);
             if (!have_coef && kl >= L.nspec) {
                 // this tile is only requested once the phase is decided
-                if (!loop_wait(&ctl.open, ph + 1, &ctl)) return;
+                loop_wait(&ctl.open, ph + 1, &ctl);
                 if (ctl.stop_at <= ph) return;
                 C0 = to_regs(sC[0]); C1 = to_regs(sC[1]);
                 act0 = C0.mode != MD_NONE; act1 = C1.mode != MD_NONE;
                 have_coef = true;
             }
-            const int row = T.row0 + t;
-            const bool in_row = t < T.nrows();
-            int rflag = (P->rowflag != nullptr && in_row) ? (int)P->rowflag[row] : 0;
-            double2 old2 = make_double2(0.0, 0.0);
-            double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+            const int rowA = T.row0 + t, rowB = rowA + kGroupThreads;
+            const bool inA = t < T.nrows(), inB = t + kGroupThreads < T.nrows();
+            const int flagA = (P.rowflag != nullptr && inA) ? (int)P.rowflag[rowA] : 0;
+            const int flagB = (P.rowflag != nullptr && inB) ? (int)P.rowflag[rowB] : 0;
+            RowOps RA{};
             bool loaded = false;
-            if (have_coef && in_row) {
-                old2 = P->self2[row];
-                if (C0.rd0()) a00 = __ldcs(P->io[0].a0 + row);
-                if (C0.rd1()) a01 = __ldcs(P->io[0].a1 + row);
-                if (C1.rd0()) a10 = __ldcs(P->io[1].a0 + row);
-                if (C1.rd1()) a11 = __ldcs(P->io[1].a1 + row);
+            if (have_coef) {
+                if (inA) load_row_ops<true>(P, C0, C1, rowA, RA);
                 loaded = true;
-            }
-            if (have_coef && ntile < nt && t < Tn.nrows()) {
-                const int r2 = Tn.row0 + t;
-                if ((t & 7) == 0) prefetch_l2(P->self2 + r2);
-                if ((t & 15) == 0) {
-                    if (C0.rd0()) prefetch_l2(P->io[0].a0 + r2);
-                    if (C0.rd1()) prefetch_l2(P->io[0].a1 + r2);
-                    if (C1.rd0()) prefetch_l2(P->io[1].a0 + r2);
-                    if (C1.rd1()) prefetch_l2(P->io[1].a1 + r2);
+                if (ntile < nt) {
+                    if (t < Tn.nrows()) prefetch_row_ops<true>(P, C0, C1, Tn.row0 + t, t);
+                    if (t + kGroupThreads < Tn.nrows()) prefetch_row_ops<true>(P, C0, C1, Tn.row0 + kGroupThreads + t, t);
                 }
             }
             const unsigned char *st = s_dyn + (size_t)s * stage_bytes;
-            const double *s_val = reinterpret_cast<const double *>(st);
-            const bool windowed = T.ccnt > 0;
-            const int *s_col = reinterpret_cast<const int *>(st + (size_t)T.elems * 8);
-            const unsigned short *s_c16 = reinterpret_cast<const unsigned short *>(st + (size_t)T.elems * 8);
-            const unsigned char *s_map = st + (size_t)T.elems * (windowed ? 10 : 12);
-            const double2 *win2 = reinterpret_cast<const double2 *>(st + blk_cap);
-
+            LS_MARK(0);
             ok = mbar_wait(&full_bar[s], (uint32_t)((k / nstage) & 1)) && ok;
-            // ---------------- phase 1: row sums, a warp per slice ----------------
+            LS_MARK(1);
+            if (ct == 0 && kl == 0) LT_STAMP(ph, 0);
+            // ---------------- phase 1: row sums ----------------
             double2 *sum = s_sum[g][(kl / kGroups) & 1];
-            {
-                int off = 0, width = T.width(0);
-#pragma unroll
-                for (int i = 1; i < kTileSlices; ++i) if (i <= wid) { off += T.width(i - 1) * 32; width = T.width(i); }
-                const int npair = width >> 1;
-                double s0 = 0.0, s1 = 0.0, u0 = 0.0, u1 = 0.0;
-                int lrow = -1;
-                if (wid < T.ns()) {
-                    lrow = s_map[wid * 32 + lane];
-                    if (lrow == 255) lrow = -1;
-                    const double2 *sv = reinterpret_cast<const double2 *>(s_val + off) + lane;
-                    const bool tail = (width & 1) != 0;
-                    if (windowed) {
-                        const ushort2 *sc16 = reinterpret_cast<const ushort2 *>(s_c16 + off) + lane;
-#pragma unroll 5
-                        for (int p = 0; p < npair; ++p) {
-                            const double2 v = sv[p * 32];
-                            const ushort2 c = sc16[p * 32];
-                            const double2 x0 = win2[c.x], x1 = win2[c.y];
-                            s0 = fma(v.x, x0.x, s0); s1 = fma(v.x, x0.y, s1);
-                            u0 = fma(v.y, x1.x, u0); u1 = fma(v.y, x1.y, u1);
-                        }
-                        if (tail) {
-                            const double v = s_val[off + npair * 64 + lane];
-                            const double2 x = win2[s_c16[off + npair * 64 + lane]];
-                            s0 = fma(v, x.x, s0); s1 = fma(v, x.y, s1);
-                        }
-                    } else {
-                        // (L2 loads: the gathered pair changes from phase to phase inside this kernel)
-                        const double2 *gin2 = P->gin2;
-                        const int2 *sc = reinterpret_cast<const int2 *>(s_col + off) + lane;
-#pragma unroll 5
-                        for (int p = 0; p < npair; ++p) {
-                            const double2 v = sv[p * 32];
-                            const int2 c = sc[p * 32];
-                            const double2 x0 = __ldcg(gin2 + c.x), x1 = __ldcg(gin2 + c.y);
-                            s0 = fma(v.x, x0.x, s0); s1 = fma(v.x, x0.y, s1);
-                            u0 = fma(v.y, x1.x, u0); u1 = fma(v.y, x1.y, u1);
-                        }
-                        if (tail) {
-                            const double v = s_val[off + npair * 64 + lane];
-                            const double2 x = __ldcg(gin2 + s_col[off + npair * 64 + lane]);
-                            s0 = fma(v, x.x, s0); s1 = fma(v, x.y, s1);
-                        }
-                    }
-                }
-                if (lrow >= 0) sum[lrow] = make_double2(s0 + u0, s1 + u1);
-            }
+            tile_row_sums<true, true>(P, T, st, st + blk_cap, true, true, wid, lane, sum);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
+            LS_MARK(2);
             group_bar(g);
+            LS_MARK(3);
             if (!have_coef) {
                 // first tile of the phase: its row sums overlapped the recurrences
-                if (!loop_wait(&ctl.open, ph + 1, &ctl)) return;
+                loop_wait(&ctl.open, ph + 1, &ctl);
                 if (ctl.stop_at <= ph) return;
                 C0 = to_regs(sC[0]); C1 = to_regs(sC[1]);
                 act0 = C0.mode != MD_NONE; act1 = C1.mode != MD_NONE;
                 have_coef = true;
             }
-            if (!loaded && in_row) {
-                old2 = P->self2[row];
-                if (C0.rd0()) a00 = __ldcs(P->io[0].a0 + row);
-                if (C0.rd1()) a01 = __ldcs(P->io[0].a1 + row);
-                if (C1.rd0()) a10 = __ldcs(P->io[1].a0 + row);
-                if (C1.rd1()) a11 = __ldcs(P->io[1].a1 + row);
-            }
-            // ---------------- phase 2: row epilogue in natural row order, a thread per row ----------------
-            if (rflag == 2 && P->raw_out == nullptr) rflag = 0;
-            if (rflag == 2) P->raw_out[row] = sum[t];
-            if (in_row && rflag == 0) {
-                const double2 sm = sum[t];
-                double n0 = old2.x, n1 = old2.y;
-                if (act0) n0 = row_epilogue(C0, sm.x, old2.x, a00, a01, acc[0], acc[1]);
-                if (act1) n1 = row_epilogue(C1, sm.y, old2.y, a10, a11, acc[2], acc[3]);
-                P->self2[row] = make_double2(n0, n1);
-                if (C0.wr0()) __stcs(P->io[0].a0 + row, a00);
-                if (C0.wr1()) __stcs(P->io[0].a1 + row, a01);
-                if (C1.wr0()) __stcs(P->io[1].a0 + row, a10);
-                if (C1.wr1()) __stcs(P->io[1].a1 + row, a11);
-            }
+            if (!loaded && inA) load_row_ops<true>(P, C0, C1, rowA, RA);
+            LS_MARK(4);
+            // ---------------- phase 2: row epilogue in natural row order ----------------
+            RowOps RB{};
+            if (inB) load_row_ops<true>(P, C0, C1, rowB, RB);
+            if (inA) finish_row<true>(P, C0, C1, act0, act1, rowA, flagA, sum[t], RA, acc);
+            if (inB) finish_row<true>(P, C0, C1, act0, act1, rowB, flagB, sum[t + kGroupThreads], RB, acc);
             T = Tn; Tn = Tnn;
             tile = ntile;
+            LS_MARK(5);
         }
         if (!have_coef) {
             // no tile of this group in the phase: still learn whether the phase runs
-            if (!loop_wait(&ctl.open, ph + 1, &ctl)) return;
+            loop_wait(&ctl.open, ph + 1, &ctl);
             if (ctl.stop_at <= ph) return;
         }
         kb += cnt;
+        if (t == 0) LT_STAMP(ph, g == 0 ? 1 : (g == 1 ? 5 : 6));
+        LS_FLUSH;
 
-        // ---- end of the phase: CTA partial -> grid barrier -> totals -> recurrences ----
+        // ---- end of the phase: the CTA's record (arrival at the grid barrier + its four norm partials) ----
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const double x = warp_sum(acc[q]);
@@ -357,75 +492,19 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_loop_kernel(const __grid_c
         }
         fence_proxy_async();                                  // this phase's generic writes vs the next phase's TMA reads
         consumers_bar();
-        if (cw < 2) {
-            if (cw == 0) {
-                double v[4];
+        if (cw == 0) {
+            double v[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) v[q] = warp_sum(lane < kGroups * kGroupWarps ? s_red[q * 32 + lane] : 0.0);
-                if (lane == 0) {
-                    double *pp = L.parts + ((size_t)(ph & 1) * gsz + cta) * 4;
-                    pp[0] = v[0]; pp[1] = v[1]; pp[2] = v[2]; pp[3] = v[3];
-                    if (!ok) atomicExch(L.done_flag + 2, 1);
-                    red_release_gpu(L.gbar, 1ull);
-                }
-            }
-            bool fine = true;
+            for (int q = 0; q < 4; ++q) v[q] = warp_sum(lane < kGroups * kGroupWarps ? s_red[q * 32 + lane] : 0.0);
             if (lane == 0) {
-                const unsigned long long want = (unsigned long long)(ph + 1) * (unsigned long long)gsz;
-                const unsigned long long t0 = global_ns();
-                unsigned it = 0;
-                while (ld_acquire_gpu(L.gbar) < want) {
-                    if ((++it & 255) == 0 && global_ns() - t0 > 2000000000ull) { fine = false; break; }   // 2 s: a CTA died
-                }
-            }
-            fine = __shfl_sync(0xffffffffu, fine ? 1 : 0, 0) != 0;
-            if (!fine) {
-                if (lane == 0) { ctl.abort = 1; atomicExch(L.done_flag + 2, 2); __threadfence_system(); }
-                __trap();
-            }
-            if (cw == 0 && lane == 0) st_release_cta(&ctl.pass, ph + 1);
-            // totals: every CTA adds the per-CTA partials in the same order
-            double tot[4] = {0.0, 0.0, 0.0, 0.0};
-            {
-                const double *base = L.parts + (size_t)(ph & 1) * gsz * 4;
-                for (int i = lane; i < gsz; i += 32) {
-                    const double2 a = __ldcg(reinterpret_cast<const double2 *>(base + (size_t)i * 4));
-                    const double2 b = __ldcg(reinterpret_cast<const double2 *>(base + (size_t)i * 4 + 2));
-                    tot[0] += a.x; tot[1] += a.y; tot[2] += b.x; tot[3] += b.y;
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) tot[q] = warp_sum(tot[q]);
-            }
-            const bool last = ph + 1 >= L.nphase;
-            if (lane == 0) {
-                const int mode = P->io[cw].mode;
-                const double t0 = cw ? tot[2] : tot[0], t1 = cw ? tot[3] : tot[1];
-                if (mode != MD_NONE && sS[cw].active) finish_step(sS[cw], mode, t0, t1);
-                const StepParams *Pn = &L.op[(L.first + ph + 1) & 1];
-                load_coef(sC[cw], Pn->io[cw], &sS[cw], true);
-                if (!(Pn->io[cw].mode != MD_NONE && sS[cw].active)) {
-                    sC[cw].mode = MD_NONE; sC[cw].rd0 = sC[cw].rd1 = sC[cw].wr0 = sC[cw].wr1 = sC[cw].rdself = 0;
-                }
-                if (cw == 1) st_release_cta(&ctl.open1, ph + 2);
-                else {
-                    loop_wait(&ctl.open1, ph + 2, &ctl);
-                    if (!sS[0].active && !sS[1].active) ctl.stop_at = ph + 1;
-                    st_release_cta(&ctl.open, ph + 2);
-                }
-            }
-            if (cw == 0 && cta == 0) {
-                __syncwarp();
-                const bool fin = last || *reinterpret_cast<volatile int *>(&ctl.stop_at) <= ph + 1;
-                if (fin) {
-                    const double *src = reinterpret_cast<const double *>(sS);
-                    double *dst = reinterpret_cast<double *>(L.st);
-                    for (int i = lane; i < (int)(2 * sizeof(SlotState) / sizeof(double)); i += 32) dst[i] = src[i];
-                    if (lane == 0) {
-                        if (!sS[0].active && !sS[1].active) L.done_flag[0] = 1;
-                        L.done_flag[1] += ph + 1;
-                    }
-                }
+                LT_STAMP(ph, 2);
+                if (!ok) atomicExch(L.done_flag + 2, 1);
+                double *pp = L.parts + ((size_t)(ph & 1) * gsz + cta) * 4;
+                pp[0] = v[0]; pp[1] = v[1]; pp[2] = v[2]; pp[3] = v[3];
+                red_release_gpu(L.gbar, 1ull);               // release: everything this CTA wrote in the phase + its record
             }
         }
+        // consumer warps 0 / 1: the boundary before phase ph + 1 (the other warps go on and wait for `pass` / `open`)
+        if (cw < 2) loop_boundary(L, ph + 1, cw, lane, cta, gsz, sS, sC, ctl, s_rsum);
     }
 }

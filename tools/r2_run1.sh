@@ -1,0 +1,22 @@
+#!/usr/bin/env bash
+# round-2 GPU call 1: parity tests with the persistent loop kernel, then bench variants
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.max.sm --format=csv,noheader > gpurun_out/r2_1_gpu.txt 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2_1_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/r2_1_tests.log
+tail -3 gpurun_out/r2_1_tests.log
+B="--steps 10 --warmup 3 --no-ldlt --no-cpu-baseline"
+for v in "0 3" "1 3" "2 3" "2 0" "2 2"; do
+  set -- $v
+  FPSB_LOOP=$1 FPSB_LOOP_NSPEC=$2 timeout 300 python bench.py $B > gpurun_out/r2_1_bench_loop$1_spec$2.json 2> gpurun_out/r2_1_bench_loop$1_spec$2.err
+  echo "loop=$1 nspec=$2 rc=$?"
+  python - <<PY
+import json
+try:
+    d=json.load(open("gpurun_out/r2_1_bench_loop$1_spec$2.json"))
+    r=d["roofline"]
+    print("  value",round(d["value"],1),"e2e",round(d["e2e"]["value"],1),"avg_us",round(r["avg_launch_us"],2),"frac",round(r["frac"],3),"iters",r["iters"],"launched",r["launched_incl_post_convergence_noops"],"gpu_launches",d["gpu_launches"])
+except Exception as e:
+    print("  parse failed",e)
+PY
+done

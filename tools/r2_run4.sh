@@ -1,0 +1,20 @@
+#!/usr/bin/env bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+B="--steps 10 --warmup 3 --no-ldlt --no-cpu-baseline"
+for v in "2 3" "2 2"; do
+  set -- $v
+  FPSB_LOOP=$1 FPSB_LOOP_NSPEC=$2 timeout 300 python bench.py $B > gpurun_out/r2_4_bench_loop$1_$2.json 2> gpurun_out/r2_4_bench_loop$1_$2.err
+  echo "loop=$1 nspec=$2 rc=$?"
+  python - <<PY
+import json
+try:
+    d=json.load(open("gpurun_out/r2_4_bench_loop$1_$2.json"))
+    r=d["roofline"]
+    print("  value",round(d["value"],1),"e2e",round(d["e2e"]["value"],1),"avg_us",round(r["avg_launch_us"],2),"frac",round(r["frac"],3),"iters",r["iters"],"extra",{k:(round(v["us"],1) if "us" in v else round(v["ms"],2)) for k,v in d["extra"].items() if isinstance(v,dict)})
+except Exception as e:
+    print("  parse failed",e)
+PY
+done
+timeout 200 python tools/kinds_bench.py
+FPSB200_LIB=$PWD/variants/libfpsb200_lt.so timeout 300 python tools/loop_timers.py
