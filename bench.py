@@ -11,7 +11,10 @@ LSQR and CRAIG advanced in lock-step by the fused two-column SpMM kernels.
 value : whole-job solves/s with rhs / Jacobian values already resident in HBM (FPSB_DEVICE)
 e2e   : the same step through the C ABI with HOST buffers (FPSB_HOST: jac values + both rhs
         copied H2D and the four result vectors copied D2H inside the timed region)
-N > 1 : independent instances sharded across GPUs, no data-path collective ("weak").
+N > 1 : `value` = independent instances sharded across GPUs, no data-path collective ("weak"); the line also
+        carries `partitioned`: the row-partitioned Krylov path (halo exchange + all-reduced inner products over
+        NVLink peer memory) STRONG-scaled over the N GPUs on BASELINE config C3 and on the headline matrix, with
+        the single-GPU time of the same operator and the parity of the two results measured in the same run.
 The reference (Julia) cannot run here: the CPU arm is the oracle's C port of the same algorithms
 (kind "port", 1 thread — the reference path is single-threaded).
 """
@@ -174,6 +177,128 @@ def run_reference(args, cfg):
     print(json.dumps(line))
 
 
+def partitioned_operators(args):
+    """The two operators of the strong-scaled row-partitioned record: BASELINE config C3
+    (Poisson-constrained control, state / control interleaved -> banded Jacobian) and the headline matrix."""
+    from fpsb200 import models
+
+    def c3():
+        N = args.part_grid
+        A = models.poisson_control(N).A.tocsr()
+        m, n = A.shape
+        perm = np.empty(n, dtype=np.int64)
+        perm[:m] = 2 * np.arange(m)
+        perm[m:] = 2 * np.arange(m) + 1
+        coo = A.tocoo()
+        return (f"C3 poisson-control grid {N}x{N}: n={n} m={m} nnz={A.nnz}", n, m, coo.row.astype(np.int64), perm[coo.col],
+                coo.data.astype(np.float64), 1e-2, args.part_iters)
+
+    def headline():
+        n, m, k, w = args.n, args.m, args.nnz_per_row, args.window
+        A, jr, jc, vals, _, _ = make_workload(n, m, k, w, args.seed)
+        return (f"headline window-random Jacobian n={n} m={m} nnz={m * k}", n, m, jr, jc, vals, args.delta, 0)
+    return [c3, headline]
+
+
+def run_partitioned(args, dist, rank, world, local_rank, make):
+    """One strong-scaled solve_two_mixed of the row-partitioned Krylov path on `world` GPUs (peer-memory halo
+    exchange + all-reduced inner products), the same operator on ONE GPU (rank 0, the plain single-GPU handle),
+    and the parity of the two results, all inside this torchrun.  itmax > 0: fixed iteration count (timing of
+    an operator the reference tolerances do not converge on in a bench-sized run); 0: reference tolerances."""
+    import torch
+    import fpsb200
+    from fpsb200 import _lib
+    from fpsb200.partition import RowPartition, DistHandle
+    name, n, m, jr, jc, vals, delta, itmax = make()
+    dev = torch.device("cuda", local_rank)
+    lib = _lib.lib()
+    o = _lib.IterOpts()
+    _lib.check(lib.fpsb_iter_default_opts(ctypes.c_int64(n), ctypes.c_int64(m), ctypes.byref(o)), "fpsb_iter_default_opts")
+    if itmax > 0:
+        o.ls_itmax = itmax
+        o.ln_itmax = itmax
+    rng = np.random.default_rng(args.seed)
+    g1, g2 = rng.standard_normal(n), rng.standard_normal(m)
+    part = RowPartition(n, m, jr, jc, world)
+    D = DistHandle(part, rank, device=local_rank, dist=dist, opts=o, peer=True)
+    D.set_jac_values(vals)
+    L = D.loc
+    r1, r2 = g1[L.col0:L.col0 + L.n_own], g2[L.row0:L.row0 + L.m_loc]
+    D.solve_two_mixed(delta, r1, r2)
+    ts = []
+    for _ in range(3):
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        out = D.solve_two_mixed(delta, r1, r2)
+        ts.append(D.H.iter_last_profile()[0])
+    t = torch.tensor([min(ts)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    loop_ms = float(t.item())
+    iters = [out[4][0]["niter"], out[4][1]["niter"]]
+    # per-launch shares (one extra solve with an event after every launch; max over ranks)
+    lib.fpsb_dist_profile(1)
+    torch.cuda.synchronize(); dist.barrier()
+    D.solve_two_mixed(delta, r1, r2)
+    lib.fpsb_dist_profile(0)
+    us4 = (ctypes.c_double * 4)(); c4 = (ctypes.c_int64 * 4)()
+    lib.fpsb_dist_last_profile(us4, c4)
+    t4 = torch.tensor(list(us4), dtype=torch.float64, device=dev)
+    dist.all_reduce(t4, op=dist.ReduceOp.MAX)
+    shares = dict(zip(["step_n_us", "xchg_after_n_us", "step_m_us", "xchg_after_m_us"], [float(x) for x in t4.tolist()]))
+    transport = "peer-memory (CUDA IPC mailboxes over NVLink)" if D.peer else "nccl"
+    halo = int(L.n_ext - L.n_own)
+    # ---- the same operator on one GPU (rank 0), then its solution to everybody for the parity check
+    full = [torch.empty(k, dtype=torch.float64, device=dev) for k in (n, m, n, m)]
+    single = torch.zeros(3, dtype=torch.float64, device=dev)
+    if rank == 0:
+        H1 = fpsb200.B200Handle(n, m, jr, jc, device=local_rank)
+        H1.iter_setup(o)
+        H1.set_jac_values(vals)
+        d1, d2 = torch.tensor(g1, device=dev), torch.tensor(g2, device=dev)
+        o1 = H1.iter_solve_two_mixed(delta, d1, d2)
+        t1 = []
+        for _ in range(3):
+            torch.cuda.synchronize()
+            o1 = H1.iter_solve_two_mixed(delta, d1, d2)
+            t1.append(H1.iter_last_profile()[0])
+        for k in range(4):
+            full[k].copy_(o1[k])
+        single[0], single[1], single[2] = min(t1), o1[4][0]["niter"], o1[4][1]["niter"]
+        H1.synchronize()
+        del H1
+    torch.cuda.synchronize()
+    dist.broadcast(single, src=0)
+    err = torch.zeros(8, dtype=torch.float64, device=dev)
+    sl = [(L.col0, L.n_own), (L.row0, L.m_loc), (L.col0, L.n_own), (L.row0, L.m_loc)]
+    for k in range(4):
+        dist.broadcast(full[k], src=0)
+        ref = full[k][sl[k][0]:sl[k][0] + sl[k][1]]
+        mine = torch.tensor(out[k], device=dev)
+        err[2 * k] = torch.sum((mine - ref) ** 2)
+        err[2 * k + 1] = torch.sum(ref ** 2)
+    dist.all_reduce(err, op=dist.ReduceOp.SUM)
+    e = err.tolist()
+    rel = [float(np.sqrt(e[2 * k] / e[2 * k + 1])) if e[2 * k + 1] > 0 else float(np.sqrt(e[2 * k])) for k in range(4)]
+    it1 = [int(single[1].item()), int(single[2].item())]
+    nit, nit1 = max(iters), max(it1)
+    del D
+    torch.cuda.synchronize(); dist.barrier()
+    us, us1 = 1e3 * loop_ms / max(nit, 1), 1e3 * float(single[0].item()) / max(nit1, 1)
+    xs = shares["xchg_after_n_us"] + shares["xchg_after_m_us"]
+    return {
+        "workload": name, "path": "row-partitioned solve_two_mixed (LSQR(A') + CRAIG(A) in lock step), strong scaling",
+        "n_gpus": world, "transport": transport, "halo_entries_rank0": halo,
+        "stopping": f"fixed {itmax} iterations" if itmax > 0 else "reference tolerances sqrt(eps)",
+        "iterations": iters, "krylov_loop_ms": loop_ms, "us_per_iteration": us,
+        "single_gpu": {"iterations": it1, "krylov_loop_ms": float(single[0].item()), "us_per_iteration": us1,
+                       "what": "the same operator on rank 0's GPU through the plain (unpartitioned) handle"},
+        "speedup_vs_single_gpu": us1 / us if us > 0 else None,
+        "per_launch_us_max_over_ranks": shares,
+        "exchange_share": xs / max(xs + shares["step_n_us"] + shares["step_m_us"], 1e-30),
+        "parity": {"rel_err_p1_q1_p2_q2_vs_single_gpu": rel, "max_rel_err": max(rel), "tol": 1e-6,
+                   "iterations_equal": iters == it1, "ok": bool(max(rel) <= 1e-6 and iters == it1)},
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -190,6 +315,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ldlt", action="store_true", help="skip the LDLt-path extra measurements")
     ap.add_argument("--ldlt-amd", action="store_true", help="also time the LDLt path with the AMD ordering")
+    ap.add_argument("--no-partitioned", action="store_true", help="N>1: skip the strong-scaled row-partitioned record")
+    ap.add_argument("--part-grid", type=int, default=2048, help="grid of the C3 operator of the partitioned record")
+    ap.add_argument("--part-iters", type=int, default=100, help="fixed Krylov iterations of the C3 partitioned run")
     args = ap.parse_args()
 
     n, m, k, w = args.n, args.m, args.nnz_per_row, args.window
@@ -287,6 +415,16 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
 
+    # ---- N > 1: the path that needs collectives (row-partitioned Krylov, strong scaling), next to the replicas
+    partitioned = None
+    if dist is not None and not args.no_partitioned:
+        partitioned = []
+        for make in partitioned_operators(args):
+            try:
+                partitioned.append(run_partitioned(args, dist, rank, world, local_rank, make))
+            except Exception as e:       # never take the headline line down
+                partitioned.append({"error": repr(e)})
+                break
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -448,6 +586,8 @@ def main():
         "solver_stats": {"lsqr": st[0], "craig": st[1]},
         "extra": extra,
     }
+    if partitioned is not None:
+        line["partitioned"] = partitioned
     print(json.dumps(line))
 
 

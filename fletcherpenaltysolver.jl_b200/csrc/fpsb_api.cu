@@ -432,6 +432,14 @@ int fpsb_dist_peer_active(fpsb_handle hh) {
     Handle *h = reinterpret_cast<Handle *>(hh);
     return (h && dist_peer_active(h)) ? 1 : 0;
 }
+int fpsb_dist_profile(int on) { dist_profile(on != 0); return FPSB_OK; }
+int fpsb_dist_last_profile(double mean_us[4], int64_t count[4]) {
+    REQUIRE(mean_us && count, FPSB_EINVAL, "fpsb_dist_last_profile: NULL argument");
+    long long c[4];
+    dist_last_profile(mean_us, c);
+    for (int i = 0; i < 4; ++i) count[i] = c[i];
+    return FPSB_OK;
+}
 static int dist_spmv(fpsb_handle hh, bool transpose, const double *x, double *y, int loc) {
     Handle *h = reinterpret_cast<Handle *>(hh);
     REQUIRE(h && x && y, FPSB_EINVAL, "NULL argument");

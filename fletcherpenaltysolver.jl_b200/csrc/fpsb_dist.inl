@@ -664,7 +664,10 @@ struct DistProf {
     std::vector<cudaEvent_t> ev;
     std::vector<int> tag;
     size_t used = 0;
-    DistProf() { const char *e = getenv("FPSB_DIST_PROF"); on = e && *e && *e != '0'; }
+    double last_us[4] = {0, 0, 0, 0};        // step_n, xchg_after_n, step_m, xchg_after_m of the last profiled solve
+    long long last_cnt[4] = {0, 0, 0, 0};
+    bool verbose = false;
+    DistProf() { const char *e = getenv("FPSB_DIST_PROF"); on = verbose = e && *e && *e != '0'; }
     void mark(int t, cudaStream_t s) {
         if (!on || used >= 8192) return;
         if (used == ev.size()) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); tag.push_back(0); }
@@ -680,13 +683,20 @@ struct DistProf {
             cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
             sum[tag[i]] += ms; cnt[tag[i]]++;
         }
-        fprintf(stderr, "[fpsb dist prof] rank %d:", rank);
-        for (int t = 1; t < 6; ++t) if (cnt[t]) fprintf(stderr, "  %s %.1f us x %d", names[t], 1e3 * sum[t] / cnt[t], cnt[t]);
-        fprintf(stderr, "\n");
+        for (int t = 1; t < 5; ++t) { last_us[t - 1] = cnt[t] ? 1e3 * sum[t] / cnt[t] : 0.0; last_cnt[t - 1] = cnt[t]; }
+        if (verbose) {
+            fprintf(stderr, "[fpsb dist prof] rank %d:", rank);
+            for (int t = 1; t < 6; ++t) if (cnt[t]) fprintf(stderr, "  %s %.1f us x %d", names[t], 1e3 * sum[t] / cnt[t], cnt[t]);
+            fprintf(stderr, "\n");
+        }
         used = 0;
     }
 };
 static DistProf g_dist_prof;
+void dist_profile(bool on) { g_dist_prof.on = on || g_dist_prof.verbose; }
+void dist_last_profile(double *us4, long long *cnt4) {
+    for (int i = 0; i < 4; ++i) { us4[i] = g_dist_prof.last_us[i]; cnt4[i] = g_dist_prof.last_cnt[i]; }
+}
 
 struct DistEngine {
     Handle *h;

@@ -165,6 +165,8 @@ void dist_peer_export(Handle *h, void *blob_out);
 void dist_peer_attach(Handle *h, const void *blobs);
 bool dist_peer_active(Handle *h);
 int64_t dist_n_own(Handle *h);
+void dist_profile(bool on);
+void dist_last_profile(double *us4, long long *cnt4);
 void dist_jprod(Handle *h, const double *x_own, double *y_loc);
 void dist_jtprod(Handle *h, const double *u_loc, double *y_own);
 void dist_solve_two_mixed(Handle *h, double delta, const double *rhs1, const double *rhs2, double *p1, double *q1,

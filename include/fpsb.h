@@ -262,6 +262,12 @@ int64_t fpsb_dist_peer_blob_bytes(void);
 int fpsb_dist_peer_export(fpsb_handle h, void *blob_out);
 int fpsb_dist_peer_attach(fpsb_handle h, const void *blobs);
 int fpsb_dist_peer_active(fpsb_handle h);
+/* Measurement only: fpsb_dist_profile(1) records a CUDA event after every launch of the row-partitioned
+ * Krylov loop; fpsb_dist_last_profile returns, for the last profiled solve of this process, the mean
+ * microseconds and the number of launches of {n-space step, exchange after it, m-space step, exchange
+ * after it} (the exchange share of an iteration that bench.py reports). */
+int fpsb_dist_profile(int on);
+int fpsb_dist_last_profile(double mean_us[4], int64_t count[4]);
 int fpsb_dist_jprod(fpsb_handle h, const double *x_own, double *y_loc, int loc);
 int fpsb_dist_jtprod(fpsb_handle h, const double *u_loc, double *y_own, int loc);
 int fpsb_dist_solve_two_mixed(fpsb_handle h, double delta, int64_t nvar_global, int64_t ncon_global,
