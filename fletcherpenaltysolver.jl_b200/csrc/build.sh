@@ -9,7 +9,7 @@ COMMON="-O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -W
 mkdir -p "$HERE/build"
 # Krylov kernels: no FMA contraction so the scalar recurrences round like the CPU reference
 "$NVCC" $COMMON -fmad=false ${FPSB_DEFS:-} ${PTXAS_V:+-Xptxas -v} -c "$HERE/fpsb_krylov.cu" -o "$HERE/build/fpsb_krylov.o"
-"$NVCC" $COMMON ${PTXAS_V:+-Xptxas -v} -c "$HERE/fpsb_ldlt.cu" -o "$HERE/build/fpsb_ldlt.o"
+"$NVCC" $COMMON ${FPSB_DEFS:-} ${PTXAS_V:+-Xptxas -v} -c "$HERE/fpsb_ldlt.cu" -o "$HERE/build/fpsb_ldlt.o"
 "$NVCC" $COMMON -c "$HERE/fpsb_api.cu" -o "$HERE/build/fpsb_api.o"
 EXTRA=""
 for f in "$HERE"/fpsb_symbolic.cpp "$HERE"/fpsb_batch.cu "$HERE"/fpsb_fpnlp.cu; do

@@ -80,8 +80,10 @@ struct Staged {
         out_off += count;
         return d;
     }
-    void finish() {
-        if (loc == FPSB_DEVICE) { caller_order_out(h); FPSB_CUDA(cudaStreamSynchronize(h->stream)); return; }
+    // device_sync = false: FPSB_DEVICE calls that return nothing to the host stay asynchronous (stream-ordered
+    // after the caller's stream on entry and before it on exit, like a library kernel launch)
+    void finish(bool device_sync = true) {
+        if (loc == FPSB_DEVICE) { caller_order_out(h); if (device_sync) FPSB_CUDA(cudaStreamSynchronize(h->stream)); return; }
         double *hp = h->pin + in_off;   // staged results go after the inputs in the pinned area
         std::vector<char> direct(outs.size(), 0);
         for (size_t i = 0; i < outs.size(); ++i) {
@@ -284,7 +286,7 @@ static int do_spmv(fpsb_handle hh, bool transpose, const double *x, double *y, i
         if ((transpose ? h->At.grid : h->A.grid) == 0) FPSB_CUDA(cudaMemsetAsync(dy, 0, nout * sizeof(double), h->stream));
         spmv_plain(h, transpose, dx, dy, ncols);
     }
-    S.finish();
+    S.finish(false);
     return FPSB_OK;
     FPSB_CATCH
 }

@@ -1679,6 +1679,9 @@ static void upload_sell(Handle *h, CsrDev &M, int nrows, int ncols, const std::v
             if (cmax >= 0) {
                 c0 = cmin & ~1;               // 16-byte aligned start for vectors of doubles
                 cnt = cmax - c0 + 1;
+                // even length: plain (8-byte) vectors are then bulk-copied in whole 16-byte units; an odd window would
+                // send the tile down the group-staged path of the one-column products.  Never past the vector's end.
+                if ((cnt & 1) && c0 + cnt + 1 <= ncols) ++cnt;
                 if (cnt > kWinCapMax) cnt = 0;
             }
             if ((size_t)tile_block_bytes(elems, (int)widths.size(), cnt) + (size_t)cnt * 16 <= (size_t)kStageBytesMax) break;
@@ -1998,6 +2001,8 @@ void iter_free(Handle *h) {
     if (W->pev[1]) cudaEventDestroy(W->pev[1]);
     delete W;
     h->iter = nullptr;
+    // the gathered vectors of this handle were marked persisting in L2 (iter_setup): give the lines back
+    if (cudaCtxResetPersistingL2Cache() != cudaSuccess) cudaGetLastError();
 }
 
 // ---- slot configuration (host fills a SlotState, uploaded before the solve) ---------------------

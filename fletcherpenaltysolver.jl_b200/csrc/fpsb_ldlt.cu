@@ -28,6 +28,15 @@ constexpr int kLdltBlock = 256;
 constexpr int kWarpsPerBlock = kLdltBlock / 32;
 constexpr int kSmallW = 8;              // warp-level supernodes: w <= kSmallW and w*(w+nr) <= 512
 constexpr int kShDoubles = (kMaxW + 1) * kMaxW + 4 * kMaxW;
+// CTA-level supernodes (fpsb_ldlt.cu "block" routines): shared-memory staging of the fronts
+constexpr int kBS = kMaxW + 1;                         // row stride of the diagonal block in shared memory
+constexpr int kUpdRows = 64;                            // rows of a descendant panel staged per pass of the Schur update
+constexpr int kTrsmRows = 2 * kUpdRows;                 // rows of L21 staged per pass (reuses the two update buffers)
+constexpr int kFacDoubles = kBS * kMaxW + 2 * kMaxW + 2 * kUpdRows * kMaxW;      // B | dd | rk | S | C
+constexpr int kSolveRows = 1024;                        // rows of a panel whose x[R[r]] are staged per pass of the backward solve
+constexpr int kSolDoubles = kMaxW * kMaxW + 2 * kMaxW + 2 * kSolveRows + 2 * kWarpsPerBlock * kMaxW;   // L11 | ys | xr | per-warp partials
+static_assert(kSmallW * (kSmallW + 1) + 4 * kSmallW <= kFacDoubles / kWarpsPerBlock, "warp-level supernodes share the block's buffer");
+static_assert(kSmallW * (kSmallW + 1) + 4 * kSmallW <= kSolDoubles / kWarpsPerBlock, "warp-level supernodes share the block's buffer");
 
 struct PlanDev {
     int N, nsuper, ntasks;
@@ -59,7 +68,14 @@ struct PlanDev {
     int n_d;
     double tol, r1, r2;
     int dynamic_reg;
+    unsigned long long *tstamp;   // debug builds (-DFPSB_LDLT_TIMERS): [3][nsuper] completion times (globaltimer ns)
 };
+#ifdef FPSB_LDLT_TIMERS
+#define LDLT_STAMP(P, phase, t) do { unsigned long long now_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_)); \
+        (P).tstamp[(size_t)(phase) * (P).nsuper + (t)] = now_; } while (0)
+#else
+#define LDLT_STAMP(P, phase, t) do { } while (0)
+#endif
 
 struct LdltPlan {
     Symbolic S;
@@ -71,6 +87,7 @@ struct LdltPlan {
     DevBuf<double> panels, D;
     DevBuf<double2> Y;
     DevBuf<int> done_f, done_s, done_b, ticket, fail;
+    DevBuf<unsigned long long> tstamp;
     int ntasks = 0;
     int epoch = 0;
     int64_t naslot = 0;
@@ -232,7 +249,7 @@ __device__ void factor_supernode(const PlanDev &P, int t, double *sh, int epoch,
     }
     __threadfence();
     gsync<WARP>();
-    if (tid == 0) st_release(&P.done_f[t], epoch);
+    if (tid == 0) { st_release(&P.done_f[t], epoch); LDLT_STAMP(P, 0, t); }
 }
 
 template <bool WARP>
@@ -279,7 +296,7 @@ __device__ void fwd_supernode(const PlanDev &P, int t, double *sh, int epoch, in
     for (int k = tid; k < w; k += nt) P.Y[f + k] = ys[k];
     __threadfence();
     gsync<WARP>();
-    if (tid == 0) st_release(&P.done_s[t], epoch);
+    if (tid == 0) { st_release(&P.done_s[t], epoch); LDLT_STAMP(P, 1, t); }
 }
 
 template <bool WARP>
@@ -323,7 +340,355 @@ __device__ void bwd_supernode(const PlanDev &P, int t, double *sh, int epoch, in
     for (int k = tid; k < w; k += nt) P.Y[f + k] = xs[k];
     __threadfence();
     gsync<WARP>();
-    if (tid == 0) st_release(&P.done_b[t], epoch);
+    if (tid == 0) { st_release(&P.done_b[t], epoch); LDLT_STAMP(P, 2, t); }
+}
+
+
+// ================================================================================================
+// CTA-level supernodes with the fronts staged in shared memory
+// ================================================================================================
+__device__ __forceinline__ void prefetch_l2_range(const double *p, size_t count, int tid, int nt) {
+    const char *c = reinterpret_cast<const char *>(p);
+    const size_t bytes = count * sizeof(double);
+    for (size_t o = (size_t)tid * 128; o < bytes; o += (size_t)nt * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(c + o));
+}
+
+// FP64 tensor-core tile (DMMA, m8n8k4): D(8x8) += A(8x4, row) * B(4x8, col); lane l holds A[l/4][l%4], B[l%4][l/4],
+// C[l/4][2*(l%4) .. +1]
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// Schur update of the target panel by one descendant d: panel(rel[i], rel[j]) -= sum_k L_d(a+i, k) D_d(k) L_d(a+j, k)
+// for 0 <= j < b - a, j <= i < nr_d - a.  The descendant's rows are staged k-major in shared memory (S: 64 rows per
+// pass, C: the b - a "column rows" scaled by D), each thread owns a 4 x 4 register tile (rows ti + 16 ii, columns
+// 4 tj + jj), or, with DMMA, each warp owns 8 x 64 strips of 8 x 8 tensor-core tiles.
+template <bool DMMA>
+__device__ __forceinline__ void schur_update_block(const PlanDev &P, int64_t q, double *panel, int ld, double *S, double *Cc,
+                                                   int tid) {
+    const int d = P.usrc[q];
+    const int fd = P.sfirst[d];
+    const int wd = P.sfirst[d + 1] - fd;
+    const int nrd = (int)(P.rptr[d + 1] - P.rptr[d]);
+    const int ldd = wd + nrd;
+    const int a = P.ua[q], b = P.ub[q];
+    const double *pd = P.panels + P.poff[d] + wd + a;     // row a of the rows below d's block
+    const double *Dd = P.D + fd;
+    const int *relq = P.rel + P.urel[q];
+    const int nrow = nrd - a, ncol = b - a;
+    for (int e = tid; e < wd * kUpdRows; e += kLdltBlock) {
+        const int k = e / kUpdRows, j = e - k * kUpdRows;
+        Cc[e] = (j < ncol) ? __ldcg(pd + (size_t)k * ldd + j) * __ldcg(Dd + k) : 0.0;
+    }
+    for (int r0 = 0; r0 < nrow; r0 += kUpdRows) {
+        for (int e = tid; e < wd * kUpdRows; e += kLdltBlock) {
+            const int k = e / kUpdRows, r = e - k * kUpdRows;
+            S[e] = (r0 + r < nrow) ? __ldcg(pd + (size_t)k * ldd + r0 + r) : 0.0;
+        }
+        __syncthreads();
+        if (!DMMA) {
+            const int ti = tid & 15, j0 = (tid >> 4) * 4;
+            if (j0 < ncol && r0 + ti < nrow && r0 + ti + 48 >= j0) {
+                double acc[4][4];
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) acc[ii][jj] = 0.0;
+                for (int k = 0; k < wd; ++k) {
+                    const double *sk = S + k * kUpdRows + ti;
+                    const double r_0 = sk[0], r_1 = sk[16], r_2 = sk[32], r_3 = sk[48];
+                    const double2 ca = *reinterpret_cast<const double2 *>(Cc + k * kUpdRows + j0);
+                    const double2 cb = *reinterpret_cast<const double2 *>(Cc + k * kUpdRows + j0 + 2);
+                    acc[0][0] += r_0 * ca.x; acc[0][1] += r_0 * ca.y; acc[0][2] += r_0 * cb.x; acc[0][3] += r_0 * cb.y;
+                    acc[1][0] += r_1 * ca.x; acc[1][1] += r_1 * ca.y; acc[1][2] += r_1 * cb.x; acc[1][3] += r_1 * cb.y;
+                    acc[2][0] += r_2 * ca.x; acc[2][1] += r_2 * ca.y; acc[2][2] += r_2 * cb.x; acc[2][3] += r_2 * cb.y;
+                    acc[3][0] += r_3 * ca.x; acc[3][1] += r_3 * ca.y; acc[3][2] += r_3 * cb.x; acc[3][3] += r_3 * cb.y;
+                }
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii) {
+                    const int gi = r0 + ti + 16 * ii;
+                    if (gi >= nrow) continue;
+                    const int ri = relq[gi];
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int gj = j0 + jj;
+                        if (gj < ncol && gi >= gj) panel[(size_t)relq[gj] * ld + ri] -= acc[ii][jj];
+                    }
+                }
+            }
+        } else {
+            // warp wi owns the 8-row strip wi of this pass; 8 column tiles of 8; k in steps of 4
+            const int lane = tid & 31, wi = tid >> 5;
+            const int rl = lane >> 2, kl = lane & 3;
+            if (r0 + wi * 8 < nrow) {
+                double c[8][2];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) { c[t][0] = 0.0; c[t][1] = 0.0; }
+                const int ntile = (ncol + 7) >> 3;
+                for (int k = 0; k < wd; k += 4) {
+                    const bool kin = k + kl < wd;
+                    const double av = kin ? S[(k + kl) * kUpdRows + wi * 8 + rl] : 0.0;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        if (t < ntile) {
+                            const double bv = kin ? Cc[(k + kl) * kUpdRows + t * 8 + rl] : 0.0;
+                            dmma_m8n8k4(c[t][0], c[t][1], av, bv);
+                        }
+                    }
+                }
+                const int gi = r0 + wi * 8 + rl;
+                if (gi < nrow) {
+                    const int ri = relq[gi];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int gj = t * 8 + 2 * kl + u;
+                            if (gj < ncol && gi >= gj) panel[(size_t)relq[gj] * ld + ri] -= c[t][u];
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <bool DMMA>
+__device__ void factor_supernode_block(const PlanDev &P, int t, double *sh, int epoch, int tid) {
+    constexpr int nt = kLdltBlock;
+    const int f = P.sfirst[t];
+    const int w = P.sfirst[t + 1] - f;
+    const int nr = (int)(P.rptr[t + 1] - P.rptr[t]);
+    const int ld = w + nr;
+    double *panel = P.panels + P.poff[t];
+    double *B = sh;                          // [w][kBS] lower triangle, row-major
+    double *dd = B + kBS * kMaxW;            // pivots
+    double *rk = dd + kMaxW;                 // regularisation value of each pivot
+    double *S = rk + kMaxW;                  // staging: descendant rows / L21 rows
+    double *Cc = S + kUpdRows * kMaxW;       // staging: D-scaled column rows of the descendant
+
+    // 1. updates of every non-leaf descendant (leaf contributions were applied by leaf_update_kernel before)
+    for (int64_t q = P.uptr[t]; q < P.umid[t]; ++q) {
+        wait_done<false>(&P.done_f[P.usrc[q]], epoch, tid, P.fail);
+        schur_update_block<DMMA>(P, q, panel, ld, S, Cc, tid);
+    }
+    __syncthreads();
+
+    // 2. dense LDL' of the w x w diagonal block in shared memory: right-looking, one barrier per column; column k
+    //    stays un-scaled (y_ik = l_ik d_k) until the end, every thread derives the pivot itself
+    for (int e = tid; e < w * w; e += nt) {
+        const int j = e / w, i = e - j * w;
+        if (i >= j) B[i * kBS + j] = panel[(size_t)j * ld + i];
+    }
+    if (tid < w) rk[tid] = (P.P[f + tid] < P.n_d) ? P.r1 : P.r2;
+    __syncthreads();
+    for (int k = 0; k < w; ++k) {
+        double dk = B[k * kBS + k];
+        if (P.dynamic_reg && fabs(dk) < P.tol) {
+            const double r = rk[k];
+            const double sg = (double)((r > 0.0) - (r < 0.0));
+            dk = sg * fmax(fabs(dk + r), fabs(r));
+        }
+        const bool zero = (dk == 0.0);
+        if (zero) dk = 1.0;
+        if (tid == 0) { dd[k] = dk; if (zero) atomicCAS(P.fail, 0, f + k + 1); }
+        const int i = k + 1 + (tid >> 2);
+        if (i < w) {
+            const double lik = B[i * kBS + k] / dk;
+            for (int j = k + 1 + (tid & 3); j <= i; j += 4) B[i * kBS + j] -= lik * B[j * kBS + k];
+        }
+        __syncthreads();
+    }
+    if (tid < w) P.D[f + tid] = dd[tid];
+    for (int e = tid; e < w * w; e += nt) {
+        const int j = e / w, i = e - j * w;
+        if (i > j) {
+            const double l = B[i * kBS + j] / dd[j];
+            B[i * kBS + j] = l;
+            panel[(size_t)j * ld + i] = l;
+        }
+    }
+    __syncthreads();
+
+    // 3. rows below the block, 128 at a time through shared memory (k-major, one thread per row):
+    //    y_k = a_k - sum_{j<k} y_j L11[k][j] ; L21[i][k] = y_k / d_k
+    double *T = S;                           // [w][kTrsmRows]
+    for (int r0 = 0; r0 < nr; r0 += kTrsmRows) {
+        const int rows = min(kTrsmRows, nr - r0);
+        for (int e = tid; e < w * kTrsmRows; e += nt) {
+            const int k = e / kTrsmRows, r = e - k * kTrsmRows;
+            if (r < rows) T[e] = panel[(size_t)k * ld + w + r0 + r];
+        }
+        __syncthreads();
+        if (tid < rows) {
+            double y[kMaxW];
+#pragma unroll
+            for (int k = 0; k < kMaxW; ++k) {
+                if (k < w) {
+                    double s0 = T[k * kTrsmRows + tid], s1 = 0.0;
+#pragma unroll
+                    for (int j = 0; j + 1 < k; j += 2) { s0 -= y[j] * B[k * kBS + j]; s1 -= y[j + 1] * B[k * kBS + j + 1]; }
+                    if (k & 1) s0 -= y[k - 1] * B[k * kBS + k - 1];
+                    const double sv = s0 + s1;
+                    y[k] = sv;
+                    T[k * kTrsmRows + tid] = sv / dd[k];
+                }
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < w * kTrsmRows; e += nt) {
+            const int k = e / kTrsmRows, r = e - k * kTrsmRows;
+            if (r < rows) panel[(size_t)k * ld + w + r0 + r] = T[e];
+        }
+        __syncthreads();
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) { st_release(&P.done_f[t], epoch); LDLT_STAMP(P, 0, t); }
+}
+
+// 2-column forward / backward substitution with the w x w unit triangle held in shared memory (k-major: Ls[k*64 + i]),
+// done by ONE warp with the two right-hand sides in registers (lane owns rows lane and lane + 32)
+__device__ __forceinline__ void tri_solve_warp(const double *Ls, double2 *ys, int w, int lane, bool backward) {
+    double2 y0 = lane < w ? ys[lane] : make_double2(0.0, 0.0);
+    double2 y1 = lane + 32 < w ? ys[lane + 32] : make_double2(0.0, 0.0);
+    if (!backward) {
+        for (int k = 0; k < w; ++k) {
+            const double2 src = (k < 32) ? y0 : y1;
+            const double bx = __shfl_sync(0xffffffffu, src.x, k & 31), by = __shfl_sync(0xffffffffu, src.y, k & 31);
+            const double *col = Ls + k * kMaxW;
+            if (lane > k && lane < w) { const double l = col[lane]; y0.x -= l * bx; y0.y -= l * by; }
+            if (lane + 32 > k && lane + 32 < w) { const double l = col[lane + 32]; y1.x -= l * bx; y1.y -= l * by; }
+        }
+    } else {
+        // x_k -= sum_{i>k} L[i][k] x_i : column i of the transposed triangle is row i of L, i.e. Ls[k*64 + i] over k < i
+        for (int i = w - 1; i > 0; --i) {
+            const double2 src = (i < 32) ? y0 : y1;
+            const double bx = __shfl_sync(0xffffffffu, src.x, i & 31), by = __shfl_sync(0xffffffffu, src.y, i & 31);
+            if (lane < i) { const double l = Ls[lane * kMaxW + i]; y0.x -= l * bx; y0.y -= l * by; }
+            if (lane + 32 < i) { const double l = Ls[(lane + 32) * kMaxW + i]; y1.x -= l * bx; y1.y -= l * by; }
+        }
+    }
+    if (lane < w) ys[lane] = y0;
+    if (lane + 32 < w) ys[lane + 32] = y1;
+}
+
+__device__ void fwd_supernode_block(const PlanDev &P, int t, double *sh, int epoch, int tid) {
+    constexpr int nt = kLdltBlock;
+    const int f = P.sfirst[t];
+    const int w = P.sfirst[t + 1] - f;
+    const int nr = (int)(P.rptr[t + 1] - P.rptr[t]);
+    const int ld = w + nr;
+    const double *panel = P.panels + P.poff[t];
+    double *Ls = sh;                                                    // [w][64] k-major strict lower triangle
+    double2 *ys = reinterpret_cast<double2 *>(sh + kMaxW * kMaxW);      // w entries
+    double2 *part = ys + kMaxW + kSolveRows;                            // [8 warps][w] partial pulls
+    const int lane = tid & 31, wid = tid >> 5;
+    // the factor is read-only here: the triangle is staged before the dependencies are waited for
+    for (int e = tid; e < w * w; e += nt) {
+        const int k = e / w, i = e - k * w;
+        if (i > k) Ls[k * kMaxW + i] = panel[(size_t)k * ld + i];
+    }
+    for (int k = tid; k < kWarpsPerBlock * kMaxW; k += nt) part[k] = make_double2(0.0, 0.0);
+    __syncthreads();
+    // pulls: warp wid takes the pairs q = uptr + wid, + 8, ... (fixed assignment and a fixed final order of the eight
+    // partial sums keep the result reproducible); lanes over the target rows
+    double2 *mine = part + wid * kMaxW;
+    for (int64_t q = P.uptr[t] + wid; q < P.umid[t]; q += kWarpsPerBlock) {
+        const int d = P.usrc[q];
+        wait_done<true>(&P.done_s[d], epoch, lane, P.fail);
+        const int fd = P.sfirst[d];
+        const int wd = P.sfirst[d + 1] - fd;
+        const int nrd = (int)(P.rptr[d + 1] - P.rptr[d]);
+        const int ldd = wd + nrd;
+        const double *pd = P.panels + P.poff[d] + wd;
+        const int a = P.ua[q], b = P.ub[q];
+        const int *relq = P.rel + P.urel[q];
+        for (int j = a + lane; j < b; j += 32) {
+            double s0 = 0.0, s1 = 0.0;
+            for (int k = 0; k < wd; ++k) {
+                const double l = __ldcg(pd + (size_t)k * ldd + j);
+                const double2 yv = __ldcg(P.Y + fd + k);
+                s0 += l * yv.x; s1 += l * yv.y;
+            }
+            const int lc = relq[j - a];
+            mine[lc].x += s0; mine[lc].y += s1;
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    for (int k = tid; k < w; k += nt) {
+        double2 y = P.Y[f + k];
+#pragma unroll
+        for (int u = 0; u < kWarpsPerBlock; ++u) { const double2 pp = part[u * kMaxW + k]; y.x -= pp.x; y.y -= pp.y; }
+        ys[k] = y;
+    }
+    __syncthreads();
+    if (wid == 0) {
+        tri_solve_warp(Ls, ys, w, lane, false);
+        __syncwarp();
+        for (int k = lane; k < w; k += 32) P.Y[f + k] = ys[k];
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) { st_release(&P.done_s[t], epoch); LDLT_STAMP(P, 1, t); }
+    }
+}
+
+__device__ void bwd_supernode_block(const PlanDev &P, int t, double *sh, int epoch, int tid, bool nowait) {
+    constexpr int nt = kLdltBlock;
+    const int f = P.sfirst[t];
+    const int w = P.sfirst[t + 1] - f;
+    const int nr = (int)(P.rptr[t + 1] - P.rptr[t]);
+    const int ld = w + nr;
+    const double *panel = P.panels + P.poff[t];
+    const int *R = P.rows + P.rptr[t];
+    double *Ls = sh;
+    double2 *xs = reinterpret_cast<double2 *>(sh + kMaxW * kMaxW);      // w entries
+    double2 *xr = xs + kMaxW;                                           // kSolveRows staged x[R[r]]
+    const int lane = tid & 31, wid = tid >> 5;
+    for (int e = tid; e < w * w; e += nt) {
+        const int k = e / w, i = e - k * w;
+        if (i > k) Ls[k * kMaxW + i] = panel[(size_t)k * ld + i];
+    }
+    prefetch_l2_range(panel, (size_t)ld * w, tid, nt);
+    if (!nowait)
+        for (int64_t q = P.tptr[t]; q < P.tptr[t + 1]; ++q)
+            wait_done<false>(&P.done_b[P.ttgt[q]], epoch, tid, P.fail);
+    // xs[k] = y_k / d_k - sum_r L21[r][k] x[R[r]] : the gathered x are staged once, a warp per column
+    for (int k = tid; k < w; k += nt) {
+        const double2 yv = P.Y[f + k];
+        const double dk = P.D[f + k];
+        xs[k] = make_double2(yv.x / dk, yv.y / dk);
+    }
+    for (int r0 = 0; r0 < nr; r0 += kSolveRows) {
+        const int rows = min(kSolveRows, nr - r0);
+        __syncthreads();
+        for (int r = tid; r < rows; r += nt) xr[r] = __ldcg(P.Y + R[r0 + r]);
+        __syncthreads();
+        for (int k = wid; k < w; k += kWarpsPerBlock) {
+            double s0 = 0.0, s1 = 0.0;
+            const double *col = panel + (size_t)k * ld + w + r0;
+            for (int r = lane; r < rows; r += 32) {
+                const double l = col[r];
+                const double2 xv = xr[r];
+                s0 += l * xv.x; s1 += l * xv.y;
+            }
+            s0 = warp_sum(s0); s1 = warp_sum(s1);
+            if (lane == 0) { xs[k].x -= s0; xs[k].y -= s1; }
+        }
+    }
+    __syncthreads();
+    if (wid == 0) {
+        tri_solve_warp(Ls, xs, w, lane, true);
+        __syncwarp();
+        for (int k = lane; k < w; k += 32) P.Y[f + k] = xs[k];
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) { st_release(&P.done_b[t], epoch); LDLT_STAMP(P, 2, t); }
+    }
 }
 
 // phase: 0 factor, 1 forward, 2 backward (tasks taken in reverse)
@@ -508,6 +873,10 @@ void ldlt_analyze(Handle *h, const int64_t *Puser, const fpsb_ldlt_opts *opts) {
     L->done_f.alloc((size_t)S.nsuper + 8); L->done_s.alloc((size_t)S.nsuper + 8); L->done_b.alloc((size_t)S.nsuper + 8);
     L->done_f.zero(s); L->done_s.zero(s); L->done_b.zero(s);
     L->ticket.alloc(8); L->fail.alloc(8);
+#ifdef FPSB_LDLT_TIMERS
+    L->tstamp.alloc((size_t)3 * S.nsuper + 8);
+    L->tstamp.zero(s);
+#endif
     L->ticket.zero(s); L->fail.zero(s);
     FPSB_CUDA(cudaStreamSynchronize(s));
     PlanDev &D = L->dev;
@@ -523,6 +892,7 @@ void ldlt_analyze(Handle *h, const int64_t *Puser, const fpsb_ldlt_opts *opts) {
     D.panels = L->panels.p; D.D = L->D.p; D.Y = L->Y.p;
     D.done_f = L->done_f.p; D.done_s = L->done_s.p; D.done_b = L->done_b.p;
     D.ticket = L->ticket.p; D.fail = L->fail.p;
+    D.tstamp = L->tstamp.p;
     D.n_d = (int)h->nvar;
     D.tol = L->opts.ldlt_tol; D.r1 = L->opts.ldlt_r1; D.r2 = L->opts.ldlt_r2;
     D.dynamic_reg = (D.r1 != 0.0) || (D.r2 != 0.0);
@@ -719,6 +1089,55 @@ int fpsb_symbolic_plan_info(fpsb_symbolic s, int64_t *nsuper, int64_t *panel_nnz
     REQ(s, FPSB_EINVAL, "NULL symbolic");
     sym_plan(s->S, nsuper, panel_nnz, npairs, flops, nlevels, nleaf);
     return FPSB_OK;
+}
+
+
+
+/* debug builds (-DFPSB_LDLT_TIMERS; not in fpsb.h): per dependency level, the latest completion time (us after the
+ * earliest stamp of the phase) of the last factorisation / forward / backward sweep */
+int fpsb_debug_ldlt_level_times(fpsb_handle hh, int phase, double *out_us, int cap) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    if (!h || !h->ldlt || !h->ldlt->tstamp.p || phase < 0 || phase > 2) return -1;
+    const Symbolic &S = h->ldlt->S;
+    std::vector<unsigned long long> ts((size_t)S.nsuper);
+    cudaMemcpy(ts.data(), h->ldlt->tstamp.p + (size_t)phase * S.nsuper, ts.size() * 8, cudaMemcpyDeviceToHost);
+    unsigned long long t0 = ~0ull;
+    for (int t = 0; t < S.nsuper; ++t) if (ts[(size_t)t] && S.level[(size_t)t] > 0) t0 = std::min(t0, ts[(size_t)t]);
+    std::vector<unsigned long long> mx((size_t)S.nlevels + 1, 0);
+    for (int t = 0; t < S.nsuper; ++t) mx[(size_t)S.level[(size_t)t]] = std::max(mx[(size_t)S.level[(size_t)t]], ts[(size_t)t]);
+    int nl = 0;
+    for (int l = 0; l <= S.nlevels && l < cap; ++l, ++nl) out_us[l] = mx[(size_t)l] >= t0 ? 1e-3 * (double)(mx[(size_t)l] - t0) : 0.0;
+    return nl;
+}
+
+/* debug (not in fpsb.h): per-level statistics of the supernodal plan on stderr */
+void fpsb_debug_plan_dump(fpsb_symbolic sy) {
+    if (!sy) return;
+    const Symbolic &S = sy->S;
+    struct Lv { long long cnt = 0, sw = 0, snr = 0, pairs = 0; int maxw = 0, maxnr = 0, maxpairs = 0; double upd = 0, self = 0; };
+    std::vector<Lv> lv((size_t)S.nlevels + 1);
+    for (int t = 0; t < S.nsuper; ++t) {
+        Lv &l = lv[(size_t)S.level[(size_t)t]];
+        const int w = S.sfirst[(size_t)t + 1] - S.sfirst[(size_t)t];
+        const int nr = (int)(S.rptr[(size_t)t + 1] - S.rptr[(size_t)t]);
+        l.cnt++; l.sw += w; l.snr += nr; l.maxw = std::max(l.maxw, w); l.maxnr = std::max(l.maxnr, nr);
+        const int np = (int)(S.umid[(size_t)t] - S.uptr[(size_t)t]);
+        l.pairs += np; l.maxpairs = std::max(l.maxpairs, np);
+        for (int64_t q = S.uptr[(size_t)t]; q < S.umid[(size_t)t]; ++q) {
+            const int d = S.usrc[(size_t)q];
+            const int wd = S.sfirst[(size_t)d + 1] - S.sfirst[(size_t)d];
+            const int nrd = (int)(S.rptr[(size_t)d + 1] - S.rptr[(size_t)d]);
+            l.upd += 2.0 * (double)(nrd - S.ua[(size_t)q]) * (double)(S.ub[(size_t)q] - S.ua[(size_t)q]) * wd;
+        }
+        l.self += (double)w * w * w / 3.0 + (double)nr * w * w;
+    }
+    fprintf(stderr, "level count sum_w max_w sum_nr max_nr pairs maxpairs upd_MFLOP self_MFLOP\n");
+    for (size_t i = 0; i < lv.size(); ++i) {
+        const Lv &l = lv[i];
+        if (!l.cnt) continue;
+        fprintf(stderr, "%3zu %8lld %8lld %3d %9lld %5d %7lld %4d %10.2f %10.2f\n", i, l.cnt, l.sw, l.maxw, l.snr, l.maxnr, l.pairs, l.maxpairs,
+                l.upd * 1e-6, l.self * 1e-6);
+    }
 }
 
 int fpsb_ldlt_analyze(fpsb_handle hh, const int64_t *P, int index_base, const fpsb_ldlt_opts *opts) {

@@ -119,7 +119,9 @@ int64_t fpsb_launch_count(fpsb_handle h);
 int fpsb_set_jac_values(fpsb_handle h, const double *vals, int loc);
 
 /* jprod! / jtprod! of the Jacobian operator (NLPModels jac_op!): out = A v, A' u.
- * Also used by the caller side for the rho-terms (src/model-Fletcherpenaltynlp.jl:388-395,552-563). */
+ * Also used by the caller side for the rho-terms (src/model-Fletcherpenaltynlp.jl:388-395,552-563).
+ * With loc = FPSB_DEVICE the four products are asynchronous: the work is ordered after the caller's stream
+ * (fpsb_set_caller_stream) on entry and the caller's stream after it on exit; nothing waits on the host. */
 int fpsb_jprod(fpsb_handle h, const double *v, double *Av, int loc);
 int fpsb_jtprod(fpsb_handle h, const double *u, double *Atu, int loc);
 /* two-column variants (columns contiguous: v is [v1 | v2], each of the natural length) */
