@@ -241,6 +241,8 @@ def run_partitioned(args, dist, rank, world, local_rank, make):
     lib.fpsb_dist_profile(1)
     torch.cuda.synchronize(); dist.barrier()
     D.solve_two_mixed(delta, r1, r2)
+    fallback_ms = torch.tensor([D.H.iter_last_profile()[0]], dtype=torch.float64, device=dev)
+    dist.all_reduce(fallback_ms, op=dist.ReduceOp.MAX)
     lib.fpsb_dist_profile(0)
     us4 = (ctypes.c_double * 4)(); c4 = (ctypes.c_int64 * 4)()
     lib.fpsb_dist_last_profile(us4, c4)
@@ -295,6 +297,14 @@ def run_partitioned(args, dist, rank, world, local_rank, make):
         "single_gpu": {"iterations": it1, "krylov_loop_ms": float(single[0].item()), "us_per_iteration": us1,
                        "what": "the same operator on rank 0's GPU through the plain (unpartitioned) handle"},
         "speedup_vs_single_gpu": us1 / us if us > 0 else None,
+        "kernel": "one persistent kernel per chunk of 24 iterations on every rank; its CTA 0 does the halo scatter-add, the boundary "
+                  "rows, the halo gather and the all-reduce of the four inner products through the peers' mailboxes (NVLink), "
+                  "the other CTAs wait for its release instead of the grid barrier" if D.peer and os.environ.get("FPSB_DIST_LOOP", "1") != "0"
+                  else "launch per half iteration (step kernel + exchange kernel)",
+        "launch_per_half_iteration_path": {"us_per_iteration": 1e3 * float(fallback_ms.item()) / max(nit, 1),
+                                           "per_launch_us_max_over_ranks": shares,
+                                           "what": "the same solve with a kernel launch per half iteration and a separate exchange kernel "
+                                                   "(round 1's path, still the fallback for operators with long rows): one profiled run"},
         "per_launch_us_max_over_ranks": shares,
         "exchange_share": xs / max(xs + shares["step_n_us"] + shares["step_m_us"], 1e-30),
         "parity": {"rel_err_p1_q1_p2_q2_vs_single_gpu": rel, "max_rel_err": max(rel), "tol": 1e-6,

@@ -118,12 +118,14 @@ struct DistCtx {
     uint64_t sig = 0, n_sc = 0, n_ga = 0, n_tot = 0;   // signals / exchanges issued so far (same on every rank)
     bool halo_fresh = false;                        // the halo slots of Gn hold the current values
     bool tail = false;                              // m-space steps all-reduce inside the step kernel's last CTA (experiment)
+    // ---- persistent loop with the exchange inside the kernel (gk_loop_kernel<true>) ----
+    DevBuf<DistLoop> d_dloop;
+    DevBuf<unsigned long long> d_seq;               // device copy of sig | n_sc | n_ga | n_tot while the loop kernel runs
+    DevBuf<double> gtot;
+    bool loop_ok = false;
 };
 
-// mailbox layout (bytes):  flags u64[8] | tot double[2][8][4] | scatter inbox double2[2][nsend] | gather inbox double2[2][nrecv]
-__host__ __device__ static inline size_t mbox_off_tot() { return 8 * sizeof(uint64_t); }
-__host__ __device__ static inline size_t mbox_off_sc() { return mbox_off_tot() + 2 * 8 * 4 * sizeof(double); }
-__host__ __device__ static inline size_t mbox_off_ga(int64_t nsend) { return mbox_off_sc() + 2 * (size_t)nsend * sizeof(double2); }
+// mailbox layout: mbox_off_tot / mbox_off_sc / mbox_off_ga (fpsb_loop.inl)
 static inline size_t mbox_size(int64_t nsend, int64_t nrecv) { return mbox_off_ga(nsend) + 2 * (size_t)nrecv * sizeof(double2) + 64; }
 
 // what a rank publishes so that its peers can map and address its mailbox
@@ -283,6 +285,29 @@ void dist_peer_attach(Handle *h, const void *blobs) {
     }
     const char *force = getenv("FPSB_DIST_NCCL");
     D->peer = !(force && *force && *force != '0');
+    {
+        // the description the persistent loop kernel's CTA 0 works from (see DistLoop)
+        D->d_seq.alloc(4); D->d_seq.zero(h->stream);
+        D->gtot.alloc(8); D->gtot.zero(h->stream);
+        DistLoop X{};
+        X.nranks = D->nranks; X.rank = D->rank;
+        X.nbound = (int)D->nbound; X.bidx = D->bidx.p; X.bptr = D->bptr.p; X.bsrc = D->bsrc.p; X.bpeer = D->bpeer.p;
+        X.meta = reinterpret_cast<const long long *>(D->d_meta.p);
+        X.S = D->S.p; X.pair = h->iter->Gn.p;
+        X.nsend = D->nsend; X.nrecv = D->nrecv;
+        X.mine = D->mbox;
+        for (int p = 0; p < D->nranks; ++p) {
+            X.peer[p] = D->peer_mbox[p];
+            X.sc_at_peer[p] = D->sc_at_peer[p]; X.ga_at_peer[p] = D->ga_at_peer[p];
+            X.peer_nsend[p] = D->peer_nsend[p]; X.peer_nrecv[p] = D->peer_nrecv[p];
+        }
+        X.seq = D->d_seq.p; X.gtot = D->gtot.p; X.xbar = h->iter->gbar.p + 1; X.err = D->d_err.p;
+        std::vector<DistLoop> v(1, X);
+        D->d_dloop.from(v, h->stream);
+        FPSB_CUDA(cudaStreamSynchronize(h->stream));
+        const char *lp = getenv("FPSB_DIST_LOOP");
+        D->loop_ok = D->peer && D->fused_n && !(lp && *lp == '0');
+    }
     // experiment (off by default: measured 130.6 vs 128.5 us per iteration on 2 GPUs, no gain over the
     // separate single-CTA exchange launch): FPSB_DIST_TAIL=1 lets the m-space step kernel's last CTA all-reduce
     const char *tl = getenv("FPSB_DIST_TAIL");
@@ -862,6 +887,22 @@ struct DistEngine {
         allreduce_finish(0, io0.mode, io1.mode);
         g_dist_prof.mark(4, h->stream);
     }
+    // The whole LSQR / CRAIG loop in the persistent kernel, exchanges included (gk_loop_kernel<true>); false when this
+    // handle cannot (NCCL transport, long rows, an operator without tiles): the launch-per-half-iteration loop then runs
+    bool run_loop(const SlotIO &n0, const SlotIO &n1, const SlotIO &m0, const SlotIO &m1) {
+        if (!D->loop_ok || g_dist_prof.on) return false;     // (per-launch profiling measures the launch-per-half-iteration path)
+        E.loop_dx = D->d_dloop.p; E.loop_raw = D->S.p;
+        if (!E.can_persist()) { E.loop_dx = nullptr; return false; }
+        unsigned long long seq[4] = {D->sig, D->n_sc, D->n_ga, D->n_tot};
+        FPSB_CUDA(cudaMemcpyAsync(D->d_seq.p, seq, sizeof(seq), cudaMemcpyHostToDevice, h->stream));
+        FPSB_CUDA(cudaStreamSynchronize(h->stream));
+        E.run_loop(n0, n1, m0, m1);                     // (ends with the stream synchronised)
+        FPSB_CUDA(cudaMemcpy(seq, D->d_seq.p, sizeof(seq), cudaMemcpyDeviceToHost));
+        D->sig = seq[0]; D->n_sc = seq[1]; D->n_ga = seq[2]; D->n_tot = seq[3];
+        D->halo_fresh = false;
+        E.loop_dx = nullptr;
+        return true;
+    }
     void ew(int op, int slot, int n, const double *in0, double *v0, double *v1, double *v2, double2 *pair, int pair_slot, double c0) {
         E.ew(op, slot, n, in0, v0, v1, v2, nullptr, nullptr, pair, pair_slot, c0, 1);
         const bool npair = pair >= E.W->Gn.p && pair < E.W->Gn.p + h->nvar;      // the n-space pair changed
@@ -933,10 +974,11 @@ void dist_solve_two_mixed(Handle *h, double delta, const double *rhs1, const dou
     E.mark_begin();
     X.step_m(l_init, io_none());
     g_dist_prof.mark(0, h->stream);
-    E.loop([&](int) {
-        X.step_n(l_u, c_v);
-        X.step_m(l_v, c_u);
-    }, kChunk);
+    if (!X.run_loop(l_u, c_v, l_v, c_u))
+        E.loop([&](int) {
+            X.step_n(l_u, c_v);
+            X.step_m(l_v, c_u);
+        }, kChunk);
     E.mark_end();
     g_dist_prof.report(D->rank);
     E.tot_out = nullptr;
@@ -978,10 +1020,11 @@ void dist_solve_two_least_squares(Handle *h, double delta, const double *rhs1, c
     SlotIO v1 = io_mode(MD_LSQR_V, W->am[1][0].p, W->am[1][1].p);
     E.mark_begin();
     X.step_m(init0, init1);
-    E.loop([&](int) {
-        X.step_n(u0, u1);
-        X.step_m(v0, v1);
-    }, kChunk);
+    if (!X.run_loop(u0, u1, v0, v1))
+        E.loop([&](int) {
+            X.step_n(u0, u1);
+            X.step_m(v0, v1);
+        }, kChunk);
     E.mark_end();
     E.tot_out = nullptr;
     E.ew(EW_COPY, 0, m_loc, W->am[0][1].p, q1, nullptr, nullptr, nullptr, nullptr, nullptr, -1, 1.0, 0);

@@ -1874,7 +1874,8 @@ void csr_build(Handle *h) {
         h->num_sms = sms;
         FPSB_CUDA(cudaFuncSetAttribute(gk_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBudget + 8 * 1024));
         FPSB_CUDA(cudaFuncSetAttribute(gk_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBudget + 8 * 1024));
-        FPSB_CUDA(cudaFuncSetAttribute(gk_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBudget + 8 * 1024));
+        FPSB_CUDA(cudaFuncSetAttribute(gk_loop_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBudget + 8 * 1024));
+        FPSB_CUDA(cudaFuncSetAttribute(gk_loop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBudget + 8 * 1024));
     }
     std::vector<int> rp, ci, perm;
     build_csr_host(m, n, h->nnzj, h->jrow.data(), h->jcol.data(), rp, ci, perm);
@@ -2185,11 +2186,13 @@ struct Engine {
     }
     // ---- persistent loop kernel (fpsb_loop.inl): a whole chunk of Krylov iterations per launch ----
     bool loop_phases_pending = false;
+    const DistLoop *loop_dx = nullptr;       // row-partitioned run: device copy of the exchange description (fpsb_dist.inl)
+    double2 *loop_raw = nullptr;             // ... and where the raw sums of the halo / boundary rows go
     static int env_int(const char *name, int dflt) { const char *e = getenv(name); return (e && *e) ? atoi(e) : dflt; }
     // one ring geometry for both operators; false when the persistent kernel cannot run this handle
     bool loop_geometry(int &blk_cap, int &win_cap, int &stage_bytes, int &nstage, int &grid) const {
         static const int mode = env_int("FPSB_LOOP", 2);
-        if (mode == 0 || tot_out != nullptr) return false;
+        if (mode == 0 || (tot_out != nullptr && loop_dx == nullptr)) return false;
         const CsrDev &A = h->A, &At = h->At;
         if (A.nlong > 0 || At.nlong > 0 || A.ntiles == 0 || At.ntiles == 0) return false;
         blk_cap = std::max(A.blk_cap, At.blk_cap);
@@ -2220,6 +2223,8 @@ struct Engine {
             L.op[i].inflight = std::min(L.op[i].inflight, nstage);
             L.op[i].st = st_cur();
         }
+        L.dx = loop_dx;
+        if (loop_dx != nullptr) L.op[0].raw_out = loop_raw;
         L.first = 0;
         L.nphase = 2 * chunk_it;
         L.nspec = std::max(0, std::min(env_int("FPSB_LOOP_NSPEC", kGroups), nstage - 1));
@@ -2237,8 +2242,9 @@ struct Engine {
         attr[0].val.cooperative = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         loop([&](int) {
-            FPSB_CUDA(cudaMemsetAsync(W->gbar.p, 0, sizeof(unsigned long long), h->stream));
-            FPSB_CUDA(cudaLaunchKernelEx(&cfg, gk_loop_kernel, L));
+            FPSB_CUDA(cudaMemsetAsync(W->gbar.p, 0, 2 * sizeof(unsigned long long), h->stream));      // arrivals | exchanges
+            if (loop_dx != nullptr) FPSB_CUDA(cudaLaunchKernelEx(&cfg, gk_loop_kernel<true>, L));
+            else FPSB_CUDA(cudaLaunchKernelEx(&cfg, gk_loop_kernel<false>, L));
             h->launches += 1;
             W->prof_loop_launches += 1;
         }, 1, chunk_it);

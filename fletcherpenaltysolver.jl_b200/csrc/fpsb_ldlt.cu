@@ -34,7 +34,7 @@ constexpr int kUpdRows = 64;                            // rows of a descendant 
 constexpr int kTrsmRows = 2 * kUpdRows;                 // rows of L21 staged per pass (reuses the two update buffers)
 constexpr int kFacDoubles = kBS * kMaxW + 2 * kMaxW + 2 * kUpdRows * kMaxW;      // B | dd | rk | S | C
 constexpr int kSolveRows = 1024;                        // rows of a panel whose x[R[r]] are staged per pass of the backward solve
-constexpr int kSolDoubles = kMaxW * kMaxW + 2 * kMaxW + 2 * kSolveRows + 2 * kWarpsPerBlock * kMaxW;   // L11 | ys | xr | per-warp partials
+constexpr int kSolDoubles = kBS * kMaxW + 2 * kMaxW + 2 * kSolveRows + 2 * kWarpsPerBlock * kMaxW;   // L11 | ys | xr | per-warp partials
 static_assert(kSmallW * (kSmallW + 1) + 4 * kSmallW <= kFacDoubles / kWarpsPerBlock, "warp-level supernodes share the block's buffer");
 static_assert(kSmallW * (kSmallW + 1) + 4 * kSmallW <= kSolDoubles / kWarpsPerBlock, "warp-level supernodes share the block's buffer");
 
@@ -523,25 +523,21 @@ __device__ void factor_supernode_block(const PlanDev &P, int t, double *sh, int 
             if (r < rows) T[e] = panel[(size_t)k * ld + w + r0 + r];
         }
         __syncthreads();
+        // a thread per row, the sums in the reference's order (j ascending: the factor is then bit-identical to the
+        // scalar routine and to the CPU oracle, which the regularised-pivot tests rely on); the un-scaled y_j stay in
+        // T until the write-back
         if (tid < rows) {
-            double y[kMaxW];
-#pragma unroll
-            for (int k = 0; k < kMaxW; ++k) {
-                if (k < w) {
-                    double s0 = T[k * kTrsmRows + tid], s1 = 0.0;
-#pragma unroll
-                    for (int j = 0; j + 1 < k; j += 2) { s0 -= y[j] * B[k * kBS + j]; s1 -= y[j + 1] * B[k * kBS + j + 1]; }
-                    if (k & 1) s0 -= y[k - 1] * B[k * kBS + k - 1];
-                    const double sv = s0 + s1;
-                    y[k] = sv;
-                    T[k * kTrsmRows + tid] = sv / dd[k];
-                }
+            for (int k = 1; k < w; ++k) {
+                double sv = T[k * kTrsmRows + tid];
+                const double *bk = B + k * kBS;
+                for (int j = 0; j < k; ++j) sv -= T[j * kTrsmRows + tid] * bk[j];
+                T[k * kTrsmRows + tid] = sv;
             }
         }
         __syncthreads();
         for (int e = tid; e < w * kTrsmRows; e += nt) {
             const int k = e / kTrsmRows, r = e - k * kTrsmRows;
-            if (r < rows) panel[(size_t)k * ld + w + r0 + r] = T[e];
+            if (r < rows) panel[(size_t)k * ld + w + r0 + r] = T[e] / dd[k];
         }
         __syncthreads();
     }
@@ -550,7 +546,8 @@ __device__ void factor_supernode_block(const PlanDev &P, int t, double *sh, int 
     if (tid == 0) { st_release(&P.done_f[t], epoch); LDLT_STAMP(P, 0, t); }
 }
 
-// 2-column forward / backward substitution with the w x w unit triangle held in shared memory (k-major: Ls[k*64 + i]),
+// 2-column forward / backward substitution with the w x w unit triangle held in shared memory (forward: k-major,
+// Ls[k*64 + i] = L(i,k); backward: row-major with stride kBS, Ls[i*kBS + k] = L(i,k) — both conflict-free),
 // done by ONE warp with the two right-hand sides in registers (lane owns rows lane and lane + 32)
 __device__ __forceinline__ void tri_solve_warp(const double *Ls, double2 *ys, int w, int lane, bool backward) {
     double2 y0 = lane < w ? ys[lane] : make_double2(0.0, 0.0);
@@ -564,12 +561,12 @@ __device__ __forceinline__ void tri_solve_warp(const double *Ls, double2 *ys, in
             if (lane + 32 > k && lane + 32 < w) { const double l = col[lane + 32]; y1.x -= l * bx; y1.y -= l * by; }
         }
     } else {
-        // x_k -= sum_{i>k} L[i][k] x_i : column i of the transposed triangle is row i of L, i.e. Ls[k*64 + i] over k < i
+        // x_k -= sum_{i>k} L[i][k] x_i : column i of the transposed triangle is row i of L
         for (int i = w - 1; i > 0; --i) {
             const double2 src = (i < 32) ? y0 : y1;
             const double bx = __shfl_sync(0xffffffffu, src.x, i & 31), by = __shfl_sync(0xffffffffu, src.y, i & 31);
-            if (lane < i) { const double l = Ls[lane * kMaxW + i]; y0.x -= l * bx; y0.y -= l * by; }
-            if (lane + 32 < i) { const double l = Ls[(lane + 32) * kMaxW + i]; y1.x -= l * bx; y1.y -= l * by; }
+            if (lane < i) { const double l = Ls[i * kBS + lane]; y0.x -= l * bx; y0.y -= l * by; }
+            if (lane + 32 < i) { const double l = Ls[i * kBS + lane + 32]; y1.x -= l * bx; y1.y -= l * by; }
         }
     }
     if (lane < w) ys[lane] = y0;
@@ -584,7 +581,7 @@ __device__ void fwd_supernode_block(const PlanDev &P, int t, double *sh, int epo
     const int ld = w + nr;
     const double *panel = P.panels + P.poff[t];
     double *Ls = sh;                                                    // [w][64] k-major strict lower triangle
-    double2 *ys = reinterpret_cast<double2 *>(sh + kMaxW * kMaxW);      // w entries
+    double2 *ys = reinterpret_cast<double2 *>(sh + kBS * kMaxW);      // w entries
     double2 *part = ys + kMaxW + kSolveRows;                            // [8 warps][w] partial pulls
     const int lane = tid & 31, wid = tid >> 5;
     // the factor is read-only here: the triangle is staged before the dependencies are waited for
@@ -645,13 +642,13 @@ __device__ void bwd_supernode_block(const PlanDev &P, int t, double *sh, int epo
     const int ld = w + nr;
     const double *panel = P.panels + P.poff[t];
     const int *R = P.rows + P.rptr[t];
-    double *Ls = sh;
-    double2 *xs = reinterpret_cast<double2 *>(sh + kMaxW * kMaxW);      // w entries
+    double *Ls = sh;                                                    // [i][kBS] row-major: Ls[i*kBS + k] = L(i, k)
+    double2 *xs = reinterpret_cast<double2 *>(sh + kBS * kMaxW);      // w entries
     double2 *xr = xs + kMaxW;                                           // kSolveRows staged x[R[r]]
     const int lane = tid & 31, wid = tid >> 5;
     for (int e = tid; e < w * w; e += nt) {
         const int k = e / w, i = e - k * w;
-        if (i > k) Ls[k * kMaxW + i] = panel[(size_t)k * ld + i];
+        if (i > k) Ls[i * kBS + k] = panel[(size_t)k * ld + i];
     }
     prefetch_l2_range(panel, (size_t)ld * w, tid, nt);
     if (!nowait)
@@ -694,10 +691,12 @@ __device__ void bwd_supernode_block(const PlanDev &P, int t, double *sh, int epo
 // phase: 0 factor, 1 forward, 2 backward (tasks taken in reverse)
 // tasks [task_lo, task_hi) are taken through ticket counter `tk`; `nowait`: every dependency is
 // known to be complete (an earlier launch), so the backward phase skips its flag waits
-template <int PHASE>
-__global__ void __launch_bounds__(kLdltBlock) ldlt_phase_kernel(PlanDev P, int epoch, int task_lo, int task_hi,
+// MODE 0: scalar CTA routines (global-memory operands); 1: fronts staged in shared memory, register-tiled Schur
+// update; 2: as 1 with the Schur update on the FP64 tensor cores (DMMA m8n8k4).  Dynamic shared memory: phase_smem().
+template <int PHASE, int MODE>
+__global__ void __launch_bounds__(kLdltBlock, MODE == 0 ? 4 : 2) ldlt_phase_kernel(PlanDev P, int epoch, int task_lo, int task_hi,
                                                                 int tk, int nowait) {
-    __shared__ double sh[kShDoubles];
+    extern __shared__ __align__(16) double sh[];
     __shared__ int s_task;
     const int tid = threadIdx.x;
     for (;;) {
@@ -710,9 +709,15 @@ __global__ void __launch_bounds__(kLdltBlock) ldlt_phase_kernel(PlanDev P, int e
         const int t0 = P.task_start[task], cnt = P.task_cnt[task];
         if (cnt == 0) {
             const int t = P.order[t0];
-            if (PHASE == 0) factor_supernode<false>(P, t, sh, epoch, tid, kLdltBlock);
-            else if (PHASE == 1) fwd_supernode<false>(P, t, sh, epoch, tid, kLdltBlock);
-            else bwd_supernode<false>(P, t, sh, epoch, tid, kLdltBlock, nowait != 0);
+            if (MODE == 0) {
+                if (PHASE == 0) factor_supernode<false>(P, t, sh, epoch, tid, kLdltBlock);
+                else if (PHASE == 1) fwd_supernode<false>(P, t, sh, epoch, tid, kLdltBlock);
+                else bwd_supernode<false>(P, t, sh, epoch, tid, kLdltBlock, nowait != 0);
+            } else {
+                if (PHASE == 0) factor_supernode_block<MODE == 2>(P, t, sh, epoch, tid);
+                else if (PHASE == 1) fwd_supernode_block(P, t, sh, epoch, tid);
+                else bwd_supernode_block(P, t, sh, epoch, tid, nowait != 0);
+            }
         } else {
             const int wid = tid >> 5, lane = tid & 31;
             if (wid < cnt) {
@@ -726,6 +731,40 @@ __global__ void __launch_bounds__(kLdltBlock) ldlt_phase_kernel(PlanDev P, int e
         }
         __syncthreads();
     }
+}
+static size_t phase_smem(int phase, int mode) {
+    if (mode == 0) return (size_t)kShDoubles * sizeof(double);
+    return (size_t)(phase == 0 ? kFacDoubles : kSolDoubles) * sizeof(double);
+}
+// FPSB_LDLT_MODE: 0 scalar, 1 staged fronts (default), 2 staged fronts + DMMA Schur update
+static int ldlt_mode() {
+    static const int mode = [] { const char *e = getenv("FPSB_LDLT_MODE"); const int v = (e && *e) ? atoi(e) : 1; return v < 0 || v > 2 ? 1 : v; }();
+    return mode;
+}
+template <int PHASE>
+static void launch_phase(Handle *h, const PlanDev &P, int ntasks, int epoch, int lo, int hi, int tk, int nowait, bool leaves = false) {
+    // the leaf launches are all warp-level bundles on the headline shapes: small shared memory, many resident CTAs
+    const int mode = leaves ? 0 : ldlt_mode();
+    const size_t smem = phase_smem(PHASE, mode);
+    const int grid = std::max(1, std::min(ntasks, h->num_sms * (mode == 0 ? 4 : 2)));
+    static bool attr_done = false;
+    if (!attr_done) {
+        attr_done = true;
+        for (int m = 1; m <= 2; ++m) {
+            const int b0 = (int)phase_smem(0, m), b1 = (int)phase_smem(1, m);
+            if (m == 1) {
+                FPSB_CUDA(cudaFuncSetAttribute(ldlt_phase_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b0));
+                FPSB_CUDA(cudaFuncSetAttribute(ldlt_phase_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b1));
+                FPSB_CUDA(cudaFuncSetAttribute(ldlt_phase_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b1));
+            } else {
+                FPSB_CUDA(cudaFuncSetAttribute(ldlt_phase_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, b0));
+            }
+        }
+    }
+    if (mode == 0) ldlt_phase_kernel<PHASE, 0><<<grid, kLdltBlock, smem, h->stream>>>(P, epoch, lo, hi, tk, nowait);
+    else if (mode == 2 && PHASE == 0) ldlt_phase_kernel<0, 2><<<grid, kLdltBlock, smem, h->stream>>>(P, epoch, lo, hi, tk, nowait);
+    else ldlt_phase_kernel<PHASE, 1><<<grid, kLdltBlock, smem, h->stream>>>(P, epoch, lo, hi, tk, nowait);
+    h->launches += 1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -754,6 +793,56 @@ __global__ void __launch_bounds__(256) leaf_update_kernel(PlanDev P) {
             col[relp[i]] -= s;
         }
         __syncwarp(gmask);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// one-wide leaf supernodes (a variable nobody was eliminated before: ~2/3 of all columns of a KKT matrix under a
+// dissection ordering).  No dependencies, no triangle: flat kernels, 8 lanes per leaf, instead of tickets and bundles.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) leaf1_factor_kernel(PlanDev P, int nleaf) {
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = gt >> 3, l8 = gt & 7;
+    if (i >= nleaf) return;
+    const int t = P.order[i];
+    const int f = P.sfirst[t];
+    if (P.sfirst[t + 1] - f != 1) return;
+    const int nr = (int)(P.rptr[t + 1] - P.rptr[t]);
+    double *panel = P.panels + P.poff[t];
+    double dk = panel[0];
+    if (P.dynamic_reg && fabs(dk) < P.tol) {
+        const double r = (P.P[f] < P.n_d) ? P.r1 : P.r2;
+        const double sg = (double)((r > 0.0) - (r < 0.0));
+        dk = sg * fmax(fabs(dk + r), fabs(r));
+    }
+    if (dk == 0.0) { if (l8 == 0) atomicCAS(P.fail, 0, f + 1); dk = 1.0; }
+    if (l8 == 0) P.D[f] = dk;
+    for (int r = l8; r < nr; r += 8) panel[1 + r] = panel[1 + r] / dk;
+}
+// backward: x_f = y_f / d_f - sum_r L21[r] x[R[r]]  (the rows R are ancestors: already final)
+__global__ void __launch_bounds__(256) leaf1_bwd_kernel(PlanDev P, int nleaf) {
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = gt >> 3, l8 = gt & 7;
+    const int t = i < nleaf ? P.order[i] : -1;
+    const int f = t >= 0 ? P.sfirst[t] : 0;
+    const bool on = t >= 0 && P.sfirst[t + 1] - f == 1;
+    double s0 = 0.0, s1 = 0.0;
+    if (on) {
+        const int nr = (int)(P.rptr[t + 1] - P.rptr[t]);
+        const double *col = P.panels + P.poff[t] + 1;
+        const int *R = P.rows + P.rptr[t];
+        for (int r = l8; r < nr; r += 8) {
+            const double l = col[r];
+            const double2 xv = P.Y[R[r]];
+            s0 += l * xv.x; s1 += l * xv.y;
+        }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+    if (on && l8 == 0) {
+        const double2 yv = P.Y[f];
+        const double dk = P.D[f];
+        P.Y[f] = make_double2(yv.x / dk - s0, yv.y / dk - s1);
     }
 }
 
@@ -841,10 +930,12 @@ void ldlt_analyze(Handle *h, const int64_t *Puser, const fpsb_ldlt_opts *opts) {
         for (int part = 0; part < 2; part++) {
             int i = part == 0 ? 0 : S.nleaf;
             const int end = part == 0 ? S.nleaf : S.nsuper;
+            auto leaf1 = [&](int s) { return part == 0 && S.sfirst[(size_t)s + 1] - S.sfirst[(size_t)s] == 1; };
             while (i < end) {
+                if (leaf1(S.order[(size_t)i])) { i++; continue; }      // leaf1_*_kernel
                 if (small(S.order[(size_t)i])) {
                     int j = i;
-                    while (j < end && j - i < kWarpsPerBlock && small(S.order[(size_t)j])) j++;
+                    while (j < end && j - i < kWarpsPerBlock && small(S.order[(size_t)j]) && !leaf1(S.order[(size_t)j])) j++;
                     tstart.push_back(i); tcnt.push_back(j - i);
                     i = j;
                 } else {
@@ -852,7 +943,7 @@ void ldlt_analyze(Handle *h, const int64_t *Puser, const fpsb_ldlt_opts *opts) {
                     i++;
                 }
             }
-            if (part == 0) L->ntasks_leaf = (int)tstart.size();
+            if (part == 0) L->ntasks_leaf = (int)tstart.size();      // tasks of the leaves wider than one column
         }
     }
     L->ntasks = (int)tstart.size();
@@ -902,8 +993,6 @@ void ldlt_free(Handle *h) {
     if (h->ldlt) { delete h->ldlt; h->ldlt = nullptr; }
 }
 
-static int phase_grid(int ntasks) { return std::max(1, std::min(ntasks, 148 * 6)); }
-
 void ldlt_factorize(Handle *h, double delta, int *factorized) {
     LdltPlan *L = h->ldlt;
     cudaStream_t s = h->stream;
@@ -920,17 +1009,18 @@ void ldlt_factorize(Handle *h, double delta, int *factorized) {
         h->launches += 1;
     }
     const int nl = L->ntasks_leaf, nn = L->ntasks - L->ntasks_leaf, N = L->S.N;
-    if (nl) {     // leaves: no dependencies at all
-        ldlt_phase_kernel<0><<<phase_grid(nl), kLdltBlock, 0, s>>>(L->dev, L->epoch, 0, nl, 0, 1);
+    const int nleaf = L->S.nleaf;
+    if (nleaf) {  // leaves: no dependencies at all
+        leaf1_factor_kernel<<<(int)(((int64_t)nleaf * 8 + 255) / 256), 256, 0, s>>>(L->dev, nleaf);
         h->launches += 1;
     }
+    if (nl) launch_phase<0>(h, L->dev, nl, L->epoch, 0, nl, 0, 1, true);
     if (nn) {
-        if (nl) {
+        if (nleaf) {
             leaf_update_kernel<<<(int)(((int64_t)N * 8 + 255) / 256), 256, 0, s>>>(L->dev);
             h->launches += 1;
         }
-        ldlt_phase_kernel<0><<<phase_grid(nn), kLdltBlock, 0, s>>>(L->dev, L->epoch, nl, L->ntasks, 1, 0);
-        h->launches += 1;
+        launch_phase<0>(h, L->dev, nn, L->epoch, nl, L->ntasks, 1, 0);
     }
     int fail = 0;
     FPSB_CUDA(cudaMemcpyAsync(&fail, L->fail.p, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -964,15 +1054,15 @@ void ldlt_solve2(Handle *h, int kind, const double *rhs1, const double *rhs2, do
     load_rhs_kernel<<<grid, 256, 0, s>>>(N, nvar, kind, L->P.p, rhs1, rhs2, L->Y.p);
     const int nl = L->ntasks_leaf, nn = L->ntasks - L->ntasks_leaf;
     // forward: leaves (independent) -> leaf contributions by target row -> the rest (dependency driven)
-    if (nl) { ldlt_phase_kernel<1><<<phase_grid(nl), kLdltBlock, 0, s>>>(L->dev, L->epoch, 0, nl, 0, 1); h->launches += 1; }
+    if (nl) launch_phase<1>(h, L->dev, nl, L->epoch, 0, nl, 0, 1, true);
     if (nn) {
-        if (nl) { leaf_fwd_update_kernel<<<grid, 256, 0, s>>>(L->dev); h->launches += 1; }
-        ldlt_phase_kernel<1><<<phase_grid(nn), kLdltBlock, 0, s>>>(L->dev, L->epoch, nl, L->ntasks, 1, 0);
+        if (L->S.nleaf) { leaf_fwd_update_kernel<<<grid, 256, 0, s>>>(L->dev); h->launches += 1; }
+        launch_phase<1>(h, L->dev, nn, L->epoch, nl, L->ntasks, 1, 0);
         // backward: the non-leaf part in reverse dependency order, then all leaves at once
-        ldlt_phase_kernel<2><<<phase_grid(nn), kLdltBlock, 0, s>>>(L->dev, L->epoch, nl, L->ntasks, 2, 0);
-        h->launches += 2;
+        launch_phase<2>(h, L->dev, nn, L->epoch, nl, L->ntasks, 2, 0);
     }
-    if (nl) { ldlt_phase_kernel<2><<<phase_grid(nl), kLdltBlock, 0, s>>>(L->dev, L->epoch, 0, nl, 3, 1); h->launches += 1; }
+    if (nl) launch_phase<2>(h, L->dev, nl, L->epoch, 0, nl, 3, 1, true);
+    if (L->S.nleaf) { leaf1_bwd_kernel<<<(int)(((int64_t)L->S.nleaf * 8 + 255) / 256), 256, 0, s>>>(L->dev, L->S.nleaf); h->launches += 1; }
     store_sol_kernel<<<grid, 256, 0, s>>>(N, nvar, L->pinv.p, L->Y.p, p1, q1, p2, q2);
     h->launches += 2;
     FPSB_CUDA(cudaGetLastError());

@@ -23,8 +23,39 @@
 //     phase that does not run any more are drained and the kernel ends.  CTA 0 publishes the states.
 // Requirements (checked by the host): both operators have no long rows, one ring geometry fits both,
 // grid <= tiles of either operator, all CTAs co-resident (cooperative launch, 1 CTA per SM).
+// Row-partitioned runs (fpsb_dist.inl): what CTA 0 needs to do the exchange of a phase boundary itself, through the
+// peers' mailboxes (CUDA IPC over NVLink), while the other CTAs wait for ITS release instead of the grid barrier:
+//   n-space phase:  halo partial sums -> owners ; owners add them (rank order), run the row epilogue of their
+//                   boundary rows and put the fresh pair values into the halo slots of the peers ; norm sums
+//   m-space phase:  norm sums only
+// The four all-reduced sums go to gtot; every CTA runs the scalar recurrences on those, exactly as on one GPU.
+// One launch = a chunk of iterations of every rank: an iteration costs two NVLink signal round trips (n) + one (m),
+// no kernel launch and no host involvement.
+struct DistLoop {
+    int nranks, rank;
+    int nbound;                               // owned rows that peers contribute to (and keep as halo)
+    const int *bidx, *bptr, *bsrc, *bpeer;    // per boundary row: its send-list entries (rank order) and their peers
+    const long long *meta;                    // recv_start[R] | recv_cnt[R] | send_ptr[R+1] | ga_off[R]
+    double2 *S;                               // raw row sums of the halo / boundary rows (StepParams::raw_out of op[0])
+    double2 *pair;                            // gathered pair of the extended n-space (Gn)
+    long long nsend, nrecv;                   // my inbox sizes (entries)
+    unsigned char *mine;
+    unsigned char *peer[kMboxMaxRanks];
+    long long sc_at_peer[kMboxMaxRanks], ga_at_peer[kMboxMaxRanks];
+    long long peer_nsend[kMboxMaxRanks], peer_nrecv[kMboxMaxRanks];
+    unsigned long long *seq;                  // device copy of [0] signals issued, [1] scatters, [2] gathers, [3] tot exchanges
+    double *gtot;                             // [2][4] all-reduced sums, ping-pong by phase parity
+    unsigned long long *xbar;                 // exchanges completed in this launch (zero at launch)
+    int *err;
+};
+// mailbox layout (bytes):  flags u64[8] | tot double[2][8][4] | scatter inbox double2[2][nsend] | gather inbox double2[2][nrecv]
+__host__ __device__ static inline size_t mbox_off_tot() { return kMboxOffTot; }
+__host__ __device__ static inline size_t mbox_off_sc() { return mbox_off_tot() + 2 * kMboxMaxRanks * 4 * sizeof(double); }
+__host__ __device__ static inline size_t mbox_off_ga(int64_t nsend) { return mbox_off_sc() + 2 * (size_t)nsend * sizeof(double2); }
+
 struct LoopParams {
     StepParams op[2];            // [0] n-space step (rows of A'), [1] m-space step (rows of A); io modes fixed for the loop
+    const DistLoop *dx;          // non-null: row-partitioned run, CTA 0 exchanges with the peers at every phase boundary
     int first;                   // operator of phase 0
     int nphase;                  // phases this launch may run at most
     int nspec;                   // tiles of a phase the block producers may request before the phase opens
@@ -110,14 +141,211 @@ __device__ unsigned long long g_loop_seg[160][2][kGroups][8];
 // (Tried and dropped: per-CTA records stamped in the sign bit so that arrival and partials are one L2 round trip:
 //  the 148 x 64 polling lanes slowed the CTAs that were still streaming by more than the round trip saved.)
 
+// The exchange of the boundary after phase `ph`, by the 384 consumer threads of CTA 0 (see DistLoop).
+__device__ __noinline__ void loop_exchange(const LoopParams &L, const DistLoop &X, int ph, int ct, int cw, int lane, int gsz,
+                                           const Coef *sC, double *s_red /* 4*32 */, double *s_x /* >= 8 */, LoopCtl &ctl) {
+    constexpr int kCons = kGroups * kGroupThreads;
+    const int R = X.nranks;
+    const int o = (L.first + ph) & 1;                      // 0: n-space phase (rows of A_loc'), 1: m-space phase
+    const long long *recv_start = X.meta, *recv_cnt = X.meta + R, *send_ptr = X.meta + 2 * R, *ga_off = X.meta + 3 * R + 1;
+    auto die = [&]() { ctl.abort = 1; atomicExch(X.err, 1); atomicExch(L.done_flag + 2, 2); __threadfence_system(); __trap(); };
+    // every CTA of this GPU has left its record and its raw sums
+    if (ct == 0) {
+        const unsigned long long want = (unsigned long long)(ph + 1) * (unsigned long long)gsz;
+        const unsigned long long t0 = global_ns();
+        unsigned spins = 0;
+        while (ld_acquire_gpu(L.gbar) < want) {
+            __nanosleep(20);
+            if ((++spins & 4095) == 0 && global_ns() - t0 > 4000000000ull) die();
+        }
+    }
+    consumers_bar();
+    unsigned long long sig = __ldcg(X.seq + 0);
+    const int sc_par = (int)(__ldcg(X.seq + 1) & 1), ga_par = (int)(__ldcg(X.seq + 2) & 1), tot_par = (int)(__ldcg(X.seq + 3) & 1);
+    auto signal_wait = [&](unsigned long long seq) {
+        // (every thread has fenced its own remote puts system-wide before the barrier)
+        consumers_bar();
+        if (ct < R && ct != X.rank) {
+            st_release_sys(reinterpret_cast<unsigned long long *>(X.peer[ct]) + X.rank, seq);
+            const unsigned long long *f = reinterpret_cast<const unsigned long long *>(X.mine) + ct;
+            const unsigned long long t0 = global_ns();
+            unsigned spins = 0;
+            while (ld_acquire_sys(f) < seq) {
+                if ((++spins & 1023) == 0 && global_ns() - t0 > 4000000000ull) die();     // 4 s: a peer died
+            }
+        }
+        consumers_bar();
+    };
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    if (o == 0) {
+        if (R > 1) {
+            // 1. halo partial sums -> the owners' scatter inboxes
+            for (int p = 0; p < R; ++p) {
+                if (p == X.rank) continue;
+                const long long cnt = recv_cnt[p];
+                double2 *dst = reinterpret_cast<double2 *>(X.peer[p] + mbox_off_sc()) + (size_t)sc_par * X.peer_nsend[p] + X.sc_at_peer[p];
+                const double2 *src = X.S + recv_start[p];
+                for (long long i = ct; i < cnt; i += kCons) dst[i] = __ldcg(src + i);
+            }
+            __threadfence_system();
+            signal_wait(++sig);
+        }
+        // 2. boundary rows: add the peers' partial sums (rank order), Krylov row epilogue, fresh value -> peers' halo slots
+        const CoefR C0 = to_regs(sC[0]), C1 = to_regs(sC[1]);
+        const bool act0 = C0.mode != MD_NONE, act1 = C1.mode != MD_NONE;
+        const StepParams &Pn = L.op[0];
+        const double2 *inbox = reinterpret_cast<const double2 *>(X.mine + mbox_off_sc()) + (size_t)sc_par * X.nsend;
+        for (int b = ct; b < X.nbound; b += kCons) {
+            const int row = X.bidx[b], kb = X.bptr[b], ke = X.bptr[b + 1];
+            double2 sm = __ldcg(X.S + row);
+            if (R > 1) for (int k = kb; k < ke; ++k) { const double2 a = __ldcg(inbox + X.bsrc[k]); sm.x += a.x; sm.y += a.y; }
+            const double2 old2 = __ldcg(X.pair + row);
+            double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+            if (C0.rd0()) a00 = __ldcg(Pn.io[0].a0 + row);
+            if (C0.rd1()) a01 = __ldcg(Pn.io[0].a1 + row);
+            if (C1.rd0()) a10 = __ldcg(Pn.io[1].a0 + row);
+            if (C1.rd1()) a11 = __ldcg(Pn.io[1].a1 + row);
+            double n0 = old2.x, n1 = old2.y;
+            if (act0) n0 = row_epilogue(C0, sm.x, old2.x, a00, a01, acc[0], acc[1]);
+            if (act1) n1 = row_epilogue(C1, sm.y, old2.y, a10, a11, acc[2], acc[3]);
+            const double2 val = make_double2(n0, n1);
+            X.pair[row] = val;
+            if (C0.wr0()) Pn.io[0].a0[row] = a00;
+            if (C0.wr1()) Pn.io[0].a1[row] = a01;
+            if (C1.wr0()) Pn.io[1].a0[row] = a10;
+            if (C1.wr1()) Pn.io[1].a1[row] = a11;
+            if (R > 1) for (int k = kb; k < ke; ++k) {
+                const int i = X.bsrc[k], p = X.bpeer[k];
+                double2 *dst = reinterpret_cast<double2 *>(X.peer[p] + mbox_off_ga(X.peer_nsend[p])) + (size_t)ga_par * X.peer_nrecv[p] + X.ga_at_peer[p];
+                dst[i - send_ptr[p]] = val;
+            }
+        }
+    }
+    // 3. local sums: the CTAs' records in CTA order, then the boundary rows
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const double x = warp_sum(acc[q]);
+        if (lane == 0) s_red[q * 32 + cw] = x;
+    }
+    consumers_bar();
+    if (cw == 0) {
+        const double *base = L.parts + (size_t)(ph & 1) * gsz * 4;
+        double tot[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int i = lane; i < gsz; i += 32) {
+            const double2 a = __ldcg(reinterpret_cast<const double2 *>(base + (size_t)i * 4));
+            const double2 b = __ldcg(reinterpret_cast<const double2 *>(base + (size_t)i * 4 + 2));
+            tot[0] += a.x; tot[1] += a.y; tot[2] += b.x; tot[3] += b.y;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tot[q] = warp_sum(tot[q]) + warp_sum(lane < kGroups * kGroupWarps ? s_red[q * 32 + lane] : 0.0);
+        if (lane < 4) {
+            const double v = lane == 0 ? tot[0] : (lane == 1 ? tot[1] : (lane == 2 ? tot[2] : tot[3]));
+            s_x[lane] = v;
+            for (int p = 0; p < R; ++p) {
+                if (p == X.rank) continue;
+                reinterpret_cast<double *>(X.peer[p] + mbox_off_tot())[((size_t)tot_par * kMboxMaxRanks + X.rank) * 4 + lane] = v;
+            }
+        }
+    }
+    __threadfence_system();
+    if (R > 1) signal_wait(++sig); else consumers_bar();
+    // 4. the peers' fresh values -> my halo slots ; the ranks' sums in rank order
+    if (o == 0 && R > 1) {
+        const double2 *inbox = reinterpret_cast<const double2 *>(X.mine + mbox_off_ga(X.nsend)) + (size_t)ga_par * X.nrecv;
+        for (int p = 0; p < R; ++p) {
+            if (p == X.rank) continue;
+            const long long cnt = recv_cnt[p];
+            double2 *dst = X.pair + recv_start[p];
+            const double2 *src = inbox + ga_off[p];
+            for (long long i = ct; i < cnt; i += kCons) dst[i] = __ldcg(src + i);
+        }
+    }
+    if (ct < 4) {
+        const double *in = reinterpret_cast<const double *>(X.mine + mbox_off_tot()) + (size_t)tot_par * kMboxMaxRanks * 4;
+        double g = 0.0;
+        for (int r = 0; r < R; ++r) g += (r == X.rank) ? s_x[ct] : __ldcg(in + r * 4 + ct);
+        X.gtot[(size_t)(ph & 1) * 4 + ct] = g;
+    }
+    if (ct == 0) {
+        X.seq[0] = sig;
+        if (o == 0) { X.seq[1] += 1; X.seq[2] += 1; }
+        X.seq[3] += 1;
+    }
+    fence_proxy_async();                                     // the halo / boundary entries of the pair vs the next phase's TMA reads
+    __threadfence();
+    consumers_bar();
+    if (ct == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(X.xbar), "l"((unsigned long long)(ph + 1)) : "memory");
+}
+
+// second half of the boundary: slot r's recurrence on its two sums, the coefficients of phase ph, the stop decision
+__device__ __forceinline__ void loop_boundary_finish(const LoopParams &L, int ph, int r, int lane, int cta, SlotState *sS, Coef *sC,
+                                                     LoopCtl &ctl, double tot0, double tot1) {
+    if (lane == 0) {
+        const StepParams &Pp = L.op[(L.first + ph - 1) & 1];
+        const int mode = Pp.io[r].mode;
+        const double t0 = tot0, t1 = tot1;
+        LT_STAMP(ph - 1, r ? 11 : 8);
+        if (mode != MD_NONE && sS[r].active) finish_step(sS[r], mode, t0, t1);
+        LT_STAMP(ph - 1, r ? 12 : 9);
+        const StepParams &Pn = L.op[(L.first + ph) & 1];
+        load_coef(sC[r], Pn.io[r], &sS[r], true);
+        if (!(Pn.io[r].mode != MD_NONE && sS[r].active)) {
+            sC[r].mode = MD_NONE; sC[r].rd0 = sC[r].rd1 = sC[r].wr0 = sC[r].wr1 = sC[r].rdself = 0;
+        }
+        LT_STAMP(ph - 1, r ? 13 : 10);
+        if (r == 1) st_release_cta(&ctl.open1, ph + 1);
+        else {
+            loop_wait_thread(&ctl.open1, ph + 1, &ctl);
+            if (!sS[0].active && !sS[1].active) ctl.stop_at = ph;
+            st_release_cta(&ctl.open, ph + 1);
+            LT_STAMP(ph - 1, 4);
+        }
+    }
+    if (r == 1) loop_wait(&ctl.open, ph + 1, &ctl);          // warp 1 learns the stop decision from warp 0
+    __syncwarp();
+    if (r == 0 && cta == 0 && (ph >= L.nphase || ctl.stop_at <= ph)) {
+        const double *src = reinterpret_cast<const double *>(sS);
+        double *dst = reinterpret_cast<double *>(L.st);
+        for (int i = lane; i < (int)(2 * sizeof(SlotState) / sizeof(double)); i += 32) dst[i] = src[i];
+        if (lane == 0) {
+            if (!sS[0].active && !sS[1].active) L.done_flag[0] = 1;
+            L.done_flag[1] += ph;
+        }
+    }
+}
+
+
 // Boundary work of recurrence warp r (consumer warp 0 or 1) before phase `ph` (1 <= ph <= nphase): wait for
 // every CTA's record of phase ph - 1, add them in a fixed order, run slot r's scalar recurrence, prepare the
 // coefficients of phase ph.  Warp 0 also publishes pass / open / stop_at and, in CTA 0, the final states.
 // (Inlined: a call inside the phase loop makes ptxas spill the tile loop. state around it.)
+template <bool DIST>
 __device__ __forceinline__ void loop_boundary(const LoopParams &L, int ph, int r, int lane, int cta, int gsz, SlotState *sS, Coef *sC,
                                               LoopCtl &ctl, double *rsum /* 64 * 4 */) {
     const double *base = L.parts + (size_t)((ph - 1) & 1) * gsz * 4;
     if (lane == 0) LT_STAMP(ph - 1, r ? 15 : 14);
+    if (DIST) {
+        // row-partitioned run: CTA 0 publishes the all-reduced sums after the exchange with the peers
+        double tot[4] = {0.0, 0.0, 0.0, 0.0};
+        if (r == 0 && lane == 0) {
+            const unsigned long long t0 = global_ns();
+            unsigned spins = 0;
+            while (ld_acquire_gpu(L.dx->xbar) < (unsigned long long)ph) {
+                __nanosleep(40);
+                if ((++spins & 4095) == 0 && global_ns() - t0 > 6000000000ull) {     // 6 s: the exchange died
+                    ctl.abort = 1; atomicExch(L.done_flag + 2, 2); __threadfence_system(); __trap();
+                }
+            }
+        }
+        asm volatile("bar.sync %0, %1;" ::"n"(2 + kGroups), "n"(64) : "memory");      // the two recurrence warps
+        if (r == 0 && lane == 0) { st_release_cta(&ctl.pass, ph); LT_STAMP(ph - 1, 3); }
+        if (lane == 0) {
+            const double2 v = __ldcg(reinterpret_cast<const double2 *>(L.dx->gtot + (size_t)((ph - 1) & 1) * 4) + r);
+            tot[0] = v.x; tot[1] = v.y;
+        }
+        loop_boundary_finish(L, ph, r, lane, cta, sS, sC, ctl, tot[0], tot[1]);
+        return;
+    }
 #ifdef FPSB_LOOP_V1B
     double tot[4] = {0.0, 0.0, 0.0, 0.0};
     {
@@ -182,40 +410,10 @@ __device__ __forceinline__ void loop_boundary(const LoopParams &L, int ph, int r
         for (int l = 0; l < 64; ++l) { const double2 v = all[2 * l]; tot[0] += v.x; tot[1] += v.y; }
     }
 #endif
-    if (lane == 0) {
-        const StepParams &Pp = L.op[(L.first + ph - 1) & 1];
-        const int mode = Pp.io[r].mode;
-        const double t0 = tot[0], t1 = tot[1];
-        LT_STAMP(ph - 1, r ? 11 : 8);
-        if (mode != MD_NONE && sS[r].active) finish_step(sS[r], mode, t0, t1);
-        LT_STAMP(ph - 1, r ? 12 : 9);
-        const StepParams &Pn = L.op[(L.first + ph) & 1];
-        load_coef(sC[r], Pn.io[r], &sS[r], true);
-        if (!(Pn.io[r].mode != MD_NONE && sS[r].active)) {
-            sC[r].mode = MD_NONE; sC[r].rd0 = sC[r].rd1 = sC[r].wr0 = sC[r].wr1 = sC[r].rdself = 0;
-        }
-        LT_STAMP(ph - 1, r ? 13 : 10);
-        if (r == 1) st_release_cta(&ctl.open1, ph + 1);
-        else {
-            loop_wait_thread(&ctl.open1, ph + 1, &ctl);
-            if (!sS[0].active && !sS[1].active) ctl.stop_at = ph;
-            st_release_cta(&ctl.open, ph + 1);
-            LT_STAMP(ph - 1, 4);
-        }
-    }
-    if (r == 1) loop_wait(&ctl.open, ph + 1, &ctl);          // warp 1 learns the stop decision from warp 0
-    __syncwarp();
-    if (r == 0 && cta == 0 && (ph >= L.nphase || ctl.stop_at <= ph)) {
-        const double *src = reinterpret_cast<const double *>(sS);
-        double *dst = reinterpret_cast<double *>(L.st);
-        for (int i = lane; i < (int)(2 * sizeof(SlotState) / sizeof(double)); i += 32) dst[i] = src[i];
-        if (lane == 0) {
-            if (!sS[0].active && !sS[1].active) L.done_flag[0] = 1;
-            L.done_flag[1] += ph;
-        }
-    }
+    loop_boundary_finish(L, ph, r, lane, cta, sS, sC, ctl, tot[0], tot[1]);
 }
 
+template <bool DIST>
 __global__ void __launch_bounds__(kStepThreads, 1) gk_loop_kernel(const __grid_constant__ LoopParams L) {
     extern __shared__ __align__(128) unsigned char s_dyn[];
     __shared__ double2 s_sum[kGroups][2][kTileRows];        // [group][double buffer][row]
@@ -505,6 +703,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_loop_kernel(const __grid_c
             }
         }
         // consumer warps 0 / 1: the boundary before phase ph + 1 (the other warps go on and wait for `pass` / `open`)
-        if (cw < 2) loop_boundary(L, ph + 1, cw, lane, cta, gsz, sS, sC, ctl, s_rsum);
+        if (DIST && cta == 0) loop_exchange(L, *L.dx, ph, ct, cw, lane, gsz, sC, s_red, s_rsum, ctl);
+        if (cw < 2) loop_boundary<DIST>(L, ph + 1, cw, lane, cta, gsz, sS, sC, ctl, s_rsum);
     }
 }
