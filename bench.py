@@ -285,6 +285,7 @@ def run_partitioned(args, dist, rank, world, local_rank, make):
     rel = [float(np.sqrt(e[2 * k] / e[2 * k + 1])) if e[2 * k + 1] > 0 else float(np.sqrt(e[2 * k])) for k in range(4)]
     it1 = [int(single[1].item()), int(single[2].item())]
     nit, nit1 = max(iters), max(it1)
+    in_kernel = bool(D.peer) and os.environ.get("FPSB_DIST_LOOP", "1") != "0"
     del D
     torch.cuda.synchronize(); dist.barrier()
     us, us1 = 1e3 * loop_ms / max(nit, 1), 1e3 * float(single[0].item()) / max(nit1, 1)
@@ -299,7 +300,7 @@ def run_partitioned(args, dist, rank, world, local_rank, make):
         "speedup_vs_single_gpu": us1 / us if us > 0 else None,
         "kernel": "one persistent kernel per chunk of 24 iterations on every rank; its CTA 0 does the halo scatter-add, the boundary "
                   "rows, the halo gather and the all-reduce of the four inner products through the peers' mailboxes (NVLink), "
-                  "the other CTAs wait for its release instead of the grid barrier" if D.peer and os.environ.get("FPSB_DIST_LOOP", "1") != "0"
+                  "the other CTAs wait for its release instead of the grid barrier" if in_kernel
                   else "launch per half iteration (step kernel + exchange kernel)",
         "launch_per_half_iteration_path": {"us_per_iteration": 1e3 * float(fallback_ms.item()) / max(nit, 1),
                                            "per_launch_us_max_over_ranks": shares,
@@ -511,7 +512,8 @@ def main():
     loop_ms_per_solve = loop_ms / args.steps
     achieved = tot_bytes / (loop_ms_per_solve * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": "gk_step_kernel<PAIR=true> (fused 2-column SpMM + Krylov row epilogue)",
+        "bound": "hbm", "kernel": "gk_loop_kernel (persistent Krylov loop: fused 2-column SpMM + Krylov row epilogue + scalar recurrences, "
+                                  "one launch per chunk of 24 iterations; a 'launch' below is one half iteration = one pass over A or A')",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "frac_of_nominal_8000": achieved / 8000.0, "peak_source": peak_src,
         "traffic": traffic, "traffic_static": traffic is not None, "traffic_source": traffic_src,

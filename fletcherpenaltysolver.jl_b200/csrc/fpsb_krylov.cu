@@ -2229,6 +2229,11 @@ struct Engine {
         L.nphase = 2 * chunk_it;
         L.nspec = std::max(0, std::min(env_int("FPSB_LOOP_NSPEC", kGroups), nstage - 1));
         L.early = mode >= 2 ? 1 : 0;
+        // Row-partitioned runs: no early row sums.  Measured at 2 GPUs on the headline operator (tools/dist_parity.py, n >= 500 000,
+        // reference tolerances): with them the result is 3e-7 off the single-GPU solve and not reproducible run to run; without
+        // them it agrees to 3e-14 and is bitwise reproducible (fixed-iteration runs and n = 200 000 agree either way).  The cause
+        // is not found yet; FPSB_DIST_EARLY=1 re-enables the combination for that investigation.
+        if (loop_dx != nullptr && env_int("FPSB_DIST_EARLY", 0) == 0) L.early = 0;
         L.st = st_cur();
         L.parts = W->loop_parts.p;
         L.gbar = W->gbar.p;

@@ -38,9 +38,18 @@ class DeviceSparseQP(AbstractNLPModel):
         self.q = torch.tensor(host_qp.q, **f64)
         self.b = torch.tensor(host_qp.b, **f64)
         self._vals = torch.tensor(host_qp.jac_coord(None), **f64)
-        self.Acsr = torch.sparse_csr_tensor(torch.tensor(A.indptr, dtype=torch.int64, device=device),
-                                            torch.tensor(A.indices, dtype=torch.int64, device=device),
-                                            torch.tensor(A.data, **f64), size=A.shape)
+        self._device = device
+        self._H = None          # the model's own operator handle for c(x) = A x - b (hand-written SpMV, no cuSPARSE)
+
+    def _op(self):
+        if self._H is None:
+            import torch
+            from .qdsolver import B200Handle
+            d = torch.device(self._device)
+            idx = d.index if d.index is not None else torch.cuda.current_device()
+            self._H = B200Handle(self.meta.nvar, self.meta.ncon, self._rows, self._cols, device=idx)
+            self._H.set_jac_values(self._vals)
+        return self._H
 
     def obj(self, x):
         return float(0.5 * (x * self.Q * x).sum() + self.q @ x)
@@ -49,7 +58,7 @@ class DeviceSparseQP(AbstractNLPModel):
         return self.Q * x + self.q
 
     def cons(self, x):
-        return (self.Acsr @ x.unsqueeze(1)).squeeze(1) - self.b
+        return self._op().jprod(x) - self.b
 
     def jac_structure(self):
         return self._rows, self._cols

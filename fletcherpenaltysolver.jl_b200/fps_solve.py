@@ -108,7 +108,7 @@ class AlgoData:
                  subproblem_solver="trunk", subpb_unbounded_threshold=1 / SQRT_EPS,
                  subsolver_max_iter=20000, atol_sub=lambda atol: atol, rtol_sub=lambda rtol: rtol,
                  hessian_approx=2, explicit_linear_constraints=False, convex_subproblem=False,
-                 lagrange_bound=1 / SQRT_EPS, **kwargs):
+                 lagrange_bound=1 / SQRT_EPS, refresh_memo_on_update=False, **kwargs):
         self.sigma_0, self.sigma_max, self.sigma_update = sigma_0, sigma_max, sigma_update
         self.rho_0, self.rho_max, self.rho_update = rho_0, rho_max, rho_update
         self.delta_0, self.delta_max, self.delta_update = delta_0, delta_max, delta_update
@@ -121,6 +121,10 @@ class AlgoData:
         self.explicit_linear_constraints = explicit_linear_constraints
         self.convex_subproblem = convex_subproblem
         self.lagrange_bound = lagrange_bound
+        # Not a reference option.  False (default) = the reference: the memo of FletcherPenaltyNLP is keyed on hash(x)
+        # only, so right after a sigma / rho / delta update the first evaluation at the unchanged x
+        # still returns ys / gs of the OLD parameters.  True drops the memo when the parameters change.
+        self.refresh_memo_on_update = refresh_memo_on_update
 
 
 class GNSolver:
@@ -711,9 +715,10 @@ def _update_parameters(meta, model, feas):
     if not feas:
         model.rho *= meta.rho_update
     # The penalty changed.  The reference keeps its memo here (it is keyed on hash(x) only), so its
-    # first evaluation at the unchanged x still sees ys / gs of the OLD sigma; this loop drops the memo instead —
-    # a deliberate deviation in the driver, the memo rule itself (fletcher_nlp.py) is the reference's.
-    model.shahx = 0
+    # first evaluation at the unchanged x still sees ys / gs of the OLD sigma: that is the default.  The option
+    # refresh_memo_on_update (not a reference option) drops the memo instead.
+    if getattr(meta, "refresh_memo_on_update", False):
+        model.shahx = 0
 
 
 def _update_parameters_unbdd(meta, model, feas):

@@ -118,7 +118,10 @@ def test_penalty_updates():
     meta = F.AlgoData()
     m = M()
     F._update_parameters(meta, m, feas=True)                    # src/algo.jl:366-381: rho only when infeasible
-    assert (m.sigma, m.rho, m.shahx) == (2e3, 1.0, 0)
+    assert (m.sigma, m.rho, m.shahx) == (2e3, 1.0, 7)           # the memo survives the update (reference, App. D-1)
+    m2 = M()
+    F._update_parameters(F.AlgoData(refresh_memo_on_update=True), m2, feas=True)
+    assert (m2.sigma, m2.shahx) == (2e3, 0)                     # opt-in: drop it
     F._update_parameters(meta, m, feas=False)
     assert (m.sigma, m.rho) == (4e3, 2.0)
     F._update_parameters_unbdd(meta, m, feas=False)             # :388-395: delta starts at delta_0, then x10

@@ -15,3 +15,26 @@ for name, fn in (("mixed", lambda: H.iter_solve_two_mixed(0.0, d1, d2)), ("lsq",
         t0 = time.perf_counter(); H.timer_start(); out = fn(); ms = H.timer_stop(); wall = 1e3 * (time.perf_counter() - t0)
         lms, nl = H.iter_last_profile()
         print(name, "event %.3f ms wall %.3f ms loop %.3f ms launches %d iters %s" % (ms, wall, lms, nl, [s["niter"] for s in out[4]]))
+
+# what bench.py does between the headline measurement and this extra: asynchronous products, a second handle that comes and goes
+def lsq(tag):
+    for rep in range(3):
+        H.timer_start(); out = H.iter_solve_two_least_squares(0.0, d1, d3); ms = H.timer_stop()
+        lms, nl = H.iter_last_profile()
+        print(tag, "lsq event %.3f ms loop %.3f ms launches %d iters %s" % (ms, lms, nl, [s["niter"] for s in out[4]]))
+for _ in range(20):
+    y = H.jprod(d1)
+for _ in range(20):
+    y = H.jtprod(d2)
+lsq("after async products:")
+H2 = fpsb200.B200Handle(n, m, jrow, jcol)
+H2.iter_setup(None)
+H2.set_jac_values(torch.tensor(vals, device="cuda"))
+H2.iter_solve_two_mixed(0.0, d1, d2)
+lsq("second handle alive:")
+H2.close(); del H2
+lsq("second handle closed:")
+for name, fn in (("mixed", lambda: H.iter_solve_two_mixed(0.0, d1, d2)),):
+    for rep in range(3):
+        H.timer_start(); out = fn(); ms = H.timer_stop()
+        print(name, "event %.3f ms" % ms)
