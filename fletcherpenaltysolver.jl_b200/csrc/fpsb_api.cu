@@ -492,6 +492,24 @@ int fpsb_dist_solve_two_least_squares(fpsb_handle h, double delta, int64_t nvar_
     return dist_solve(h, 1, delta, nvar_global, ncon_global, rhs1, rhs2, p1, q1, p2, q2, loc, stats);
 }
 
+int fpsb_dist_solve_two_extras(fpsb_handle hh, double delta, int64_t nvar_global, int64_t ncon_global, const double *rhs1,
+                               const double *rhs2, double *u1, double *u2, int loc, fpsb_krylov_stats stats[2]) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQUIRE(h && rhs1 && rhs2 && u1 && u2 && stats, FPSB_EINVAL, "NULL argument");
+    REQUIRE(h->dist, FPSB_ESTATE, "not a row-partitioned handle (call fpsb_dist_attach first)");
+    REQUIRE(h->have_vals, FPSB_ESTATE, "Jacobian values not set (call fpsb_set_jac_values first)");
+    FPSB_TRY
+    FPSB_CUDA(cudaSetDevice(h->device));
+    const size_t n = (size_t)dist_n_own(h), m = (size_t)h->ncon;
+    Staged S(h, loc, n + m, 2 * m);
+    const double *d1 = S.in(rhs1, n), *d2 = S.in(rhs2, m);
+    double *du1 = S.out(u1, m), *du2 = S.out(u2, m);
+    dist_solve_two_extras(h, delta, d1, d2, du1, du2, stats, nvar_global, ncon_global);
+    S.finish();
+    return FPSB_OK;
+    FPSB_CATCH
+}
+
 /* ---- device-resident FletcherPenaltyNLP glue; all vector arguments are DEVICE pointers ---- */
 int fpsb_fp_ys_gs(fpsb_handle hh, double sigma, const double *p1, const double *q1, const double *p2, const double *q2,
                   double *gs, double *ys, double *v, double *w) {

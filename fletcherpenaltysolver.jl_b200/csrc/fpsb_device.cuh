@@ -39,6 +39,23 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity) {
         if (mbar_try_wait(bar, parity)) return true;
     return false;
 }
+// A parity wait is only meaningful while the waiter is at most ONE phase ahead of the barrier.  The ring's stages are
+// consumed by rotating consumer groups (stage count and group count are coprime in general), so a group that runs two
+// tiles ahead of its neighbours could ask for round r of a stage whose round r - 1 has not even been filled: the parity
+// test then passes at once and the group reads the stage's OLD contents (measured: wrong results at n = 450-550 K with
+// early row sums, where two groups get a head start of a tile at every phase boundary).  So the first warp of a group
+// publishes, per stage, the number of rounds it has SEEN filled (stage_seen, right after its own full-barrier wait), and
+// a warp only parity-waits for round r once round r - 1 was seen (stage_turn_wait): one broadcast shared-memory load per
+// tile and warp, one store per tile and group.  The chain only points backwards in the ring, so it cannot deadlock.
+__device__ __forceinline__ void stage_turn_wait(const int *seen, int round) {     // every lane (same address: one broadcast)
+    int it = 0;
+    while (*reinterpret_cast<const volatile int *>(seen) < round) {
+        if (++it > (1 << 24)) __trap();          // ~0.3 s: a mis-counted ring must end the launch, not hang the box
+    }
+}
+__device__ __forceinline__ void stage_seen(int *seen, int round) {                // one lane of the group's first warp
+    *reinterpret_cast<volatile int *>(seen) = round + 1;
+}
 // TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
     asm volatile(

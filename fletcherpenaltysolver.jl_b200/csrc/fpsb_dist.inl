@@ -903,8 +903,9 @@ struct DistEngine {
         E.loop_dx = nullptr;
         return true;
     }
-    void ew(int op, int slot, int n, const double *in0, double *v0, double *v1, double *v2, double2 *pair, int pair_slot, double c0) {
-        E.ew(op, slot, n, in0, v0, v1, v2, nullptr, nullptr, pair, pair_slot, c0, 1);
+    void ew(int op, int slot, int n, const double *in0, double *v0, double *v1, double *v2, double2 *pair, int pair_slot, double c0,
+            double *v3 = nullptr, double *v4 = nullptr) {
+        E.ew(op, slot, n, in0, v0, v1, v2, v3, v4, pair, pair_slot, c0, 1);
         const bool npair = pair >= E.W->Gn.p && pair < E.W->Gn.p + h->nvar;      // the n-space pair changed
         if (npair) D->halo_fresh = false;
         allreduce_finish(1, op, slot);
@@ -1042,3 +1043,86 @@ void dist_solve_two_least_squares(Handle *h, double delta, const double *rhs1, c
     E.fetch(st);
     X.check_peer_error();
 }
+
+// one column of an interleaved pair -> the same column of another pair / a plain vector
+__global__ void pair_set_col_kernel(int n, const double2 *src, double2 *dst, int col) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const double2 v = src[i]; reinterpret_cast<double *>(dst + i)[col] = col ? v.y : v.x; }
+}
+
+// Row-partitioned solve_two_extras of IterativeSolver (src/solve_linear_system.jl:45-77):
+//   u1 = LSQR(A', rhs1, lambda = sqrt(tau))          rhs1 = the OWNED n-space slice
+//   u2 = MINRES(A A' + tau I, rhs2)                  rhs2 / u1 / u2 = the local m-space slices
+// tau = max(delta, 1e-14).  LSQR is the one-slot case of dist_solve_two_least_squares (persistent loop kernel with the
+// exchange inside when the handle allows it).  MINRES keeps all its vectors in the m-space (rows of A: local, no halo);
+// only its operator needs the exchange: t = A' r2 is formed as partial sums of A_loc', scatter-added to the owners,
+// gathered back into the halo slots, and the fused MINRES row epilogue then runs on A_loc t; the inner products are
+// all-reduced after every step.
+void dist_solve_two_extras(Handle *h, double delta, const double *rhs1, const double *rhs2, double *u1, double *u2,
+                           fpsb_krylov_stats *st, int64_t nvar_global, int64_t ncon_global) {
+    DistEngine X(h);
+    Engine &E = X.E;
+    IterWs *W = h->iter;
+    DistCtx *D = h->dist;
+    const fpsb_iter_opts &o = h->iopts;
+    const int64_t n = nvar_global, m = ncon_global;
+    const int n_own = (int)D->n_own, m_loc = (int)h->ncon, n_ext = (int)h->nvar;
+    const double tau = std::max(delta, 1e-14);
+    fpsb_krylov_stats tmp[2];
+    // ---- LSQR(A', rhs1, lambda = sqrt(tau)) in slot 0
+    E.begin(make_lsqr(sqrt(tau), o.ls_atol, o.ls_rtol, o.ls_itmax, n, m), make_none());
+    W->Gn.zero(h->stream); W->Gm.zero(h->stream);
+    W->am[0][1].zero(h->stream);
+    X.ew(EW_INIT_LSQR, 0, n_own, rhs1, nullptr, nullptr, nullptr, W->Gn.p + D->own_off, 0, 1.0);
+    {
+        SlotIO l_init = io_mode(MD_LSQR_INIT_M), l_u = io_mode(MD_LSQR_U);
+        SlotIO l_v = io_mode(MD_LSQR_V, W->am[0][0].p, W->am[0][1].p);
+        X.step_m(l_init, io_none());
+        if (!X.run_loop(l_u, io_none(), l_v, io_none()))
+            E.loop([&](int) {
+                X.step_n(l_u, io_none());
+                X.step_m(l_v, io_none());
+            }, kChunk);
+    }
+    E.tot_out = nullptr;
+    E.ew(EW_COPY, 0, m_loc, W->am[0][1].p, u1, nullptr, nullptr, nullptr, nullptr, nullptr, -1, 1.0, 0);
+    E.fetch(tmp);
+    st[0] = tmp[0];
+    // ---- MINRES(A A' + tau I, rhs2) in slot 1
+    E.tot_out = D->tot.p;
+    E.begin(make_none(), make_minres(tau, o.ne_atol, o.ne_rtol, o.ne_etol, o.ne_conlim, o.ne_itmax, m));
+    const int slot = 1;
+    double *r1 = W->am[slot][0].p, *r2 = W->am[slot][1].p, *wa = W->am[slot][2].p, *wb = W->am[slot][3].p,
+           *x = W->am[slot][4].p, *y = W->ym.p, *t = W->an[slot][0].p;
+    W->Gn.zero(h->stream); W->Gm.zero(h->stream);
+    X.ew(EW_MINRES_INIT, slot, m_loc, rhs2, r1, r2, wa, nullptr, -1, 1.0, wb, x);
+    double *w1 = wa, *w2 = wb;
+    E.loop([&](int k) {
+        // t = A' r2 on the owned + halo columns
+        E.tot_out = nullptr;
+        E.ew(EW_INIT_LSQR, slot, m_loc, r2, nullptr, nullptr, nullptr, nullptr, nullptr, W->Gm.p, slot, 1.0, 0);
+        X.jt_partials(W->Gm.p);
+        pair_set_col_kernel<<<(unsigned)((n_own + 255) / 256), 256, 0, h->stream>>>(n_own, D->S.p + D->own_off, W->Gn.p + D->own_off, slot);
+        h->launches += 1;
+        D->halo_fresh = false;
+        X.gather_halo(W->Gn.p);
+        unpack_cols_kernel<<<(unsigned)((n_ext + 255) / 256), 256, 0, h->stream>>>(n_ext, W->Gn.p, slot == 0 ? t : nullptr, slot == 1 ? t : nullptr);
+        h->launches += 1;
+        // y = (A t + lambda r2)/beta - (beta/oldbeta) r1 ; alpha = r2'y / beta
+        E.tot_out = D->tot.p;
+        SlotIO m_io = io_mode(MD_MINRES_M, r2, r1);
+        m_io.gin = t; m_io.self = y;
+        E.step(true, false, io_none(), m_io);
+        X.allreduce_finish(0, MD_NONE, m_io.mode);
+        X.ew(EW_MINRES_E1, slot, m_loc, y, r1, r2, w1, nullptr, -1, 1.0, w2, nullptr);
+        double *wcur = (k == 1) ? w2 : w1;
+        X.ew(EW_MINRES_E2, slot, m_loc, nullptr, nullptr, nullptr, wcur, nullptr, -1, 1.0, nullptr, x);
+        if (k >= 2) std::swap(w1, w2);
+    }, 2);
+    E.tot_out = nullptr;
+    E.ew(EW_COPY, slot, m_loc, x, u2, nullptr, nullptr, nullptr, nullptr, nullptr, -1, 1.0, 0);
+    E.fetch(tmp);
+    st[1] = tmp[1];
+    X.check_peer_error();
+}
+

@@ -174,6 +174,9 @@ void dist_solve_two_mixed(Handle *h, double delta, const double *rhs1, const dou
 void dist_solve_two_least_squares(Handle *h, double delta, const double *rhs1, const double *rhs2, double *p1, double *q1,
                                   double *p2, double *q2, fpsb_krylov_stats *st, int64_t nvar_global, int64_t ncon_global);
 
+void dist_solve_two_extras(Handle *h, double delta, const double *rhs1, const double *rhs2, double *u1, double *u2,
+                           fpsb_krylov_stats *st, int64_t nvar_global, int64_t ncon_global);
+
 // fpsb_fpnlp.cu (device-resident FletcherPenaltyNLP glue)
 void fp_free(Handle *h);
 void fp_ys_gs(Handle *h, int64_t n, int64_t m, double sigma, const double *p1, const double *q1, const double *p2,

@@ -1057,6 +1057,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(const __grid_c
     __shared__ double s_red[4 * 32];
     __shared__ alignas(8) uint64_t full_bar[kMaxStages];
     __shared__ alignas(8) uint64_t empty_bar[kMaxStages];
+    __shared__ int s_rel[kMaxStages];                       // rounds seen filled, per stage (see stage_turn_wait)
     __shared__ SlotState sS[2];
     __shared__ Coef sC[2];
     __shared__ int s_last;
@@ -1068,7 +1069,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(const __grid_c
     // this CTA's own shared memory; everything below may read what the previous kernel wrote.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) {
-        for (int s = 0; s < nstage; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], kGroupWarps); }
+        for (int s = 0; s < nstage; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], kGroupWarps); s_rel[s] = 0; }
         mbar_fence_init();
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -1206,7 +1207,9 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(const __grid_c
             }
             const unsigned char *st = s_dyn + (size_t)s * stage_bytes;
             unsigned char *s_win = const_cast<unsigned char *>(st) + (size_t)P.blk_cap;
+            stage_turn_wait(&s_rel[s], k / nstage);
             ok = mbar_wait(&full_bar[s], (uint32_t)((k / nstage) & 1)) && ok;
+            if (t == 0) stage_seen(&s_rel[s], k / nstage);
             if (!PAIR && T.ccnt > 0 && !(win_tma && !(T.ccnt & 1))) {
                 // unaligned / odd-sized caller vectors: the group stages the window itself
                 double *win0 = reinterpret_cast<double *>(s_win);

@@ -330,15 +330,30 @@ __device__ __forceinline__ void loop_boundary(const LoopParams &L, int ph, int r
         if (r == 0 && lane == 0) {
             const unsigned long long t0 = global_ns();
             unsigned spins = 0;
+            // After an m-space phase the next phase gathers the m-space pair, which has no halo: it is complete as soon as
+            // this GPU's own CTAs arrived, so `pass` (early row sums, gather windows) does not wait for the peers; only the
+            // coefficients do.  After an n-space phase the halo slots must have been refreshed first.
+            const bool local_pass = ((L.first + ph - 1) & 1) == 1;
+            if (local_pass) {
+                const unsigned long long want = (unsigned long long)ph * (unsigned long long)gsz;
+                while (ld_acquire_gpu(L.gbar) < want) {
+                    __nanosleep(40);
+                    if ((++spins & 4095) == 0 && global_ns() - t0 > 6000000000ull) {
+                        ctl.abort = 1; atomicExch(L.done_flag + 2, 2); __threadfence_system(); __trap();
+                    }
+                }
+                st_release_cta(&ctl.pass, ph);
+            }
             while (ld_acquire_gpu(L.dx->xbar) < (unsigned long long)ph) {
                 __nanosleep(40);
                 if ((++spins & 4095) == 0 && global_ns() - t0 > 6000000000ull) {     // 6 s: the exchange died
                     ctl.abort = 1; atomicExch(L.done_flag + 2, 2); __threadfence_system(); __trap();
                 }
             }
+            if (!local_pass) st_release_cta(&ctl.pass, ph);
+            LT_STAMP(ph - 1, 3);
         }
         asm volatile("bar.sync %0, %1;" ::"n"(2 + kGroups), "n"(64) : "memory");      // the two recurrence warps
-        if (r == 0 && lane == 0) { st_release_cta(&ctl.pass, ph); LT_STAMP(ph - 1, 3); }
         if (lane == 0) {
             const double2 v = __ldcg(reinterpret_cast<const double2 *>(L.dx->gtot + (size_t)((ph - 1) & 1) * 4) + r);
             tot[0] = v.x; tot[1] = v.y;
@@ -420,6 +435,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_loop_kernel(const __grid_c
     __shared__ double s_red[4 * 32];
     __shared__ alignas(8) uint64_t full_bar[kMaxStages];
     __shared__ alignas(8) uint64_t empty_bar[kMaxStages];
+    __shared__ int s_rel[kMaxStages];                       // rounds seen filled, per stage (see stage_turn_wait)
     __shared__ SlotState sS[2];
     __shared__ Coef sC[2];
     __shared__ LoopCtl ctl;
@@ -442,7 +458,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_loop_kernel(const __grid_c
         for (int i = tid; i < (int)(2 * sizeof(SlotState) / sizeof(double)); i += kStepThreads) d[i] = __ldcg(g + i);
     }
     if (tid == 0) {
-        for (int s = 0; s < nstage; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], kGroupWarps); }
+        for (int s = 0; s < nstage; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], kGroupWarps); s_rel[s] = 0; }
         mbar_fence_init();
         ctl.pass = 0; ctl.open1 = 1; ctl.open = 1; ctl.stop_at = 0x7fffffff; ctl.abort = 0;
     }
@@ -598,7 +614,9 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_loop_kernel(const __grid_c
                 // drain the tiles the block producers requested before the phase was decided
                 for (int kl = g; kl < cnt && kl < L.nspec; kl += kGroups) {
                     const int k = kb + kl, s = k % nstage;
+                    stage_turn_wait(&s_rel[s], k / nstage);
                     ok = mbar_wait(&full_bar[s], (uint32_t)((k / nstage) & 1)) && ok;
+                    if (t == 0) stage_seen(&s_rel[s], k / nstage);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty_bar[s]);
                 }
@@ -643,7 +661,9 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_loop_kernel(const __grid_c
             }
             const unsigned char *st = s_dyn + (size_t)s * stage_bytes;
             LS_MARK(0);
+            stage_turn_wait(&s_rel[s], k / nstage);
             ok = mbar_wait(&full_bar[s], (uint32_t)((k / nstage) & 1)) && ok;
+            if (t == 0) stage_seen(&s_rel[s], k / nstage);
             LS_MARK(1);
             if (ct == 0 && kl == 0) LT_STAMP(ph, 0);
             // ---------------- phase 1: row sums ----------------

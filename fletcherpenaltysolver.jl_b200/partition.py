@@ -192,6 +192,21 @@ class DistHandle:
         from . import _lib
         return self._solve(_lib.lib().fpsb_dist_solve_two_mixed, "fpsb_dist_solve_two_mixed", delta, rhs1_own, rhs2_loc)
 
+    def solve_two_extras(self, delta, rhs1_own, rhs2_loc):
+        """(u1, u2, stats): u1 = LSQR(A', rhs1, sqrt(tau)), u2 = MINRES(A A' + tau I, rhs2) on the local m-space rows
+        (src/solve_linear_system.jl:45-77)."""
+        from . import _lib
+        m = self.loc.m_loc
+        rhs1 = np.ascontiguousarray(rhs1_own, dtype=np.float64)
+        rhs2 = np.ascontiguousarray(rhs2_loc, dtype=np.float64)
+        u1, u2 = np.empty(m), np.empty(m)
+        st = (_lib.KrylovStats * 2)()
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        _lib.check(_lib.lib().fpsb_dist_solve_two_extras(self.H.h, C.c_double(delta), C.c_int64(self.part.nvar), C.c_int64(self.part.ncon),
+                                                         vp(rhs1), vp(rhs2), vp(u1), vp(u2), C.c_int(_lib.FPSB_HOST), st),
+                   "fpsb_dist_solve_two_extras")
+        return u1, u2, [st[0].as_dict(), st[1].as_dict()]
+
     def solve_two_least_squares(self, delta, rhs1_own, rhs2_own):
         from . import _lib
         return self._solve(_lib.lib().fpsb_dist_solve_two_least_squares, "fpsb_dist_solve_two_least_squares", delta,

@@ -279,6 +279,12 @@ int fpsb_dist_solve_two_least_squares(fpsb_handle h, double delta, int64_t nvar_
                                       int64_t ncon_global, const double *rhs1, const double *rhs2,
                                       double *p1, double *q1, double *p2, double *q2, int loc,
                                       fpsb_krylov_stats stats[2]);
+/* solve_two_extras of IterativeSolver (src/solve_linear_system.jl:45-77) on the row-partitioned operator:
+ * u1 = LSQR(A', rhs1, lambda = sqrt(tau)), u2 = MINRES(A A' + tau I, rhs2), tau = max(delta, 1e-14).
+ * rhs1: the OWNED n-space slice; rhs2, u1, u2: the local m-space slices. */
+int fpsb_dist_solve_two_extras(fpsb_handle h, double delta, int64_t nvar_global, int64_t ncon_global,
+                               const double *rhs1, const double *rhs2, double *u1, double *u2, int loc,
+                               fpsb_krylov_stats stats[2]);
 
 /* ---------------------------------------------------------------------------------------------
  * Device-resident FletcherPenaltyNLP glue: the vector combinations either side of the

@@ -71,6 +71,32 @@ def test_headline_krylov_reference_tolerances(oracle, headline):
         assert _rel(a, b) < 1e-6
 
 
+@pytest.mark.parametrize("n", [450_000, 500_000])
+def test_ring_release_order_mid_sizes(oracle, n):
+    """Regression (round 2): with 4 ring stages and 3 consumer groups a group that got two tiles ahead of its
+    neighbours read a stage's previous contents (mbarrier parity one phase ahead).  It showed at n = 450-550 K with the
+    early row sums of the persistent loop kernel, never at the headline size: repeated solves must be bitwise equal and
+    agree with the oracle."""
+    import fpsb200
+    from fpsb200 import models
+    m = n // 2
+    A = models.window_random_jacobian(m, n, 20, w=64, seed=1234)
+    coo = A.tocoo()
+    rng = np.random.default_rng(1234)
+    r1, r2 = rng.standard_normal(n), rng.standard_normal(m)
+    H = fpsb200.B200Handle(n, m, coo.row.astype(np.int64), coo.col.astype(np.int64))
+    H.set_jac_values(coo.data)
+    outs = [H.iter_solve_two_mixed(0.0, r1, r2) for _ in range(4)]
+    for o in outs[1:]:
+        for a, b in zip(o[:4], outs[0][:4]):
+            assert np.array_equal(a, b)
+    ref = oracle.IterativeOracle(A).solve_two_mixed(0.0, r1, r2)
+    for s, o in zip(outs[0][4], ref[4]):
+        assert s["solved"] == o["solved"] is True and abs(s["niter"] - o["niter"]) <= 1
+    for a, b in zip(outs[0][:4], ref[:4]):
+        assert _rel(a, b) < 1e-6
+
+
 def test_headline_krylov_tight_tolerances_1e8(oracle, headline):
     """north_star's floating-point bars on the Krylov path.  With the IterativeSolver tolerances tightened the
     least-norm half (CRAIG: p2, q2 -> the `v`, `w` blocks of ys / gs) converges to the solution itself on both

@@ -60,6 +60,29 @@ def test_dist_world1_matches_oracle(oracle):
     b4 = H.iter_solve_two_least_squares(1e-2, r1, r3)
     for a, b in zip(a4[:4], b4[:4]):
         assert _rel(a, b) < 1e-11
+    # solve_two_extras (LSQR + MINRES on A A' + tau I) at a fixed iteration count: distributed == single GPU
+    o.ne_itmax = 25
+    D.H.iter_setup(o); H.iter_setup(o)
+    u1, u2, stx = D.solve_two_extras(1e-2, r1, r2)
+    v1, v2, sty = H.iter_solve_two_extras(1e-2, r1, r2)
+    assert [s["niter"] for s in stx] == [s["niter"] for s in sty]
+    assert _rel(u1, v1) < 1e-11 and _rel(u2, v2) < 1e-10
+
+
+def test_dist_world1_extras_match_oracle(oracle):
+    """src/solve_linear_system.jl:45-77 through the row-partitioned handle at the reference tolerances."""
+    from fpsb200.partition import RowPartition, DistHandle
+    A, jr, jc, vals, r1, r2, r3 = _problem()
+    m, n = A.shape
+    D = DistHandle(RowPartition(n, m, jr, jc, 1), 0, device=0)
+    D.set_jac_values(vals)
+    for delta in (0.0, 1e-2):
+        u1, u2, st = D.solve_two_extras(delta, r1, r2)
+        ref = oracle.IterativeOracle(A).solve_two_extras(delta, r1, r2)
+        assert _rel(u1, ref[0]) < 1e-6 and _rel(u2, ref[1]) < 2e-4        # MINRES at convergence: see test_gpu_krylov.py
+        tau = max(delta, 1e-14)
+        if delta > 0:       # the normal equations both solve: (A A' + tau I) u2 = rhs2
+            assert _rel(A @ (A.T @ u2) + tau * u2, r2) < 1e-3             # MINRES stops on its own sqrt(eps)-level tests
 
 
 def _worker(rank, world, port, q, peer=True):
@@ -83,7 +106,8 @@ def _worker(rank, world, port, q, peer=True):
     z = D.jtprod(r2[rows])
     p1, q1, p2, q2, st = D.solve_two_mixed(1e-2, r1[own], r2[rows])
     P1, Q1, P2, Q2, st2 = D.solve_two_least_squares(0.0, r1[own], r3[own])
-    q.put((rank, L.row0, L.col0, y, z, p1, q1, p2, q2, st, P1, Q1, P2, Q2, st2))
+    u1, u2, st3 = D.solve_two_extras(1e-2, r1[own], r2[rows])
+    q.put((rank, L.row0, L.col0, y, z, p1, q1, p2, q2, st, P1, Q1, P2, Q2, st2, u1, u2, st3))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -120,3 +144,8 @@ def test_dist_world2_matches_single_gpu(oracle, transport):
     two = H.iter_solve_two_least_squares(0.0, r1, r3)
     for i, b in zip((10, 11, 12, 13), two[:4]):
         assert _rel(cat(i), b) < 1e-6
+    ex = H.iter_solve_two_extras(1e-2, r1, r2)
+    assert _rel(cat(15), ex[0]) < 1e-6 and _rel(cat(16), ex[1]) < 1e-6
+    for r in res:
+        assert [s["niter"] for s in r[17]] == [s["niter"] for s in res[0][17]]
+        assert abs(r[17][1]["niter"] - ex[2][1]["niter"]) <= 1
