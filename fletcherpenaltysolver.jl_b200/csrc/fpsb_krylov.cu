@@ -807,7 +807,10 @@ constexpr int kProducerThreads = 128;                          // warps 0,1: til
 constexpr int kStepThreads = kProducerThreads + kGroups * kGroupThreads;
 constexpr int kStageBytesMax = 40 * 1024;                      // tile block + window
 constexpr int kMaxStages = 8;
-constexpr int kRingBudget = 188 * 1024;
+#ifndef FPSB_RING_KB
+#define FPSB_RING_KB 188
+#endif
+constexpr int kRingBudget = FPSB_RING_KB * 1024;
 constexpr int kWinCapMax = 1536;          // window capacity (entries of 16 bytes) a tile may ask for
 constexpr int kLongThreads = 256;
 
@@ -1981,7 +1984,7 @@ void iter_setup(Handle *h) {
     W->counter.zero(h->stream);
     W->done.zero(h->stream);
     W->loop_parts.alloc((size_t)2 * 4 * (size_t)std::max(h->num_sms, 1) + 16);
-    W->gbar.alloc(2);
+    W->gbar.alloc(4);       // grid-barrier arrivals | exchanges | scatter-complete | boundary-slice arrivals (fpsb_loop.inl)
     W->gbar.zero(h->stream);
     FPSB_CUDA(cudaMallocHost((void **)&W->h_fin, 4 * sizeof(int)));
     FPSB_CUDA(cudaMallocHost((void **)&W->h_done, 2 * sizeof(int)));
@@ -2232,11 +2235,8 @@ struct Engine {
         L.nphase = 2 * chunk_it;
         L.nspec = std::max(0, std::min(env_int("FPSB_LOOP_NSPEC", kGroups), nstage - 1));
         L.early = mode >= 2 ? 1 : 0;
-        // Row-partitioned runs: no early row sums.  Measured at 2 GPUs on the headline operator (tools/dist_parity.py, n >= 500 000,
-        // reference tolerances): with them the result is 3e-7 off the single-GPU solve and not reproducible run to run; without
-        // them it agrees to 3e-14 and is bitwise reproducible (fixed-iteration runs and n = 200 000 agree either way).  The cause
-        // is not found yet; FPSB_DIST_EARLY=1 re-enables the combination for that investigation.
-        if (loop_dx != nullptr && env_int("FPSB_DIST_EARLY", 0) == 0) L.early = 0;
+        // (FPSB_DIST_EARLY=0: row-partitioned runs without the early row sums, for A/B timing)
+        if (loop_dx != nullptr && env_int("FPSB_DIST_EARLY", 1) == 0) L.early = 0;
         L.st = st_cur();
         L.parts = W->loop_parts.p;
         L.gbar = W->gbar.p;
@@ -2250,7 +2250,7 @@ struct Engine {
         attr[0].val.cooperative = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         loop([&](int) {
-            FPSB_CUDA(cudaMemsetAsync(W->gbar.p, 0, 2 * sizeof(unsigned long long), h->stream));      // arrivals | exchanges
+            FPSB_CUDA(cudaMemsetAsync(W->gbar.p, 0, 4 * sizeof(unsigned long long), h->stream));      // arrivals | exchanges | ...
             if (loop_dx != nullptr) FPSB_CUDA(cudaLaunchKernelEx(&cfg, gk_loop_kernel<true>, L));
             else FPSB_CUDA(cudaLaunchKernelEx(&cfg, gk_loop_kernel<false>, L));
             h->launches += 1;
