@@ -177,6 +177,36 @@ def run_reference(args, cfg):
     print(json.dumps(line))
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Run this rank's host threads on the CPUs of the NUMA node its GPU hangs off (sysfs: the PCI device's
+    local_cpulist), BEFORE any host buffer is allocated: first-touch then places the pinned e2e buffers on that node,
+    so that at N > 1 the H2D / D2H copies of the ranks do not all cross one socket's memory controller.
+    Returns what was done for the JSON line; never fatal (containers may hide sysfs or restrict the cpuset)."""
+    info = {"bound": False}
+    try:
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        node = int(open(base + "/numa_node").read().strip())
+        cpulist = open(base + "/local_cpulist").read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            if not part:
+                continue
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        info.update({"pci": bdf, "numa_node": node, "local_cpus": len(cpus), "allowed_cpus": len(allowed)})
+        if node >= 0 and len(use) >= 4 and use != allowed:
+            os.sched_setaffinity(0, use)
+            info["bound"] = True
+            info["cpus_used"] = len(use)
+    except Exception as e:      # noqa: BLE001
+        info["error"] = repr(e)[:120]
+    return info
+
+
 def partitioned_operators(args):
     """The two operators of the strong-scaled row-partitioned record: BASELINE config C3
     (Poisson-constrained control, state / control interleaved -> banded Jacobian) and the headline matrix."""
@@ -355,6 +385,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -649,6 +680,7 @@ def main():
                 "h2d_bytes_per_step": 8 * (nnz + n + m), "d2h_bytes_per_step": 16 * (n + m),
                 "ms_per_step": e2e_ms / args.steps, "solves_in_flight": in_flight,
                 "one_at_a_time": {"value": args.gpus * args.steps / (e2e_serial_ms * 1e-3), "ms_per_step": e2e_serial_ms / args.steps},
+                "host_numa": numa,
                 "note": "host buffers through the C ABI; every step copies its Jacobian values + both rhs H2D and its four "
                         "result vectors D2H inside the timed region; value = two independent solves in flight per GPU (two "
                         "handles, two host threads) so that the copies of one overlap the Krylov loop of the other; "

@@ -9,12 +9,12 @@ from ._lib import FPSB_DEVICE, FPSB_HOST, FpsbError, IterOpts, KrylovStats, Ldlt
 from .qdsolver import (B200Handle, IterativeSolver, LDLtSolver, QDSolver, batch_solve_two, qdsolver_correspondence,
                        solve_two_extras, solve_two_least_squares, solve_two_mixed)
 from .fletcher_nlp import FletcherPenaltyNLP
-from .device_nlp import DeviceFletcherPenaltyNLP, DeviceSparseQP
+from .device_nlp import DeviceCurvedQP, DeviceFletcherPenaltyNLP, DeviceSparseQP
 from .fps_solve import AlgoData, FPSSSolver, GenericExecutionStats, GNSolver, fps_solve, solve, trunk
 from . import models
 
 __all__ = ["B200Handle", "IterativeSolver", "LDLtSolver", "QDSolver", "qdsolver_correspondence",
            "solve_two_extras", "solve_two_least_squares", "solve_two_mixed", "FletcherPenaltyNLP",
-           "DeviceFletcherPenaltyNLP", "DeviceSparseQP", "fps_solve", "FPSSSolver", "AlgoData", "GNSolver",
+           "DeviceFletcherPenaltyNLP", "DeviceSparseQP", "DeviceCurvedQP", "fps_solve", "FPSSSolver", "AlgoData", "GNSolver",
            "GenericExecutionStats", "solve", "trunk",
            "models", "batch_solve_two", "FPSB_HOST", "FPSB_DEVICE", "FpsbError", "IterOpts", "KrylovStats", "LdltOpts"]

@@ -245,6 +245,13 @@ int fpsb_timer_stop(fpsb_handle hh, double *ms) {
     FPSB_CATCH
 }
 int64_t fpsb_launch_count(fpsb_handle hh) { return hh ? reinterpret_cast<Handle *>(hh)->launches : 0; }
+int fpsb_tile_stats(fpsb_handle hh, int64_t out[6]) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQUIRE(h && out, FPSB_EINVAL, "fpsb_tile_stats: NULL argument");
+    out[0] = h->A.ntiles;  out[1] = h->A.nwin_tiles;  out[2] = h->A.nseg_tiles;
+    out[3] = h->At.ntiles; out[4] = h->At.nwin_tiles; out[5] = h->At.nseg_tiles;
+    return FPSB_OK;
+}
 
 int fpsb_set_jac_values(fpsb_handle hh, const double *vals, int loc) {
     Handle *h = reinterpret_cast<Handle *>(hh);
@@ -568,6 +575,20 @@ int fpsb_fp_hprod2(fpsb_handle hh, double sigma, double rho, double eta, double 
     FPSB_CUDA(cudaSetDevice(h->device));
     caller_order_in(h);
     fp_hprod2(h, h->nvar, sigma, rho, eta, obj_weight, p2, HsPtv, Ptv, Hcv, JtJv, v, Hv);
+    caller_order_out(h);
+    return FPSB_OK;
+    FPSB_CATCH
+}
+int fpsb_fp_hprod1(fpsb_handle hh, double sigma, double rho, double eta, double obj_weight, const double *p2,
+                   const double *HsPtv, const double *Ptv, const double *JtinvJtJSsv, const double *SsinvJtJJv,
+                   const double *Hcv, const double *JtJv, const double *v, double *Hv) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQUIRE(h && p2 && HsPtv && Ptv && JtinvJtJSsv && SsinvJtJJv && v && Hv, FPSB_EINVAL, "fpsb_fp_hprod1: NULL argument");
+    REQUIRE(!(rho > 0.0) || (Hcv && JtJv), FPSB_EINVAL, "fpsb_fp_hprod1: rho > 0 needs Hcv and J'Jv");
+    FPSB_TRY
+    FPSB_CUDA(cudaSetDevice(h->device));
+    caller_order_in(h);
+    fp_hprod1(h, h->nvar, sigma, rho, eta, obj_weight, p2, HsPtv, Ptv, JtinvJtJSsv, SsinvJtJJv, Hcv, JtJv, v, Hv);
     caller_order_out(h);
     return FPSB_OK;
     FPSB_CATCH

@@ -76,6 +76,19 @@ __global__ void fp_hprod2_kernel(int n, double sigma, double rho, double eta, do
     Hv[i] = obj_weight * r;
 }
 
+// Val(1): the two extra terms of the exact Hessian (src/model-Fletcherpenaltynlp.jl:572-634), same operation order as the host mirror
+__global__ void fp_hprod1_kernel(int n, double sigma, double rho, double eta, double obj_weight, const double *p2,
+                                 const double *HsPtv, const double *Ptv, const double *JtinvJtJSsv, const double *SsinvJtJJv,
+                                 const double *Hcv, const double *JtJv, const double *v, double *Hv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double r = p2[i] - HsPtv[i] + 2.0 * sigma * Ptv[i] - JtinvJtJSsv[i];
+    r = r - SsinvJtJJv[i];
+    if (rho > 0.0 && Hcv != nullptr && JtJv != nullptr) r = r + rho * (Hcv[i] + JtJv[i]);
+    if (eta > 0.0) r = r + eta * v[i];
+    Hv[i] = obj_weight * r;
+}
+
 // memo key of x: order-independent sum of per-element mixes of (bit pattern, index) — any 64-bit key
 // that changes when x changes serves the reference's purpose (it memoises on hash(x) alone)
 __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
@@ -156,6 +169,14 @@ void fp_hprod2(Handle *h, int64_t n, double sigma, double rho, double eta, doubl
                const double *Ptv, const double *Hcv, const double *JtJv, const double *v, double *Hv) {
     if (n == 0) return;
     fp_hprod2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>((int)n, sigma, rho, eta, obj_weight, p2, HsPtv, Ptv, Hcv, JtJv, v, Hv);
+    h->launches += 1;
+}
+void fp_hprod1(Handle *h, int64_t n, double sigma, double rho, double eta, double obj_weight, const double *p2, const double *HsPtv,
+               const double *Ptv, const double *JtinvJtJSsv, const double *SsinvJtJJv, const double *Hcv, const double *JtJv,
+               const double *v, double *Hv) {
+    if (n == 0) return;
+    fp_hprod1_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>((int)n, sigma, rho, eta, obj_weight, p2, HsPtv, Ptv, JtinvJtJSsv,
+                                                                        SsinvJtJJv, Hcv, JtJv, v, Hv);
     h->launches += 1;
 }
 uint64_t fp_hash(Handle *h, int64_t n, const double *x) {

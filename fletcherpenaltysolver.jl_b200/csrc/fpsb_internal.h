@@ -68,6 +68,8 @@ struct CsrDev {
     DevBuf<unsigned char> tiles;               // TileMeta[ntiles] (fpsb_krylov.cu)
     DevBuf<unsigned char> rowflag;             // 1 = long row, 2 = raw row (row-partitioned runs)
     bool has_raw_rows = false;
+    DevBuf<int> wsegs;                         // multi-segment gather windows: 4 x {start, offset | length << 16} per tile
+    int nseg_tiles = 0, nwin_tiles = 0;        // tiles whose window has more than one segment / tiles with a window at all
     int ntiles = 0, win_cap = 0, blk_cap = 0, stage_bytes = 0, nstage = 0;
     DevBuf<int> long_row, long_rp, long_col, long_perm;
     DevBuf<double> long_val;
@@ -188,6 +190,9 @@ void fp_grad(Handle *h, int64_t n, double sigma, double rho, double eta, const d
 void fp_ptv(Handle *h, int64_t n, const double *v, const double *p1, double *Ptv);
 void fp_hprod2(Handle *h, int64_t n, double sigma, double rho, double eta, double obj_weight, const double *p2, const double *HsPtv,
                const double *Ptv, const double *Hcv, const double *JtJv, const double *v, double *Hv);
+void fp_hprod1(Handle *h, int64_t n, double sigma, double rho, double eta, double obj_weight, const double *p2, const double *HsPtv,
+               const double *Ptv, const double *JtinvJtJSsv, const double *SsinvJtJJv, const double *Hcv, const double *JtJv,
+               const double *v, double *Hv);
 uint64_t fp_hash(Handle *h, int64_t n, const double *x);
 
 // symbolic.cpp / ldlt.cu

@@ -21,6 +21,7 @@
 #include "fpsb_internal.h"
 #include "fpsb_device.cuh"
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
@@ -121,6 +122,8 @@ struct StepParams {
     int nlong;
     const unsigned char *tbuf;   // the tiles' blocks, back to back
     int blk_cap;           // capacity of the block part of a ring stage (bytes)
+    const int2 *wsegs;     // multi-segment windows (stencil operators): per tile 4 x {source start, window offset | length << 16};
+                           // nullptr: every window is the one segment [cmin, cmin + ccnt)
     const unsigned char *rowflag;   // nrows : 1 long row (own kernel), 2 raw row (row sums go to raw_out, no epilogue); nullptr: all 0
     double2 *raw_out;               // row-partitioned runs: raw sums of the halo / boundary rows (see fpsb_dist.inl)
     // long rows (CSR)
@@ -812,6 +815,8 @@ constexpr int kMaxStages = 8;
 #endif
 constexpr int kRingBudget = FPSB_RING_KB * 1024;
 constexpr int kWinCapMax = 1536;          // window capacity (entries of 16 bytes) a tile may ask for
+constexpr int kSegCapMax = 1664;          // ... when the window is multi-segment (three 2 x 256 + 4 runs of an interleaved 5-point stencil: 1 548)
+constexpr int kSegStageBytesMax = 44 * 1024;   // tile block + multi-segment window (still four ring stages)
 constexpr int kLongThreads = 256;
 
 struct __align__(16) TileMeta {
@@ -1125,19 +1130,25 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(const __grid_c
     if (tid < kProducerThreads) {
         // ------------------------------- producers -------------------------------
         reg_dec<kProducerRegs>();
-        if ((tid & 31) == 0) {
+        // multi-segment windows: lanes 0..3 of a window producer warp own one segment each (they issue their bulk copies
+        // side by side); everything else is lane 0's
+        const int seg_lane = tid & 31;
+        if (seg_lane == 0 || (seg_lane < 4 && (tid >> 5) >= 2 && P.wsegs != nullptr)) {
             // a bulk copy costs its issuing thread a few hundred ns whatever its size: two warps share
             // the tile blocks (even / odd tiles of this CTA), two more the gather windows
             const int role = tid >> 5;
             const bool blocks = role < 2;
             const int par = role & 1;
+            const bool segd = !blocks && P.wsegs != nullptr;
+            const unsigned seg_mask = segd ? 0xfu : 0x1u;
+            int2 G = make_int2(0, 0), G1 = make_int2(0, 0);        // this lane's segment of tiles T / T1
             // tile descriptors are fetched one of this producer's tiles ahead of their use
             int k = par, tile = cta + par * gsz;
             PTile T{}, T1{};
-            if (tile < P.ntiles) T = load_ptile(P.tiles, tile);
+            if (tile < P.ntiles) { T = load_ptile(P.tiles, tile); if (segd) G = __ldg(P.wsegs + (size_t)tile * 4 + seg_lane); }
             for (; tile < P.ntiles; k += 2) {
                 const int t1 = tile + 2 * gsz;
-                if (t1 < P.ntiles) T1 = load_ptile(P.tiles, t1);
+                if (t1 < P.ntiles) { T1 = load_ptile(P.tiles, t1); if (segd) G1 = __ldg(P.wsegs + (size_t)t1 * 4 + seg_lane); }
                 const int s = k % nstage;
                 if (k >= nstage) ok = mbar_wait(&empty_bar[s], (uint32_t)((k / nstage - 1) & 1)) && ok;
                 // bounded run-ahead: tile k - inflight must have landed.  Everything an SM requests is
@@ -1158,8 +1169,20 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(const __grid_c
                         if (PAIR) { wbytes = (uint32_t)T.ccnt * 16u; tot = wbytes; }
                         else if (win_tma && !(T.ccnt & 1)) { wbytes = (uint32_t)T.ccnt * 8u; tot = wbytes * ((act0 ? 1u : 0u) + (act1 ? 1u : 0u)); }
                     }
-                    mbar_expect_tx(&full_bar[s], tot);
-                    if (wbytes) {
+                    if (seg_lane == 0) mbar_expect_tx(&full_bar[s], tot);
+                    if (segd) {
+                        // the expectation is posted before any of the four lanes' copies can complete
+                        __syncwarp(seg_mask);
+                        const int glen = G.y >> 16, goff = G.y & 0xffff;
+                        if (wbytes && glen > 0) {
+                            if (PAIR) tma_bulk_g2s(s_win + (size_t)goff * 16, P.gin2 + G.x, (uint32_t)glen * 16u, &full_bar[s]);
+                            else {
+                                double *w0 = reinterpret_cast<double *>(s_win);
+                                if (act0) tma_bulk_g2s(w0 + goff, P.io[0].gin + G.x, (uint32_t)glen * 8u, &full_bar[s]);
+                                if (act1) tma_bulk_g2s(w0 + P.win_cap + goff, P.io[1].gin + G.x, (uint32_t)glen * 8u, &full_bar[s]);
+                            }
+                        }
+                    } else if (wbytes) {
                         if (PAIR) tma_bulk_g2s(s_win, P.gin2 + T.cmin, wbytes, &full_bar[s]);
                         else {
                             double *w0 = reinterpret_cast<double *>(s_win);
@@ -1168,7 +1191,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(const __grid_c
                         }
                     }
                 }
-                T = T1; tile = t1;
+                T = T1; G = G1; tile = t1;
             }
             if (!ok) atomicExch(P.done_flag, -1);
         }
@@ -1217,6 +1240,16 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_step_kernel(const __grid_c
                 // unaligned / odd-sized caller vectors: the group stages the window itself
                 double *win0 = reinterpret_cast<double *>(s_win);
                 double *win1 = win0 + P.win_cap;
+                if (P.wsegs != nullptr) {
+                    for (int sgi = 0; sgi < 4; ++sgi) {
+                        const int2 G = __ldg(P.wsegs + (size_t)tile * 4 + sgi);
+                        const int glen = G.y >> 16, goff = G.y & 0xffff;
+                        for (int i = t; i < glen; i += kGroupThreads) {
+                            if (act0) win0[goff + i] = P.io[0].gin[G.x + i];
+                            if (act1) win1[goff + i] = P.io[1].gin[G.x + i];
+                        }
+                    }
+                } else
                 for (int i = t; i < T.ccnt; i += kGroupThreads) {
                     if (act0) win0[i] = P.io[0].gin[T.cmin + i];
                     if (act1) win1[i] = P.io[1].gin[T.cmin + i];
@@ -1645,6 +1678,7 @@ constexpr int kLongRow = 96;     // rows longer than this leave the SELL part (a
 static void upload_sell(Handle *h, CsrDev &M, int nrows, int ncols, const std::vector<int> &rp,
                         const std::vector<int> &ci, const std::vector<int> &perm) {
     M.nrows = nrows; M.ncols = ncols; M.nnz = (int64_t)ci.size();
+    M.nseg_tiles = M.nwin_tiles = 0;
     std::vector<int> long_row, long_rp(1, 0), long_col, long_perm;
     std::vector<unsigned char> rowflag((size_t)nrows + 8, 0);
     std::vector<TileMeta> tiles;
@@ -1662,6 +1696,53 @@ static void upload_sell(Handle *h, CsrDev &M, int nrows, int ncols, const std::v
             long_rp.push_back((int)long_col.size());
         }
     }
+    // Multi-segment windows (stencil operators, BASELINE config C3: a 5-point stencil row touches columns a grid line apart,
+    // so the column SPAN of a tile never fits a window while the columns it actually touches are a few short runs): when
+    // the span exceeds the capacity the distinct columns of the tile are cut at their (up to kMaxSeg - 1) largest gaps
+    // into segments; the window in shared memory is the segments back to back (one bulk copy each) and the 16-bit
+    // indices are relative to that concatenation, so the consumers do not know the difference.  Starts are even and all
+    // lengths but possibly the last are even (16-byte units of plain vectors); the segments are sorted and may overlap.
+    constexpr int kMaxSeg = 4, kMinGap = 32;
+    static const bool no_segs = getenv("FPSB_NO_SEGS") != nullptr;
+    std::vector<int> ucols, gapidx;
+    struct Seg { int start, len; };
+    std::vector<Seg> segs;                // of the tile fit_tile looked at last (empty: one segment or no window)
+    std::vector<std::array<Seg, kMaxSeg>> tile_segs;
+    auto find_segments = [&](int w0, int R) {      // -> total window entries (0: does not fit)
+        segs.clear();
+        if (no_segs) return 0;
+        ucols.clear();
+        for (int r = w0; r < w0 + R; ++r) {
+            if (rowflag[(size_t)r]) continue;
+            for (int p = rp[(size_t)r]; p < rp[(size_t)r + 1]; ++p) ucols.push_back(ci[(size_t)p]);
+        }
+        std::sort(ucols.begin(), ucols.end());
+        ucols.erase(std::unique(ucols.begin(), ucols.end()), ucols.end());
+        if (ucols.empty()) return 0;
+        // the kMaxSeg - 1 largest gaps (ties: the leftmost), at least kMinGap wide
+        gapidx.clear();
+        for (size_t i = 0; i + 1 < ucols.size(); ++i) if (ucols[i + 1] - ucols[i] >= kMinGap) gapidx.push_back((int)i);
+        if (gapidx.size() > (size_t)(kMaxSeg - 1)) {
+            std::stable_sort(gapidx.begin(), gapidx.end(), [&](int a, int b) { return ucols[(size_t)a + 1] - ucols[(size_t)a] > ucols[(size_t)b + 1] - ucols[(size_t)b]; });
+            gapidx.resize((size_t)(kMaxSeg - 1));
+            std::sort(gapidx.begin(), gapidx.end());
+        }
+        int total = 0;
+        size_t a = 0;
+        for (size_t g = 0; g <= gapidx.size(); ++g) {
+            const size_t b = g < gapidx.size() ? (size_t)gapidx[g] : ucols.size() - 1;     // last column of this segment
+            Seg sg;
+            sg.start = ucols[a] & ~1;
+            sg.len = ucols[b] - sg.start + 1;
+            if ((sg.len & 1) && sg.start + sg.len + 1 <= ncols) ++sg.len;                  // never past the vector's end
+            segs.push_back(sg);
+            total += sg.len;
+            a = b + 1;
+        }
+        if (total > kSegCapMax || segs.size() < 2) { segs.clear(); return 0; }
+        for (size_t g = 0; g + 1 < segs.size(); ++g) if (segs[g].len & 1) { segs.clear(); return 0; }   // (cannot happen: only the last may be odd)
+        return total;
+    };
     // largest tile starting at row w0 with at most `want` rows whose block + window fit a stage (halving)
     int cnt = 0, c0 = 0, elems = 0;
     auto fit_tile = [&](int w0, int want) {
@@ -1688,11 +1769,16 @@ static void upload_sell(Handle *h, CsrDev &M, int nrows, int ncols, const std::v
                 // even length: plain (8-byte) vectors are then bulk-copied in whole 16-byte units; an odd window would
                 // send the tile down the group-staged path of the one-column products.  Never past the vector's end.
                 if ((cnt & 1) && c0 + cnt + 1 <= ncols) ++cnt;
-                if (cnt > kWinCapMax) cnt = 0;
-            }
-            if ((size_t)tile_block_bytes(elems, (int)widths.size(), cnt) + (size_t)cnt * 16 <= (size_t)kStageBytesMax) break;
+                segs.clear();
+                if (cnt > kWinCapMax) {
+                    cnt = find_segments(w0, R);
+                    if (cnt > 0) c0 = segs[0].start;
+                }
+            } else segs.clear();
+            if ((size_t)tile_block_bytes(elems, (int)widths.size(), cnt) + (size_t)cnt * 16 <= (size_t)(segs.empty() ? kStageBytesMax : kSegStageBytesMax)) break;
             if (R > 32) { R = std::max(32, ((R / 2) + 31) & ~31); continue; }
             cnt = 0;     // a single slice (at most kLongRow wide, 36 KB): drop the window
+            segs.clear();
             break;
         }
         return R;
@@ -1731,6 +1817,13 @@ static void upload_sell(Handle *h, CsrDev &M, int nrows, int ncols, const std::v
         const size_t bytes = (((size_t)tile_block_bytes(elems, T.ns, cnt)) + 127) & ~(size_t)127;    // blocks start 128-byte aligned
         win_cap = std::max(win_cap, cnt);
         blk_cap = std::max(blk_cap, bytes);
+        {
+            std::array<Seg, kMaxSeg> sg{};
+            if (!segs.empty()) { for (size_t g = 0; g < segs.size(); ++g) sg[g] = segs[g]; ++M.nseg_tiles; }
+            else if (cnt > 0) sg[0] = Seg{c0, cnt};
+            if (cnt > 0) ++M.nwin_tiles;
+            tile_segs.push_back(sg);
+        }
         tperm0.push_back((int)total_elems);
         total_bytes += bytes;
         total_elems += (size_t)elems;
@@ -1751,8 +1844,17 @@ static void upload_sell(Handle *h, CsrDev &M, int nrows, int ncols, const std::v
     std::vector<int> sperm(total_elems + 8, -1);
     for (size_t ti = 0; ti < tiles.size(); ++ti) {
         const TileMeta &T = tiles[ti];
-        const int cbase = T.ccnt > 0 ? T.cmin : 0;
         const bool win = T.ccnt > 0;
+        const std::array<Seg, kMaxSeg> &sg = tile_segs[ti];
+        int sg_off[kMaxSeg];
+        { int o = 0; for (int g = 0; g < kMaxSeg; ++g) { sg_off[g] = o; o += sg[g].len; } }
+        // window-relative index of column c: its position in the concatenated segments (the last segment that starts at or before c)
+        auto wrel = [&](int c) {
+            if (!win) return c;
+            int g = kMaxSeg - 1;
+            while (g > 0 && (sg[g].len == 0 || sg[g].start > c)) --g;
+            return sg_off[g] + (c - sg[g].start);
+        };
         int *cols = reinterpret_cast<int *>(tbuf.data() + T.boff + (size_t)T.elems * 8);
         unsigned short *cols16 = reinterpret_cast<unsigned short *>(tbuf.data() + T.boff + (size_t)T.elems * 8);
         unsigned char *rmap = tbuf.data() + T.boff + (size_t)T.elems * (win ? 10 : 12);
@@ -1774,12 +1876,12 @@ static void upload_sell(Handle *h, CsrDev &M, int nrows, int ncols, const std::v
                         int best = -1, bestc = 1 << 30;
                         for (int e = 0; e < len; ++e) {
                             if (used[(size_t)l * width + e]) continue;
-                            const int bg = T.ccnt > 0 ? ((ci[(size_t)(base + e)] - cbase) & 7) : 0;
+                            const int bg = win ? (wrel(ci[(size_t)(base + e)]) & 7) : 0;
                             if (cnt8[bg] < bestc) { bestc = cnt8[bg]; best = e; }
                         }
                         used[(size_t)l * width + best] = 1;
                         eorder[(size_t)l * width + j] = best;
-                        if (T.ccnt > 0) cnt8[(ci[(size_t)(base + best)] - cbase) & 7]++;
+                        if (win) cnt8[wrel(ci[(size_t)(base + best)]) & 7]++;
                     }
                 }
             }
@@ -1794,7 +1896,7 @@ static void upload_sell(Handle *h, CsrDev &M, int nrows, int ncols, const std::v
                     int cval = 0;
                     if (j < len) {
                         const int e = eorder[(size_t)l * width + j];
-                        cval = ci[(size_t)(base + e)] - cbase; tp[q] = perm[(size_t)(base + e)];
+                        cval = wrel(ci[(size_t)(base + e)]); tp[q] = perm[(size_t)(base + e)];
                     } else tp[q] = -1;                       // padding: value 0, valid column
                     if (win) cols16[q] = (unsigned short)cval; else cols[q] = cval;
                 }
@@ -1815,6 +1917,18 @@ static void upload_sell(Handle *h, CsrDev &M, int nrows, int ncols, const std::v
     M.tiles.alloc((tiles.size() + 1) * sizeof(TileMeta));
     if (!tiles.empty()) FPSB_CUDA(cudaMemcpyAsync(M.tiles.p, tiles.data(), tiles.size() * sizeof(TileMeta), cudaMemcpyHostToDevice, h->stream));
     M.rowflag.from(rowflag, h->stream);
+    if (M.nseg_tiles > 0) {
+        std::vector<int> ws(tiles.size() * 2 * kMaxSeg + 8, 0);
+        for (size_t ti = 0; ti < tiles.size(); ++ti) {
+            int o = 0;
+            for (int g = 0; g < kMaxSeg; ++g) {
+                ws[(ti * kMaxSeg + g) * 2] = tile_segs[ti][g].start;
+                ws[(ti * kMaxSeg + g) * 2 + 1] = o | (tile_segs[ti][g].len << 16);
+                o += tile_segs[ti][g].len;
+            }
+        }
+        M.wsegs.from(ws, h->stream);
+    }
     M.long_row.from(long_row, h->stream);
     M.long_rp.from(long_rp, h->stream);
     M.long_col.from(long_col, h->stream);
@@ -1918,6 +2032,7 @@ static void fill_csr(StepParams &P, const CsrDev &M) {
         if (P.inflight > M.nstage) P.inflight = M.nstage;
     }
     P.rowflag = (M.nlong > 0 || M.has_raw_rows) ? M.rowflag.p : nullptr;
+    P.wsegs = M.nseg_tiles > 0 ? reinterpret_cast<const int2 *>(M.wsegs.p) : nullptr;
     P.long_row = M.long_row.p; P.long_rp = M.long_rp.p; P.long_col = M.long_col.p; P.long_val = M.long_val.p;
     P.nrows = M.nrows;
 }

@@ -479,9 +479,14 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_loop_kernel(const __grid_c
 
     if (tid < kProducerThreads) {
         reg_dec<kProducerRegs>();
-        if ((tid & 31) != 0) return;
         const int role = tid >> 5;
         const int par = role & 1;
+        // multi-segment windows (stencil operators): lanes 0..3 of a window producer warp own one segment each and issue
+        // their bulk copies side by side; everything else is lane 0's
+        const int seg_lane = tid & 31;
+        const bool segd = role >= 2 && (L.op[0].wsegs != nullptr || L.op[1].wsegs != nullptr);
+        if (seg_lane != 0 && !(segd && seg_lane < 4)) return;
+        const unsigned seg_mask = segd ? 0xfu : 0x1u;
         if (role < 2) {
             // ---- warps 0 / 1: tile blocks of the CTA's even / odd tiles.  The blocks do not depend on the previous
             //      phase: the first nspec tiles of a phase are requested before the phase is decided ----
@@ -562,7 +567,9 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_loop_kernel(const __grid_c
 #endif
             int kl = kl0, tile = cta + kl0 * gsz;
             PTile T{}, T1{};
-            if (tile < nt) T = load_ptile(tiles, tile);
+            const bool psegs = P.wsegs != nullptr;           // this phase's operator has multi-segment tiles
+            int2 G = make_int2(0, 0), G1 = make_int2(0, 0);  // this lane's segment of tiles T / T1
+            if (tile < nt) { T = load_ptile(tiles, tile); if (psegs) G = __ldg(P.wsegs + (size_t)tile * 4 + seg_lane); }
             bool stop = false;
             for (; kl < cnt; kl += 2) {
                 if (!opened && kl >= L.nspec) {
@@ -571,14 +578,20 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_loop_kernel(const __grid_c
                     if (ctl.stop_at <= ph) { stop = true; break; }
                 }
                 const int t1 = tile + 2 * gsz;
-                if (t1 < nt) T1 = load_ptile(tiles, t1);
+                if (t1 < nt) { T1 = load_ptile(tiles, t1); if (psegs) G1 = __ldg(P.wsegs + (size_t)t1 * 4 + seg_lane); }
                 const int k = kb + kl, s = k % nstage;
                 if (k >= nstage) ok = mbar_wait(&empty_bar[s], (uint32_t)((k / nstage - 1) & 1)) && ok;
                 if (k >= 2) ok = mbar_wait(&full_bar[(k - 2) % nstage], (uint32_t)(((k - 2) / nstage) & 1)) && ok;
                 const uint32_t wbytes = T.ccnt > 0 ? (uint32_t)T.ccnt * 16u : 0u;
-                mbar_expect_tx(&full_bar[s], wbytes);
-                if (wbytes) tma_bulk_g2s(s_dyn + (size_t)s * stage_bytes + blk_cap, P.gin2 + T.cmin, wbytes, &full_bar[s]);
-                T = T1; tile = t1;
+                if (seg_lane == 0) mbar_expect_tx(&full_bar[s], wbytes);
+                if (segd) __syncwarp(seg_mask);              // the expectation is posted before any lane's copy can complete
+                if (psegs) {
+                    const int glen = G.y >> 16, goff = G.y & 0xffff;
+                    if (wbytes && glen > 0)
+                        tma_bulk_g2s(s_dyn + (size_t)s * stage_bytes + blk_cap + (size_t)goff * 16, P.gin2 + G.x, (uint32_t)glen * 16u, &full_bar[s]);
+                } else if (wbytes && seg_lane == 0)
+                    tma_bulk_g2s(s_dyn + (size_t)s * stage_bytes + blk_cap, P.gin2 + T.cmin, wbytes, &full_bar[s]);
+                T = T1; G = G1; tile = t1;
             }
             if (!ok || stop) break;
             if (!opened) {

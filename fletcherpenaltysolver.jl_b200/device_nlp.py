@@ -6,8 +6,9 @@ key is computed on the device (fpsb_fp_hash) instead of hash(x) on the host.
 
 The user model must evaluate on the device: `obj(x) -> float`, `grad(x)`, `cons(x)`, `jac_coord(x)`,
 `hprod(x, y, v, obj_weight)` taking / returning torch CUDA float64 tensors (DeviceSparseQP below is
-the synthetic model of BASELINE configs C2 / C4).  Only hessian_approx = Val(2) is device-resident;
-Val(1) needs ghjvprod and solve_two_extras and stays on the host mirror.
+the synthetic model of BASELINE configs C2 / C4, DeviceCurvedQP its variant with curved constraints).  Both Hessian
+variants are device-resident: Val(2), and Val(1) (round 2) which adds `ghjvprod(x, g, v)` on the device model and the
+`solve_two_extras` pair with device pointers (src/model-Fletcherpenaltynlp.jl:572-634).
 """
 import ctypes as C
 
@@ -15,7 +16,7 @@ import numpy as np
 
 from . import _lib
 from .models import AbstractNLPModel, NLPModelMeta
-from .qdsolver import LDLtSolver, solve_two_least_squares, solve_two_mixed
+from .qdsolver import LDLtSolver, solve_two_extras, solve_two_least_squares, solve_two_mixed
 
 
 def _dp(t):
@@ -37,7 +38,7 @@ class DeviceSparseQP(AbstractNLPModel):
         self.Q = torch.tensor(host_qp.Q, **f64)
         self.q = torch.tensor(host_qp.q, **f64)
         self.b = torch.tensor(host_qp.b, **f64)
-        self._vals = torch.tensor(host_qp.jac_coord(None), **f64)
+        self._vals = torch.tensor(host_qp._vals, **f64)          # the values of A in the COO order of jac_structure
         self._device = device
         self._H = None          # the model's own operator handle for c(x) = A x - b (hand-written SpMV, no cuSPARSE)
 
@@ -70,13 +71,42 @@ class DeviceSparseQP(AbstractNLPModel):
         return obj_weight * self.Q * v
 
 
+class DeviceCurvedQP(DeviceSparseQP):
+    """models.CurvedQPModel with all data on the GPU: curved constraints, so `hprod` depends on y and `ghjvprod` is not
+    zero (the model side is user code: torch for its own arithmetic, the repo's SpMV for A x)."""
+
+    def __init__(self, host_model, device="cuda"):
+        import torch
+        super().__init__(host_model, device=device)
+        f64 = dict(dtype=torch.float64, device=device)
+        self.d = torch.tensor(host_model.d, **f64)
+        self._k = torch.tensor(host_model._k, dtype=torch.int64, device=device)
+        self._first = torch.tensor(host_model._first, dtype=torch.int64, device=device)
+
+    def cons(self, x):
+        return self._op().jprod(x) + 0.5 * self.d * x[self._k] ** 2 - self.b
+
+    def jac_coord(self, x):
+        vals = self._vals.clone()
+        vals[self._first] += self.d * x[self._k]
+        return vals
+
+    def hprod(self, x, y, v, obj_weight=1.0):
+        out = obj_weight * self.Q * v
+        out.index_add_(0, self._k, y * self.d * v[self._k])
+        return out
+
+    def ghjvprod(self, x, g, v):
+        return g[self._k] * self.d * v[self._k]
+
+
 class DeviceFletcherPenaltyNLP:
-    """FletcherPenaltyNLP(nlp, sigma, rho, delta, Val(2); qds = ...) with device-resident state."""
+    """FletcherPenaltyNLP(nlp, sigma, rho, delta, Val(1) | Val(2); qds = ...) with device-resident state."""
 
     def __init__(self, nlp, sigma=1.0, rho=0.0, delta=0.0, hessian_approx=2, *, qds=None, device="cuda",
                  consistent_gradient=False):
         import torch
-        assert hessian_approx == 2, "Val(1) needs ghjvprod and stays on the host mirror"
+        assert hessian_approx in (1, 2), "hessian_approx is Val(1) or Val(2)"
         self.consistent_gradient = consistent_gradient      # see FletcherPenaltyNLP
         self.torch = torch
         self.nlp = nlp
@@ -85,7 +115,7 @@ class DeviceFletcherPenaltyNLP:
         self.sigma, self.rho, self.delta, self.eta = sigma, rho, delta, 0.0
         self.qdsolver = qds if qds is not None else LDLtSolver(nlp, 0.0)
         self.handle = self.qdsolver.handle
-        self.hessian_approx = 2
+        self.hessian_approx = int(hessian_approx)
         f64 = dict(dtype=torch.float64, device=device)
         n, m = self.nvar, self.npen
         self.key = None
@@ -161,6 +191,17 @@ class DeviceFletcherPenaltyNLP:
             JtJv = self.handle.jtprod(self.handle.jprod(v))
             Hcv = self.nlp.hprod(x, self.cx, v, obj_weight=0.0)
         Hv = self.torch.empty_like(v)
+        if self.hessian_approx == 1:
+            # the exact Hessian's two extra terms (src/model-Fletcherpenaltynlp.jl:603-634): ghjvprod on the device model,
+            # the MINRES / LSQR (or LDLt) pair of solve_two_extras with device pointers, one product with A'
+            Ssv = self.nlp.ghjvprod(x, gs, v)
+            invJtJJv, invJtJSsv = solve_two_extras(self, x, v, Ssv)
+            JtinvJtJSsv = self.handle.jtprod(invJtJSsv)
+            SsinvJtJJv = self.nlp.hprod(x, invJtJJv, gs, obj_weight=0.0)
+            _lib.check(self._lib.fpsb_fp_hprod1(self.handle.h, C.c_double(self.sigma), C.c_double(self.rho), C.c_double(self.eta),
+                                                C.c_double(obj_weight), _dp(p2), _dp(HsPtv), _dp(Ptv), _dp(JtinvJtJSsv),
+                                                _dp(SsinvJtJJv), _dp(Hcv), _dp(JtJv), _dp(v), _dp(Hv)), "fpsb_fp_hprod1")
+            return Hv
         _lib.check(self._lib.fpsb_fp_hprod2(self.handle.h, C.c_double(self.sigma), C.c_double(self.rho), C.c_double(self.eta),
                                             C.c_double(obj_weight), _dp(p2), _dp(HsPtv), _dp(Ptv), _dp(Hcv), _dp(JtJv), _dp(v),
                                             _dp(Hv)), "fpsb_fp_hprod2")

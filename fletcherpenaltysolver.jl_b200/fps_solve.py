@@ -131,10 +131,14 @@ class GNSolver:
     """GNSolver(x, y; kwargs...)  (src/parameters.jl:143-195): parameters of the feasibility step."""
 
     def __init__(self, x0=None, y0=None, *, eta1=1e-3, eta2=0.66, sigma1=0.25, sigma2=2.0, Delta0=1.0,
-                 bad_steps_lim=3, feas_expected_decrease=0.95):
+                 bad_steps_lim=3, feas_expected_decrease=0.95, fused=False):
         self.eta1, self.eta2, self.sigma1, self.sigma2, self.Delta0 = eta1, eta2, sigma1, sigma2, Delta0
         self.bad_steps_lim = bad_steps_lim
         self.feas_expected_decrease = feas_expected_decrease
+        # not a reference option: compute the normal steps with the QDSolver's fused kernels (TR_fused) instead of the
+        # host-loop LSMR (TR_lsmr).  Off by default: LSMR's truncated iterate and the scaled minimum-norm step are both
+        # valid trust-region steps but not the same vector, and the reference's is LSMR's.
+        self.fused = fused
 
 
 class GenericExecutionStats:
@@ -567,8 +571,34 @@ def TR_lsmr(nlp, z, cz, ctol, Delta, normcz):
     return d, nlp.jprod(z, d), infeasible, solved
 
 
+def TR_fused(qds, nlp, z, cz, ctol, Delta, normcz):
+    """TR_lsmr's job on the fused Krylov kernels of libfpsb200 (SURVEY §8 f4): the Jacobian values at z go into the QDSolver's
+    tiled operator, u = (JJ')⁻¹ c comes from the MINRES slot of `solve_two_extras` (Krylov path: the device-resident
+    recurrences over the fused 2-column SpMM; LDLt path: one refactorisation), d = −J'u is the minimum-norm Gauss–Newton
+    step, cut back to the trust-region boundary when it leaves the ball.  z, cz may be numpy arrays or device tensors."""
+    from .qdsolver import IterativeSolver
+    H = qds.handle
+    H.set_jac_values(nlp.jac_coord(z))
+    zero = _V.zeros_like(z)
+    if isinstance(qds, IterativeSolver):
+        _, u, st = H.iter_solve_two_extras(0.0, zero, cz)
+        solved = bool(st[1]["solved"])
+    else:
+        _, u, _ = H.ldlt_solve_two_extras(0.0, zero, cz)
+        solved = True
+    d = -H.jtprod(u)
+    nd = _V.norm(d)
+    if Delta > 0.0 and nd > Delta:
+        d = (Delta / nd) * d
+        nd = Delta
+    infeasible = nd < ctol * min(normcz, 1.0)
+    if not solved:
+        warnings.warn("Fail minres in TR_fused")
+    return d, H.jprod(d), infeasible, solved
+
+
 def feasibility_step(fs, nlp, x, cx, normcx, rho, ctol, verbose=0, *, max_eval=1000, max_time=60.0,
-                     max_feas_iter=2 ** 62):
+                     max_feas_iter=2 ** 62, qds=None):
     """Trust-region Levenberg–Marquardt on ‖c(x) − l‖   (src/feasibility.jl:21-189).
     `nlp` supplies cons / jprod / jtprod / hprod (the products run on whatever the model runs on)."""
     lcon = nlp.meta.lcon
@@ -581,7 +611,10 @@ def feasibility_step(fs, nlp, x, cx, normcx, rho, ctol, verbose=0, *, max_eval=1
     t0 = time.time()
     tired = nev() > max_eval
     while not (normcz <= rho or tired or infeasible):
-        d, Jd, infeasible, _ = TR_lsmr(nlp, z, cz, ctol, Delta, normcz)
+        if qds is not None and getattr(fs, "fused", False):
+            d, Jd, infeasible, _ = TR_fused(qds, nlp, z, cz, ctol, Delta, normcz)
+        else:
+            d, Jd, infeasible, _ = TR_lsmr(nlp, z, cz, ctol, Delta, normcz)
         if infeasible:
             failed_step_comp = True
         else:
@@ -649,7 +682,7 @@ class FPSSSolver:
             self.qdsolver = qds_solver(nlp, 0.0, **kwargs)
         else:
             self.qdsolver = qdsolver_correspondence[str(qds_solver).lstrip(":")](nlp, 0.0, **kwargs)
-        self.feasibility_solver = GNSolver()
+        self.feasibility_solver = GNSolver(fused=bool(kwargs.get("feas_fused", False)))
         factory = model_factory or FletcherPenaltyNLP
         self.model = factory(nlp, self.meta.sigma_0, self.meta.rho_0, 0.0, self.meta.hessian_approx,
                              qds=self.qdsolver, consistent_gradient=bool(kwargs.get("consistent_gradient", False)))
@@ -741,7 +774,10 @@ def _restoration_feasibility(fs, stp, model, feas_tol, ncx, verbose, rng):
     """src/algo.jl:295-333"""
     st = stp.current_state
     host = stp.pb
-    z, cz, _, status = feasibility_step(fs, host, st.x, st.cx - stp._lcon, ncx, feas_tol, feas_tol, verbose)
+    qds = getattr(model, "qdsolver", None) if getattr(fs, "fused", False) else None
+    if qds is not None and (not hasattr(qds, "handle") or getattr(model, "explicit_linear_constraints", False)):
+        qds = None                                   # a user-defined QDSolver, or a handle on the nonlinear rows only
+    z, cz, _, status = feasibility_step(fs, host, st.x, st.cx - stp._lcon, ncx, feas_tol, feas_tol, verbose, qds=qds)
     if status == "success":
         st.x, st.cx = z, cz + stp._lcon
     else:

@@ -175,6 +175,47 @@ class SparseQPModel(AbstractNLPModel):
         return obj_weight * self.Q * v
 
 
+class CurvedQPModel(SparseQPModel):
+    """SparseQPModel with curved constraints: c_i(x) = (A x)_i + d_i/2 x_{k_i}^2 - b_i, k_i the column of the first
+    stored entry of row i — so the Jacobian keeps A's sparsity pattern (its entry (i, k_i) becomes a_{i k_i} + d_i x_{k_i})
+    while the constraint Hessians d_i e_k e_k' make `hprod` depend on y and `ghjvprod` nonzero: the smallest large sparse
+    model that exercises the Val(1) Hessian product (src/model-Fletcherpenaltynlp.jl:572-634) with real terms."""
+
+    def __init__(self, Qdiag, q, A, b, d, name="curved-qp"):
+        super().__init__(Qdiag, q, A, b, name=name)
+        self.d = np.asarray(d, float)
+        assert np.all(np.diff(self.A.indptr) > 0), "every row needs an entry"
+        self._first = self.A.indptr[:-1].astype(np.int64)         # position of (i, k_i) in the CSR / COO order
+        self._k = self.A.indices[self._first].astype(np.int64)
+
+    def cons(self, x):
+        self.counters.neval_cons += 1
+        return self.A @ x + 0.5 * self.d * x[self._k] ** 2 - self.b
+
+    def jac_coord(self, x):
+        self.counters.neval_jac += 1
+        vals = self._vals.copy()
+        vals[self._first] += self.d * x[self._k]
+        return vals
+
+    def jprod(self, x, v):
+        return self.A @ v + self.d * x[self._k] * v[self._k]
+
+    def jtprod(self, x, u):
+        out = self.A.T @ u
+        np.add.at(out, self._k, self.d * x[self._k] * u)
+        return out
+
+    def hprod(self, x, y, v, obj_weight=1.0):
+        self.counters.neval_hprod += 1
+        out = obj_weight * self.Q * v
+        np.add.at(out, self._k, y * self.d * v[self._k])
+        return out
+
+    def ghjvprod(self, x, g, v):
+        return g[self._k] * self.d * v[self._k]
+
+
 # --------------------------------------------------------------------------------------------------
 # synthetic generators (seeded; BASELINE.md §4)
 # --------------------------------------------------------------------------------------------------

@@ -104,6 +104,14 @@ class B200Handle:
     def launch_count(self):
         return int(_lib.lib().fpsb_launch_count(self.h))
 
+    def tile_stats(self):
+        """{tiles, windowed, multi-segment} of A and of A' (fpsb_tile_stats)."""
+        out = (C.c_int64 * 6)()
+        check(_lib.lib().fpsb_tile_stats(self.h, out), "fpsb_tile_stats")
+        v = [int(x) for x in out]
+        return {"A": dict(tiles=v[0], windowed=v[1], multi_segment=v[2]),
+                "At": dict(tiles=v[3], windowed=v[4], multi_segment=v[5])}
+
     # -- Jacobian ------------------------------------------------------------------------------
     def set_jac_values(self, vals):
         if isinstance(vals, np.ndarray):

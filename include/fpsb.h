@@ -112,6 +112,10 @@ int fpsb_timer_start(fpsb_handle h);
 int fpsb_timer_stop(fpsb_handle h, double *elapsed_ms);
 /* number of kernels launched by this handle since creation (bench.py's gpu_launches) */
 int64_t fpsb_launch_count(fpsb_handle h);
+/* Layout of the tiled operators behind jprod / jtprod and the Krylov loops (the storage that replaces the reference's
+ * LinearOperator `jac_op!`, src/solve_linear_system.jl:119-121): out = {tiles of A, of those with a shared-memory gather
+ * window, of those with a multi-segment window (stencil operators), the same three for A'}. */
+int fpsb_tile_stats(fpsb_handle h, int64_t out[6]);
 
 /* Replaces jac_coord!(nlp, x, vals[nvar+1 : nvar+nnzj]) feeding both paths
  *   src/solve_linear_system.jl:224-228 (LDLt)  and  jac_op! at :119-121 (Iterative).
@@ -296,7 +300,9 @@ int fpsb_dist_solve_two_extras(fpsb_handle h, double delta, int64_t nvar_global,
  *   fpsb_fp_obj     phi = fx - c'ys + rho/2 |c|^2 (+ eta/2 |x - xk|^2)       :364-367   (x, xk may be NULL when eta = 0)
  *   fpsb_fp_grad    g = gs - Hsv + sigma v + Sstw (+ rho Jtc) (+ eta (x - xk))   :382-398
  *   fpsb_fp_ptv     Ptv = v - p1                                              :544
- *   fpsb_fp_hprod2  Hv = obj_weight (p2 - HsPtv + 2 sigma Ptv (+ Hcv + rho JtJv) (+ eta v))   :546-568 (Val(2)) */
+ *   fpsb_fp_hprod2  Hv = obj_weight (p2 - HsPtv + 2 sigma Ptv (+ Hcv + rho JtJv) (+ eta v))   :546-568 (Val(2))
+ *   fpsb_fp_hprod1  Hv = obj_weight (p2 - HsPtv + 2 sigma Ptv - J'(JJ')^-1 Ss v - Ss'(JJ')^-1 J v (+ rho (Hcv + JtJv)) (+ eta v))
+ *                   :572-634 (Val(1): the two extra terms come from ghjvprod + fpsb_*_solve_two_extras) */
 int fpsb_fp_ys_gs(fpsb_handle h, double sigma, const double *p1, const double *q1, const double *p2,
                   const double *q2, double *gs, double *ys, double *v, double *w);
 int fpsb_fp_hash(fpsb_handle h, const double *x, uint64_t *key);
@@ -309,6 +315,9 @@ int fpsb_fp_ptv(fpsb_handle h, const double *v, const double *p1, double *Ptv);
 int fpsb_fp_hprod2(fpsb_handle h, double sigma, double rho, double eta, double obj_weight, const double *p2,
                    const double *HsPtv, const double *Ptv, const double *Hcv, const double *JtJv,
                    const double *v, double *Hv);
+int fpsb_fp_hprod1(fpsb_handle h, double sigma, double rho, double eta, double obj_weight, const double *p2,
+                   const double *HsPtv, const double *Ptv, const double *JtinvJtJSsv, const double *SsinvJtJJv,
+                   const double *Hcv, const double *JtJv, const double *v, double *Hv);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,7 @@ perm = np.empty(n, dtype=np.int64); perm[:m] = 2 * np.arange(m); perm[m:] = 2 * 
 coo = A.tocoo()
 H = fpsb200.B200Handle(n, m, coo.row.astype(np.int64), perm[coo.col])
 o = _lib.IterOpts(); _lib.lib().fpsb_iter_default_opts(C.c_int64(n), C.c_int64(m), C.byref(o)); o.ls_itmax = 100; o.ln_itmax = 100
+o.ls_atol = o.ls_rtol = 0.0; o.ln_atol = o.ln_rtol = o.ln_btol = 0.0; o.ln_conlim = 1e300     # both methods run every iteration (as bench.py's partitioned record)
 H.iter_setup(o)
 H.set_jac_values(coo.data)
 rng = np.random.default_rng(1234)
@@ -19,4 +20,5 @@ d1 = torch.tensor(rng.standard_normal(n), device="cuda"); d2 = torch.tensor(rng.
 for _ in range(3):
     out = H.iter_solve_two_mixed(1e-2, d1, d2)
     ms, nl = H.iter_last_profile()
+print("tiles", H.tile_stats(), "FPSB_NO_SEGS" in os.environ)
 print("grid %d: n=%d m=%d nnz=%d: loop %.2f ms, %d iterations -> %.1f us per iteration (fused single-GPU path)" % (N, n, m, A.nnz, ms, max(s["niter"] for s in out[4]), 1e3 * ms / max(s["niter"] for s in out[4])))
