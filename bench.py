@@ -65,8 +65,69 @@ def algorithmic_bytes(n, m, nnz, it0, it1, delta):
     return total, launches
 
 
+class NvmlClockSampler:
+    """In-process NVML sampler (pynvml): SM clock, max SM clock and the clock-event reasons every 10 ms while the timed
+    region runs.  nvidia-smi takes longer to start than a short timed region lasts (0 samples at 8 GPUs); NVML does not."""
+    _REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, gpu_index, uuid=None):
+        import pynvml
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        self.h = None
+        if uuid:
+            for cand in (f"GPU-{uuid}", str(uuid)):
+                try:
+                    self.h = pynvml.nvmlDeviceGetHandleByUUID(cand.encode())
+                    break
+                except Exception:      # noqa: BLE001
+                    try:
+                        self.h = pynvml.nvmlDeviceGetHandleByUUID(cand)
+                        break
+                    except Exception:  # noqa: BLE001
+                        pass
+        if self.h is None:
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        self._reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        self.sm, self.bits, self.run = [], 0, False
+
+    def _sample(self):
+        self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+        self.bits |= int(self._reasons_fn(self.h))
+
+    def _loop(self):
+        while self.run:
+            try:
+                self._sample()
+            except Exception:          # noqa: BLE001
+                pass
+            time.sleep(0.01)
+
+    def start(self):
+        self.run = True
+        self.th = threading.Thread(target=self._loop, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        self.run = False
+        self.th.join(timeout=1.0)
+        reasons = sorted(name for bit, name in self._REASONS.items() if self.bits & bit)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx,
+                "samples": len(self.sm), "reasons": reasons, "source": "nvml"}
+
+
+def make_clock_sampler(torch, gpu_index):
+    try:
+        uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+        return NvmlClockSampler(gpu_index, uuid)
+    except Exception:                  # noqa: BLE001
+        return ClockSampler(gpu_index)
+
+
 class ClockSampler:
-    """nvidia-smi clock/throttle sampler running during the timed region."""
+    """nvidia-smi clock/throttle sampler running during the timed region (fallback when NVML is not importable)."""
 
     def __init__(self, gpu_index):
         self.rows = []
@@ -424,7 +485,7 @@ def main():
     # ---- resident (value) -------------------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
         out = step_resident()
-    sampler = ClockSampler(local_rank)
+    sampler = make_clock_sampler(torch, local_rank)
     barrier()
     sampler.start()
     l0 = H.launch_count()

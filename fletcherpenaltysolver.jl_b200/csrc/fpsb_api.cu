@@ -593,6 +593,27 @@ int fpsb_fp_hprod1(fpsb_handle hh, double sigma, double rho, double eta, double 
     return FPSB_OK;
     FPSB_CATCH
 }
+int fpsb_trcg_init(fpsb_handle hh, const double *g, const double *free_mask, double *s, double *r, double *d, double out[5]) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQUIRE(h && out && ((g && s && r && d) || h->nvar == 0), FPSB_EINVAL, "fpsb_trcg_init: NULL argument");
+    FPSB_TRY
+    FPSB_CUDA(cudaSetDevice(h->device));
+    caller_order_in(h);
+    trcg_init(h, h->nvar, g, free_mask, s, r, d, out);
+    return FPSB_OK;
+    FPSB_CATCH
+}
+int fpsb_trcg_step(fpsb_handle hh, const double *Hd, const double *free_mask, double *s, double *r, double *d, double radius,
+                   double tol, double out[5]) {
+    Handle *h = reinterpret_cast<Handle *>(hh);
+    REQUIRE(h && out && ((Hd && s && r && d) || h->nvar == 0), FPSB_EINVAL, "fpsb_trcg_step: NULL argument");
+    FPSB_TRY
+    FPSB_CUDA(cudaSetDevice(h->device));
+    caller_order_in(h);
+    trcg_step(h, h->nvar, Hd, free_mask, s, r, d, radius, tol, out);
+    return FPSB_OK;
+    FPSB_CATCH
+}
 int fpsb_fp_hash(fpsb_handle hh, const double *x, uint64_t *key) {
     Handle *h = reinterpret_cast<Handle *>(hh);
     REQUIRE(h && key && (x || h->nvar == 0), FPSB_EINVAL, "fpsb_fp_hash: NULL argument");

@@ -113,6 +113,7 @@ struct DistCtx {
     unsigned long long bar_base = 0;
     static constexpr int kXchgMaxGrid = 64;
     DevBuf<double> xparts;                          // per-CTA norm partials of the boundary rows
+    DevBuf<int> brow;                               // per boundary row {row, first entry, end entry, inbox position of the first entry}: one 16-byte load
     DevBuf<int> bptr, bsrc, bpeer;                  // per boundary row: its entries of the send list (= scatter-inbox positions) and their peers
     DevBuf<PeerTail> d_ptail;                       // for the m-space step kernel's own exchange (see gk_step_kernel)
     uint64_t sig = 0, n_sc = 0, n_ga = 0, n_tot = 0;   // signals / exchanges issued so far (same on every rank)
@@ -204,6 +205,12 @@ void dist_attach(Handle *h, int nranks, int rank, const void *id128, int64_t own
                 while (pp + 1 < nranks && (int64_t)bs[k] >= send_ptr[pp + 1]) ++pp;
                 bpr[k] = pp;
             }
+            std::vector<int> br(4 * b.size() + 8, 0);
+            for (size_t r = 0; r < b.size(); ++r) {
+                br[4 * r] = b[r]; br[4 * r + 1] = bp[r]; br[4 * r + 2] = bp[r + 1];
+                br[4 * r + 3] = bp[r] < bp[r + 1] ? bs[(size_t)bp[r]] : -1;
+            }
+            D->brow.from(br, h->stream);
             D->bptr.from(bp, h->stream);
             D->bsrc.from(bs, h->stream);
             D->bpeer.from(bpr, h->stream);
@@ -291,7 +298,7 @@ void dist_peer_attach(Handle *h, const void *blobs) {
         D->gtot.alloc(8); D->gtot.zero(h->stream);
         DistLoop X{};
         X.nranks = D->nranks; X.rank = D->rank;
-        X.nbound = (int)D->nbound; X.bidx = D->bidx.p; X.bptr = D->bptr.p; X.bsrc = D->bsrc.p; X.bpeer = D->bpeer.p;
+        X.nbound = (int)D->nbound; X.brow = reinterpret_cast<const int4 *>(D->brow.p); X.bidx = D->bidx.p; X.bptr = D->bptr.p; X.bsrc = D->bsrc.p; X.bpeer = D->bpeer.p;
         X.meta = reinterpret_cast<const long long *>(D->d_meta.p);
         X.S = D->S.p; X.pair = h->iter->Gn.p;
         X.nsend = D->nsend; X.nrecv = D->nrecv;

@@ -104,8 +104,120 @@ __global__ void __launch_bounds__(256) fp_hash_kernel(int n, const double *x, un
     if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);      // integer addition: order-independent, exact
 }
 
+// ------------------------------------------------------------------------------------------------
+// Steihaug–Toint truncated CG of the trust-region subproblem (the matrix-free subsolver that drives the
+// penalty model, `trunk` in fps_solve.py).  One CG iteration = the model's Hessian product (the 2-RHS solves) + the three
+// kernels below; every inner product, the step to the boundary, alpha, beta, the model decrease q and the exit decision
+// stay on the device (state st[]), the host reads five doubles once per iteration.
+//   st: [0] rr  [1] q  [2] tau (step taken along d)  [3] beta  [4] flag (0 go on, 1 left through the boundary /
+//       non-positive curvature, 2 converged)
+// Reductions: per-thread over a fixed stride -> block_sum -> the last block adds the per-block partials in index order.
+// ------------------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ bool trcg_last_block(double (&acc)[K], double *s_red, int *s_last, double *partials, unsigned *counter) {
+    block_sum<K>(acc, s_red);
+    if (threadIdx.x == 0) {
+        double *pp = partials + (size_t)blockIdx.x * K;
+#pragma unroll
+        for (int k = 0; k < K; ++k) pp[k] = acc[k];
+        __threadfence();
+        *s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!*s_last) return false;
+    __threadfence();
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += 256)
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] += __ldcg(partials + (size_t)i * K + k);
+    block_sum<K>(acc, s_red);
+    if (threadIdx.x == 0) *counter = 0;
+    return true;
+}
+
+__global__ void __launch_bounds__(256) trcg_init_kernel(int n, const double *g, const double *fr, double *s, double *r, double *d,
+                                                         double *partials, unsigned *counter, double *st) {
+    __shared__ double s_red[32];
+    __shared__ int s_last;
+    double acc[1] = {0.0};
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double ri = fr != nullptr ? -g[i] * fr[i] : -g[i];
+        s[i] = 0.0; r[i] = ri; d[i] = ri;
+        acc[0] += ri * ri;
+    }
+    if (!trcg_last_block<1>(acc, s_red, &s_last, partials, counter)) return;
+    if (threadIdx.x == 0) { st[0] = acc[0]; st[1] = 0.0; st[2] = 0.0; st[3] = 0.0; st[4] = 0.0; }
+}
+
+// the five inner products of an iteration and every scalar decision that follows from them
+__global__ void __launch_bounds__(256) trcg_dots_kernel(int n, const double *d, const double *Hd, const double *s, const double *r,
+                                                         const double *fr, double radius, double *partials, unsigned *counter,
+                                                         double *st) {
+    __shared__ double s_red[5 * 32];
+    __shared__ int s_last;
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double di = d[i], si = s[i];
+        const double hd = fr != nullptr ? Hd[i] * fr[i] : Hd[i];
+        acc[0] += di * hd; acc[1] += si * si; acc[2] += si * di; acc[3] += di * di; acc[4] += r[i] * di;
+    }
+    if (!trcg_last_block<5>(acc, s_red, &s_last, partials, counter)) return;
+    if (threadIdx.x == 0) {
+        const double dHd = acc[0], ss = acc[1], sd = acc[2], dd = acc[3], rd = acc[4];
+        const double rr = st[0];
+        const double disc = fmax(sd * sd + dd * (radius * radius - ss), 0.0);
+        const double to_boundary = dd > 0.0 ? (-sd + sqrt(disc)) / dd : 0.0;      // positive step to the boundary along d
+        double tau, flag;
+        if (dHd <= 2.220446049250313e-16 * dd) { tau = to_boundary; flag = 1.0; }   // negative / zero curvature
+        else {
+            const double alpha = rr / dHd;
+            if (alpha >= to_boundary) { tau = to_boundary; flag = 1.0; } else { tau = alpha; flag = 0.0; }
+        }
+        st[1] = st[1] + (tau * (-rd) + 0.5 * tau * tau * dHd);
+        st[2] = tau; st[4] = flag;
+    }
+}
+
+// s += tau d ; inside the ball also r -= tau Hd, rr_new, beta and the convergence test
+__global__ void __launch_bounds__(256) trcg_update_kernel(int n, const double *d, const double *Hd, double *s, double *r,
+                                                           const double *fr, double tol, double *partials, unsigned *counter,
+                                                           double *st) {
+    __shared__ double s_red[32];
+    __shared__ int s_last;
+    const double tau = __ldcg(st + 2);
+    const bool inside = __ldcg(st + 4) == 0.0;
+    double acc[1] = {0.0};
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        s[i] = s[i] + tau * d[i];
+        if (inside) {
+            const double hd = fr != nullptr ? Hd[i] * fr[i] : Hd[i];
+            const double ri = r[i] - tau * hd;
+            r[i] = ri;
+            acc[0] += ri * ri;
+        }
+    }
+    if (!trcg_last_block<1>(acc, s_red, &s_last, partials, counter)) return;
+    if (threadIdx.x == 0 && inside) {
+        const double rr = st[0], rr_new = acc[0];
+        st[3] = rr_new / rr;
+        st[0] = rr_new;
+        if (sqrt(rr_new) <= tol) st[4] = 2.0;
+    }
+}
+
+__global__ void trcg_dir_kernel(int n, const double *r, double *d, const double *st) {
+    if (__ldcg(st + 4) != 0.0) return;
+    const double beta = __ldcg(st + 3);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = r[i] + beta * d[i];
+}
+
 struct FpWs {
-    DevBuf<double> partials, out;
+    DevBuf<double> partials, out, trcg;
     DevBuf<unsigned> counter;
     DevBuf<unsigned long long> key;
     double *h_out = nullptr;               // pinned: 3 doubles + 1 u64
@@ -114,7 +226,9 @@ struct FpWs {
 static FpWs *fp_ws(Handle *h) {
     if (!h->fp) {
         FpWs *W = new FpWs();
-        W->partials.alloc(3 * 1024 + 8);
+        W->partials.alloc(5 * 1024 + 8);
+        W->trcg.alloc(8);
+        W->trcg.zero(h->stream);
         W->out.alloc(8);
         W->counter.alloc(4);
         W->key.alloc(2);
@@ -178,6 +292,30 @@ void fp_hprod1(Handle *h, int64_t n, double sigma, double rho, double eta, doubl
     fp_hprod1_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>((int)n, sigma, rho, eta, obj_weight, p2, HsPtv, Ptv, JtinvJtJSsv,
                                                                         SsinvJtJJv, Hcv, JtJv, v, Hv);
     h->launches += 1;
+}
+static void trcg_read(Handle *h, FpWs *W, double *out5) {
+    FPSB_CUDA(cudaMemcpyAsync(W->h_out, W->trcg.p, 5 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    FPSB_CUDA(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < 5; ++k) out5[k] = W->h_out[k];
+}
+void trcg_init(Handle *h, int64_t n, const double *g, const double *fr, double *s, double *r, double *d, double *out5) {
+    FpWs *W = fp_ws(h);
+    const int grid = (int)std::min<int64_t>(1024, std::max<int64_t>(1, (n + 255) / 256));
+    trcg_init_kernel<<<grid, 256, 0, h->stream>>>((int)n, g, fr, s, r, d, W->partials.p, W->counter.p, W->trcg.p);
+    h->launches += 1;
+    FPSB_CUDA(cudaGetLastError());
+    trcg_read(h, W, out5);
+}
+void trcg_step(Handle *h, int64_t n, const double *Hd, const double *fr, double *s, double *r, double *d, double radius, double tol,
+               double *out5) {
+    FpWs *W = fp_ws(h);
+    const int grid = (int)std::min<int64_t>(1024, std::max<int64_t>(1, (n + 255) / 256));
+    trcg_dots_kernel<<<grid, 256, 0, h->stream>>>((int)n, d, Hd, s, r, fr, radius, W->partials.p, W->counter.p, W->trcg.p);
+    trcg_update_kernel<<<grid, 256, 0, h->stream>>>((int)n, d, Hd, s, r, fr, tol, W->partials.p, W->counter.p, W->trcg.p);
+    if (n > 0) trcg_dir_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>((int)n, r, d, W->trcg.p);
+    h->launches += 3;
+    FPSB_CUDA(cudaGetLastError());
+    trcg_read(h, W, out5);
 }
 uint64_t fp_hash(Handle *h, int64_t n, const double *x) {
     FpWs *W = fp_ws(h);

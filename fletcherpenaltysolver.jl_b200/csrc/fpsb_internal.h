@@ -193,6 +193,9 @@ void fp_hprod2(Handle *h, int64_t n, double sigma, double rho, double eta, doubl
 void fp_hprod1(Handle *h, int64_t n, double sigma, double rho, double eta, double obj_weight, const double *p2, const double *HsPtv,
                const double *Ptv, const double *JtinvJtJSsv, const double *SsinvJtJJv, const double *Hcv, const double *JtJv,
                const double *v, double *Hv);
+void trcg_init(Handle *h, int64_t n, const double *g, const double *fr, double *s, double *r, double *d, double *out5);
+void trcg_step(Handle *h, int64_t n, const double *Hd, const double *fr, double *s, double *r, double *d, double radius, double tol,
+               double *out5);
 uint64_t fp_hash(Handle *h, int64_t n, const double *x);
 
 // symbolic.cpp / ldlt.cu

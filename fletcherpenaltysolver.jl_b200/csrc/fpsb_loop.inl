@@ -34,6 +34,7 @@
 struct DistLoop {
     int nranks, rank;
     int nbound;                               // owned rows that peers contribute to (and keep as halo)
+    const int4 *brow;                         // per boundary row {row, first entry, end entry, inbox position of the first entry}
     const int *bidx, *bptr, *bsrc, *bpeer;    // per boundary row: its send-list entries (rank order) and their peers
     const long long *meta;                    // recv_start[R] | recv_cnt[R] | send_ptr[R+1] | ga_off[R]
     double2 *S;                               // raw row sums of the halo / boundary rows (StepParams::raw_out of op[0])
@@ -116,6 +117,9 @@ __device__ __forceinline__ void loop_wait(const int *p, int want, const LoopCtl 
 #endif
 }
 
+#ifndef FPSB_BOUNDARY_UNROLL
+#define FPSB_BOUNDARY_UNROLL 2
+#endif
 #ifdef FPSB_LOOP_TIMERS
 // debug builds: per phase (first 64 of a launch) and CTA, globaltimer stamps of 8 points of the phase
 __device__ unsigned long long g_loop_t[64][160][16];
@@ -140,6 +144,19 @@ __device__ unsigned long long g_loop_seg[160][2][kGroups][8];
 
 // (Tried and dropped: per-CTA records stamped in the sign bit so that arrival and partials are one L2 round trip:
 //  the 148 x 64 polling lanes slowed the CTAs that were still streaming by more than the round trip saved.)
+
+// dst[i] = src[i] (16-byte entries, dst possibly remote) by the CTA's consumer threads, 4 loads in flight per thread
+// (a plain `dst[i] = src[i]` loop serialises an L2 round trip per entry: the remote store may alias the next load)
+__device__ __forceinline__ void copy_batched(double2 *dst, const double2 *src, long long cnt, int ct) {
+    constexpr int kCons = kGroups * kGroupThreads, kU = 4;
+    for (long long i0 = ct; i0 < cnt; i0 += (long long)kCons * kU) {
+        double2 v[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) { const long long i = i0 + (long long)u * kCons; v[u] = i < cnt ? __ldcg(src + i) : make_double2(0.0, 0.0); }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) { const long long i = i0 + (long long)u * kCons; if (i < cnt) dst[i] = v[u]; }
+    }
+}
 
 // The exchange of the boundary after phase `ph`, by the 384 consumer threads of CTA 0 (see DistLoop).
 __device__ __noinline__ void loop_exchange(const LoopParams &L, const DistLoop &X, int ph, int ct, int cw, int lane, int gsz,
@@ -185,7 +202,7 @@ __device__ __noinline__ void loop_exchange(const LoopParams &L, const DistLoop &
                 const long long cnt = recv_cnt[p];
                 double2 *dst = reinterpret_cast<double2 *>(X.peer[p] + mbox_off_sc()) + (size_t)sc_par * X.peer_nsend[p] + X.sc_at_peer[p];
                 const double2 *src = X.S + recv_start[p];
-                for (long long i = ct; i < cnt; i += kCons) dst[i] = __ldcg(src + i);
+                copy_batched(dst, src, cnt, ct);
             }
             __threadfence_system();
             signal_wait(++sig);
@@ -195,29 +212,60 @@ __device__ __noinline__ void loop_exchange(const LoopParams &L, const DistLoop &
         const bool act0 = C0.mode != MD_NONE, act1 = C1.mode != MD_NONE;
         const StepParams &Pn = L.op[0];
         const double2 *inbox = reinterpret_cast<const double2 *>(X.mine + mbox_off_sc()) + (size_t)sc_par * X.nsend;
-        for (int b = ct; b < X.nbound; b += kCons) {
-            const int row = X.bidx[b], kb = X.bptr[b], ke = X.bptr[b + 1];
-            double2 sm = __ldcg(X.S + row);
-            if (R > 1) for (int k = kb; k < ke; ++k) { const double2 a = __ldcg(inbox + X.bsrc[k]); sm.x += a.x; sm.y += a.y; }
-            const double2 old2 = __ldcg(X.pair + row);
-            double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
-            if (C0.rd0()) a00 = __ldcg(Pn.io[0].a0 + row);
-            if (C0.rd1()) a01 = __ldcg(Pn.io[0].a1 + row);
-            if (C1.rd0()) a10 = __ldcg(Pn.io[1].a0 + row);
-            if (C1.rd1()) a11 = __ldcg(Pn.io[1].a1 + row);
-            double n0 = old2.x, n1 = old2.y;
-            if (act0) n0 = row_epilogue(C0, sm.x, old2.x, a00, a01, acc[0], acc[1]);
-            if (act1) n1 = row_epilogue(C1, sm.y, old2.y, a10, a11, acc[2], acc[3]);
-            const double2 val = make_double2(n0, n1);
-            X.pair[row] = val;
-            if (C0.wr0()) Pn.io[0].a0[row] = a00;
-            if (C0.wr1()) Pn.io[0].a1[row] = a01;
-            if (C1.wr0()) Pn.io[1].a0[row] = a10;
-            if (C1.wr1()) Pn.io[1].a1[row] = a11;
-            if (R > 1) for (int k = kb; k < ke; ++k) {
-                const int i = X.bsrc[k], p = X.bpeer[k];
-                double2 *dst = reinterpret_cast<double2 *>(X.peer[p] + mbox_off_ga(X.peer_nsend[p])) + (size_t)ga_par * X.peer_nrecv[p] + X.ga_at_peer[p];
-                dst[i - send_ptr[p]] = val;
+        // kU rows per thread at a time, both levels of the dependent load chain (packed row record -> operands and first
+        // inbox entry) issued for all of them before the first use: a thread has ~16 rows at the C3 strip boundary, and
+        // one row at a time through bidx / bptr / bsrc cost three L2 round trips each
+        constexpr int kU = FPSB_BOUNDARY_UNROLL;
+        for (int b0 = ct; b0 < X.nbound; b0 += kCons * kU) {
+            int row[kU], kb[kU], ke[kU], s0[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int b = b0 + u * kCons;
+                row[u] = -1; kb[u] = ke[u] = 0; s0[u] = -1;
+                if (b < X.nbound) { const int4 q = __ldg(X.brow + b); row[u] = q.x; kb[u] = q.y; ke[u] = q.z; s0[u] = R > 1 ? q.w : -1; }
+            }
+            double2 sm[kU], old2[kU], in0[kU];
+            double a00[kU], a01[kU], a10[kU], a11[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                sm[u] = old2[u] = in0[u] = make_double2(0.0, 0.0);
+                a00[u] = a01[u] = a10[u] = a11[u] = 0.0;
+                if (s0[u] >= 0) in0[u] = __ldcg(inbox + s0[u]);
+                if (row[u] >= 0) {
+                    sm[u] = __ldcg(X.S + row[u]);
+                    old2[u] = __ldcg(X.pair + row[u]);
+                    if (C0.rd0()) a00[u] = __ldcg(Pn.io[0].a0 + row[u]);
+                    if (C0.rd1()) a01[u] = __ldcg(Pn.io[0].a1 + row[u]);
+                    if (C1.rd0()) a10[u] = __ldcg(Pn.io[1].a0 + row[u]);
+                    if (C1.rd1()) a11[u] = __ldcg(Pn.io[1].a1 + row[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                if (row[u] < 0) continue;
+                if (s0[u] >= 0) {
+                    // contributions in rank order: the first was requested above, more than one is rare (a row shared by 3 ranks)
+                    sm[u].x += in0[u].x; sm[u].y += in0[u].y;
+                    for (int k = kb[u] + 1; k < ke[u]; ++k) { const double2 a = __ldcg(inbox + X.bsrc[k]); sm[u].x += a.x; sm[u].y += a.y; }
+                }
+                double n0 = old2[u].x, n1 = old2[u].y;
+                if (act0) n0 = row_epilogue(C0, sm[u].x, old2[u].x, a00[u], a01[u], acc[0], acc[1]);
+                if (act1) n1 = row_epilogue(C1, sm[u].y, old2[u].y, a10[u], a11[u], acc[2], acc[3]);
+                const double2 val = make_double2(n0, n1);
+                X.pair[row[u]] = val;
+                if (C0.wr0()) Pn.io[0].a0[row[u]] = a00[u];
+                if (C0.wr1()) Pn.io[0].a1[row[u]] = a01[u];
+                if (C1.wr0()) Pn.io[1].a0[row[u]] = a10[u];
+                if (C1.wr1()) Pn.io[1].a1[row[u]] = a11[u];
+                if (s0[u] >= 0) {
+                    int i = s0[u];
+                    for (int k = kb[u]; k < ke[u]; ++k) {
+                        if (k > kb[u]) i = X.bsrc[k];
+                        const int p = X.bpeer[k];
+                        double2 *dst = reinterpret_cast<double2 *>(X.peer[p] + mbox_off_ga(X.peer_nsend[p])) + (size_t)ga_par * X.peer_nrecv[p] + X.ga_at_peer[p];
+                        dst[i - send_ptr[p]] = val;
+                    }
+                }
             }
         }
     }
@@ -257,13 +305,17 @@ __device__ __noinline__ void loop_exchange(const LoopParams &L, const DistLoop &
             const long long cnt = recv_cnt[p];
             double2 *dst = X.pair + recv_start[p];
             const double2 *src = inbox + ga_off[p];
-            for (long long i = ct; i < cnt; i += kCons) dst[i] = __ldcg(src + i);
+            copy_batched(dst, src, cnt, ct);
         }
     }
     if (ct < 4) {
         const double *in = reinterpret_cast<const double *>(X.mine + mbox_off_tot()) + (size_t)tot_par * kMboxMaxRanks * 4;
+        double v[kMboxMaxRanks];                             // all ranks' sums requested at once, added in rank order
+#pragma unroll
+        for (int r = 0; r < kMboxMaxRanks; ++r) v[r] = (r < R && r != X.rank) ? __ldcg(in + r * 4 + ct) : 0.0;
         double g = 0.0;
-        for (int r = 0; r < R; ++r) g += (r == X.rank) ? s_x[ct] : __ldcg(in + r * 4 + ct);
+#pragma unroll
+        for (int r = 0; r < kMboxMaxRanks; ++r) if (r < R) g += (r == X.rank) ? s_x[ct] : v[r];
         X.gtot[(size_t)(ph & 1) * 4 + ct] = g;
     }
     if (ct == 0) {

@@ -20,6 +20,7 @@ Two pieces of the reference are third-party programs that cannot be restated her
 All vector arithmetic goes through the small `_V` helpers, which accept numpy arrays and torch tensors.
 """
 import math
+import os
 import time
 import warnings
 
@@ -346,6 +347,43 @@ def _steihaug(hv, g, radius, tol, itmax, free=None):
     return s, -q, nprod
 
 
+def _steihaug_device(handle, hv, g, radius, tol, itmax, free=None):
+    """`_steihaug` with the CG state resident in HBM: s, r, d are device vectors, the five inner products
+    of an iteration, the step to the boundary, alpha, beta, the model decrease and the exit decision are computed by the
+    fused kernels behind fpsb_trcg_init / fpsb_trcg_step; the host reads five doubles per iteration (one synchronisation
+    instead of six) and only supplies Hd = hv(d), i.e. the model's 2-RHS solves."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    L = _lib.lib()
+    handle._follow_torch_stream(g)
+    s, r, d = torch.empty_like(g), torch.empty_like(g), torch.empty_like(g)
+    out = (C.c_double * 5)()
+    p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    fr = None if free is None else free.to(torch.float64).contiguous()
+    _lib.check(L.fpsb_trcg_init(handle.h, p(g), p(fr), p(s), p(r), p(d), out), "fpsb_trcg_init")
+    if math.sqrt(max(out[0], 0.0)) <= tol:
+        return s, 0.0, 0
+    nprod = 0
+    for _ in range(itmax):
+        Hd = hv(d)
+        nprod += 1
+        handle._follow_torch_stream(Hd)
+        _lib.check(L.fpsb_trcg_step(handle.h, p(Hd), p(fr), p(s), p(r), p(d), C.c_double(radius), C.c_double(tol), out),
+                   "fpsb_trcg_step")
+        if out[4] != 0.0:
+            break
+    return s, -out[1], nprod
+
+
+def _cg_solver_for(model, g):
+    """The device-resident CG when the iterate lives on the GPU and the model owns a libfpsb200 handle, else the host loop."""
+    h = getattr(model, "handle", None)
+    if h is not None and hasattr(g, "is_cuda") and g.is_cuda and os.environ.get("FPSB_TRCG_HOST", "0") != "1":
+        return lambda hv, g_, radius, tol, itmax, free: _steihaug_device(h, hv, g_, radius, tol, itmax, free)
+    return _steihaug
+
+
 def trunk(model, x0, *, atol=1e-7, rtol=1e-7, max_iter=20000, max_time=300.0, unbounded_threshold=1 / SQRT_EPS,
           lvar=None, uvar=None, verbose=0, stop_callback=None):
     """Trust-region Newton-CG for  min φσ(x)  [l ≤ x ≤ u].  Optimality as Stopping's
@@ -399,7 +437,7 @@ def trunk(model, x0, *, atol=1e-7, rtol=1e-7, max_iter=20000, max_time=300.0, un
             free = (~act) * 1.0
         gn = _V.norm(g if free is None else g * free)
         cgtol = max(EPS, min(0.1, math.sqrt(gn)) * gn)
-        s, pred, nprod = _steihaug(lambda v: model.hprod(x, v), g, radius, cgtol, max(2 * n, 10), free)
+        s, pred, nprod = _cg_solver_for(model, g)(lambda v: model.hprod(x, v), g, radius, cgtol, max(2 * n, 10), free)
         out.cg_iter += nprod
         if bounded:
             xt = _V.clip(x + s, lvar, uvar)

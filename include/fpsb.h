@@ -315,6 +315,19 @@ int fpsb_fp_ptv(fpsb_handle h, const double *v, const double *p1, double *Ptv);
 int fpsb_fp_hprod2(fpsb_handle h, double sigma, double rho, double eta, double obj_weight, const double *p2,
                    const double *HsPtv, const double *Ptv, const double *Hcv, const double *JtJv,
                    const double *v, double *Hv);
+/* Steihaug-Toint truncated CG of the trust-region subproblem  min g's + s'Hs/2, |s| <= radius  (in the
+ * reference this is the third-party subproblem solver that calls obj / grad! / hprod! of FletcherPenaltyNLP,
+ * src/parameters.jl:199-206, src/algo.jl:113-116).  All vectors are DEVICE pointers of length nvar; the caller supplies
+ * Hd = H d between the calls (the 2-RHS solves).  free_mask (nullable): 1.0 on free variables, 0.0 on active bounds.
+ * out = {rr, q (model value at s), tau (step taken along d), beta, flag}: flag 0 go on, 1 left through the boundary or
+ * non-positive curvature (s is final), 2 converged (sqrt(rr) <= tol).  The five inner products, alpha, beta, the step
+ * to the boundary and the exit decision are computed on the device; one 40-byte read-back per iteration.
+ *   fpsb_trcg_init  s = 0, r = d = -g (masked), rr = r'r
+ *   fpsb_trcg_step  one iteration given Hd: updates s, r, d in place */
+int fpsb_trcg_init(fpsb_handle h, const double *g, const double *free_mask, double *s, double *r, double *d,
+                   double out[5]);
+int fpsb_trcg_step(fpsb_handle h, const double *Hd, const double *free_mask, double *s, double *r, double *d,
+                   double radius, double tol, double out[5]);
 int fpsb_fp_hprod1(fpsb_handle h, double sigma, double rho, double eta, double obj_weight, const double *p2,
                    const double *HsPtv, const double *Ptv, const double *JtinvJtJSsv, const double *SsinvJtJJv,
                    const double *Hcv, const double *JtJv, const double *v, double *Hv);
