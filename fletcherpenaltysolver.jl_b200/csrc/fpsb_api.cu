@@ -325,6 +325,7 @@ int fpsb_iter_setup(fpsb_handle hh, const fpsb_iter_opts *opts) {
 /* debug builds only (-DFPSB_PHASE_TIMERS): accumulated clock64 cycles per kernel phase; not in fpsb.h */
 void fpsb_debug_phase_timers(unsigned long long *out, int reset) { fpsb::phase_timers(out, reset); }
 void fpsb_debug_loop_timers(unsigned long long *out) { fpsb::loop_timers(out); }
+void fpsb_debug_xchg_timers(unsigned long long *out) { fpsb::xchg_timers(out); }
 
 int fpsb_iter_last_profile(fpsb_handle hh, double *loop_ms, int64_t *step_launches) {
     Handle *h = reinterpret_cast<Handle *>(hh);

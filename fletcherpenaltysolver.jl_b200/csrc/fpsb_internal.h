@@ -146,7 +146,8 @@ void csr_build(Handle *h);
 void csr_refresh_values(Handle *h);
 void spmv_plain(Handle *h, bool transpose, const double *x, double *y, int ncols_rhs);
 void phase_timers(unsigned long long *out, int reset);   // debug builds (-DFPSB_PHASE_TIMERS)
-void loop_timers(unsigned long long *out);                // debug builds (-DFPSB_LOOP_TIMERS)
+void loop_timers(unsigned long long *out);
+void xchg_timers(unsigned long long *out);                // debug builds (-DFPSB_LOOP_TIMERS)
 void iter_setup(Handle *h);
 void iter_free(Handle *h);
 void iter_solve_two_mixed(Handle *h, double delta, const double *rhs1, const double *rhs2, double *p1,

@@ -1962,6 +1962,13 @@ static void launch_step(Handle *h, const CsrDev &M, const StepParams &P, bool pa
     h->launches += 1;
 }
 
+// debug builds (-DFPSB_XCHG_TIMERS): read and reset the exchange segment timers, [2][16]
+void xchg_timers(unsigned long long *out) {
+    cudaMemcpyFromSymbol(out, g_xchg_t, sizeof(unsigned long long) * 32);
+    unsigned long long z[32] = {};
+    cudaMemcpyToSymbol(g_xchg_t, z, sizeof(z));
+}
+
 // debug builds (-DFPSB_LOOP_TIMERS): the stamps of the last persistent-loop launch, [64][160][8]
 void loop_timers(unsigned long long *out) {
 #ifdef FPSB_LOOP_TIMERS

@@ -117,6 +117,16 @@ __device__ __forceinline__ void loop_wait(const int *p, int want, const LoopCtl 
 #endif
 }
 
+// debug builds (-DFPSB_XCHG_TIMERS, tools/xchg_timers.py): globaltimer ns CTA 0's thread 0 spent in the segments of
+// loop_exchange, summed per phase kind [o][segment]; [o][15] counts the exchanges; [o][12] is CTA 1's wait for the release
+__device__ unsigned long long g_xchg_t[2][16];
+#ifdef FPSB_XCHG_TIMERS
+#define XT_DECL unsigned long long xt0 = global_ns()
+#define XT_MARK(i) do { if (ct == 0) { const unsigned long long xt1 = global_ns(); g_xchg_t[o][(i)] += xt1 - xt0; xt0 = xt1; } } while (0)
+#else
+#define XT_DECL
+#define XT_MARK(i)
+#endif
 #ifndef FPSB_BOUNDARY_UNROLL
 #define FPSB_BOUNDARY_UNROLL 2
 #endif
@@ -166,6 +176,7 @@ __device__ __noinline__ void loop_exchange(const LoopParams &L, const DistLoop &
     const int o = (L.first + ph) & 1;                      // 0: n-space phase (rows of A_loc'), 1: m-space phase
     const long long *recv_start = X.meta, *recv_cnt = X.meta + R, *send_ptr = X.meta + 2 * R, *ga_off = X.meta + 3 * R + 1;
     auto die = [&]() { ctl.abort = 1; atomicExch(X.err, 1); atomicExch(L.done_flag + 2, 2); __threadfence_system(); __trap(); };
+    XT_DECL;
     // every CTA of this GPU has left its record and its raw sums
     if (ct == 0) {
         const unsigned long long want = (unsigned long long)(ph + 1) * (unsigned long long)gsz;
@@ -177,6 +188,7 @@ __device__ __noinline__ void loop_exchange(const LoopParams &L, const DistLoop &
         }
     }
     consumers_bar();
+    XT_MARK(0);                                              // waited for the local grid
     unsigned long long sig = __ldcg(X.seq + 0);
     const int sc_par = (int)(__ldcg(X.seq + 1) & 1), ga_par = (int)(__ldcg(X.seq + 2) & 1), tot_par = (int)(__ldcg(X.seq + 3) & 1);
     auto signal_wait = [&](unsigned long long seq) {
@@ -205,7 +217,9 @@ __device__ __noinline__ void loop_exchange(const LoopParams &L, const DistLoop &
                 copy_batched(dst, src, cnt, ct);
             }
             __threadfence_system();
+            XT_MARK(1);                                      // scatter puts + fence
             signal_wait(++sig);
+            XT_MARK(2);                                      // signal round trip 1
         }
         // 2. boundary rows: add the peers' partial sums (rank order), Krylov row epilogue, fresh value -> peers' halo slots
         const CoefR C0 = to_regs(sC[0]), C1 = to_regs(sC[1]);
@@ -269,6 +283,7 @@ __device__ __noinline__ void loop_exchange(const LoopParams &L, const DistLoop &
             }
         }
     }
+    XT_MARK(3);                                              // boundary rows
     // 3. local sums: the CTAs' records in CTA order, then the boundary rows
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -296,7 +311,9 @@ __device__ __noinline__ void loop_exchange(const LoopParams &L, const DistLoop &
         }
     }
     __threadfence_system();
+    XT_MARK(4);                                              // local sums + puts of the totals + fence
     if (R > 1) signal_wait(++sig); else consumers_bar();
+    XT_MARK(5);                                              // signal round trip 2
     // 4. the peers' fresh values -> my halo slots ; the ranks' sums in rank order
     if (o == 0 && R > 1) {
         const double2 *inbox = reinterpret_cast<const double2 *>(X.mine + mbox_off_ga(X.nsend)) + (size_t)ga_par * X.nrecv;
@@ -326,6 +343,10 @@ __device__ __noinline__ void loop_exchange(const LoopParams &L, const DistLoop &
     fence_proxy_async();                                     // the halo / boundary entries of the pair vs the next phase's TMA reads
     __threadfence();
     consumers_bar();
+    XT_MARK(6);                                              // gather copy-in, totals, fences
+#ifdef FPSB_XCHG_TIMERS
+    if (ct == 0) g_xchg_t[o][15] += 1;
+#endif
     if (ct == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(X.xbar), "l"((unsigned long long)(ph + 1)) : "memory");
 }
 
@@ -396,12 +417,18 @@ __device__ __forceinline__ void loop_boundary(const LoopParams &L, int ph, int r
                 }
                 st_release_cta(&ctl.pass, ph);
             }
+#ifdef FPSB_XCHG_TIMERS
+            const unsigned long long xw0 = global_ns();
+#endif
             while (ld_acquire_gpu(L.dx->xbar) < (unsigned long long)ph) {
                 __nanosleep(40);
                 if ((++spins & 4095) == 0 && global_ns() - t0 > 6000000000ull) {     // 6 s: the exchange died
                     ctl.abort = 1; atomicExch(L.done_flag + 2, 2); __threadfence_system(); __trap();
                 }
             }
+#ifdef FPSB_XCHG_TIMERS
+            if (cta == 1) g_xchg_t[(L.first + ph - 1) & 1][12] += global_ns() - xw0;
+#endif
             if (!local_pass) st_release_cta(&ctl.pass, ph);
             LT_STAMP(ph - 1, 3);
         }
