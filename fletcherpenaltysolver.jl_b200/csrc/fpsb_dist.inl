@@ -122,7 +122,8 @@ struct DistCtx {
     // ---- persistent loop with the exchange inside the kernel (gk_loop_kernel<true>) ----
     DevBuf<DistLoop> d_dloop;
     DevBuf<unsigned long long> d_seq;               // device copy of sig | n_sc | n_ga | n_tot while the loop kernel runs
-    DevBuf<double> gtot;
+    DevBuf<double> gtot, bparts;
+    DevBuf<double2> gastage;                        // fresh boundary values in send-list order (see DistLoop)
     bool loop_ok = false;
 };
 
@@ -296,6 +297,8 @@ void dist_peer_attach(Handle *h, const void *blobs) {
         // the description the persistent loop kernel's CTA 0 works from (see DistLoop)
         D->d_seq.alloc(4); D->d_seq.zero(h->stream);
         D->gtot.alloc(8); D->gtot.zero(h->stream);
+        D->bparts.alloc((size_t)kLoopMaxGrid * 4 + 8); D->bparts.zero(h->stream);
+        D->gastage.alloc((size_t)D->nsend + 8); D->gastage.zero(h->stream);
         DistLoop X{};
         X.nranks = D->nranks; X.rank = D->rank;
         X.nbound = (int)D->nbound; X.brow = reinterpret_cast<const int4 *>(D->brow.p); X.bidx = D->bidx.p; X.bptr = D->bptr.p; X.bsrc = D->bsrc.p; X.bpeer = D->bpeer.p;
@@ -309,6 +312,9 @@ void dist_peer_attach(Handle *h, const void *blobs) {
             X.peer_nsend[p] = D->peer_nsend[p]; X.peer_nrecv[p] = D->peer_nrecv[p];
         }
         X.seq = D->d_seq.p; X.gtot = D->gtot.p; X.xbar = h->iter->gbar.p + 1; X.err = D->d_err.p;
+        // helper CTAs for the boundary rows (FPSB_DIST_HELPERS=1: CTA 0 alone)
+        { const char *e = getenv("FPSB_DIST_HELPERS"); X.nhelp = std::max(1, std::min(kLoopMaxGrid, (e && *e) ? atoi(e) : 16)); }
+        X.sbar = h->iter->gbar.p + 2; X.hbar = h->iter->gbar.p + 3; X.bparts = D->bparts.p; X.gastage = D->gastage.p;
         std::vector<DistLoop> v(1, X);
         D->d_dloop.from(v, h->stream);
         FPSB_CUDA(cudaStreamSynchronize(h->stream));

@@ -47,6 +47,13 @@ struct DistLoop {
     unsigned long long *seq;                  // device copy of [0] signals issued, [1] scatters, [2] gathers, [3] tot exchanges
     double *gtot;                             // [2][4] all-reduced sums, ping-pong by phase parity
     unsigned long long *xbar;                 // exchanges completed in this launch (zero at launch)
+    // boundary rows shared out over the consumer threads of CTAs 0 .. nhelp-1 (one SM's L2 bandwidth, ~100 GB/s, was the
+    // bound: 2.5 MB of row operands per exchange at an interior C3 strip = 36 of 67 us, tools/xchg_timers.py)
+    int nhelp;
+    unsigned long long *sbar;                 // n-space exchanges whose scatter inbox is complete (zero at launch)
+    unsigned long long *hbar;                 // arrivals of the helper CTAs that finished their slice (zero at launch)
+    double *bparts;                           // [nhelp][4] norm partials of the helpers' slices
+    double2 *gastage;                         // fresh values of the boundary rows in send-list order (local): CTA 0 puts them to the peers
     int *err;
 };
 // mailbox layout (bytes):  flags u64[8] | tot double[2][8][4] | scatter inbox double2[2][nsend] | gather inbox double2[2][nrecv]
@@ -168,13 +175,161 @@ __device__ __forceinline__ void copy_batched(double2 *dst, const double2 *src, l
     }
 }
 
+// helper CTAs of this rank: none for a short boundary (the hand-shake costs more than 4 rows per thread of CTA 0:
+// measured on the headline operator, 108 boundary rows, 79 -> 89 us per iteration with 16 helpers)
+__device__ __forceinline__ int loop_helpers(const DistLoop &X, int gsz) {
+    return X.nbound >= 4 * kGroups * kGroupThreads ? max(1, min(X.nhelp, gsz)) : 1;
+}
+
+// Boundary rows [lo, hi) by the CTA's 384 consumer threads: add the peers' partial sums (rank order), Krylov row epilogue,
+// fresh pair value -> the row itself and the send-list slots of the peers that keep it as halo (gastage, local).
+// kU rows per thread at a time; the packed record {row, first entry, end entry, inbox position of the first entry} of the
+// NEXT batch is requested before the operands of the current one, the operands and the first inbox entry of all kU rows
+// before the first use.
+__device__ __noinline__ void boundary_rows_slice(const LoopParams &L, const DistLoop &X, const Coef *sC, int lo, int hi, int ct,
+                                                 double (&acc)[4]) {
+    constexpr int kCons = kGroups * kGroupThreads;
+    constexpr int kU = FPSB_BOUNDARY_UNROLL;
+    const CoefR C0 = to_regs(sC[0]), C1 = to_regs(sC[1]);
+    const bool act0 = C0.mode != MD_NONE, act1 = C1.mode != MD_NONE;
+    const StepParams &Pn = L.op[0];
+    const bool peers = X.nranks > 1;
+    const int4 *brow = X.brow;
+    const double2 *S = X.S;
+    double2 *pair = X.pair;
+    double2 *stage = X.gastage;
+    const double2 *inbox = reinterpret_cast<const double2 *>(X.mine + mbox_off_sc()) + (size_t)(__ldcg(X.seq + 1) & 1) * X.nsend;
+    int4 ra[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+        const int b = lo + ct + u * kCons;
+        ra[u] = make_int4(-1, 0, 0, -1);
+        if (b < hi) ra[u] = __ldg(brow + b);
+    }
+    for (int b0 = lo + ct; b0 < hi; b0 += kCons * kU) {
+        int4 na[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int b = b0 + (kU + u) * kCons;
+            na[u] = make_int4(-1, 0, 0, -1);
+            if (b < hi) na[u] = __ldg(brow + b);
+        }
+        double2 sm[kU], old2[kU], in0[kU];
+        double a00[kU], a01[kU], a10[kU], a11[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            sm[u] = old2[u] = in0[u] = make_double2(0.0, 0.0);
+            a00[u] = a01[u] = a10[u] = a11[u] = 0.0;
+            const int row = ra[u].x;
+            if (peers && ra[u].w >= 0) in0[u] = __ldcg(inbox + ra[u].w);
+            if (row >= 0) {
+                sm[u] = __ldcg(S + row);
+                old2[u] = __ldcg(pair + row);
+                if (C0.rd0()) a00[u] = __ldcg(Pn.io[0].a0 + row);
+                if (C0.rd1()) a01[u] = __ldcg(Pn.io[0].a1 + row);
+                if (C1.rd0()) a10[u] = __ldcg(Pn.io[1].a0 + row);
+                if (C1.rd1()) a11[u] = __ldcg(Pn.io[1].a1 + row);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int row = ra[u].x, kb = ra[u].y, ke = ra[u].z;
+            if (row < 0) continue;
+            const bool contrib = peers && ra[u].w >= 0;
+            if (contrib) {
+                // contributions in rank order: the first was requested above, more than one is rare (a row shared by 3 ranks)
+                sm[u].x += in0[u].x; sm[u].y += in0[u].y;
+                for (int k = kb + 1; k < ke; ++k) { const double2 a = __ldcg(inbox + X.bsrc[k]); sm[u].x += a.x; sm[u].y += a.y; }
+            }
+            double n0 = old2[u].x, n1 = old2[u].y;
+            if (act0) n0 = row_epilogue(C0, sm[u].x, old2[u].x, a00[u], a01[u], acc[0], acc[1]);
+            if (act1) n1 = row_epilogue(C1, sm[u].y, old2[u].y, a10[u], a11[u], acc[2], acc[3]);
+            const double2 val = make_double2(n0, n1);
+            pair[row] = val;
+            if (C0.wr0()) Pn.io[0].a0[row] = a00[u];
+            if (C0.wr1()) Pn.io[0].a1[row] = a01[u];
+            if (C1.wr0()) Pn.io[1].a0[row] = a10[u];
+            if (C1.wr1()) Pn.io[1].a1[row] = a11[u];
+            if (contrib) {
+                stage[ra[u].w] = val;
+                for (int k = kb + 1; k < ke; ++k) stage[X.bsrc[k]] = val;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) ra[u] = na[u];
+    }
+}
+
+// CTAs 1 .. nhelp-1 after an n-space phase: their consumer threads (idle until the exchange is over: the next phase
+// gathers the halo) take a slice of the boundary rows once CTA 0 says the scatter inbox is complete, leave the slice's norm
+// partials in bparts and arrive at hbar.  No remote traffic here: the fresh values go to gastage, CTA 0 puts them to the peers.
+__device__ __noinline__ void loop_help(const LoopParams &L, const DistLoop &X, int ph, int ct, int cw, int lane, int cta, int gsz,
+                                       const Coef *sC, double *s_red /* 4*32 */, LoopCtl &ctl) {
+    if (((L.first + ph) & 1) != 0 || X.nranks <= 1) return;
+    const int K = loop_helpers(X, gsz);
+    if (cta >= K) return;
+    const unsigned long long nn = (unsigned long long)((ph + 2 - (L.first & 1)) >> 1);
+    if (ct == 0) {
+        const unsigned long long t0 = global_ns();
+        unsigned spins = 0;
+        while (ld_acquire_gpu(X.sbar) < nn) {
+            __nanosleep(40);
+            if ((++spins & 4095) == 0 && global_ns() - t0 > 6000000000ull) {
+                ctl.abort = 1; atomicExch(L.done_flag + 2, 2); __threadfence_system(); __trap();
+            }
+        }
+    }
+    consumers_bar();
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    const int chunk = (X.nbound + K - 1) / K;
+    boundary_rows_slice(L, X, sC, min(cta * chunk, X.nbound), min((cta + 1) * chunk, X.nbound), ct, acc);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const double x = warp_sum(acc[q]);
+        if (lane == 0) s_red[q * 32 + cw] = x;
+    }
+    fence_proxy_async();                                     // this slice's generic writes of the pair vs the next phase's TMA reads
+    consumers_bar();                                         // every thread's stores of the slice precede the arrival below
+    if (cw == 0) {
+        double v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = warp_sum(lane < kGroups * kGroupWarps ? s_red[q * 32 + lane] : 0.0);
+        if (lane == 0) {
+            double *pp = X.bparts + (size_t)cta * 4;
+            pp[0] = v[0]; pp[1] = v[1]; pp[2] = v[2]; pp[3] = v[3];
+            __threadfence();
+            red_release_gpu(X.hbar, 1ull);
+        }
+    }
+    consumers_bar();                                         // s_red is free again
+}
+
+// What loop_exchange needs of a peer for ONE exchange, gathered once into shared memory (every field of DistLoop lives in
+// global memory: a dependent L2 round trip per use — measured at 8 GPUs: 36 of 67 us of the n-space exchange went into the
+// per-row chains bpeer -> peer -> inbox sizes -> store address, tools/xchg_timers.py)
+struct XPeer {
+    double2 *sc_dst;                  // my slice of the peer's scatter inbox (this exchange's half)
+    const double2 *sc_src;            // the raw sums of the peer's columns: S + recv_start[p]
+    double2 *ga_dst;                  // the peer's gather inbox (this exchange's half); my entries start at ga_at_peer[p]
+    const double2 *ga_src;            // the peer's slice of my gather inbox (this exchange's half)
+    double2 *ga_copy_dst;             // my halo slots of the peer's columns: pair + recv_start[p]
+    double *tot_dst;                  // my slot of the peer's tot inbox (this exchange's half)
+    long long cnt;                    // halo entries shared with the peer (0: not a neighbour)
+    long long send_cnt;               // my boundary values the peer keeps as halo
+    double2 *ga_put_dst;              // my slice of the peer's gather inbox (this exchange's half)
+    const double2 *ga_put_src;        // gastage + send_ptr[p]
+    unsigned long long *flag_dst;     // my flag in the peer's mailbox
+    const unsigned long long *flag_src;   // the peer's flag in mine
+};
+
 // The exchange of the boundary after phase `ph`, by the 384 consumer threads of CTA 0 (see DistLoop).
 __device__ __noinline__ void loop_exchange(const LoopParams &L, const DistLoop &X, int ph, int ct, int cw, int lane, int gsz,
                                            const Coef *sC, double *s_red /* 4*32 */, double *s_x /* >= 8 */, LoopCtl &ctl) {
     constexpr int kCons = kGroups * kGroupThreads;
+    __shared__ XPeer s_peer[kMboxMaxRanks];
+    __shared__ const double *s_tot_in;
     const int R = X.nranks;
     const int o = (L.first + ph) & 1;                      // 0: n-space phase (rows of A_loc'), 1: m-space phase
-    const long long *recv_start = X.meta, *recv_cnt = X.meta + R, *send_ptr = X.meta + 2 * R, *ga_off = X.meta + 3 * R + 1;
     auto die = [&]() { ctl.abort = 1; atomicExch(X.err, 1); atomicExch(L.done_flag + 2, 2); __threadfence_system(); __trap(); };
     XT_DECL;
     // every CTA of this GPU has left its record and its raw sums
@@ -187,16 +342,43 @@ __device__ __noinline__ void loop_exchange(const LoopParams &L, const DistLoop &
             if ((++spins & 4095) == 0 && global_ns() - t0 > 4000000000ull) die();
         }
     }
+    // meanwhile consumer warp 1 gathers the peers' descriptions of this exchange (the sequence numbers were left by the
+    // previous exchange, everything else is constant)
+    if (ct >= 32 && ct < 32 + R) {
+        const int p = ct - 32;
+        const long long *recv_start = X.meta, *recv_cnt = X.meta + R, *ga_off = X.meta + 3 * R + 1;
+        const int sc_par = (int)(__ldcg(X.seq + 1) & 1), ga_par = (int)(__ldcg(X.seq + 2) & 1), tot_par = (int)(__ldcg(X.seq + 3) & 1);
+        XPeer P;
+        unsigned char *pm = X.peer[p];
+        const long long pns = X.peer_nsend[p], pnr = X.peer_nrecv[p];
+        P.cnt = p == X.rank ? 0 : recv_cnt[p];
+        P.sc_dst = reinterpret_cast<double2 *>(pm + mbox_off_sc()) + (size_t)sc_par * pns + X.sc_at_peer[p];
+        P.sc_src = X.S + recv_start[p];
+        P.ga_dst = reinterpret_cast<double2 *>(pm + mbox_off_ga(pns)) + (size_t)ga_par * pnr;
+        {
+            const long long *send_ptr = X.meta + 2 * R;
+            P.send_cnt = p == X.rank ? 0 : send_ptr[p + 1] - send_ptr[p];
+            P.ga_put_dst = P.ga_dst + X.ga_at_peer[p];
+            P.ga_put_src = X.gastage + send_ptr[p];
+        }
+        P.ga_src = reinterpret_cast<const double2 *>(X.mine + mbox_off_ga(X.nsend)) + (size_t)ga_par * X.nrecv + ga_off[p];
+        P.ga_copy_dst = X.pair + recv_start[p];
+        P.tot_dst = reinterpret_cast<double *>(pm + mbox_off_tot()) + ((size_t)tot_par * kMboxMaxRanks + X.rank) * 4;
+        P.flag_dst = reinterpret_cast<unsigned long long *>(pm) + X.rank;
+        P.flag_src = reinterpret_cast<const unsigned long long *>(X.mine) + p;
+        s_peer[p] = P;
+        if (p == 0) s_tot_in = reinterpret_cast<const double *>(X.mine + mbox_off_tot()) + (size_t)tot_par * kMboxMaxRanks * 4;
+    }
     consumers_bar();
     XT_MARK(0);                                              // waited for the local grid
     unsigned long long sig = __ldcg(X.seq + 0);
-    const int sc_par = (int)(__ldcg(X.seq + 1) & 1), ga_par = (int)(__ldcg(X.seq + 2) & 1), tot_par = (int)(__ldcg(X.seq + 3) & 1);
+    const int rank = X.rank;
     auto signal_wait = [&](unsigned long long seq) {
         // (every thread has fenced its own remote puts system-wide before the barrier)
         consumers_bar();
-        if (ct < R && ct != X.rank) {
-            st_release_sys(reinterpret_cast<unsigned long long *>(X.peer[ct]) + X.rank, seq);
-            const unsigned long long *f = reinterpret_cast<const unsigned long long *>(X.mine) + ct;
+        if (ct < R && ct != rank) {
+            st_release_sys(s_peer[ct].flag_dst, seq);
+            const unsigned long long *f = s_peer[ct].flag_src;
             const unsigned long long t0 = global_ns();
             unsigned spins = 0;
             while (ld_acquire_sys(f) < seq) {
@@ -210,76 +392,38 @@ __device__ __noinline__ void loop_exchange(const LoopParams &L, const DistLoop &
         if (R > 1) {
             // 1. halo partial sums -> the owners' scatter inboxes
             for (int p = 0; p < R; ++p) {
-                if (p == X.rank) continue;
-                const long long cnt = recv_cnt[p];
-                double2 *dst = reinterpret_cast<double2 *>(X.peer[p] + mbox_off_sc()) + (size_t)sc_par * X.peer_nsend[p] + X.sc_at_peer[p];
-                const double2 *src = X.S + recv_start[p];
-                copy_batched(dst, src, cnt, ct);
+                const long long cnt = s_peer[p].cnt;
+                if (cnt > 0) copy_batched(s_peer[p].sc_dst, s_peer[p].sc_src, cnt, ct);
             }
             __threadfence_system();
             XT_MARK(1);                                      // scatter puts + fence
             signal_wait(++sig);
             XT_MARK(2);                                      // signal round trip 1
         }
-        // 2. boundary rows: add the peers' partial sums (rank order), Krylov row epilogue, fresh value -> peers' halo slots
-        const CoefR C0 = to_regs(sC[0]), C1 = to_regs(sC[1]);
-        const bool act0 = C0.mode != MD_NONE, act1 = C1.mode != MD_NONE;
-        const StepParams &Pn = L.op[0];
-        const double2 *inbox = reinterpret_cast<const double2 *>(X.mine + mbox_off_sc()) + (size_t)sc_par * X.nsend;
-        // kU rows per thread at a time, both levels of the dependent load chain (packed row record -> operands and first
-        // inbox entry) issued for all of them before the first use: a thread has ~16 rows at the C3 strip boundary, and
-        // one row at a time through bidx / bptr / bsrc cost three L2 round trips each
-        constexpr int kU = FPSB_BOUNDARY_UNROLL;
-        for (int b0 = ct; b0 < X.nbound; b0 += kCons * kU) {
-            int row[kU], kb[kU], ke[kU], s0[kU];
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                const int b = b0 + u * kCons;
-                row[u] = -1; kb[u] = ke[u] = 0; s0[u] = -1;
-                if (b < X.nbound) { const int4 q = __ldg(X.brow + b); row[u] = q.x; kb[u] = q.y; ke[u] = q.z; s0[u] = R > 1 ? q.w : -1; }
-            }
-            double2 sm[kU], old2[kU], in0[kU];
-            double a00[kU], a01[kU], a10[kU], a11[kU];
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                sm[u] = old2[u] = in0[u] = make_double2(0.0, 0.0);
-                a00[u] = a01[u] = a10[u] = a11[u] = 0.0;
-                if (s0[u] >= 0) in0[u] = __ldcg(inbox + s0[u]);
-                if (row[u] >= 0) {
-                    sm[u] = __ldcg(X.S + row[u]);
-                    old2[u] = __ldcg(X.pair + row[u]);
-                    if (C0.rd0()) a00[u] = __ldcg(Pn.io[0].a0 + row[u]);
-                    if (C0.rd1()) a01[u] = __ldcg(Pn.io[0].a1 + row[u]);
-                    if (C1.rd0()) a10[u] = __ldcg(Pn.io[1].a0 + row[u]);
-                    if (C1.rd1()) a11[u] = __ldcg(Pn.io[1].a1 + row[u]);
+        // 2. boundary rows (add the peers' partial sums in rank order, Krylov row epilogue, fresh value -> gastage), shared
+        //    with the helper CTAs; then the fresh values go to the peers' gather inboxes in whole slices
+        const int K = loop_helpers(X, gsz);
+        const unsigned long long nn = (unsigned long long)((ph + 2 - (L.first & 1)) >> 1);     // n-space exchanges of this launch so far
+        if (K > 1 && ct == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(X.sbar), "l"(nn) : "memory");
+        {
+            const int chunk = (X.nbound + K - 1) / K;
+            boundary_rows_slice(L, X, sC, 0, min(chunk, X.nbound), ct, acc);
+        }
+        if (R > 1) {
+            consumers_bar();
+            if (K > 1 && ct == 0) {
+                const unsigned long long want = nn * (unsigned long long)(K - 1);
+                const unsigned long long t0 = global_ns();
+                unsigned spins = 0;
+                while (ld_acquire_gpu(X.hbar) < want) {
+                    __nanosleep(20);
+                    if ((++spins & 4095) == 0 && global_ns() - t0 > 4000000000ull) die();
                 }
             }
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                if (row[u] < 0) continue;
-                if (s0[u] >= 0) {
-                    // contributions in rank order: the first was requested above, more than one is rare (a row shared by 3 ranks)
-                    sm[u].x += in0[u].x; sm[u].y += in0[u].y;
-                    for (int k = kb[u] + 1; k < ke[u]; ++k) { const double2 a = __ldcg(inbox + X.bsrc[k]); sm[u].x += a.x; sm[u].y += a.y; }
-                }
-                double n0 = old2[u].x, n1 = old2[u].y;
-                if (act0) n0 = row_epilogue(C0, sm[u].x, old2[u].x, a00[u], a01[u], acc[0], acc[1]);
-                if (act1) n1 = row_epilogue(C1, sm[u].y, old2[u].y, a10[u], a11[u], acc[2], acc[3]);
-                const double2 val = make_double2(n0, n1);
-                X.pair[row[u]] = val;
-                if (C0.wr0()) Pn.io[0].a0[row[u]] = a00[u];
-                if (C0.wr1()) Pn.io[0].a1[row[u]] = a01[u];
-                if (C1.wr0()) Pn.io[1].a0[row[u]] = a10[u];
-                if (C1.wr1()) Pn.io[1].a1[row[u]] = a11[u];
-                if (s0[u] >= 0) {
-                    int i = s0[u];
-                    for (int k = kb[u]; k < ke[u]; ++k) {
-                        if (k > kb[u]) i = X.bsrc[k];
-                        const int p = X.bpeer[k];
-                        double2 *dst = reinterpret_cast<double2 *>(X.peer[p] + mbox_off_ga(X.peer_nsend[p])) + (size_t)ga_par * X.peer_nrecv[p] + X.ga_at_peer[p];
-                        dst[i - send_ptr[p]] = val;
-                    }
-                }
+            if (K > 1) consumers_bar();
+            for (int p = 0; p < R; ++p) {
+                const long long cnt = s_peer[p].send_cnt;
+                if (cnt > 0) copy_batched(s_peer[p].ga_put_dst, s_peer[p].ga_put_src, cnt, ct);
             }
         }
     }
@@ -299,40 +443,46 @@ __device__ __noinline__ void loop_exchange(const LoopParams &L, const DistLoop &
             const double2 b = __ldcg(reinterpret_cast<const double2 *>(base + (size_t)i * 4 + 2));
             tot[0] += a.x; tot[1] += a.y; tot[2] += b.x; tot[3] += b.y;
         }
+        double bt[4] = {0.0, 0.0, 0.0, 0.0};                 // the helpers' slices of the boundary rows, in CTA order
+        if (o == 0 && R > 1) {
+            const int K = loop_helpers(X, gsz);
+            for (int i = 1 + lane; i < K; i += 32) {
+                const double2 a = __ldcg(reinterpret_cast<const double2 *>(X.bparts + (size_t)i * 4));
+                const double2 b = __ldcg(reinterpret_cast<const double2 *>(X.bparts + (size_t)i * 4 + 2));
+                bt[0] += a.x; bt[1] += a.y; bt[2] += b.x; bt[3] += b.y;
+            }
+        }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) tot[q] = warp_sum(tot[q]) + warp_sum(lane < kGroups * kGroupWarps ? s_red[q * 32 + lane] : 0.0);
+        for (int q = 0; q < 4; ++q)
+            tot[q] = warp_sum(tot[q]) + (warp_sum(lane < kGroups * kGroupWarps ? s_red[q * 32 + lane] : 0.0) + warp_sum(bt[q]));
         if (lane < 4) {
             const double v = lane == 0 ? tot[0] : (lane == 1 ? tot[1] : (lane == 2 ? tot[2] : tot[3]));
             s_x[lane] = v;
             for (int p = 0; p < R; ++p) {
-                if (p == X.rank) continue;
-                reinterpret_cast<double *>(X.peer[p] + mbox_off_tot())[((size_t)tot_par * kMboxMaxRanks + X.rank) * 4 + lane] = v;
+                if (p == rank) continue;
+                s_peer[p].tot_dst[lane] = v;
             }
         }
     }
-    __threadfence_system();
+    if (o == 0 || cw == 0) __threadfence_system();           // (after an m-space phase only warp 0 has put anything to the peers)
     XT_MARK(4);                                              // local sums + puts of the totals + fence
     if (R > 1) signal_wait(++sig); else consumers_bar();
     XT_MARK(5);                                              // signal round trip 2
     // 4. the peers' fresh values -> my halo slots ; the ranks' sums in rank order
     if (o == 0 && R > 1) {
-        const double2 *inbox = reinterpret_cast<const double2 *>(X.mine + mbox_off_ga(X.nsend)) + (size_t)ga_par * X.nrecv;
         for (int p = 0; p < R; ++p) {
-            if (p == X.rank) continue;
-            const long long cnt = recv_cnt[p];
-            double2 *dst = X.pair + recv_start[p];
-            const double2 *src = inbox + ga_off[p];
-            copy_batched(dst, src, cnt, ct);
+            const long long cnt = s_peer[p].cnt;
+            if (cnt > 0) copy_batched(s_peer[p].ga_copy_dst, s_peer[p].ga_src, cnt, ct);
         }
     }
     if (ct < 4) {
-        const double *in = reinterpret_cast<const double *>(X.mine + mbox_off_tot()) + (size_t)tot_par * kMboxMaxRanks * 4;
+        const double *in = s_tot_in;
         double v[kMboxMaxRanks];                             // all ranks' sums requested at once, added in rank order
 #pragma unroll
-        for (int r = 0; r < kMboxMaxRanks; ++r) v[r] = (r < R && r != X.rank) ? __ldcg(in + r * 4 + ct) : 0.0;
+        for (int r = 0; r < kMboxMaxRanks; ++r) v[r] = (r < R && r != rank) ? __ldcg(in + r * 4 + ct) : 0.0;
         double g = 0.0;
 #pragma unroll
-        for (int r = 0; r < kMboxMaxRanks; ++r) if (r < R) g += (r == X.rank) ? s_x[ct] : v[r];
+        for (int r = 0; r < kMboxMaxRanks; ++r) if (r < R) g += (r == rank) ? s_x[ct] : v[r];
         X.gtot[(size_t)(ph & 1) * 4 + ct] = g;
     }
     if (ct == 0) {
@@ -816,6 +966,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) gk_loop_kernel(const __grid_c
         }
         // consumer warps 0 / 1: the boundary before phase ph + 1 (the other warps go on and wait for `pass` / `open`)
         if (DIST && cta == 0) loop_exchange(L, *L.dx, ph, ct, cw, lane, gsz, sC, s_red, s_rsum, ctl);
+        if (DIST && cta != 0) loop_help(L, *L.dx, ph, ct, cw, lane, cta, gsz, sC, s_red, ctl);
         if (cw < 2) loop_boundary<DIST>(L, ph + 1, cw, lane, cta, gsz, sS, sC, ctl, s_rsum);
     }
 }
