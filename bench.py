@@ -389,9 +389,10 @@ def run_partitioned(args, dist, rank, world, local_rank, make):
         "single_gpu": {"iterations": it1, "krylov_loop_ms": float(single[0].item()), "us_per_iteration": us1,
                        "what": "the same operator on rank 0's GPU through the plain (unpartitioned) handle"},
         "speedup_vs_single_gpu": us1 / us if us > 0 else None,
-        "kernel": "one persistent kernel per chunk of 24 iterations on every rank; its CTA 0 does the halo scatter-add, the boundary "
-                  "rows, the halo gather and the all-reduce of the four inner products through the peers' mailboxes (NVLink), "
-                  "the other CTAs wait for its release instead of the grid barrier" if in_kernel
+        "kernel": "one persistent kernel per chunk of 24 iterations on every rank; its CTA 0 does the halo scatter-add, the halo "
+                  "gather and the all-reduce of the four inner products through the peers' mailboxes (NVLink), the boundary rows "
+                  "are shared out over 16 helper CTAs (long boundaries only), the other CTAs wait for CTA 0's release instead of "
+                  "the grid barrier" if in_kernel
                   else "launch per half iteration (step kernel + exchange kernel)",
         "launch_per_half_iteration_path": {"us_per_iteration": 1e3 * float(fallback_ms.item()) / max(nit, 1),
                                            "per_launch_us_max_over_ranks": shares,
