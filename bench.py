@@ -635,6 +635,9 @@ def main():
     try:
         if args.gpus > 1:
             raise RuntimeError("skipped at N>1")
+        import gc
+        gc.collect()                           # the e2e lanes' handles and buffers go now, not inside a timed extra
+        torch.cuda.synchronize()
         t_warm = time.perf_counter()           # the e2e phase above is PCIe-bound: let the SM clocks ramp up again
         while time.perf_counter() - t_warm < 0.5:
             step_resident()
@@ -653,11 +656,14 @@ def main():
         d_r3 = torch.tensor(np.random.default_rng(7).standard_normal(n), device=dev)
         for _ in range(3):
             H.iter_solve_two_least_squares(args.delta, d_r1, d_r3)
-        H.timer_start()
-        for _ in range(5):
+        per_call = []
+        for _ in range(7):            # per-call device times: one host hiccup (allocator, GC) must not pass for kernel time
+            H.timer_start()
             o2 = H.iter_solve_two_least_squares(args.delta, d_r1, d_r3)
-        ms = H.timer_stop() / 5
-        extra["iter_solve_two_least_squares"] = {"ms": ms, "solves/s": 1e3 / ms, "krylov_loop_ms_last": H.iter_last_profile()[0],
+            per_call.append(H.timer_stop())
+        ms = float(np.median(per_call))
+        extra["iter_solve_two_least_squares"] = {"ms": ms, "solves/s": 1e3 / ms, "ms_max_of_7": max(per_call),
+                                                 "krylov_loop_ms_last": H.iter_last_profile()[0],
                                                  "iters": [o2[4][0]["niter"], o2[4][1]["niter"]]}
     except Exception as e:   # extras must never take the headline down
         extra["error_spmv"] = repr(e)
