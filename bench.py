@@ -484,8 +484,11 @@ def main():
         return H.iter_solve_two_mixed(args.delta, rhs1, rhs2, out=h_out)
 
     # ---- resident (value) -------------------------------------------------------------------
+    import gc
     for _ in range(max(args.warmup, 3)):
         out = step_resident()
+    gc.collect()
+    gc.disable()          # no collector pause inside the timed regions (re-enabled after the e2e measurement)
     sampler = make_clock_sampler(torch, local_rank)
     barrier()
     sampler.start()
@@ -570,6 +573,7 @@ def main():
         del H2, H3
     else:
         e2e_ms = e2e_serial_ms
+    gc.enable()
     t = torch.tensor([e2e_ms, e2e_serial_ms], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -635,7 +639,6 @@ def main():
     try:
         if args.gpus > 1:
             raise RuntimeError("skipped at N>1")
-        import gc
         gc.collect()                           # the e2e lanes' handles and buffers go now, not inside a timed extra
         torch.cuda.synchronize()
         t_warm = time.perf_counter()           # the e2e phase above is PCIe-bound: let the SM clocks ramp up again

@@ -53,7 +53,16 @@ class FletcherPenaltyNLP:
         return nlp.cons(x) - nlp.meta.lcon
 
     def _hprod_nln(self, x, y, v, obj_weight=1.0):
+        """hprod_nln!: multipliers of the penalised (nonlinear) rows only   (:277-290)."""
+        if self.explicit_linear_constraints and self.nlp.meta.ncon > 0:
+            lag_mul = np.zeros(self.nlp.meta.ncon)
+            lag_mul[list(self.nlp.meta.nln)] = y
+            return self.nlp.hprod(x, lag_mul, v, obj_weight=obj_weight)
         return self.nlp.hprod(x, y, v, obj_weight=obj_weight)
+
+    def _ghjvprod_nln(self, x, g, v):
+        out = self.nlp.ghjvprod(x, g, v)
+        return np.asarray(out)[list(self.nlp.meta.nln)] if self.explicit_linear_constraints else out
 
     def linear_system2(self, x):
         """p1, q1, p2, q2 = solve_two_mixed(nlp, x, gx, cx)   (:215-227)."""
@@ -113,12 +122,22 @@ class FletcherPenaltyNLP:
         QDSolver subtypes without a device handle fall back to the user model's jprod!."""
         h = getattr(self.qdsolver, "handle", None)
         if h is None:
+            if self.explicit_linear_constraints:
+                r, c = self.nlp.jac_nln_structure()
+                out = np.zeros(self.npen)
+                np.add.at(out, r, self.nlp.jac_nln_coord(x) * np.asarray(v)[c])
+                return out
             return self.nlp.jprod(x, v)
         return h.jprod(np.ascontiguousarray(v, dtype=np.float64))
 
     def _jtprod(self, x, u):
         h = getattr(self.qdsolver, "handle", None)
         if h is None:
+            if self.explicit_linear_constraints:
+                r, c = self.nlp.jac_nln_structure()
+                out = np.zeros(self.nvar)
+                np.add.at(out, c, self.nlp.jac_nln_coord(x) * np.asarray(u)[r])
+                return out
             return self.nlp.jtprod(x, u)
         return h.jtprod(np.ascontiguousarray(u, dtype=np.float64))
 
@@ -141,7 +160,7 @@ class FletcherPenaltyNLP:
                 Hcv = self._hprod_nln(x, c, v, obj_weight=0.0)
                 Hv = Hv + Hcv + rho * JtJv
         else:
-            Ssv = self.nlp.ghjvprod(x, gs, v)
+            Ssv = self._ghjvprod_nln(x, gs, v)
             invJtJJv, invJtJSsv = solve_two_extras(self, x, v, Ssv)
             JtinvJtJSsv = self._jtprod(x, invJtJSsv)
             Hv = p2 - HsPtv + 2 * sigma * Ptv - JtinvJtJSsv

@@ -296,6 +296,7 @@ class SubStats:
         self.x = None
         self.fx = float("nan")
         self.gx = None
+        self.lam = self.res = None       # explicit linear constraints: their multipliers and g + A'lam
         self.current_score = float("inf")
         self.iter = 0
         self.cg_iter = 0
@@ -347,6 +348,67 @@ def _steihaug(hv, g, radius, tol, itmax, free=None):
     return s, -q, nprod
 
 
+class _LinearRows:
+    """The linear rows of `nlp` as a model of their own (what a QDSolver constructor reads: meta, jac_structure, jac_coord)."""
+
+    def __init__(self, nlp):
+        from .models import NLPModelMeta
+        self.parent = nlp
+        lin = list(nlp.meta.lin)
+        self.meta = NLPModelMeta(nlp.meta.nvar, len(lin), x0=nlp.meta.x0, lcon=np.asarray(nlp.meta.lcon)[lin],
+                                 ucon=np.asarray(nlp.meta.ucon)[lin], name=nlp.meta.name + "-linear-rows")
+        self._rows, self._cols = nlp.jac_lin_structure()
+        self.meta.nnzj = len(self._rows)
+
+    def jac_structure(self):
+        return self._rows, self._cols
+
+    def jac_coord(self, x):
+        return self.parent.jac_lin_coord(x)
+
+
+class LinearConstraintProjector:
+    """Null-space projections for the explicit linear constraints `A x = b` of the subproblem
+    (`explicit_linear_constraints = true`, src/parameters.jl:290-309; in the reference the constraints are simply handed
+    to ipopt / knitro).  Both operations are 2-RHS solves of the SAME kernel family as the penalty's own — a QDSolver
+    on `[I A'; A 0]` with the constant linear rows:
+        project(v)  = (I - A'(AA')^-1 A) v  and  (AA')^-1 A v          <- p1, q1 of solve_two_least_squares(v, v)
+        correct(r)  = A'(AA')^-1 r   (minimum-norm d with A d = r)      <- p2 of solve_two_mixed(0, r)"""
+
+    def __init__(self, nlp, qds_factory):
+        self.rows = _LinearRows(nlp)
+        self.nlp = self.rows                    # what solve_two_* read through `fpnlp.nlp`
+        self.explicit_linear_constraints = False
+        self.delta = 0.0
+        self.qdsolver = qds_factory(self.rows)
+        self.b = np.asarray(self.rows.meta.lcon, dtype=np.float64)
+        self._ready = False
+        self._x0 = np.asarray(nlp.meta.x0, dtype=np.float64)
+
+    def _setup(self):
+        if not self._ready:                     # values / factorisation of the constant rows: once
+            from .qdsolver import solve_two_mixed
+            n, m = self.rows.meta.nvar, self.rows.meta.ncon
+            solve_two_mixed(self, self._x0, np.zeros(n), np.zeros(m))
+            self._ready = True
+
+    def residual(self, x):
+        return self.rows.parent.cons_lin(x) - self.b
+
+    def project(self, v):
+        from .qdsolver import solve_two_least_squares
+        self._setup()
+        p1, q1, _, _ = solve_two_least_squares(self, self._x0, v, v)
+        return np.array(p1, copy=True), np.array(q1, copy=True)
+
+    def correct(self, r):
+        from .qdsolver import solve_two_mixed
+        n = self.rows.meta.nvar
+        _, _, p2, _ = solve_two_mixed(self, self._x0, np.zeros(n), np.asarray(r, dtype=np.float64))
+        self._ready = True
+        return np.array(p2, copy=True)
+
+
 def _steihaug_device(handle, hv, g, radius, tol, itmax, free=None):
     """`_steihaug` with the CG state resident in HBM: s, r, d are device vectors, the five inner products
     of an iteration, the step to the boundary, alpha, beta, the model decrease and the exit decision are computed by the
@@ -385,7 +447,7 @@ def _cg_solver_for(model, g):
 
 
 def trunk(model, x0, *, atol=1e-7, rtol=1e-7, max_iter=20000, max_time=300.0, unbounded_threshold=1 / SQRT_EPS,
-          lvar=None, uvar=None, verbose=0, stop_callback=None):
+          lvar=None, uvar=None, verbose=0, stop_callback=None, lin=None):
     """Trust-region Newton-CG for  min φσ(x)  [l ≤ x ≤ u].  Optimality as Stopping's
     `unconstrained_check` / `optim_check_bounded`: ‖∇φσ‖∞ (projected) ≤ max(atol, rtol·score(x0)).
     `stop_callback(model, x)` may name a SubStats flag to leave with (the outer loop uses it to stop a
@@ -397,13 +459,27 @@ def trunk(model, x0, *, atol=1e-7, rtol=1e-7, max_iter=20000, max_time=300.0, un
     x = _V.copy(x0)
     if bounded:
         x = _V.clip(x, lvar, uvar)
+    # `lin` (LinearConstraintProjector): linear equality constraints A x = b kept explicit in the subproblem.  The
+    # iterates stay on the manifold (minimum-norm correction of the start, steps in the null space of A), the CG runs on
+    # the projected Hessian P H P, optimality is the reduced gradient P g = g + A'lam with lam = -(AA')^-1 A g.
+    lam = None
+    if lin is not None:
+        if bounded:
+            raise NotImplementedError("explicit linear constraints together with bounds")
+        x = x - lin.correct(lin.residual(x))
     f, g = model.objgrad(x)
     n = len(x)
 
     def pgrad(x, g):
+        nonlocal lam
+        if lin is not None:
+            gp, q = lin.project(g)
+            lam = -q
+            return gp
         return x - _V.clip(x - g, lvar, uvar) if bounded else g
 
-    score = _V.ninf(pgrad(x, g))
+    gred = pgrad(x, g)                                        # the gradient the steps are computed from
+    score = _V.ninf(gred)
     tol = max(atol, rtol * score)
     radius = min(max(0.1 * _V.norm(g), 1.0), 100.0)
     it = 0
@@ -435,9 +511,13 @@ def trunk(model, x0, *, atol=1e-7, rtol=1e-7, max_iter=20000, max_time=300.0, un
         if bounded:
             act = ((x <= lvar) & (g > 0)) | ((x >= uvar) & (g < 0))
             free = (~act) * 1.0
-        gn = _V.norm(g if free is None else g * free)
+        gcg = gred if lin is not None else g
+        gn = _V.norm(gcg if free is None else gcg * free)
         cgtol = max(EPS, min(0.1, math.sqrt(gn)) * gn)
-        s, pred, nprod = _cg_solver_for(model, g)(lambda v: model.hprod(x, v), g, radius, cgtol, max(2 * n, 10), free)
+        hv = (lambda v: lin.project(model.hprod(x, v))[0]) if lin is not None else (lambda v: model.hprod(x, v))
+        s, pred, nprod = _cg_solver_for(model, gcg)(hv, gcg, radius, cgtol, max(2 * n, 10), free)
+        if lin is not None:
+            s = lin.project(s)[0]                             # rounding drift out of the null space
         out.cg_iter += nprod
         if bounded:
             xt = _V.clip(x + s, lvar, uvar)
@@ -477,7 +557,8 @@ def trunk(model, x0, *, atol=1e-7, rtol=1e-7, max_iter=20000, max_time=300.0, un
         if rho >= 1e-4:
             x, f = xt, ft
             g = gt if gt is not None else model.grad(x)
-            new_score = _V.ninf(pgrad(x, g))
+            gred = pgrad(x, g)
+            new_score = _V.ninf(gred)
             if in_noise:                                      # unverifiable step: a stall unless the gradient still drops
                 noise_steps = 0 if new_score <= 0.9 * score else noise_steps + 1
             score = new_score
@@ -495,6 +576,7 @@ def trunk(model, x0, *, atol=1e-7, rtol=1e-7, max_iter=20000, max_time=300.0, un
     # leave the model's memo (fx, cx, gx, ys — read by the outer loop, src/algo.jl:118-145) at x
     out.fx = model.obj(x)
     out.x, out.gx, out.iter = x, g, it
+    out.lam, out.res = lam, (gred if lin is not None else g)  # multipliers of the explicit linear constraints, g + A'lam
     return out
 
 
@@ -711,19 +793,33 @@ class FPSSSolver:
         self.kwargs = kwargs
         x0 = nlp.meta.x0 if x0 is None else x0
         self.meta = AlgoData(**kwargs)
-        if self.meta.explicit_linear_constraints and nlp.meta.nlin > 0:
-            raise NotImplementedError("explicit linear constraints need a linearly constrained subproblem "
-                                      "solver (ipopt / knitro in the reference); not provided here")
+        explicit = bool(self.meta.explicit_linear_constraints)
         if isinstance(qds_solver, QDSolver):
             self.qdsolver = qds_solver
+            qds_cls = type(qds_solver)
         elif isinstance(qds_solver, type) or callable(qds_solver):
             self.qdsolver = qds_solver(nlp, 0.0, **kwargs)
+            qds_cls = qds_solver
         else:
-            self.qdsolver = qdsolver_correspondence[str(qds_solver).lstrip(":")](nlp, 0.0, **kwargs)
+            qds_cls = qdsolver_correspondence[str(qds_solver).lstrip(":")]
+            self.qdsolver = qds_cls(nlp, 0.0, **kwargs)
         self.feasibility_solver = GNSolver(fused=bool(kwargs.get("feas_fused", False)))
         factory = model_factory or FletcherPenaltyNLP
-        self.model = factory(nlp, self.meta.sigma_0, self.meta.rho_0, 0.0, self.meta.hessian_approx,
-                             qds=self.qdsolver, consistent_gradient=bool(kwargs.get("consistent_gradient", False)))
+        model_kw = dict(qds=self.qdsolver, consistent_gradient=bool(kwargs.get("consistent_gradient", False)))
+        if explicit:
+            # the linear rows stay constraints of the subproblem (src/parameters.jl:300-309); here they are kept by
+            # null-space projections that run on a second QDSolver of the same type (LinearConstraintProjector)
+            if model_factory is not None:
+                raise NotImplementedError("explicit_linear_constraints with a custom / device-resident model factory")
+            model_kw["explicit_linear_constraints"] = True
+        self.model = factory(nlp, self.meta.sigma_0, self.meta.rho_0, 0.0, self.meta.hessian_approx, **model_kw)
+        self.lin_projector = None
+        if explicit and nlp.meta.nlin > 0:
+            if np.any(np.asarray(nlp.meta.lcon)[list(nlp.meta.lin)] != np.asarray(nlp.meta.ucon)[list(nlp.meta.lin)]):
+                raise NotImplementedError("explicit linear constraints: equalities only (SlackModel turns the others into "
+                                          "equalities with bounded slacks, which the projected subsolver does not handle)")
+            lin_kw = {k: v for k, v in kwargs.items() if k != "explicit_linear_constraints"}
+            self.lin_projector = LinearConstraintProjector(nlp, lambda rows: qds_cls(rows, 0.0, **lin_kw))
         self.subproblem_solver = self.meta.subproblem_solver if callable(self.meta.subproblem_solver) \
             else subproblem_solver_correspondence[str(self.meta.subproblem_solver)]
         self.sub_stats = None
@@ -839,6 +935,8 @@ def solve(fpssolver, *, verbose=0, subsolver_verbose=0, callback=None, seed=1234
     feasibility_phase = restoration_phase = False
     sub_x = _V.copy(st.x)
     bounds = dict(lvar=stp._lvar, uvar=stp._uvar) if stp.has_bounds else {}
+    lin_proj = getattr(fpssolver, "lin_projector", None)
+    lin_kw = dict(lin=lin_proj) if lin_proj is not None else {}
     sub = SubStats()
     ys_blown_up = lambda mdl, x: "unbounded" if _V.ninf(mdl.ys) >= meta.lagrange_bound else None
     if callback:
@@ -848,7 +946,7 @@ def solve(fpssolver, *, verbose=0, subsolver_verbose=0, callback=None, seed=1234
         sub = fpssolver.subproblem_solver(model, sub_x, atol=sub_atol, rtol=sub_rtol,
                                           max_iter=meta.subsolver_max_iter, max_time=max_time,
                                           unbounded_threshold=meta.subpb_unbounded_threshold,
-                                          verbose=subsolver_verbose, stop_callback=ys_blown_up, **bounds)
+                                          verbose=subsolver_verbose, stop_callback=ys_blown_up, **bounds, **lin_kw)
         fpssolver.sub_stats = sub
         unbounded_lagrange_multiplier = _V.ninf(model.ys) >= meta.lagrange_bound
         sub_ok = sub.optimal or sub.suboptimal
@@ -858,9 +956,23 @@ def solve(fpssolver, *, verbose=0, subsolver_verbose=0, callback=None, seed=1234
             if _V.equal(sub.x, st.x):
                 stalling += 1
             unsuccessful_subpb = unbounded_subpb = 0
-            st.lam = -model.ys
-            st.cx = model.cx + stp._lcon
-            st.res = sub.gx
+            if lin_proj is not None:
+                # src/algo.jl:127-137: multipliers and constraint values of the linear rows come from the subproblem,
+                # those of the nonlinear rows from the penalty model; the residual is the subproblem's g + J_lin' lambda.
+                # Sign: sub.lam = -(AA')^-1 A g, the convention of the penalised rows (lambda = -ys, ys = (JJ')^-1 J g),
+                # so that both modes report the same multipliers for a linear row.
+                lin_i, nln_i = list(stp.pb.meta.lin), list(stp.pb.meta.nln)
+                lam = np.zeros(stp.pb.meta.ncon)
+                lam[lin_i] = sub.lam
+                lam[nln_i] = -model.ys
+                cx = np.zeros(stp.pb.meta.ncon)
+                cx[lin_i] = stp.pb.cons_lin(sub.x)
+                cx[nln_i] = model.cx + np.asarray(stp.pb.meta.lcon)[nln_i]
+                st.lam, st.cx, st.res = lam, cx, sub.res
+            else:
+                st.lam = -model.ys
+                st.cx = model.cx + stp._lcon
+                st.res = sub.gx
             st.x, st.fx, st.gx = _V.copy(sub.x), model.fx, model.gx
             _go_log(stp, sub, model, st.fx, _V.norm(model.cx), "Optml", verbose)
         elif sub_unbdd:

@@ -60,6 +60,40 @@ class AbstractNLPModel:
         """(g' H_j(x) v)_j for each constraint j."""
         return np.zeros(self.meta.ncon)
 
+    # linear / nonlinear rows (NLPModels' cons_lin!, cons_nln!, jac_lin_structure!, jac_nln_coord!, ...): generic
+    # versions that filter the rows of cons / jac_structure / jac_coord by meta.lin / meta.nln
+    def _rows_of(self, which):
+        key = tuple(int(i) for i in which)
+        cache = self.__dict__.setdefault("_rowsel", {})
+        if key not in cache:
+            r, c = self.jac_structure()
+            r, c = np.asarray(r, dtype=np.int64), np.asarray(c, dtype=np.int64)
+            pos = -np.ones(max(self.meta.ncon, 1), dtype=np.int64)
+            pos[list(key)] = np.arange(len(key))
+            sel = np.nonzero(pos[r] >= 0)[0] if len(r) else np.zeros(0, dtype=np.int64)
+            cache[key] = (sel, pos[r[sel]], c[sel])
+        return cache[key]
+
+    def jac_lin_structure(self):
+        _, r, c = self._rows_of(self.meta.lin)
+        return r, c
+
+    def jac_nln_structure(self):
+        _, r, c = self._rows_of(self.meta.nln)
+        return r, c
+
+    def jac_lin_coord(self, x):
+        return np.asarray(self.jac_coord(x), dtype=np.float64)[self._rows_of(self.meta.lin)[0]]
+
+    def jac_nln_coord(self, x):
+        return np.asarray(self.jac_coord(x), dtype=np.float64)[self._rows_of(self.meta.nln)[0]]
+
+    def cons_lin(self, x):
+        return np.asarray(self.cons(x), dtype=np.float64)[list(self.meta.lin)]
+
+    def cons_nln(self, x):
+        return np.asarray(self.cons(x), dtype=np.float64)[list(self.meta.nln)]
+
 
 class CallableModel(AbstractNLPModel):
     """Small dense model from callables (the role ADNLPModel plays in the reference's tests).
@@ -69,7 +103,7 @@ class CallableModel(AbstractNLPModel):
     """
 
     def __init__(self, f, grad, cons, jac, hess_f, hess_c, x0, ncon, lcon=None, ucon=None,
-                 name="callable"):
+                 name="callable", lin=()):
         super().__init__()
         nvar = len(x0)
         self._f, self._g, self._c, self._J, self._Hf, self._Hc = f, grad, cons, jac, hess_f, hess_c
@@ -77,7 +111,7 @@ class CallableModel(AbstractNLPModel):
         self._rows = rows.ravel().astype(np.int64)
         self._cols = cols.ravel().astype(np.int64)
         self.meta = NLPModelMeta(nvar, ncon, x0=x0, lcon=lcon, ucon=ucon if ucon is not None else lcon,
-                                 nnzj=nvar * ncon, name=name)
+                                 nnzj=nvar * ncon, name=name, lin=lin)
 
     def obj(self, x):
         self.counters.neval_obj += 1

@@ -226,3 +226,81 @@ def test_stats_fields_and_multipliers_sign(qds):
     assert np.linalg.norm(nlp.grad(x) + J.T @ lam) < 1e-5
     assert s.elapsed_time >= 0 and s.objective == pytest.approx(-np.sqrt(3), abs=1e-6)
     assert set(s.solver_specific) >= {"sigma", "rho", "delta", "restoration", "feasibility", "solver"}
+
+
+def _mgh01feas(rhs2):
+    """test/test-2.jl:290-322: f = 0, one linear row -x1 = -1 and c(x) = 10 (x2 - x1^2) = rhs2 (rows: linear first)."""
+    A = np.array
+    return models.CallableModel(lambda x: 0.0, lambda x: np.zeros(2),
+                                lambda x: A([-x[0], 10 * (x[1] - x[0] ** 2)]),
+                                lambda x: A([[-1.0, 0.0], [-20 * x[0], 10.0]]),
+                                lambda x: np.zeros((2, 2)),
+                                lambda x, j: np.zeros((2, 2)) if j == 0 else A([[-20.0, 0.0], [0.0, 0.0]]),
+                                [-1.2, 1.0], 2, lcon=[-1.0, rhs2], ucon=[-1.0, rhs2], lin=[0], name="mgh01feas")
+
+
+@pytest.mark.parametrize("solver", ["ldlt", "iterative"])
+@pytest.mark.parametrize("rhs2,x2", [(0.0, 1.0), (1.0, 1.1)])
+def test_explicit_linear_constraints(qds, solver, rhs2, x2):
+    """"Problems with explicit linear constraints" (test/test-2.jl:290-322): the linear row stays a constraint of the
+    subproblem (kept by null-space projections through a second QDSolver), only the nonlinear row is penalised."""
+    nlp = _mgh01feas(rhs2)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        stats = F.fps_solve(nlp, explicit_linear_constraints=True, qds_solver=qds[solver])
+    assert stats.status == "first_order"
+    assert np.linalg.norm(nlp.cons(stats.solution) - nlp.meta.lcon) <= 1e-10          # the reference's four assertions
+    assert stats.dual_feas <= 1e-10 and stats.primal_feas <= 1e-10
+    assert np.linalg.norm(stats.solution - np.array([1.0, x2])) <= 1e-9
+    assert stats.multipliers.shape == (2,)
+
+
+def test_explicit_linear_constraints_model_and_projector(qds):
+    """The pieces: the penalty model only sees the nonlinear rows (ys, cx of size nnln, hprod with zero multipliers on
+    the linear rows), the projector returns (I - A'(AA')^-1 A) v, (AA')^-1 A v and the minimum-norm correction."""
+    import oracle_qds
+    nlp = models.CallableModel(lambda x: float(x @ x), lambda x: 2 * x,
+                               lambda x: np.array([x[0] + 2 * x[1] - x[2], x[0] * x[1] - 1.0, x[1] - x[3]]),
+                               lambda x: np.array([[1.0, 2.0, -1.0, 0.0], [x[1], x[0], 0.0, 0.0], [0.0, 1.0, 0.0, -1.0]]),
+                               lambda x: 2 * np.eye(4),
+                               lambda x, j: np.array([[0, 1.0, 0, 0], [1.0, 0, 0, 0], [0, 0, 0, 0], [0, 0, 0, 0]]) if j == 1 else np.zeros((4, 4)),
+                               [1.0, 2.0, 0.5, -1.0], 3, lcon=[0.5, 0.0, -0.25], ucon=[0.5, 0.0, -0.25], lin=[0, 2], name="mixed-rows")
+    assert nlp.meta.nlin == 2 and nlp.meta.nln == [1]
+    x = np.array([0.3, -0.7, 1.1, 0.2])
+    r, c = nlp.jac_lin_structure()
+    Al = np.zeros((2, 4)); np.add.at(Al, (r, c), nlp.jac_lin_coord(x))
+    assert np.allclose(Al, [[1, 2, -1, 0], [0, 1, 0, -1]]) and np.allclose(nlp.cons_lin(x), Al @ x)
+    model = fpsb200.FletcherPenaltyNLP(nlp, 2.0, 1.0, 0.0, 2, qds=oracle_qds.OracleLDLt(nlp, 0.0, explicit_linear_constraints=True),
+                                       explicit_linear_constraints=True)
+    assert model.npen == 1
+    model.obj(x)
+    assert model.cx.shape == (1,) and abs(model.cx[0] - (x[0] * x[1] - 1.0)) < 1e-15 and model.ys.shape == (1,)
+    v = np.array([1.0, -2.0, 0.5, 3.0])
+    assert np.allclose(model._hprod_nln(x, np.array([3.0]), v, obj_weight=0.0), 3.0 * np.array([v[1], v[0], 0, 0]))
+    assert np.all(np.isfinite(model.grad(x))) and np.all(np.isfinite(model.hprod(x, v)))
+    P = F.LinearConstraintProjector(nlp, lambda rows: oracle_qds.OracleLDLt(rows, 0.0))
+    pv, lam = P.project(v)
+    G = Al @ Al.T
+    assert np.allclose(pv, v - Al.T @ np.linalg.solve(G, Al @ v), atol=1e-10) and np.allclose(lam, np.linalg.solve(G, Al @ v), atol=1e-10)
+    d = P.correct(P.residual(x))
+    assert np.allclose(Al @ (x - d), [0.5, -0.25], atol=1e-10) and np.allclose(d, Al.T @ np.linalg.solve(G, Al @ x - [0.5, -0.25]), atol=1e-10)
+    # a whole solve with objective, curved and linear rows.  consistent_gradient: with the reference's gradient formula
+    # (+ys where the derivative of obj has -ys, DESIGN §2) the projected subproblem stalls away from c = 0 on this problem
+    kw = dict(qds_solver=oracle_qds.OracleLDLt, consistent_gradient=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        nlp.counters.__init__()
+        stats = F.fps_solve(nlp, explicit_linear_constraints=True, **kw)
+        nlp.counters.__init__()
+        ref = F.fps_solve(nlp, **kw)
+    assert stats.status == ref.status == "first_order"
+    assert np.linalg.norm(stats.solution - ref.solution) <= 1e-5
+    assert np.abs(Al @ stats.solution - [0.5, -0.25]).max() <= 1e-10                  # the linear rows hold to rounding
+    assert np.allclose(stats.multipliers[[0, 2]], ref.multipliers[[0, 2]], rtol=1e-4)  # same sign convention in both modes
+
+
+def test_explicit_linear_constraints_rejects_what_it_cannot_do(qds):
+    nlp = _mgh01feas(0.0)
+    nlp.meta.ucon = np.array([0.0, 0.0])                     # a linear inequality
+    with pytest.raises(NotImplementedError):
+        F.FPSSSolver(nlp, explicit_linear_constraints=True, qds_solver=qds["ldlt"])

@@ -82,3 +82,26 @@ def test_fps_solve_sparse_qp_host_and_device_resident(solver):
     assert dev.status == host.status and abs(dev.iter - host.iter) <= 1
     assert np.linalg.norm(dev.solution - host.solution) <= 1e-6 * np.linalg.norm(host.solution)
     assert np.linalg.norm(dev.multipliers - host.multipliers) <= 1e-6 * max(1.0, np.linalg.norm(host.multipliers))
+
+
+@pytest.mark.parametrize("solver", ["ldlt", "iterative"])
+@pytest.mark.parametrize("rhs2,x2", [(0.0, 1.0), (1.0, 1.1)])
+def test_explicit_linear_constraints_on_the_gpu_solvers(solver, rhs2, x2):
+    """"Problems with explicit linear constraints" (test/test-2.jl:290-322) with both QDSolvers of the run on the GPU: the
+    penalty's (nonlinear rows) and the null-space projector's (linear rows) — the same 2-RHS kernels, two handles."""
+    import fpsb200
+    from fpsb200 import models
+    A = np.array
+    nlp = models.CallableModel(lambda x: 0.0, lambda x: np.zeros(2), lambda x: A([-x[0], 10 * (x[1] - x[0] ** 2)]),
+                               lambda x: A([[-1.0, 0.0], [-20 * x[0], 10.0]]), lambda x: np.zeros((2, 2)),
+                               lambda x, j: np.zeros((2, 2)) if j == 0 else A([[-20.0, 0.0], [0.0, 0.0]]),
+                               [-1.2, 1.0], 2, lcon=[-1.0, rhs2], ucon=[-1.0, rhs2], lin=[0], name="mgh01feas")
+    stats = _run(nlp, solver, explicit_linear_constraints=True)
+    s = stats.solver_specific["solver"]
+    cls = fpsb200.LDLtSolver if solver == "ldlt" else fpsb200.IterativeSolver
+    assert isinstance(s.qdsolver, cls) and isinstance(s.lin_projector.qdsolver, cls)
+    assert s.qdsolver.handle.ncon == 1 and s.lin_projector.qdsolver.handle.ncon == 1
+    assert stats.status == "first_order"
+    assert np.linalg.norm(nlp.cons(stats.solution) - nlp.meta.lcon) <= 1e-10
+    assert stats.dual_feas <= 1e-10 and stats.primal_feas <= 1e-10
+    assert np.linalg.norm(stats.solution - A([1.0, x2])) <= 1e-9
