@@ -149,3 +149,78 @@ def test_dist_world2_matches_single_gpu(oracle, transport):
     for r in res:
         assert [s["niter"] for s in r[17]] == [s["niter"] for s in res[0][17]]
         assert abs(r[17][1]["niter"] - ex[2][1]["niter"]) <= 1
+
+
+def _stencil_problem(nx=1100, ny=64):
+    """Interleaved 5-point-stencil operator [L -I] (BASELINE config C3 shape), wide enough for a strip boundary of
+    ~3 300 rows: multi-segment gather windows and the helper-CTA path of the in-kernel exchange (>= 1 536 boundary rows)."""
+    import scipy.sparse as sp
+    Tx = sp.diags([-1.0, 2.0, -1.0], [-1, 0, 1], shape=(nx, nx))
+    Ty = sp.diags([-1.0, 2.0, -1.0], [-1, 0, 1], shape=(ny, ny))
+    L = sp.kron(Ty, sp.identity(nx)) + sp.kron(sp.identity(ny), Tx)
+    m = nx * ny
+    A = sp.hstack([L, -sp.identity(m)]).tocoo()
+    rng = np.random.default_rng(21)
+    vals = A.data * (1.0 + 0.1 * rng.standard_normal(A.nnz))
+    perm = np.empty(2 * m, dtype=np.int64)
+    perm[:m] = 2 * np.arange(m)
+    perm[m:] = 2 * np.arange(m) + 1
+    jr, jc = A.row.astype(np.int64), perm[A.col]
+    return m, 2 * m, jr, jc, vals, rng.standard_normal(2 * m), rng.standard_normal(m)
+
+
+def _stencil_worker(rank, world, port, q):
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import fpsb200
+    from fpsb200.partition import RowPartition, DistHandle
+    m, n, jr, jc, vals, r1, r2 = _stencil_problem()
+    o = fpsb200.IterOpts()
+    fpsb200._lib.lib().fpsb_iter_default_opts(ctypes.c_int64(n), ctypes.c_int64(m), ctypes.byref(o))
+    o.ls_itmax = o.ln_itmax = 30
+    D = DistHandle(RowPartition(n, m, jr, jc, world), rank, device=rank, dist=dist, opts=o, peer=True)
+    D.set_jac_values(vals)
+    L = D.loc
+    own, rows = slice(L.col0, L.col0 + L.n_own), slice(L.row0, L.row0 + L.m_loc)
+    a = D.solve_two_mixed(1e-2, r1[own], r2[rows])
+    b = D.solve_two_mixed(1e-2, r1[own], r2[rows])                 # again: bitwise reproducible
+    q.put((rank, int(L.n_ext - L.n_own), a[:4], [s["niter"] for s in a[4]], all(np.array_equal(x, y) for x, y in zip(a[:4], b[:4]))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dist_world2_long_boundary_helper_ctas(oracle):
+    import ctypes
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    import fpsb200
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 36500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_stencil_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=600) for _ in range(2)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    m, n, jr, jc, vals, r1, r2 = _stencil_problem()
+    assert max(r[1] for r in res) >= 1536                           # long enough for the helper CTAs
+    assert all(r[4] for r in res)
+    o = fpsb200.IterOpts()
+    fpsb200._lib.lib().fpsb_iter_default_opts(ctypes.c_int64(n), ctypes.c_int64(m), ctypes.byref(o))
+    o.ls_itmax = o.ln_itmax = 30
+    H = fpsb200.B200Handle(n, m, jr, jc)
+    H.iter_setup(o)
+    H.set_jac_values(vals)
+    one = H.iter_solve_two_mixed(1e-2, r1, r2)
+    assert res[0][3] == res[1][3] == [s["niter"] for s in one[4]]
+    for i in range(4):
+        assert _rel(np.concatenate([r[2][i] for r in res]), one[i]) < 1e-9
