@@ -26,7 +26,9 @@
 // Row-partitioned runs (fpsb_dist.inl): what CTA 0 needs to do the exchange of a phase boundary itself, through the
 // peers' mailboxes (CUDA IPC over NVLink), while the other CTAs wait for ITS release instead of the grid barrier:
 //   n-space phase:  halo partial sums -> owners ; owners add them (rank order), run the row epilogue of their
-//                   boundary rows and put the fresh pair values into the halo slots of the peers ; norm sums
+//                   boundary rows (long boundaries: shared out over the consumer threads of a few helper CTAs, which
+//                   are idle until the halo is back) and put the fresh pair values into the halo slots of the peers ;
+//                   norm sums
 //   m-space phase:  norm sums only
 // The four all-reduced sums go to gtot; every CTA runs the scalar recurrences on those, exactly as on one GPU.
 // One launch = a chunk of iterations of every rank: an iteration costs two NVLink signal round trips (n) + one (m),
