@@ -539,6 +539,10 @@ def main():
             H.pin_host(a)
         lanes = [(H3, h_out3), (H2, h_out2)]
         errs = []
+        # fpsb_pipeline_gate: one solve computes at a time, the copies of the other lane ride on the copy engines under it.
+        # Without the turn-taking both loops interleave chunk by chunk, finish together and copy together: how much overlap
+        # is left is luck (measured box to box: 148-182 solves/s for the same build).
+        fpsb200._lib.lib().fpsb_pipeline_gate(0 if os.environ.get("FPSB_BENCH_NO_GATE") else 1)
 
         def lane(i, count):
             try:
@@ -566,6 +570,7 @@ def main():
         if errs or not all(np.array_equal(a, b) and np.array_equal(a, c) for a, b, c in zip(h_out, h_out2, h_out3)):
             raise SystemExit(f"bench.py: pipelined e2e lanes failed or disagree: {errs}")
         lanes.clear()
+        fpsb200._lib.lib().fpsb_pipeline_gate(0)
         for a in h_out2 + h_out3:
             H.unpin_host(a)
         H2.close()          # (their L2 persistence windows must not shrink the cache of the measurements that follow)
@@ -754,8 +759,8 @@ def main():
                 "host_numa": numa,
                 "note": "host buffers through the C ABI; every step copies its Jacobian values + both rhs H2D and its four "
                         "result vectors D2H inside the timed region; value = two independent solves in flight per GPU (two "
-                        "handles, two host threads) so that the copies of one overlap the Krylov loop of the other; "
-                        "one_at_a_time = the strictly serial figure"},
+                        "handles, two host threads, fpsb_pipeline_gate on: one solve computes at a time) so that the copies of "
+                        "one overlap the Krylov loop of the other; one_at_a_time = the strictly serial figure"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,

@@ -6,6 +6,8 @@
 #include <cstring>
 #include <cmath>
 #include <new>
+#include <atomic>
+#include <mutex>
 
 namespace fpsb {
 
@@ -335,6 +337,19 @@ int fpsb_iter_last_profile(fpsb_handle hh, double *loop_ms, int64_t *step_launch
     return FPSB_OK;
 }
 
+// Pipelined throughput mode (several handles of one process driven by their own host threads): one solve COMPUTES at
+// a time per device.  The H2D copies of a waiting handle are already enqueued on its stream and the D2H of a finished
+// one happens after it leaves the gate, so they ride on the copy engines under the running Krylov loop; without the
+// gate two persistent loops interleave chunk by chunk, finish together and copy together.
+static std::atomic<int> g_gate_on{0};
+static std::mutex g_gate[16];
+struct ComputeGate {
+    std::mutex *m = nullptr;
+    explicit ComputeGate(int device) { if (g_gate_on.load(std::memory_order_relaxed)) { m = &g_gate[device & 15]; m->lock(); } }
+    ~ComputeGate() { if (m) m->unlock(); }
+};
+int fpsb_pipeline_gate(int on) { g_gate_on.store(on ? 1 : 0); return FPSB_OK; }
+
 static int iter_solve(fpsb_handle hh, int kind, double delta, const double *rhs1, const double *rhs2,
                       double *p1, double *q1, double *p2, double *q2, int loc, fpsb_krylov_stats *stats) {
     Handle *h = reinterpret_cast<Handle *>(hh);
@@ -348,8 +363,11 @@ static int iter_solve(fpsb_handle hh, int kind, double delta, const double *rhs1
     Staged S(h, loc, n + n2, 2 * n + 2 * m);
     const double *d1 = S.in(rhs1, n), *d2 = S.in(rhs2, n2);
     double *dp1 = S.out(p1, n), *dq1 = S.out(q1, m), *dp2 = S.out(p2, n), *dq2 = S.out(q2, m);
-    if (kind == 0) iter_solve_two_mixed(h, delta, d1, d2, dp1, dq1, dp2, dq2, stats);
-    else iter_solve_two_least_squares(h, delta, d1, d2, dp1, dq1, dp2, dq2, stats);
+    {
+        ComputeGate gate(h->device);
+        if (kind == 0) iter_solve_two_mixed(h, delta, d1, d2, dp1, dq1, dp2, dq2, stats);
+        else iter_solve_two_least_squares(h, delta, d1, d2, dp1, dq1, dp2, dq2, stats);
+    }
     S.finish();
     return FPSB_OK;
     FPSB_CATCH

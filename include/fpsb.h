@@ -110,6 +110,10 @@ int fpsb_synchronize(fpsb_handle h);
 /* CUDA-event stopwatch on the handle's stream (used by bench.py for device-side timing) */
 int fpsb_timer_start(fpsb_handle h);
 int fpsb_timer_stop(fpsb_handle h, double *elapsed_ms);
+/* Pipelined throughput mode for host buffers (not in the reference, whose caller is one thread): with the gate on, the
+ * fpsb_iter_solve_two_* calls of different handles / host threads of this process take turns for the compute part on a
+ * device, while their host<->device copies overlap the solve that is running (process-wide switch, default off). */
+int fpsb_pipeline_gate(int on);
 /* number of kernels launched by this handle since creation (bench.py's gpu_launches) */
 int64_t fpsb_launch_count(fpsb_handle h);
 /* Layout of the tiled operators behind jprod / jtprod and the Krylov loops (the storage that replaces the reference's
