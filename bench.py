@@ -645,20 +645,24 @@ def main():
         if args.gpus > 1:
             raise RuntimeError("skipped at N>1")
         gc.collect()                           # the e2e lanes' handles and buffers go now, not inside a timed extra
+        gc.disable()                           # (a generation-2 pass between two launches reads as 25 ms of 'kernel' time)
         torch.cuda.synchronize()
         t_warm = time.perf_counter()           # the e2e phase above is PCIe-bound: let the SM clocks ramp up again
         while time.perf_counter() - t_warm < 0.5:
             step_resident()
+        reps = 100                             # (20 left 1-2 us of event / launch-pipeline start-up in every figure)
+        for _ in range(5):
+            H.jprod(d_r1); H.jtprod(d_r2)
         H.timer_start()
-        for _ in range(20):
+        for _ in range(reps):
             y = H.jprod(d_r1)
-        ms = H.timer_stop() / 20
+        ms = H.timer_stop() / reps
         b = 12 * nnz + 4 * (m + 1) + 8 * n + 8 * m
         extra["spmv_A"] = {"us": 1e3 * ms, "GB/s": b / ms / 1e6, "frac_of_measured_peak": b / ms / 1e6 / peak}
         H.timer_start()
-        for _ in range(20):
+        for _ in range(reps):
             y = H.jtprod(d_r2)
-        ms = H.timer_stop() / 20
+        ms = H.timer_stop() / reps
         b = 12 * nnz + 4 * (n + 1) + 8 * n + 8 * m
         extra["spmv_At"] = {"us": 1e3 * ms, "GB/s": b / ms / 1e6, "frac_of_measured_peak": b / ms / 1e6 / peak}
         d_r3 = torch.tensor(np.random.default_rng(7).standard_normal(n), device=dev)
@@ -687,21 +691,27 @@ def main():
             extra["ldlt_analyze_host_s"] = time.perf_counter() - t0
             lnz = int(H.ldlt_symbolic()["Lp"][-1])
             extra["ldlt_plan_dissection"] = dict(H.ldlt_plan_info(), lnz=lnz)
-            H.ldlt_solve_two_mixed(SQRT_EPS, d_r1, d_r2)
-            H.timer_start()
-            for _ in range(3):
+            for _ in range(2):
+                H.ldlt_solve_two_mixed(SQRT_EPS, d_r1, d_r2)
+            per_call = []
+            for _ in range(5):        # per-call device times, median (see the two-LSQR extra)
+                H.timer_start()
                 H.set_jac_values(d_vals)
                 o3 = H.ldlt_solve_two_mixed(SQRT_EPS, d_r1, d_r2)
-            ms = H.timer_stop() / 3
-            extra["ldlt_solve_two_mixed"] = {"ms": ms, "solves/s": 1e3 / ms, "factorized": bool(o3[4]),
+                per_call.append(H.timer_stop())
+            ms = float(np.median(per_call))
+            extra["ldlt_solve_two_mixed"] = {"ms": ms, "solves/s": 1e3 / ms, "ms_all": [round(x, 2) for x in per_call],
+                                             "factorized": bool(o3[4]),
                                              "delta": SQRT_EPS, "ordering": "dissection",
                                              "GFLOP/s": extra["ldlt_plan_dissection"]["flops"] / ms / 1e6}
-            H.timer_start()
-            for _ in range(5):
+            per_call = []
+            for _ in range(7):
+                H.timer_start()
                 o3 = H.ldlt_solve_two_least_squares(d_r1, d_r3)
-            ms = H.timer_stop() / 5
+                per_call.append(H.timer_stop())
+            ms = float(np.median(per_call))
             sb = 24 * lnz + 88 * sym_N
-            extra["ldlt_solve_two_least_squares"] = {"ms": ms, "solves/s": 1e3 / ms, "GB/s": sb / ms / 1e6,
+            extra["ldlt_solve_two_least_squares"] = {"ms": ms, "solves/s": 1e3 / ms, "ms_max_of_7": max(per_call), "GB/s": sb / ms / 1e6,
                                                      "frac_of_measured_peak": sb / ms / 1e6 / peak,
                                                      "ordering": "dissection"}
             res = o3[0] + H.jtprod(o3[1]) - d_r1          # K-residual of the first system, on the device
@@ -715,6 +725,7 @@ def main():
         except Exception as e:
             extra["error_ldlt"] = repr(e)
 
+    gc.enable()
     # ---- CPU baseline (oracle port, bounded sample) -------------------------------------------------
     cpu = None
     if not args.no_cpu_baseline:

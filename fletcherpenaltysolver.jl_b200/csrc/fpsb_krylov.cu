@@ -2036,7 +2036,7 @@ static void fill_csr(StepParams &P, const CsrDev &M) {
     {
         static const int env_inflight = [] { const char *e = getenv("FPSB_INFLIGHT"); return e ? atoi(e) : 0; }();
         P.inflight = env_inflight > 0 ? env_inflight : 2;
-        if (P.inflight > M.nstage) P.inflight = M.nstage;
+        if (P.inflight > M.nstage - 1) P.inflight = std::max(1, M.nstage - 1);      // a tile must not wait for the stage it is about to refill
     }
     P.rowflag = (M.nlong > 0 || M.has_raw_rows) ? M.rowflag.p : nullptr;
     P.wsegs = M.nseg_tiles > 0 ? reinterpret_cast<const int2 *>(M.wsegs.p) : nullptr;
